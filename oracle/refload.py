@@ -1,0 +1,116 @@
+"""Load the UNMODIFIED reference hot-path files -- authoring container only.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  ``/root/reference`` does not
+exist on the GPU box, so nothing that runs there may call this module; it is
+used by ``tests/golden/make_golden.py`` (which writes the committed fixtures)
+and by CPU tests that skip themselves when the reference tree is absent.
+
+The reference package cannot be imported as a whole (``core.py:6`` needs
+xarray, which is not installed).  ``spectral.py`` and ``phase.py`` only need
+numpy plus ``TSeries`` / ``FSeries`` from ``.core`` (``spectral.py:1-5``,
+``phase.py:1-5``), so they are executed as-is with ``periodicity.core`` seeded
+by the numpy-only stand-in below, which carries exactly the attributes the two
+files touch: ``time, values, size, baseline, median_dt, __len__, copy``
+(``core.py:60-66,94-99,144-145,460-511``) and ``frequency, values``
+(``core.py:859-889``).
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("PERIODICITY_REFERENCE_ROOT", "/root/reference")
+
+
+class _StubTSeries:
+    def __init__(self, time=None, values=None, assume_sorted=False):
+        if time is None:
+            time = np.arange(len(values))
+        if values is None:
+            values = np.ones(len(time))
+        time = np.asarray(time)
+        values = np.asarray(values)
+        if time.size != values.size:
+            raise ValueError("Input arrays have incompatible lengths.")
+        if not assume_sorted and np.any(np.diff(time) < 0):
+            order = np.argsort(time, kind="stable")
+            time, values = time[order], values[order]
+        self.time = time
+        self.values = values
+
+    @property
+    def size(self):
+        return self.values.size
+
+    def __len__(self):
+        return self.values.size
+
+    @property
+    def baseline(self):
+        return self.time[-1] - self.time[0]
+
+    @property
+    def median_dt(self):
+        return np.median(np.diff(self.time))
+
+    def copy(self):
+        return _StubTSeries(self.time, self.values.copy(), assume_sorted=True)
+
+    def __mul__(self, k):
+        return _StubTSeries(self.time, self.values * k, assume_sorted=True)
+
+    __rmul__ = __mul__
+
+    def __add__(self, k):
+        return _StubTSeries(self.time, self.values + k, assume_sorted=True)
+
+    __radd__ = __add__
+
+
+class _StubFSeries:
+    def __init__(self, frequency=None, values=None, assume_sorted=False):
+        frequency = np.asarray(frequency)
+        values = np.asarray(values)
+        if not assume_sorted and np.any(np.diff(frequency) < 0):
+            order = np.argsort(frequency, kind="stable")
+            frequency, values = frequency[order], values[order]
+        self.frequency = frequency
+        self.values = values
+
+    def amax(self):
+        return np.nanmax(self.values)
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "periodicity", "spectral.py"))
+
+
+def load():
+    """Return ``(spectral, phase)`` modules of the unmodified reference."""
+    if not available():
+        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+    pkg_name = "_periodicity_reference"
+    if pkg_name + ".spectral" in sys.modules:
+        return sys.modules[pkg_name + ".spectral"], sys.modules[pkg_name + ".phase"]
+    pkg = types.ModuleType(pkg_name)
+    pkg.__path__ = []
+    core = types.ModuleType(pkg_name + ".core")
+    core.TSeries = _StubTSeries
+    core.FSeries = _StubFSeries
+    sys.modules[pkg_name] = pkg
+    sys.modules[pkg_name + ".core"] = core
+    mods = []
+    for name in ("spectral", "phase"):
+        path = os.path.join(REFERENCE_ROOT, "src", "periodicity", name + ".py")
+        spec = importlib.util.spec_from_file_location(f"{pkg_name}.{name}", path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"{pkg_name}.{name}"] = mod
+        spec.loader.exec_module(mod)
+        mods.append(mod)
+    return tuple(mods)
+
+
+TSeries = _StubTSeries
+FSeries = _StubFSeries

@@ -1,0 +1,424 @@
+// Per-pipe throughput microbenchmarks for B200 (sm_100a).
+//
+// MEASURED_PEAKS.json only records HBM and bf16 tensor
+// peaks; the GLS / PDM hot path is bound by the FP32, FP64, XU (MUFU + 64-bit
+// conversions) and shared-memory pipes, so their achievable rates are measured
+// here and used as roofline denominators (profiles/pipes_r01.json).
+//
+// Every test is one persistent wave (148 * BPS blocks of 256 threads) running
+// an unrolled body of independent dependency chains. Reported:
+//   ops/clk/SM (from in-kernel clock64) and Gops/s (from CUDA events).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipes pipes.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int THREADS = 256;
+constexpr int CH = 16;  // independent chains per thread
+
+struct Result { unsigned long long cyc; };
+
+#define KHEAD(name) __global__ void __launch_bounds__(THREADS) name(float* out, unsigned long long* cyc, int iters, float seed)
+#define KTIME_BEGIN unsigned long long t0_ = clock64();
+#define KTIME_END   unsigned long long t1_ = clock64(); \
+  if (threadIdx.x == 0) atomicMax(cyc, t1_ - t0_);
+
+// ---- T0: scalar FFMA, shared multiplier/addend (operand reuse friendly)
+KHEAD(k_ffma_shared) {
+  float a[CH]; float b = seed, c = seed * 0.5f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = threadIdx.x * 1e-3f + i;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  KTIME_END
+  float s = 0; for (int i = 0; i < CH; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;
+}
+
+// ---- T1: scalar FFMA, three distinct registers per instruction (acc += x*y)
+KHEAD(k_ffma_distinct) {
+  float a[CH], x[CH], y[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) { a[i] = 0.f; x[i] = seed + i + threadIdx.x; y[i] = seed * 0.25f - i; }
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = fmaf(x[i], y[(i + r) % CH], a[i]);
+  }
+  KTIME_END
+  float s = 0; for (int i = 0; i < CH; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;
+}
+
+// ---- T2: packed FFMA2, shared multiplier/addend
+KHEAD(k_ffma2_shared) {
+  float2 a[CH]; float2 b = make_float2(seed, seed * 1.01f), c = make_float2(seed * .5f, seed * .25f);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = make_float2(threadIdx.x * 1e-3f + i, i);
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = __ffma2_rn(a[i], b, c);
+  }
+  KTIME_END
+  float s = 0; for (int i = 0; i < CH; ++i) s += a[i].x + a[i].y;
+  if (s == 123.456f) out[0] = s;
+}
+
+// ---- T3: packed FFMA2, three distinct register pairs per instruction
+KHEAD(k_ffma2_distinct) {
+  float2 a[CH], x[CH], y[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    a[i] = make_float2(0.f, 0.f);
+    x[i] = make_float2(seed + i + threadIdx.x, seed - i);
+    y[i] = make_float2(seed * 0.25f - i, seed * 0.125f + i);
+  }
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = __ffma2_rn(x[i], y[(i + r) % CH], a[i]);
+  }
+  KTIME_END
+  float s = 0; for (int i = 0; i < CH; ++i) s += a[i].x + a[i].y;
+  if (s == 123.456f) out[0] = s;
+}
+
+// ---- T4: packed FMUL2 + FADD2 alternating
+KHEAD(k_fmul2_fadd2) {
+  float2 a[CH]; float2 b = make_float2(seed, seed * 1.01f), c = make_float2(seed * .5f, seed * .25f);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = make_float2(threadIdx.x * 1e-3f + i, i);
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = __fmul2_rn(a[i], b);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = __fadd2_rn(a[i], c);
+    }
+  }
+  KTIME_END
+  float s = 0; for (int i = 0; i < CH; ++i) s += a[i].x + a[i].y;
+  if (s == 123.456f) out[0] = s;
+}
+
+// ---- T5: MUFU.SIN (sin.approx = FMUL + MUFU)
+KHEAD(k_mufu_sin) {
+  float a[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = threadIdx.x * 1e-3f + i * seed;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = __sinf(a[i]);
+  }
+  KTIME_END
+  float s = 0; for (int i = 0; i < CH; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;
+}
+
+// ---- T6: DFMA
+KHEAD(k_dfma) {
+  double a[CH]; double b = seed, c = seed * 0.5;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = threadIdx.x * 1e-3 + i;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = fma(a[i], b, c);
+  }
+  KTIME_END
+  double s = 0; for (int i = 0; i < CH; ++i) s += a[i];
+  if (s == 123.456) out[0] = (float)s;
+}
+
+// ---- T7: DADD
+KHEAD(k_dadd) {
+  double a[CH]; double c = seed * 0.5;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = threadIdx.x * 1e-3 + i;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = a[i] + c;
+  }
+  KTIME_END
+  double s = 0; for (int i = 0; i < CH; ++i) s += a[i];
+  if (s == 123.456) out[0] = (float)s;
+}
+
+// ---- T8: F2F.F32.F64 + F2F.F64.F32 round trip (2 conversions per op)
+KHEAD(k_cvt_f64_f32) {
+  double a[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = threadIdx.x * 1e-3 + i * (double)seed;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) { float f = __double2float_rn(a[i]); a[i] = (double)f; }
+  }
+  KTIME_END
+  double s = 0; for (int i = 0; i < CH; ++i) s += a[i];
+  if (s == 123.456) out[0] = (float)s;
+}
+
+// ---- T9: FP64 floor + F2I.F64 (the PDM binning conversions)
+KHEAD(k_floor_f2i_f64) {
+  double a[CH]; int acc = 0;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = threadIdx.x * 1.37e-3 + i * (double)seed;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        double f = floor(a[i]);
+        int q = __double2int_rz((a[i] - f) * 20.0);
+        acc += q; a[i] += 0.37;
+      }
+  }
+  KTIME_END
+  double s = acc; for (int i = 0; i < CH; ++i) s += a[i];
+  if (s == 123.456) out[0] = (float)s;
+}
+
+// ---- T10: I2F.S32 (fixed-point phase to float)
+KHEAD(k_i2f) {
+  int a[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = threadIdx.x * 977 + i * 131;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) { float f = __int2float_rn(a[i]); a[i] = __float_as_int(f) + 12345; }
+  }
+  KTIME_END
+  int s = 0; for (int i = 0; i < CH; ++i) s += a[i];
+  if (s == 123456) out[0] = (float)s;
+}
+
+// ---- T11: private-column shared-memory histogram RMW: hist[bin][tid] += v (3 stats)
+// one "op" = one sample update = 3 LDS + 3 FADD + 3 STS
+constexpr int M0 = 20;
+__global__ void __launch_bounds__(THREADS) k_smem_private(float* out, unsigned long long* cyc, int iters, float seed) {
+  extern __shared__ float hist[];  // [3][M0][THREADS]
+  for (int i = threadIdx.x; i < 3 * M0 * THREADS; i += THREADS) hist[i] = 0.f;
+  __syncthreads();
+  unsigned s = threadIdx.x * 2654435761u + 12345u;
+  float v = seed;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      s = s * 1664525u + 1013904223u;
+      int q = (int)(((unsigned long long)(s >> 8) * M0) >> 24);
+      float* p = hist + q * THREADS + threadIdx.x;
+      p[0] += 1.0f;
+      p[M0 * THREADS] += v;
+      p[2 * M0 * THREADS] += v * v;
+    }
+  }
+  KTIME_END
+  __syncthreads();
+  float t = 0; for (int i = 0; i < 3 * M0; ++i) t += hist[i * THREADS + threadIdx.x];
+  if (t == 123.456f) out[0] = t;
+}
+
+// ---- T12: same, but stats interleaved float4 (n, sx, sxx, pad): LDS.128 + STS.128
+__global__ void __launch_bounds__(THREADS) k_smem_private_v4(float* out, unsigned long long* cyc, int iters, float seed) {
+  extern __shared__ float hist[];  // [M0][THREADS] float4
+  float4* h4 = reinterpret_cast<float4*>(hist);
+  for (int i = threadIdx.x; i < M0 * THREADS; i += THREADS) h4[i] = make_float4(0, 0, 0, 0);
+  __syncthreads();
+  unsigned s = threadIdx.x * 2654435761u + 12345u;
+  float v = seed;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      s = s * 1664525u + 1013904223u;
+      int q = (int)(((unsigned long long)(s >> 8) * M0) >> 24);
+      float4 h = h4[q * THREADS + threadIdx.x];
+      h.x += 1.0f; h.y += v; h.z += v * v;
+      h4[q * THREADS + threadIdx.x] = h;
+    }
+  }
+  KTIME_END
+  __syncthreads();
+  float t = 0; for (int i = 0; i < M0; ++i) { float4 h = h4[i * THREADS + threadIdx.x]; t += h.x + h.y + h.z; }
+  if (t == 123.456f) out[0] = t;
+}
+
+// ---- T13: shared-memory float atomics, one histogram per warp ([warp][3][M0]), 32 lanes contend
+__global__ void __launch_bounds__(THREADS) k_smem_atomic(float* out, unsigned long long* cyc, int iters, float seed) {
+  __shared__ float hist[(THREADS / 32) * 3 * M0];
+  for (int i = threadIdx.x; i < (THREADS / 32) * 3 * M0; i += THREADS) hist[i] = 0.f;
+  __syncthreads();
+  float* h = hist + (threadIdx.x / 32) * 3 * M0;
+  unsigned s = threadIdx.x * 2654435761u + 12345u;
+  float v = seed;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      s = s * 1664525u + 1013904223u;
+      int q = (int)(((unsigned long long)(s >> 8) * M0) >> 24);
+      atomicAdd(h + q, 1.0f);
+      atomicAdd(h + M0 + q, v);
+      atomicAdd(h + 2 * M0 + q, v * v);
+    }
+  }
+  KTIME_END
+  __syncthreads();
+  float t = 0; for (int i = 0; i < 3 * M0; ++i) t += h[i];
+  if (t == 123.456f) out[0] = t;
+}
+
+// ---- T14: GLS inner step, scalar: rotate (4) + 6 accumulations, 8 frequencies per thread
+KHEAD(k_gls_scalar) {
+  constexpr int K = 8;
+  float C[K], S[K], YC[K], YS[K], CC[K], CS[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) C[i] = S[i] = YC[i] = YS[i] = CC[i] = CS[i] = 0.f;
+  float c = 1.f, s = 0.f, cr = cosf(seed), sr = sinf(seed), y = seed;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        C[i] += c; S[i] += s;
+        YC[i] = fmaf(y, c, YC[i]); YS[i] = fmaf(y, s, YS[i]);
+        CC[i] = fmaf(c, c, CC[i]); CS[i] = fmaf(c, s, CS[i]);
+        float cn = fmaf(c, cr, -(s * sr));
+        float sn = fmaf(s, cr, c * sr);
+        c = cn; s = sn;
+      }
+      y += 0.001f;
+    }
+  }
+  KTIME_END
+  float t = 0; for (int i = 0; i < K; ++i) t += C[i] + S[i] + YC[i] + YS[i] + CC[i] + CS[i];
+  if (t == 123.456f) out[0] = t;
+}
+
+// ---- T15: GLS inner step, packed: two frequency strips per thread as f32x2 lanes
+KHEAD(k_gls_packed) {
+  constexpr int K = 8;
+  float2 C[K], S[K], YC[K], YS[K], CC[K], CS[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) C[i] = S[i] = YC[i] = YS[i] = CC[i] = CS[i] = make_float2(0.f, 0.f);
+  float2 c = make_float2(1.f, 0.5f), s = make_float2(0.f, 0.8f);
+  float crf = cosf(seed), srf = sinf(seed);
+  float2 cr = make_float2(crf, crf), sr = make_float2(srf, srf), nsr = make_float2(-srf, -srf), y = make_float2(seed, seed);
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        C[i] = __fadd2_rn(C[i], c); S[i] = __fadd2_rn(S[i], s);
+        YC[i] = __ffma2_rn(y, c, YC[i]); YS[i] = __ffma2_rn(y, s, YS[i]);
+        CC[i] = __ffma2_rn(c, c, CC[i]); CS[i] = __ffma2_rn(c, s, CS[i]);
+        float2 cn = __ffma2_rn(s, nsr, __fmul2_rn(c, cr));
+        float2 sn = __ffma2_rn(c, sr, __fmul2_rn(s, cr));
+        c = cn; s = sn;
+      }
+      y.x += 0.001f; y.y += 0.001f;
+    }
+  }
+  KTIME_END
+  float t = 0; for (int i = 0; i < K; ++i) t += C[i].x + S[i].y + YC[i].x + YS[i].y + CC[i].x + CS[i].y + C[i].y + S[i].x + YC[i].y + YS[i].x + CC[i].y + CS[i].x;
+  if (t == 123.456f) out[0] = t;
+}
+
+typedef void (*kern_t)(float*, unsigned long long*, int, float);
+
+struct Test { const char* name; kern_t k; double ops_per_thread_iter; int bps; size_t smem; const char* unit; };
+
+int main(int argc, char** argv) {
+  int dev = 0; CK(cudaSetDevice(dev));
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, dev));
+  int nsm = p.multiProcessorCount;
+  float* out; unsigned long long* cyc;
+  CK(cudaMalloc(&out, 64)); CK(cudaMalloc(&cyc, 8));
+  int iters = argc > 1 ? atoi(argv[1]) : 2000;
+  Test tests[] = {
+    {"ffma_shared_operands",   k_ffma_shared,    8.0 * CH, 4, 0, "FFMA"},
+    {"ffma_distinct_operands", k_ffma_distinct,  8.0 * CH, 4, 0, "FFMA"},
+    {"ffma2_shared_operands",  k_ffma2_shared,   8.0 * CH, 4, 0, "FFMA2"},
+    {"ffma2_distinct_operands",k_ffma2_distinct, 8.0 * CH, 2, 0, "FFMA2"},
+    {"fmul2_fadd2",            k_fmul2_fadd2,    8.0 * CH, 4, 0, "F*2"},
+    {"mufu_sin",               k_mufu_sin,       8.0 * CH, 4, 0, "MUFU"},
+    {"dfma",                   k_dfma,           8.0 * CH, 4, 0, "DFMA"},
+    {"dadd",                   k_dadd,           8.0 * CH, 4, 0, "DADD"},
+    {"cvt_f64_f32_roundtrip",  k_cvt_f64_f32,    8.0 * CH, 4, 0, "cvt-pair"},
+    {"floor_f2i_f64",          k_floor_f2i_f64,  8.0 * CH, 4, 0, "floor+f2i"},
+    {"i2f_s32",                k_i2f,            8.0 * CH, 4, 0, "I2F"},
+    {"smem_private_rmw3",      k_smem_private,   16.0,     3, 3 * M0 * THREADS * sizeof(float), "sample-update"},
+    {"smem_private_rmw_v4",    k_smem_private_v4,16.0,     2, 4 * M0 * THREADS * sizeof(float), "sample-update"},
+    {"smem_atomic_warp_hist",  k_smem_atomic,    16.0,     4, 0, "sample-update"},
+    {"gls_step_scalar",        k_gls_scalar,     16.0,     4, 0, "eval"},
+    {"gls_step_packed",        k_gls_packed,     32.0,     2, 0, "eval"},
+  };
+  printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz_nominal\": %d, \"tests\": [\n", p.name, nsm, p.clockRate);
+  int nt = sizeof(tests) / sizeof(tests[0]);
+  for (int t = 0; t < nt; ++t) {
+    Test& T = tests[t];
+    if (T.smem) CK(cudaFuncSetAttribute(T.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.smem));
+    int grid = nsm * T.bps;
+    int its = iters;
+    if (T.smem || t == 13) its = iters / 4 + 1;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best_ms = 1e30; unsigned long long best_cyc = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      CK(cudaMemset(cyc, 0, 8));
+      CK(cudaEventRecord(e0));
+      T.k<<<grid, THREADS, T.smem>>>(out, cyc, its, 1.0001f);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaGetLastError());
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      unsigned long long c; CK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
+      if (rep > 0 && ms < best_ms) { best_ms = ms; best_cyc = c; }
+    }
+    double ops = T.ops_per_thread_iter * (double)its * THREADS * grid;
+    double per_clk_sm = ops / ((double)best_cyc * nsm);
+    double gops = ops / (best_ms * 1e-3) / 1e9;
+    double mhz = (double)best_cyc / (best_ms * 1e-3) / 1e6;
+    printf("  {\"name\": \"%s\", \"unit\": \"%s\", \"blocks_per_sm\": %d, \"ops_per_clk_per_sm\": %.3f, \"gops_per_s\": %.1f, \"ms\": %.4f, \"sm_mhz_eff\": %.0f}%s\n",
+           T.name, T.unit, T.bps, per_clk_sm, gops, best_ms, mhz, t + 1 < nt ? "," : "");
+    fflush(stdout);
+  }
+  printf("]}\n");
+  return 0;
+}
