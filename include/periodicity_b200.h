@@ -1,0 +1,169 @@
+/*
+ * periodicity_b200 -- C ABI of the B200-native trial-frequency search.
+ *
+ * The reference (dioph/periodicity, pure Python) has no FFI of its own; the
+ * seams these entry points replace are Python call sites:
+ *
+ *   pdc_gls*   replaces the three `_trig_sum` calls plus the numpy epilogue of
+ *              `GLS.__call__`          (src/periodicity/spectral.py:109-132)
+ *   pdc_pdm*   replaces `pool.map(self._pdm, self.periods)` in `PDM.__call__`
+ *                                      (src/periodicity/phase.py:185-187,128-149)
+ *
+ * Everything before those lines (signal coercion, grid derivation, weight
+ * normalisation) and after them (FSeries wrap, sub-harmonic averaging) stays in
+ * the Python drop-in classes `periodicity_b200.spectral.GLS` and
+ * `periodicity_b200.phase.PDM`, which call this library through ctypes
+ * (see INTEGRATION.md for the binding).
+ *
+ * Conventions
+ *   - All functions return 0 (PDC_OK) or a pdc_status error; nothing throws or
+ *     aborts across the ABI.  The message for the last error on the calling
+ *     thread is returned by pdc_last_error().
+ *   - The caller owns every buffer passed in; the library never retains a
+ *     caller pointer past return.  A pdc_ctx owns one CUDA device, one stream
+ *     and grow-only device scratch.  A ctx is not thread-safe; distinct ctxs
+ *     may be used concurrently.
+ *   - Host entry points (`pdc_gls`, `pdc_gls_batch`, `pdc_pdm`) take host
+ *     pointers and are synchronous: inputs are copied to the device, results
+ *     are back in the output buffers on return.
+ *   - Device entry points (`*_dev`) take device pointers on the ctx's device,
+ *     are ordered on `stream` (a cudaStream_t passed as void*; NULL = the ctx's
+ *     own stream) and return without synchronising.
+ *   - All arrays are C-contiguous float64 (what TSeries.time / .values yield,
+ *     core.py:60-66,479-481); FP32 is an internal detail of the kernels.
+ *   - There is no CPU fallback: without a usable CUDA device the ctx cannot be
+ *     created (PDC_ENODEVICE).
+ */
+#ifndef PERIODICITY_B200_H_
+#define PERIODICITY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDC_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define PDC_API __attribute__((visibility("default")))
+#else
+#define PDC_API
+#endif
+
+typedef enum pdc_status {
+  PDC_OK = 0,
+  PDC_EINVAL = 1,    /* bad argument (Python raises ValueError, cf. core.py:469-470) */
+  PDC_ECUDA = 2,     /* CUDA runtime error */
+  PDC_ENOMEM = 3,    /* device or host allocation failed */
+  PDC_ENODEVICE = 4  /* no usable CUDA device */
+} pdc_status;
+
+/* pdc_gls flags */
+#define PDC_GLS_FIT_MEAN 1u /* fit_mean=True   (spectral.py:104-108,112-113,125-127) */
+#define PDC_GLS_PSD 2u      /* psd=True        (spectral.py:129-130): power *= psd_scale */
+
+typedef struct pdc_ctx pdc_ctx;
+
+PDC_API int pdc_version(void);
+PDC_API const char* pdc_last_error(void);
+
+/* Create / destroy a context bound to CUDA device `device` (ordinal as seen by
+ * the process).  Creation initialises the device, a non-blocking stream and
+ * reads the SM count used to size grids. */
+PDC_API int pdc_ctx_create(pdc_ctx** out, int device);
+PDC_API int pdc_ctx_destroy(pdc_ctx* ctx);
+/* Block until all work queued on the ctx's stream has finished. */
+PDC_API int pdc_ctx_synchronize(pdc_ctx* ctx);
+/* SM count of the ctx's device (148 on B200); negative on error. */
+PDC_API int pdc_ctx_sm_count(pdc_ctx* ctx);
+
+/*
+ * Generalised Lomb-Scargle power on the uniform grid f_j = fmin + (j0 + j)*df,
+ * j = 0..nf-1, with exact trigonometric sums (the quantities `_trig_sum`
+ * approximates, spectral.py:11-16) and the tau-offset algebra of
+ * spectral.py:113-128 evaluated in float64 per frequency.
+ *
+ *   t, y        float64[n]  sample times and values (times need not be sorted)
+ *   w           float64[n]  sample weights err**-2 (any positive scale; they are
+ *                           normalised to sum 1 as in spectral.py:102-103), or
+ *                           NULL for uniform weights (err=None, spectral.py:99-100)
+ *   fmin, df    grid origin and spacing (spectral.py:88-97; Python owns the grid)
+ *   j0          index of the first frequency this call evaluates (0 for a whole
+ *               grid; the shard offset when the grid is split across GPUs)
+ *   nf          number of frequencies evaluated by this call
+ *   flags       PDC_GLS_FIT_MEAN | PDC_GLS_PSD
+ *   psd_scale   0.5 * sum(err**-2) (spectral.py:130); ignored without PDC_GLS_PSD,
+ *               in which case power is divided by YY = sum w y^2 (spectral.py:132)
+ *   power_out   float64[nf]  periodogram values
+ *   argmax_out  index (0-based within this call's nf) of the largest non-NaN
+ *               power, first occurrence (np.nanargmax, core.py:202-205); -1 if
+ *               every value is NaN.  May be NULL.
+ *   max_out     that power (np.nanmax, core.py:212-215).  May be NULL.
+ */
+PDC_API int pdc_gls(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+            double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,
+            double* power_out, int64_t* argmax_out, double* max_out);
+
+/* Same, device pointers, stream-ordered, no synchronisation. `argmax_out` /
+ * `max_out` are device pointers too (or NULL). */
+PDC_API int pdc_gls_dev(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+                double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,
+                double* power_out, int64_t* argmax_out, double* max_out, void* stream);
+
+/*
+ * Batched GLS: B independent light curves stored back to back
+ * (curve b = samples offsets[b] .. offsets[b+1]-1), each with its own grid
+ * origin fmin[b] and spacing df[b] but a common number of frequencies nf
+ * (the survey workload, and GLS.bootstrap, spectral.py:140-152).
+ *
+ *   offsets     int64[B+1]   (host pointer in both variants)
+ *   fmin, df    float64[B]   (host pointers in both variants)
+ *   psd_scale   float64[B] or NULL (host pointer; required with PDC_GLS_PSD)
+ *   power_out   float64[B*nf] row-major, or NULL to keep only the peaks
+ *   argmax_out  int64[B], max_out float64[B]  (either may be NULL)
+ */
+PDC_API int pdc_gls_batch(pdc_ctx* ctx, const double* t, const double* y, const double* w,
+                  const int64_t* offsets, int64_t B, const double* fmin, const double* df,
+                  int64_t nf, unsigned flags, const double* psd_scale,
+                  double* power_out, int64_t* argmax_out, double* max_out);
+
+PDC_API int pdc_gls_batch_dev(pdc_ctx* ctx, const double* t, const double* y, const double* w,
+                      const int64_t* offsets, int64_t B, const double* fmin, const double* df,
+                      int64_t nf, unsigned flags, const double* psd_scale,
+                      double* power_out, int64_t* argmax_out, double* max_out, void* stream);
+
+/*
+ * Phase Dispersion Minimisation: theta statistic of `PDM._pdm`
+ * (phase.py:128-149) for each trial period.
+ *
+ *   t, x        float64[n]   sample times and values
+ *   periods     float64[np]  trial periods (phase.py:180; any order, all != 0)
+ *   nb, nc      bins and covers (phase.py:108-112); m0 = nb*nc fine bins
+ *   theta_out   float64[np]  theta in the order of `periods`
+ *   argmin_out  index of the smallest non-NaN theta, first occurrence; -1 if all
+ *               NaN.  May be NULL.
+ *   min_out     that theta.  May be NULL.
+ */
+PDC_API int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+            const double* periods, int64_t np, int nb, int nc,
+            double* theta_out, int64_t* argmin_out, double* min_out);
+
+PDC_API int pdc_pdm_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+                const double* periods, int64_t np, int nb, int nc,
+                double* theta_out, int64_t* argmin_out, double* min_out, void* stream);
+
+/* Number of kernels this ctx has launched since creation (bench.py's
+ * `gpu_launches` claim is the difference across the timed region). */
+PDC_API int64_t pdc_ctx_launch_count(pdc_ctx* ctx);
+
+/* Duration in milliseconds of the dominant kernel (GLS strip kernel or PDM
+ * histogram kernel) of the most recent call on this ctx, from CUDA events
+ * recorded on the launching stream.  Synchronises on the end event.
+ * Negative on error / if no call has been made. */
+PDC_API double pdc_ctx_last_main_kernel_ms(pdc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERIODICITY_B200_H_ */

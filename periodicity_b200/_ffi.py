@@ -1,0 +1,228 @@
+"""ctypes binding of ``libperiodicity_b200.so`` (C ABI: ``include/periodicity_b200.h``).
+
+The library is the only compute path: there is no CPU fallback.  If the shared
+object is missing or no B200 is visible, the first call raises ``RuntimeError``.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libperiodicity_b200.so")
+
+PDC_OK, PDC_EINVAL, PDC_ECUDA, PDC_ENOMEM, PDC_ENODEVICE = range(5)
+GLS_FIT_MEAN = 1
+GLS_PSD = 2
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int64_p = ctypes.POINTER(ctypes.c_int64)
+
+#: every symbol declared in include/periodicity_b200.h -> (restype, argtypes)
+SIGNATURES = {
+    "pdc_version": (ctypes.c_int, []),
+    "pdc_last_error": (ctypes.c_char_p, []),
+    "pdc_ctx_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "pdc_ctx_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pdc_ctx_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+    "pdc_ctx_sm_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "pdc_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "pdc_ctx_last_main_kernel_ms": (ctypes.c_double, [ctypes.c_void_p]),
+    "pdc_gls": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                               ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
+                               ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
+                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gls_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
+                                   ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gls_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int64, ctypes.c_uint, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gls_batch_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int64, ctypes.c_uint, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_pdm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                               ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_pdm_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                   ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """Load the shared object and attach prototypes. Raises RuntimeError if absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "or `make -C periodicity_b200/csrc`. periodicity_b200 has no CPU fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (restype, argtypes) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = restype
+                fn.argtypes = argtypes
+            _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc == PDC_OK:
+        return
+    msg = load_library().pdc_last_error().decode("utf-8", "replace")
+    if rc == PDC_EINVAL:
+        raise ValueError(msg)
+    if rc == PDC_ENOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def _f64(a):
+    """C-contiguous float64 view/copy of ``a`` (what the C ABI consumes)."""
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One CUDA device + stream + grow-only scratch (``pdc_ctx``). Not thread-safe."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        self.device = int(device)
+        _check(self._lib.pdc_ctx_create(ctypes.byref(self._h), self.device))
+        self._lock = threading.Lock()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.pdc_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self):
+        return self._lib.pdc_ctx_sm_count(self._h)
+
+    @property
+    def launch_count(self):
+        return self._lib.pdc_ctx_launch_count(self._h)
+
+    def last_main_kernel_ms(self):
+        return self._lib.pdc_ctx_last_main_kernel_ms(self._h)
+
+    def synchronize(self):
+        _check(self._lib.pdc_ctx_synchronize(self._h))
+
+    # ---- host-pointer entry points (numpy in, numpy out) --------------------
+    def gls(self, t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, j0=0, want_power=True):
+        t = _f64(t)
+        y = _f64(y)
+        if t.ndim != 1 or t.shape != y.shape:
+            raise ValueError("Input arrays have incompatible lengths.")
+        if w is not None:
+            w = _f64(w)
+            if w.shape != t.shape:
+                raise ValueError("Input arrays have incompatible lengths.")
+        nf = int(nf)
+        flags = (GLS_FIT_MEAN if fit_mean else 0) | (GLS_PSD if psd_scale is not None else 0)
+        power = np.empty(nf, dtype=np.float64) if want_power else None
+        arg = ctypes.c_int64(-1)
+        mx = ctypes.c_double(float("nan"))
+        with self._lock:
+            _check(self._lib.pdc_gls(self._h, _ptr(t), _ptr(y), _ptr(w), t.size, float(fmin), float(df),
+                                     int(j0), nf, flags, float(psd_scale if psd_scale is not None else 1.0),
+                                     _ptr(power), ctypes.addressof(arg), ctypes.addressof(mx)))
+        return power, arg.value, mx.value
+
+    def gls_batch(self, t, y, w, offsets, fmin, df, nf, fit_mean=True, psd_scale=None, want_power=True):
+        t = _f64(t)
+        y = _f64(y)
+        if w is not None:
+            w = _f64(w)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = offsets.size - 1
+        fmin = _f64(np.broadcast_to(fmin, (B,)))
+        df = _f64(np.broadcast_to(df, (B,)))
+        if psd_scale is not None:
+            psd_scale = _f64(np.broadcast_to(psd_scale, (B,)))
+        nf = int(nf)
+        if B < 1 or offsets[0] < 0 or offsets[-1] > t.size or np.any(np.diff(offsets) < 1):
+            raise ValueError("offsets must be increasing and within the sample arrays")
+        flags = (GLS_FIT_MEAN if fit_mean else 0) | (GLS_PSD if psd_scale is not None else 0)
+        power = np.empty((B, nf), dtype=np.float64) if want_power else None
+        arg = np.empty(B, dtype=np.int64)
+        mx = np.empty(B, dtype=np.float64)
+        with self._lock:
+            _check(self._lib.pdc_gls_batch(self._h, _ptr(t), _ptr(y), _ptr(w), _ptr(offsets), B, _ptr(fmin),
+                                           _ptr(df), nf, flags, _ptr(psd_scale), _ptr(power), _ptr(arg), _ptr(mx)))
+        return power, arg, mx
+
+    def pdm(self, t, x, periods, nb, nc):
+        t = _f64(t)
+        x = _f64(x)
+        periods = _f64(periods)
+        if t.ndim != 1 or t.shape != x.shape:
+            raise ValueError("Input arrays have incompatible lengths.")
+        theta = np.empty(periods.size, dtype=np.float64)
+        arg = ctypes.c_int64(-1)
+        mn = ctypes.c_double(float("nan"))
+        with self._lock:
+            _check(self._lib.pdc_pdm(self._h, _ptr(t), _ptr(x), t.size, _ptr(periods), periods.size,
+                                     int(nb), int(nc), _ptr(theta), ctypes.addressof(arg), ctypes.addressof(mn)))
+        return theta, arg.value, mn.value
+
+    # ---- device-pointer entry points (raw addresses, stream ordered) ---------
+    def gls_dev(self, t_ptr, y_ptr, w_ptr, n, fmin, df, j0, nf, flags, psd_scale, power_ptr, argmax_ptr,
+                max_ptr, stream=0):
+        _check(self._lib.pdc_gls_dev(self._h, t_ptr, y_ptr, w_ptr or None, int(n), float(fmin), float(df),
+                                     int(j0), int(nf), int(flags), float(psd_scale), power_ptr or None,
+                                     argmax_ptr or None, max_ptr or None, stream or None))
+
+    def gls_batch_dev(self, t_ptr, y_ptr, w_ptr, offsets, fmin, df, nf, flags, psd_scale, power_ptr,
+                      argmax_ptr, max_ptr, stream=0):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = offsets.size - 1
+        fmin = _f64(np.broadcast_to(fmin, (B,)))
+        df = _f64(np.broadcast_to(df, (B,)))
+        if psd_scale is not None:
+            psd_scale = _f64(np.broadcast_to(psd_scale, (B,)))
+        _check(self._lib.pdc_gls_batch_dev(self._h, t_ptr, y_ptr, w_ptr or None, _ptr(offsets), B, _ptr(fmin),
+                                           _ptr(df), int(nf), int(flags), _ptr(psd_scale), power_ptr or None,
+                                           argmax_ptr or None, max_ptr or None, stream or None))
+
+    def pdm_dev(self, t_ptr, x_ptr, n, periods_ptr, np_, nb, nc, theta_ptr, argmin_ptr, min_ptr, stream=0):
+        _check(self._lib.pdc_pdm_dev(self._h, t_ptr, x_ptr, int(n), periods_ptr, int(np_), int(nb), int(nc),
+                                     theta_ptr, argmin_ptr or None, min_ptr or None, stream or None))
+
+
+_default_ctx = {}
+_default_lock = threading.Lock()
+
+
+def default_context(device=None):
+    """Process-wide context for ``device`` (default: LOCAL_RANK or 0), created on first use."""
+    if device is None:
+        device = int(os.environ.get("PERIODICITY_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        ctx = _default_ctx.get(device)
+        if ctx is None:
+            ctx = Context(device)
+            _default_ctx[device] = ctx
+    return ctx

@@ -1,0 +1,330 @@
+// extern "C" surface of libperiodicity_b200.so (see include/periodicity_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "pdc_common.cuh"
+
+namespace pdc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) in `%s` at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();  // clear the sticky-less OOM so the ctx stays usable
+    return PDC_ENOMEM;
+  }
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice)
+    return PDC_ENODEVICE;
+  return PDC_ECUDA;
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap && p) return PDC_OK;
+  if (bytes == 0) bytes = 16;
+  // grow geometrically below 1 GiB to limit reallocations, exactly above
+  size_t want = bytes;
+  if (cap && bytes < ((size_t)1 << 30) && bytes < cap * 2) want = cap * 2;
+  if (p) {
+    cudaError_t e = cudaFree(p);  // implicit device sync: no kernel can still be using it
+    p = nullptr;
+    cap = 0;
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFree", __FILE__, __LINE__);
+  }
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess && want != bytes) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess) {
+    p = nullptr;
+    return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+  }
+  cap = want;
+  return PDC_OK;
+}
+
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+int PinnedBuf::reserve(size_t bytes) {
+  if (bytes <= cap && p) return PDC_OK;
+  if (bytes == 0) bytes = 16;
+  if (p) {
+    cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  cudaError_t e = cudaMallocHost(&p, bytes);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    return cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+  }
+  cap = bytes;
+  return PDC_OK;
+}
+
+void PinnedBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace pdc
+
+using namespace pdc;
+
+extern "C" {
+
+int pdc_version(void) { return PDC_VERSION; }
+
+const char* pdc_last_error(void) { return g_err; }
+
+int pdc_ctx_create(pdc_ctx** out, int device) {
+  if (!out) { set_error("pdc_ctx_create: out is NULL"); return PDC_EINVAL; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("pdc_ctx_create: no usable CUDA device (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return PDC_ENODEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("pdc_ctx_create: device %d out of range (0..%d)", device, ndev - 1);
+    return PDC_EINVAL;
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) { set_error("pdc_ctx_create: cudaSetDevice(%d) failed", device); return PDC_ECUDA; }
+  cudaDeviceProp prop;
+  PDC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("pdc_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+              device, prop.major, prop.minor);
+    return PDC_ENODEVICE;
+  }
+  pdc_ctx* ctx = new (std::nothrow) pdc_ctx();
+  if (!ctx) { set_error("pdc_ctx_create: out of host memory"); return PDC_ENOMEM; }
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  cudaError_t e2 = cudaEventCreate(&ctx->ev_begin);
+  cudaError_t e3 = cudaEventCreate(&ctx->ev_end);
+  cudaError_t e4 = cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+    pdc_ctx_destroy(ctx);
+    return cuda_fail(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4)),
+                     "stream/event creation", __FILE__, __LINE__);
+  }
+  *out = ctx;
+  return PDC_OK;
+}
+
+int pdc_ctx_destroy(pdc_ctx* ctx) {
+  if (!ctx) return PDC_OK;
+  DeviceGuard guard(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->in_a.release(); ctx->in_b.release(); ctx->in_c.release(); ctx->in_d.release();
+  ctx->out_a.release(); ctx->out_small.release(); ctx->pin_small.release();
+  ctx->gls_curves.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release();
+  ctx->partial.release(); ctx->blockred.release(); ctx->pin_meta.release();
+  ctx->pdm_meta.release(); ctx->pdm_x.release();
+  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+  if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return PDC_OK;
+}
+
+int pdc_ctx_synchronize(pdc_ctx* ctx) {
+  if (!ctx) { set_error("ctx is NULL"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  PDC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PDC_OK;
+}
+
+int pdc_ctx_sm_count(pdc_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
+
+int64_t pdc_ctx_launch_count(pdc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+double pdc_ctx_last_main_kernel_ms(pdc_ctx* ctx) {
+  if (!ctx || !ctx->have_main_ev) return -1.0;
+  DeviceGuard guard(ctx->device);
+  if (cudaEventSynchronize(ctx->ev_end) != cudaSuccess) return -1.0;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+// ---------------------------------------------------------------------------
+// GLS
+// ---------------------------------------------------------------------------
+int pdc_gls_batch_dev(pdc_ctx* ctx, const double* t, const double* y, const double* w,
+                      const int64_t* offsets, int64_t B, const double* fmin, const double* df,
+                      int64_t nf, unsigned flags, const double* psd_scale,
+                      double* power_out, int64_t* argmax_out, double* max_out, void* stream) {
+  if (!ctx || !t || !y || !offsets || !fmin || !df) { set_error("pdc_gls_batch_dev: NULL argument"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return gls_run(ctx, t, y, w, offsets, B, fmin, df, 0, nf, flags, psd_scale, power_out, argmax_out, max_out, st);
+}
+
+int pdc_gls_dev(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+                double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,
+                double* power_out, int64_t* argmax_out, double* max_out, void* stream) {
+  if (!ctx || !t || !y) { set_error("pdc_gls_dev: NULL argument"); return PDC_EINVAL; }
+  if (n < 1) { set_error("pdc_gls: n must be >= 1"); return PDC_EINVAL; }
+  if (j0 < 0) { set_error("pdc_gls: j0 must be >= 0"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const int64_t offsets[2] = {0, n};
+  return gls_run(ctx, t, y, w, offsets, 1, &fmin, &df, j0, nf, flags, &psd_scale, power_out, argmax_out, max_out, st);
+}
+
+struct SmallRec {
+  long long arg;
+  double val;
+};
+
+static int gls_host_common(pdc_ctx* ctx, const double* t, const double* y, const double* w,
+                           const int64_t* offsets, int64_t B, const double* fmin, const double* df,
+                           int64_t j0, int64_t nf, unsigned flags, const double* psd_scale,
+                           double* power_out, int64_t* argmax_out, double* max_out) {
+  if (B < 1 || nf < 1) { set_error("pdc_gls: need at least one curve and one frequency"); return PDC_EINVAL; }
+  const int64_t off0 = offsets[0];
+  const int64_t ntot = offsets[B] - off0;
+  if (ntot < 1) { set_error("pdc_gls: no samples"); return PDC_EINVAL; }
+  cudaStream_t st = ctx->stream;
+  const size_t nbytes = sizeof(double) * (size_t)ntot;
+  PDC_TRY(ctx->in_a.reserve(nbytes));
+  PDC_TRY(ctx->in_b.reserve(nbytes));
+  if (w) PDC_TRY(ctx->in_c.reserve(nbytes));
+  if (power_out) PDC_TRY(ctx->out_a.reserve(sizeof(double) * (size_t)nf * B));
+  PDC_TRY(ctx->out_small.reserve((sizeof(long long) + sizeof(double)) * (size_t)B));
+  PDC_TRY(ctx->pin_small.reserve((sizeof(long long) + sizeof(double)) * (size_t)B));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_a.p, t + off0, nbytes, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_b.p, y + off0, nbytes, cudaMemcpyHostToDevice, st));
+  if (w) PDC_CUDA(cudaMemcpyAsync(ctx->in_c.p, w + off0, nbytes, cudaMemcpyHostToDevice, st));
+
+  // offsets rebased to the device copies
+  int64_t local_off[2];
+  const int64_t* use_off = offsets;
+  int64_t* heap_off = nullptr;
+  if (off0 != 0) {
+    if (B == 1) { local_off[0] = 0; local_off[1] = ntot; use_off = local_off; }
+    else {
+      heap_off = new (std::nothrow) int64_t[B + 1];
+      if (!heap_off) { set_error("out of host memory"); return PDC_ENOMEM; }
+      for (int64_t b = 0; b <= B; ++b) heap_off[b] = offsets[b] - off0;
+      use_off = heap_off;
+    }
+  }
+  long long* d_arg = ctx->out_small.as<long long>();
+  double* d_val = reinterpret_cast<double*>(d_arg + B);
+  int rc = gls_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), w ? ctx->in_c.as<double>() : nullptr,
+                   use_off, B, fmin, df, j0, nf, flags, psd_scale,
+                   power_out ? ctx->out_a.as<double>() : nullptr, (int64_t*)d_arg, d_val, st);
+  delete[] heap_off;
+  PDC_TRY(rc);
+  if (power_out)
+    PDC_CUDA(cudaMemcpyAsync(power_out, ctx->out_a.p, sizeof(double) * (size_t)nf * B, cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, ctx->out_small.p, (sizeof(long long) + sizeof(double)) * (size_t)B,
+                           cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaStreamSynchronize(st));
+  const long long* h_arg = ctx->pin_small.as<long long>();
+  const double* h_val = reinterpret_cast<const double*>(h_arg + B);
+  for (int64_t b = 0; b < B; ++b) {
+    if (argmax_out) argmax_out[b] = h_arg[b];
+    if (max_out) max_out[b] = h_val[b];
+  }
+  return PDC_OK;
+}
+
+int pdc_gls(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+            double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,
+            double* power_out, int64_t* argmax_out, double* max_out) {
+  if (!ctx || !t || !y) { set_error("pdc_gls: NULL argument"); return PDC_EINVAL; }
+  if (n < 1) { set_error("pdc_gls: n must be >= 1"); return PDC_EINVAL; }
+  if (j0 < 0) { set_error("pdc_gls: j0 must be >= 0"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  const int64_t offsets[2] = {0, n};
+  return gls_host_common(ctx, t, y, w, offsets, 1, &fmin, &df, j0, nf, flags, &psd_scale, power_out, argmax_out, max_out);
+}
+
+int pdc_gls_batch(pdc_ctx* ctx, const double* t, const double* y, const double* w,
+                  const int64_t* offsets, int64_t B, const double* fmin, const double* df,
+                  int64_t nf, unsigned flags, const double* psd_scale,
+                  double* power_out, int64_t* argmax_out, double* max_out) {
+  if (!ctx || !t || !y || !offsets || !fmin || !df) { set_error("pdc_gls_batch: NULL argument"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  return gls_host_common(ctx, t, y, w, offsets, B, fmin, df, 0, nf, flags, psd_scale, power_out, argmax_out, max_out);
+}
+
+// ---------------------------------------------------------------------------
+// PDM
+// ---------------------------------------------------------------------------
+int pdc_pdm_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+                const double* periods, int64_t np, int nb, int nc,
+                double* theta_out, int64_t* argmin_out, double* min_out, void* stream) {
+  if (!ctx || !t || !x || !periods || !theta_out) { set_error("pdc_pdm_dev: NULL argument"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return pdm_run(ctx, t, x, n, periods, np, nb, nc, theta_out, argmin_out, min_out, st);
+}
+
+int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+            const double* periods, int64_t np, int nb, int nc,
+            double* theta_out, int64_t* argmin_out, double* min_out) {
+  if (!ctx || !t || !x || !periods || !theta_out) { set_error("pdc_pdm: NULL argument"); return PDC_EINVAL; }
+  if (n < 2 || np < 1) { set_error("pdc_pdm: need n >= 2 samples and np >= 1 periods"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  PDC_TRY(ctx->in_a.reserve(sizeof(double) * (size_t)n));
+  PDC_TRY(ctx->in_b.reserve(sizeof(double) * (size_t)n));
+  PDC_TRY(ctx->in_d.reserve(sizeof(double) * (size_t)np));
+  PDC_TRY(ctx->out_a.reserve(sizeof(double) * (size_t)np));
+  PDC_TRY(ctx->out_small.reserve(sizeof(SmallRec)));
+  PDC_TRY(ctx->pin_small.reserve(sizeof(SmallRec)));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_a.p, t, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_b.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_d.p, periods, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, st));
+  SmallRec* d_rec = ctx->out_small.as<SmallRec>();
+  PDC_TRY(pdm_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), n, ctx->in_d.as<double>(), np, nb, nc,
+                  ctx->out_a.as<double>(), (int64_t*)&d_rec->arg, &d_rec->val, st));
+  PDC_CUDA(cudaMemcpyAsync(theta_out, ctx->out_a.p, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, d_rec, sizeof(SmallRec), cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaStreamSynchronize(st));
+  const SmallRec* h = ctx->pin_small.as<SmallRec>();
+  if (argmin_out) *argmin_out = h->arg;
+  if (min_out) *min_out = h->val;
+  return PDC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,466 @@
+// Generalised Lomb-Scargle periodogram on a uniform frequency grid, exact sums.
+//
+// Replaces the three `_trig_sum` calls and the numpy epilogue of
+// `GLS.__call__` (reference src/periodicity/spectral.py:109-132).  The reference
+// approximates
+//     S_j = sum_i w_i sin(2 pi f_j t_i),  C_j = sum_i w_i cos(2 pi f_j t_i)
+// (spectral.py:12-16) with an extirpolation + FFT; this file evaluates the sums
+// themselves.
+//
+// Interpretation of "angle-addition recurrence reseeded every K samples"
+// (BASELINE.json north_star; SURVEY.md §7 hard part 5): samples are irregular, so
+// there is no constant rotation along the sample axis.  The frequency grid IS
+// uniform, f_j = fmin + j df (spectral.py:36,97), hence for a fixed sample i
+//     exp(2 pi i f_{j+1} t_i) = exp(2 pi i f_j t_i) * exp(2 pi i df t_i)
+// and the rotation exp(2 pi i df t_i) depends on the sample only.  A thread owns a
+// strip of K consecutive frequencies; for every sample it seeds (cos, sin) at the
+// first frequency of its strip EXACTLY (phase reduced mod 1 in FP64, then
+// MUFU sin/cos) and rotates K-1 times in FP32.  "K" = strip length = reseed period.
+//
+// Kernels (launch order):
+//   gls_stats_kernel    per curve: t_min, sum w, weighted mean, YY      (FP64)
+//   gls_records_kernel  per sample: (t - t_min, frac(df (t - t_min))) as double2 and
+//                       (cos, sin of 2 pi df (t - t_min), y', w') as float4
+//   gls_strip_kernel    the hot kernel: six FP32 sums per frequency
+//                       {C, S, YC, YS, CC, CS}, flushed to FP64 partials per tile
+//   gls_epilogue_kernel FP64: merge partials, tau-offset algebra
+//                       (spectral.py:113-132), per-block NaN-aware argmax
+//   gls_argmax_kernel   per curve: final (max, argmax)
+//
+// Algorithmic work of the hot kernel: per sample*frequency evaluation
+// 4 FP32 instructions for the rotation + 6 for the sums (7 with weights).
+#include "pdc_common.cuh"
+
+namespace pdc {
+
+struct GlsCurve {
+  long long begin, n;
+  double fmin, df;
+  double psd_scale;
+  // filled on the device by gls_stats_kernel
+  double tmin, wsum, ymean, yy, inv_rms;
+};
+
+constexpr int GLS_TILE = 1024;  // samples per shared-memory tile == FP32 flush interval
+
+// ---------------------------------------------------------------------------
+// per-curve statistics (one block per curve)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y,
+                 const double* __restrict__ w, GlsCurve* curves, unsigned flags) {
+  __shared__ double scratch[33];
+  GlsCurve& cv = curves[blockIdx.x];
+  const long long b = cv.begin, n = cv.n;
+  double tmin = INFINITY, sw = 0.0, swy = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    double ti = t[b + i], yi = y[b + i], wi = w ? w[b + i] : 1.0;
+    tmin = fmin(tmin, ti);
+    sw += wi;
+    swy = fma(wi, yi, swy);
+  }
+  tmin = block_min(tmin, scratch);
+  sw = block_sum(sw, scratch);
+  swy = block_sum(swy, scratch);
+  // spectral.py:102-108: w /= w.sum(); y = values - dot(w, values) if fit_mean
+  const double ymean = (flags & PDC_GLS_FIT_MEAN) ? swy / sw : 0.0;
+  double syy = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    double d = y[b + i] - ymean, wi = w ? w[b + i] : 1.0;
+    syy = fma(wi * d, d, syy);
+  }
+  syy = block_sum(syy, scratch);
+  if (threadIdx.x == 0) {
+    double yy = syy / sw;  // spectral.py:120  YY = dot(w, y**2)
+    cv.tmin = tmin;
+    cv.wsum = sw;
+    cv.ymean = ymean;
+    cv.yy = yy;
+    cv.inv_rms = yy > 0.0 ? rsqrt(yy) : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-sample records
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gls_records_kernel(const double* __restrict__ t, const double* __restrict__ y,
+                   const double* __restrict__ w, const GlsCurve* __restrict__ curves,
+                   double2* __restrict__ rec1, float4* __restrict__ rec2) {
+  const GlsCurve cv = curves[blockIdx.y];
+  const double wscale = (double)cv.n / cv.wsum;  // weights rescaled to mean 1 (O(1) in FP32)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cv.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long g = cv.begin + i;
+    const double tt = t[g] - cv.tmin;  // power is shift invariant; the reference shifts too (spectral.py:19-21)
+    const double b = frac_of_product(cv.df, tt);
+    double sb, cb;
+    sincospi(2.0 * b, &sb, &cb);
+    const double yv = (y[g] - cv.ymean) * cv.inv_rms;  // unit weighted RMS before the FP32 cast
+    float4 r;
+    r.x = (float)cb;
+    r.y = (float)sb;
+    if (w) {
+      const double wn = w[g] * wscale;
+      r.z = (float)(wn * yv);
+      r.w = (float)wn;
+    } else {
+      r.z = (float)yv;
+      r.w = 1.0f;
+    }
+    rec1[g] = make_double2(tt, b);
+    rec2[g] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the hot kernel
+// ---------------------------------------------------------------------------
+struct GlsMainArgs {
+  const GlsCurve* curves;
+  const double2* rec1;
+  const float4* rec2;
+  double* partial;    // [nsplit][6][nf_tot]
+  long long nf;       // frequencies per curve in this call
+  long long nf_tot;   // B * nf
+  long long j0;       // absolute index of this call's first frequency
+  int nfb;            // frequency blocks per curve
+  int nsplit;         // sample splits per curve
+};
+
+// Exact seed: phase = A + lK*b cycles (FP64), reduced mod 1 by a magic-number add
+// whose low mantissa word is the fraction in units of 2^-32 cycle, then MUFU sin/cos.
+__device__ __forceinline__ void gls_seed(double A, double b, double lKd, float& c, float& s) {
+  const double ph = __fma_rn(lKd, b, A);
+  const double v = __dadd_rn(ph, 1572864.0);  // 1.5 * 2^20: ulp(v) = 2^-32
+  const int fx = __double2loint(v);           // two's-complement fraction, [-0.5, 0.5) cycle
+  const float x = (float)fx * 1.4629180792671596e-9f;  // 2 pi / 2^32 -> radians in [-pi, pi)
+  __sincosf(x, &s, &c);
+}
+
+template <int K, int THREADS, int MINB, bool WEIGHTED>
+__global__ void __launch_bounds__(THREADS, MINB)
+gls_strip_kernel(const GlsMainArgs a) {
+  __shared__ __align__(16) double2 s_ab[GLS_TILE];  // (phase at block base frequency, phase step per index)
+  __shared__ __align__(16) float4 s_r2[GLS_TILE];   // (cos, sin of the rotation, y' or w'y', w')
+
+  const int item = blockIdx.x;
+  const int split = item % a.nsplit;
+  const int rest = item / a.nsplit;
+  const int fb = rest % a.nfb;
+  const int curve = rest / a.nfb;
+
+  const GlsCurve* cvp = a.curves + curve;
+  const long long cbegin = cvp->begin, cn = cvp->n;
+  const double fmin = cvp->fmin, df = cvp->df;
+
+  const long long per = (cn + a.nsplit - 1) / a.nsplit;
+  const long long sb = (long long)split * per;
+  const long long se = sb + per < cn ? sb + per : cn;
+
+  const long long jB = (long long)fb * (THREADS * K);
+  const double fB = fmin + (double)(a.j0 + jB) * df;  // spectral.py:36: f = fmin + df * arange(nf)
+  const int lK = threadIdx.x * K;
+  const double lKd = (double)lK;
+
+  double* pbase = a.partial + (long long)split * 6 * a.nf_tot + (long long)curve * a.nf + jB + lK;
+  const long long jrem = a.nf - (jB + lK);  // strip entries with k < jrem are real frequencies
+
+  bool first = true;
+  long long tile0 = sb;
+  do {
+    long long left = se - tile0;
+    const int cnt = left <= 0 ? 0 : (left < GLS_TILE ? (int)left : GLS_TILE);
+    __syncthreads();  // previous tile fully consumed
+    for (int i = threadIdx.x; i < cnt; i += THREADS) {
+      const double2 r1 = a.rec1[cbegin + tile0 + i];
+      s_ab[i] = make_double2(frac_of_product(fB, r1.x), r1.y);
+      s_r2[i] = a.rec2[cbegin + tile0 + i];
+    }
+    __syncthreads();
+
+    float aC[K], aS[K], aYC[K], aYS[K], aCC[K], aCS[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) aC[k] = aS[k] = aYC[k] = aYS[k] = aCC[k] = aCS[k] = 0.f;
+
+    if (cnt > 0) {
+      float c, s;
+      float4 r2 = s_r2[0];
+      {
+        const double2 ab = s_ab[0];
+        gls_seed(ab.x, ab.y, lKd, c, s);
+      }
+      for (int i = 0; i < cnt; ++i) {
+        // software pipeline: seed of the next sample overlaps this sample's strip
+        const int in = i + 1 < cnt ? i + 1 : i;
+        const double2 abn = s_ab[in];
+        const float4 r2n = s_r2[in];
+        float cn_, sn_;
+        gls_seed(abn.x, abn.y, lKd, cn_, sn_);
+
+        const float cr = r2.x, sr = r2.y, yv = r2.z;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (WEIGHTED) {
+            const float wc = r2.w * c;
+            aC[k] += wc;
+            aS[k] = fmaf(r2.w, s, aS[k]);
+            aCC[k] = fmaf(wc, c, aCC[k]);
+            aCS[k] = fmaf(wc, s, aCS[k]);
+          } else {
+            aC[k] += c;
+            aS[k] += s;
+            aCC[k] = fmaf(c, c, aCC[k]);
+            aCS[k] = fmaf(c, s, aCS[k]);
+          }
+          aYC[k] = fmaf(yv, c, aYC[k]);
+          aYS[k] = fmaf(yv, s, aYS[k]);
+          if (k + 1 < K) {
+            const float c2 = fmaf(c, cr, -(s * sr));
+            const float s2 = fmaf(s, cr, c * sr);
+            c = c2;
+            s = s2;
+          }
+        }
+        c = cn_;
+        s = sn_;
+        r2 = r2n;
+      }
+    }
+
+    // flush this tile's FP32 sums into the FP64 partials this item owns
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (k < jrem) {
+        double* p = pbase + k;
+        if (first) {
+          p[0] = (double)aC[k];
+          p[a.nf_tot] = (double)aS[k];
+          p[2 * a.nf_tot] = (double)aYC[k];
+          p[3 * a.nf_tot] = (double)aYS[k];
+          p[4 * a.nf_tot] = (double)aCC[k];
+          p[5 * a.nf_tot] = (double)aCS[k];
+        } else {
+          p[0] += (double)aC[k];
+          p[a.nf_tot] += (double)aS[k];
+          p[2 * a.nf_tot] += (double)aYC[k];
+          p[3 * a.nf_tot] += (double)aYS[k];
+          p[4 * a.nf_tot] += (double)aCC[k];
+          p[5 * a.nf_tot] += (double)aCS[k];
+        }
+      }
+    }
+    first = false;
+    tile0 += GLS_TILE;
+  } while (tile0 < se);
+}
+
+// ---------------------------------------------------------------------------
+// FP64 epilogue: spectral.py:113-132 per frequency + block argmax
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double np_sign(double x) {
+  if (x != x) return x;
+  return (double)((x > 0.0) - (x < 0.0));
+}
+
+__global__ void __launch_bounds__(256)
+gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restrict__ partial,
+                    int nsplit, long long nf, long long nf_tot, unsigned flags,
+                    double* __restrict__ power_out, double* __restrict__ red_val,
+                    long long* __restrict__ red_idx) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  const int curve = blockIdx.y;
+  const GlsCurve cv = curves[curve];
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double power = 0.0;
+  long long idx = -1;
+  if (j < nf) {
+    double sums[6];
+    const double* p = partial + (long long)curve * nf + j;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      double acc = 0.0;
+      for (int s = 0; s < nsplit; ++s) acc += p[((long long)s * 6 + q) * nf_tot];
+      sums[q] = acc;
+    }
+    const double inv_n = 1.0 / (double)cv.n;
+    const double C = sums[0] * inv_n, S = sums[1] * inv_n;
+    const double Ch = sums[2] * inv_n, Sh = sums[3] * inv_n;
+    // sum w cos(2x) = 2 sum w cos^2 x - 1,  sum w sin(2x) = 2 sum w sin x cos x   (sum w = 1)
+    const double C2 = 2.0 * sums[4] * inv_n - 1.0, S2 = 2.0 * sums[5] * inv_n;
+    const bool fit_mean = flags & PDC_GLS_FIT_MEAN;
+    double tan2;
+    if (fit_mean) tan2 = (S2 - 2.0 * S * C) / (C2 - (C * C - S * S));  // spectral.py:113
+    else tan2 = S2 / C2;                                               // spectral.py:115
+    const double hyp = sqrt(1.0 + tan2 * tan2);
+    const double S2w = tan2 / hyp;
+    const double C2w = 1.0 / hyp;
+    const double Cw = sqrt(0.5) * sqrt(1.0 + C2w);
+    const double Sw = sqrt(0.5) * np_sign(S2w) * sqrt(1.0 - C2w);
+    const double YC = Ch * Cw + Sh * Sw;
+    const double YS = Sh * Cw - Ch * Sw;
+    double CC = 0.5 * (1.0 + C2 * C2w + S2 * S2w);
+    double SS = 0.5 * (1.0 - C2 * C2w - S2 * S2w);
+    if (fit_mean) {
+      const double a1 = C * Cw + S * Sw, a2 = S * Cw - C * Sw;
+      CC -= a1 * a1;
+      SS -= a2 * a2;
+    }
+    power = YC * YC / CC + YS * YS / SS;  // spectral.py:128 (y was pre-scaled: YY == 1)
+    if (flags & PDC_GLS_PSD) power *= cv.yy * cv.psd_scale;  // spectral.py:130
+    else if (!(cv.yy > 0.0)) power = nan("");               // spectral.py:132 with YY == 0
+    if (power_out) power_out[(long long)curve * nf + j] = power;
+    idx = j;
+  }
+  block_argext<+1>(power, idx, sv, si);
+  if (threadIdx.x == 0) {
+    red_val[(long long)curve * gridDim.x + blockIdx.x] = power;
+    red_idx[(long long)curve * gridDim.x + blockIdx.x] = idx;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launcher
+// ---------------------------------------------------------------------------
+struct GlsGeom {
+  int K, threads, minb;
+};
+
+template <int K, int THREADS, int MINB>
+static int launch_strip(pdc_ctx* ctx, const GlsMainArgs& a, bool weighted, long long items,
+                        cudaStream_t st) {
+  if (weighted) gls_strip_kernel<K, THREADS, MINB, true><<<(unsigned)items, THREADS, 0, st>>>(a);
+  else gls_strip_kernel<K, THREADS, MINB, false><<<(unsigned)items, THREADS, 0, st>>>(a);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return PDC_OK;
+}
+
+// Pick the sample split so that (curves * frequency blocks * nsplit) work items
+// fill whole waves of resident blocks.  Cost model: every wave costs the samples
+// of one item plus a fixed per-item overhead (staging, flush) worth ~48 samples.
+static int choose_nsplit(long long base_items, long long nmax, long long resident) {
+  if (base_items >= 24 * resident) return 1;
+  long long cap = nmax / 256;
+  if (cap < 1) cap = 1;
+  if (cap > 4096) cap = 4096;
+  double best = 1e300;
+  int best_s = 1;
+  for (long long s = 1; s <= cap; ++s) {
+    long long items = base_items * s;
+    long long waves = (items + resident - 1) / resident;
+    double per = (double)((nmax + s - 1) / s) + 48.0;
+    double cost = (double)waves * per;
+    if (cost < best * 0.999) { best = cost; best_s = (int)s; }
+    if (items > 64 * resident) break;
+  }
+  return best_s;
+}
+
+int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
+            const int64_t* offsets_host, int64_t B, const double* fmin_host, const double* df_host,
+            int64_t j0, int64_t nf, unsigned flags, const double* psd_scale_host,
+            double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t st) {
+  if (B <= 0 || nf <= 0) { set_error("pdc_gls: need at least one curve and one frequency"); return PDC_EINVAL; }
+  const long long ntot = offsets_host[B] - offsets_host[0];
+  long long nmax = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    long long nb = offsets_host[b + 1] - offsets_host[b];
+    if (nb < 1) { set_error("pdc_gls: curve %lld is empty", (long long)b); return PDC_EINVAL; }
+    if (!(df_host[b] == df_host[b]) || !(fmin_host[b] == fmin_host[b])) {
+      set_error("pdc_gls: fmin/df of curve %lld is NaN", (long long)b);
+      return PDC_EINVAL;
+    }
+    if (nb > nmax) nmax = nb;
+  }
+  if ((flags & PDC_GLS_PSD) && !psd_scale_host) { set_error("pdc_gls: PSD flag needs psd_scale"); return PDC_EINVAL; }
+  const long long nf_tot = (long long)B * nf;
+
+  // geometry of the hot kernel
+  constexpr int K = 16, THREADS = 256, MINB = 2;
+  const long long fpb = (long long)K * THREADS;
+  const long long nfb = (nf + fpb - 1) / fpb;
+  const long long resident = (long long)ctx->sm_count * MINB;
+  const int nsplit = choose_nsplit((long long)B * nfb, nmax, resident);
+  const long long items = (long long)B * nfb * nsplit;
+  if (items > 0x7fffffffLL) { set_error("pdc_gls: problem too large for one call (%lld work items)", items); return PDC_EINVAL; }
+
+  if (B > 65535) { set_error("pdc_gls_batch: at most 65535 curves per call"); return PDC_EINVAL; }
+
+  // the pinned staging buffer is reused by every call: wait for the previous upload
+  PDC_CUDA(cudaEventSynchronize(ctx->ev_fence));
+
+  // scratch
+  PDC_TRY(ctx->gls_curves.reserve(sizeof(GlsCurve) * B));
+  PDC_TRY(ctx->pin_meta.reserve(sizeof(GlsCurve) * B));
+  PDC_TRY(ctx->gls_rec1.reserve(sizeof(double2) * ntot));
+  PDC_TRY(ctx->gls_rec2.reserve(sizeof(float4) * ntot));
+  PDC_TRY(ctx->partial.reserve(sizeof(double) * 6 * nf_tot * nsplit));
+  const int eblk = (int)((nf + 255) / 256);
+  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk * B));
+
+  GlsCurve* hc = ctx->pin_meta.as<GlsCurve>();
+  const long long off0 = offsets_host[0];
+  for (int64_t b = 0; b < B; ++b) {
+    hc[b].begin = offsets_host[b] - off0;
+    hc[b].n = offsets_host[b + 1] - offsets_host[b];
+    hc[b].fmin = fmin_host[b];
+    hc[b].df = df_host[b];
+    hc[b].psd_scale = psd_scale_host ? psd_scale_host[b] : 1.0;
+    hc[b].tmin = hc[b].wsum = hc[b].ymean = hc[b].yy = hc[b].inv_rms = 0.0;
+  }
+  GlsCurve* dc = ctx->gls_curves.as<GlsCurve>();
+  PDC_CUDA(cudaMemcpyAsync(dc, hc, sizeof(GlsCurve) * B, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaEventRecord(ctx->ev_fence, st));
+
+  const double* tt = t + off0;
+  const double* yy = y + off0;
+  const double* ww = w ? w + off0 : nullptr;
+
+  gls_stats_kernel<<<(unsigned)B, 1024, 0, st>>>(tt, yy, ww, dc, flags);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+
+  {
+    long long bx = (nmax + 255) / 256;
+    if (bx > 1024) bx = 1024;
+    dim3 grid((unsigned)bx, (unsigned)B);
+    gls_records_kernel<<<grid, 256, 0, st>>>(tt, yy, ww, dc, ctx->gls_rec1.as<double2>(), ctx->gls_rec2.as<float4>());
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+
+  GlsMainArgs a;
+  a.curves = dc;
+  a.rec1 = ctx->gls_rec1.as<double2>();
+  a.rec2 = ctx->gls_rec2.as<float4>();
+  a.partial = ctx->partial.as<double>();
+  a.nf = nf;
+  a.nf_tot = nf_tot;
+  a.j0 = j0;
+  a.nfb = (int)nfb;
+  a.nsplit = nsplit;
+
+  PDC_CUDA(cudaEventRecord(ctx->ev_begin, st));
+  PDC_TRY((launch_strip<K, THREADS, MINB>(ctx, a, w != nullptr, items, st)));
+  PDC_CUDA(cudaEventRecord(ctx->ev_end, st));
+  ctx->have_main_ev = true;
+
+  double* red_val = ctx->blockred.as<double>();
+  long long* red_idx = reinterpret_cast<long long*>(red_val + (size_t)eblk * B);
+  {
+    dim3 grid((unsigned)eblk, (unsigned)B);
+    gls_epilogue_kernel<<<grid, 256, 0, st>>>(dc, a.partial, nsplit, nf, nf_tot, flags, power_out, red_val, red_idx);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (argmax_out || max_out) {
+    argext_final_kernel<+1><<<(unsigned)B, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmax_out, max_out);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  return PDC_OK;
+}
+
+}  // namespace pdc

@@ -1,0 +1,208 @@
+// Shared declarations for the periodicity_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/periodicity_b200.h"
+
+namespace pdc {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define PDC_CUDA(expr)                                                       \
+  do {                                                                       \
+    cudaError_t e__ = (expr);                                                \
+    if (e__ != cudaSuccess) return ::pdc::cuda_fail(e__, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define PDC_TRY(expr)                 \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != PDC_OK) return rc__;  \
+  } while (0)
+
+// ---- grow-only device / pinned buffers -------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);  // keeps contents only if no growth is needed
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace pdc
+
+// The context: one device, one stream, scratch that only grows.
+struct pdc_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // around the dominant kernel
+  cudaEvent_t ev_fence = nullptr;                     // caller-stream -> scratch reuse fence
+  bool have_main_ev = false;
+  int64_t launches = 0;
+
+  // host-pointer entry points: device copies of the caller's arrays
+  pdc::DevBuf in_a, in_b, in_c, in_d;
+  pdc::DevBuf out_a;           // power / theta
+  pdc::DevBuf out_small;       // argmax/max records
+  pdc::PinnedBuf pin_small;    // pinned landing zone for the small records
+
+  // GLS scratch
+  pdc::DevBuf gls_curves;      // GlsCurve[B]
+  pdc::DevBuf gls_rec1;        // double2[n]  (t - tmin, frac(df (t - tmin)))
+  pdc::DevBuf gls_rec2;        // float4[n]   (cos, sin of the per-index rotation, y or w*y, w)
+  pdc::DevBuf partial;         // float64 partial sums [nsplit][rows][units]
+  pdc::DevBuf blockred;        // per-block (value, index) candidates
+  pdc::PinnedBuf pin_meta;     // host staging for per-curve metadata
+
+  // PDM scratch
+  pdc::DevBuf pdm_meta;        // PdmMeta
+  pdc::DevBuf pdm_x;           // float[n] centred, unit-variance values
+};
+
+namespace pdc {
+
+// launchers implemented in gls.cu / pdm.cu; all device pointers, stream ordered
+int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
+            const int64_t* offsets_host, int64_t B, const double* fmin_host, const double* df_host,
+            int64_t j0, int64_t nf, unsigned flags, const double* psd_scale_host,
+            double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t stream);
+
+int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods,
+            int64_t np, int nb, int nc, double* theta_out, int64_t* argmin_out, double* min_out,
+            cudaStream_t stream);
+
+// ---- small device helpers ---------------------------------------------------
+#ifdef __CUDACC__
+
+// 1.5 * 2^52: adding it rounds a |x| < 2^51 double to the nearest integer.
+__device__ __forceinline__ double round_magic(double x) {
+  const double M = 6755399441055744.0;
+  return __dadd_rn(__dadd_rn(x, M), -M);
+}
+
+// frac(a*b) in [-0.5, 0.5], using the exact product a*b = p + e (FMA residual) so
+// the result carries the full precision of a and b even when a*b is ~1e7 cycles.
+__device__ __forceinline__ double frac_of_product(double a, double b) {
+  double p = __dmul_rn(a, b);
+  double e = __fma_rn(a, b, -p);
+  double r = __dadd_rn(p, -round_magic(p));
+  return __dadd_rn(r, e);
+}
+
+template <class T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of doubles; result valid in every thread. `scratch` >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double s = lane < nw ? scratch[lane] : 0.0;
+    s = warp_sum(s);
+    if (lane == 0) scratch[32] = s;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+__device__ __forceinline__ double block_min(double v, double* scratch) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double s = lane < nw ? scratch[lane] : v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fmin(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (lane == 0) scratch[32] = s;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// NaN-ignoring "better" test for arg-extremum with first-occurrence tie break.
+// SIGN = +1: maximum, -1: minimum.  idx < 0 means "no candidate yet".
+template <int SIGN>
+__device__ __forceinline__ bool better(double v, long long i, double bv, long long bi) {
+  if (i < 0 || v != v) return false;
+  if (bi < 0) return true;
+  if (SIGN > 0 ? (v > bv) : (v < bv)) return true;
+  return v == bv && i < bi;
+}
+
+// Block-wide arg-extremum; result in thread 0.  sv/si: shared scratch of 32 each.
+template <int SIGN>
+__device__ __forceinline__ void block_argext(double& v, long long& i, double* sv, long long* si) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    long long oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (better<SIGN>(ov, oi, v, i)) { v = ov; i = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { sv[wid] = v; si[wid] = i; }
+  __syncthreads();
+  if (wid == 0) {
+    double bv = lane < nw ? sv[lane] : 0.0;
+    long long bi = lane < nw ? si[lane] : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better<SIGN>(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    v = bv; i = bi;
+  }
+}
+
+// Final reduction of per-block (value, index) candidates: one block per unit
+// (GLS curve / PDM call).  SIGN = +1 arg-max, -1 arg-min; NaN ignored, first
+// occurrence wins (np.nanargmax / np.nanargmin, reference core.py:202-210).
+template <int SIGN>
+__global__ void __launch_bounds__(256)
+argext_final_kernel(const double* __restrict__ red_val, const long long* __restrict__ red_idx,
+                    int nblk, long long* __restrict__ arg_out, double* __restrict__ val_out) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  const int unit = blockIdx.x;
+  double bv = 0.0;
+  long long bi = -1;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+    double v = red_val[(long long)unit * nblk + k];
+    long long i = red_idx[(long long)unit * nblk + k];
+    if (better<SIGN>(v, i, bv, bi)) { bv = v; bi = i; }
+  }
+  block_argext<SIGN>(bv, bi, sv, si);
+  if (threadIdx.x == 0) {
+    if (arg_out) arg_out[unit] = bi;
+    if (val_out) val_out[unit] = bi >= 0 ? bv : nan("");
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace pdc

@@ -1,0 +1,334 @@
+// Phase Dispersion Minimisation: theta statistic for a grid of trial periods.
+//
+// Replaces `pool.map(self._pdm, self.periods)` of `PDM.__call__`
+// (reference src/periodicity/phase.py:185-187) and `PDM._pdm` (phase.py:128-149).
+//
+// Restatement implemented here (SURVEY.md §8a "PDM restatement"): with
+// m0 = nb*nc (phase.py:130) every sample has phase phi = (t/P) % 1 (phase.py:131)
+// and lies in exactly one FINE bin q, thr[q] <= phi < thr[q+1], thr[k] = k/m0
+// being the very float64 thresholds the reference compares against
+// (phase.py:138-140).  The reference's coarse bin k (phase.py:137-141) is the
+// circular union of fine bins k .. k+nc-1.  Per fine bin only (n, sum x', sum x'^2)
+// is needed, x' = (x - mean(x)) / std(x, ddof=1):
+//     theta = sum_{k good} (Q_k - S_k^2 / n_k) / (sum_{k good} n_k - M)
+// over the M coarse bins with n_k > 1 (phase.py:142-149; the division by
+// sigma^2 = var(x, ddof=1), phase.py:148,165, is folded into x').
+// The argsort of phase.py:132-134 does not influence the result and is dropped.
+//
+// Mapping (north_star: "per-trial-period phase-bin variance histograms in shared
+// memory"): one thread owns one trial period and a PRIVATE histogram column in
+// shared memory, hist[stat][bin][thread] -- bank = thread % 32 whatever the bin,
+// so the read-modify-write is conflict free and needs no atomics.  On sm_100a a
+// shared-memory float atomicAdd is a CAS loop (ATOMS.CAST.SPIN); measured
+// (profiles/pipes_r01.json) the private-column update sustains 5.07 sample
+// updates/clk/SM against 0.96 for warp-shared atomic histograms, so the
+// atomic-free mapping is the one kept (SURVEY.md §7 hard part 8 allows either).
+//
+// Bin fidelity: t/P is the correctly rounded quotient (one Newton correction of
+// t * (1/P) with the exact FMA residual), phi = q - floor(q) is exact, and the
+// bin index from phi*m0 is re-checked against thr[] whenever phi*m0 is within
+// 2^-30 of an integer, so ties on bin edges (integer times, rational periods)
+// fall exactly where the reference puts them.
+//
+// Kernels: pdm_stats_kernel (mean, 1/std), pdm_center_kernel (x' as float),
+// pdm_hist_kernel (hot), pdm_epilogue_kernel (FP64 theta + block argmin),
+// argext_final_kernel<-1>.
+#include "pdc_common.cuh"
+
+namespace pdc {
+
+struct PdmMeta {
+  double mean, inv_sd;
+};
+
+constexpr int PDM_TILE = 1024;        // samples per shared-memory tile
+constexpr int PDM_FLUSH_TILES = 8;    // FP32 histograms are merged into FP64 every 8192 samples
+
+__global__ void __launch_bounds__(1024)
+pdm_stats_kernel(const double* __restrict__ x, long long n, PdmMeta* meta) {
+  __shared__ double scratch[33];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_sum(s, scratch);
+  const double mean = s / (double)n;
+  double q = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    double d = x[i] - mean;
+    q = fma(d, d, q);
+  }
+  q = block_sum(q, scratch);
+  if (threadIdx.x == 0) {
+    const double var = q / (double)(n - 1);  // phase.py:165  np.var(values, ddof=1)
+    meta->mean = mean;
+    meta->inv_sd = 1.0 / sqrt(var);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pdm_center_kernel(const double* __restrict__ x, long long n, const PdmMeta* __restrict__ meta,
+                  float* __restrict__ xs) {
+  const double mean = meta->mean, inv_sd = meta->inv_sd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    xs[i] = (float)((x[i] - mean) * inv_sd);
+}
+
+struct PdmArgs {
+  const double* t;
+  const float* xs;
+  const double* periods;
+  double* partial;  // [nsplit][3*m0][np]
+  long long n, np;
+  int m0, nsplit;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pdm_hist_kernel(const PdmArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int m0 = a.m0;
+  double* s_t = reinterpret_cast<double*>(smem_raw);                 // [PDM_TILE]
+  double* s_thr = s_t + PDM_TILE;                                    // [m0 + 1]  (padded to even)
+  float* s_x = reinterpret_cast<float*>(s_thr + ((m0 + 2) & ~1));    // [PDM_TILE]
+  float* hist = s_x + PDM_TILE;                                      // [3][m0][THREADS]
+
+  const int split = blockIdx.x % a.nsplit;
+  const long long pb = blockIdx.x / a.nsplit;
+  const long long pi = pb * THREADS + threadIdx.x;
+  const bool valid = pi < a.np;
+  const double P = valid ? a.periods[pi] : 1.0;
+  const double rP = 1.0 / P;
+  const double m0d = (double)m0;
+
+  for (int k = threadIdx.x; k <= m0; k += THREADS) s_thr[k] = (double)k / m0d;  // phase.py:138-140
+  for (int k = threadIdx.x; k < 3 * m0 * THREADS; k += THREADS) hist[k] = 0.f;
+
+  const long long per = (a.n + a.nsplit - 1) / a.nsplit;
+  const long long sb = (long long)split * per;
+  const long long se = sb + per < a.n ? sb + per : a.n;
+
+  float* col = hist + threadIdx.x;
+  const int stat_stride = m0 * THREADS;
+  double* pcol = a.partial + (long long)split * 3 * m0 * a.np + pi;
+
+  bool first = true;
+  int tiles_since_flush = 0;
+  long long tile0 = sb;
+  do {
+    long long left = se - tile0;
+    const int cnt = left <= 0 ? 0 : (left < PDM_TILE ? (int)left : PDM_TILE);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += THREADS) {
+      s_t[i] = a.t[tile0 + i];
+      s_x[i] = a.xs[tile0 + i];
+    }
+    __syncthreads();
+
+#pragma unroll 4
+    for (int i = 0; i < cnt; ++i) {
+      const double tv = s_t[i];
+      const float xv = s_x[i];
+      // correctly rounded t / P: q0 = t * (1/P), exact residual, one correction (phase.py:131)
+      const double q0 = __dmul_rn(tv, rP);
+      const double r = __fma_rn(-q0, P, tv);
+      const double q1 = __fma_rn(r, rP, q0);
+      const double phi = __dadd_rn(q1, -floor(q1));  // exact; == np.remainder(q1, 1)
+      const double u = __dmul_rn(phi, m0d);
+      const double v = __dadd_rn(u, 6755399441055744.0);  // low word = rint(u)
+      const double d = __dadd_rn(u, -__dadd_rn(v, -6755399441055744.0));
+      const int dhi = __double2hiint(d);
+      int k = __double2loint(v) + (dhi >> 31);  // floor(u)
+      if ((unsigned)(dhi << 1) < (unsigned)((1023 - 30) << 21)) {
+        // phi*m0 within 2^-30 of an integer: decide with the reference's own thresholds
+        k = k < 0 ? 0 : (k > m0 - 1 ? m0 - 1 : k);
+        if (phi < s_thr[k]) --k;
+        else if (k < m0 - 1 && phi >= s_thr[k + 1]) ++k;
+      }
+      k = (int)min((unsigned)k, (unsigned)(m0 - 1));  // also keeps NaN / phi == 1.0 in range
+      float* p = col + k * THREADS;
+      p[0] += 1.0f;
+      p[stat_stride] += xv;
+      p[2 * stat_stride] = fmaf(xv, xv, p[2 * stat_stride]);
+    }
+
+    tile0 += PDM_TILE;
+    ++tiles_since_flush;
+    if (tiles_since_flush == PDM_FLUSH_TILES || tile0 >= se) {
+      // merge this thread's FP32 column into the FP64 partials it owns
+      if (valid) {
+        for (int b = 0; b < 3 * m0; ++b) {
+          const double val = (double)col[b * THREADS];
+          double* g = pcol + (long long)b * a.np;
+          if (first) *g = val;
+          else *g += val;
+          col[b * THREADS] = 0.f;
+        }
+      }
+      first = false;
+      tiles_since_flush = 0;
+    }
+  } while (tile0 < se);
+}
+
+__global__ void __launch_bounds__(256)
+pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, long long np,
+                    double* __restrict__ theta_out, double* __restrict__ red_val,
+                    long long* __restrict__ red_idx) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  const long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double theta = 0.0;
+  long long idx = -1;
+  if (pi < np) {
+    // fold the sample splits into split 0 (this thread's own column only)
+    const long long rows = 3LL * m0;
+    for (long long b = 0; b < rows; ++b) {
+      double acc = 0.0;
+      for (int s = 0; s < nsplit; ++s) acc += partial[((long long)s * rows + b) * np + pi];
+      partial[b * np + pi] = acc;
+    }
+    const double* pn = partial + pi;
+    const double* p1 = pn + (long long)m0 * np;
+    const double* p2 = p1 + (long long)m0 * np;
+    double num = 0.0, ntot = 0.0;
+    int good = 0;
+    for (int k = 0; k < m0; ++k) {
+      double N = 0.0, S = 0.0, Q = 0.0;
+      for (int c = 0; c < nc; ++c) {
+        int q = k + c;
+        if (q >= m0) q -= m0;
+        N += pn[(long long)q * np];
+        S += p1[(long long)q * np];
+        Q += p2[(long long)q * np];
+      }
+      if (N > 1.0) {  // phase.py:142  mk.size > 1
+        num += Q - S * S / N;
+        ntot += N;
+        ++good;
+      }
+    }
+    theta = num / (ntot - (double)good);  // phase.py:147-148 (sigma folded into x')
+    theta_out[pi] = theta;
+    idx = pi;
+  }
+  block_argext<-1>(theta, idx, sv, si);
+  if (threadIdx.x == 0) {
+    red_val[blockIdx.x] = theta;
+    red_idx[blockIdx.x] = idx;
+  }
+}
+
+static size_t pdm_smem_bytes(int m0, int threads) {
+  return sizeof(double) * (PDM_TILE + ((m0 + 2) & ~1)) + sizeof(float) * PDM_TILE +
+         sizeof(float) * 3 * (size_t)m0 * threads;
+}
+
+template <int THREADS>
+static int pdm_launch(pdc_ctx* ctx, const PdmArgs& a, size_t smem, long long blocks, cudaStream_t st) {
+  PDC_CUDA(cudaFuncSetAttribute(pdm_hist_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pdm_hist_kernel<THREADS><<<(unsigned)blocks, THREADS, smem, st>>>(a);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return PDC_OK;
+}
+
+int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods,
+            int64_t np, int nb, int nc, double* theta_out, int64_t* argmin_out, double* min_out,
+            cudaStream_t st) {
+  if (n < 2) { set_error("pdc_pdm: need at least 2 samples"); return PDC_EINVAL; }
+  if (np < 1) { set_error("pdc_pdm: need at least one trial period"); return PDC_EINVAL; }
+  if (nb < 1 || nc < 1) { set_error("pdc_pdm: nb and nc must be >= 1"); return PDC_EINVAL; }
+  const long long m0l = (long long)nb * nc;
+  const size_t smem_max = 227 * 1024;
+  if (m0l > 100000 || pdm_smem_bytes((int)m0l, 32) > smem_max) {
+    set_error("pdc_pdm: nb*nc = %lld fine bins do not fit a shared-memory histogram (max %d)",
+              m0l, (int)((smem_max - 13 * 1024) / (12 * 32)));
+    return PDC_EINVAL;
+  }
+  const int m0 = (int)m0l;
+
+  // threads per block: the candidate that keeps the most period-threads resident per SM
+  int threads = 32, best_res = 0;
+  const int cands[4] = {256, 128, 64, 32};
+  for (int c = 0; c < 4; ++c) {
+    size_t sm = pdm_smem_bytes(m0, cands[c]);
+    if (sm > smem_max) continue;
+    int blocks = (int)((228 * 1024) / (sm + 1024));
+    if (blocks > 2048 / cands[c]) blocks = 2048 / cands[c];
+    int res = blocks * cands[c];
+    if (res > best_res) { best_res = res; threads = cands[c]; }
+  }
+  const size_t smem = pdm_smem_bytes(m0, threads);
+  const long long resident = (long long)ctx->sm_count * (best_res / threads);
+  const long long npb = (np + threads - 1) / threads;
+
+  // sample split: same cost model as GLS (per-item overhead ~ one histogram flush)
+  int nsplit = 1;
+  if (npb < 24 * resident) {
+    long long cap = n / 512;
+    if (cap < 1) cap = 1;
+    if (cap > 1024) cap = 1024;
+    double best = 1e300;
+    for (long long s = 1; s <= cap; ++s) {
+      long long items = npb * s;
+      long long waves = (items + resident - 1) / resident;
+      double cost = (double)waves * ((double)((n + s - 1) / s) + 3.0 * m0 + 64.0);
+      if (cost < best * 0.999) { best = cost; nsplit = (int)s; }
+      if (items > 64 * resident) break;
+    }
+  }
+  const long long blocks = npb * nsplit;
+  if (blocks > 0x7fffffffLL) { set_error("pdc_pdm: problem too large for one call"); return PDC_EINVAL; }
+
+  PDC_TRY(ctx->pdm_meta.reserve(sizeof(PdmMeta)));
+  PDC_TRY(ctx->pdm_x.reserve(sizeof(float) * n));
+  PDC_TRY(ctx->partial.reserve(sizeof(double) * 3 * m0 * (size_t)np * nsplit));
+  const int eblk = (int)((np + 255) / 256);
+  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk));
+
+  PdmMeta* meta = ctx->pdm_meta.as<PdmMeta>();
+  pdm_stats_kernel<<<1, 1024, 0, st>>>(x, n, meta);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  {
+    long long bx = (n + 255) / 256;
+    if (bx > 2048) bx = 2048;
+    pdm_center_kernel<<<(unsigned)bx, 256, 0, st>>>(x, n, meta, ctx->pdm_x.as<float>());
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+
+  PdmArgs a;
+  a.t = t;
+  a.xs = ctx->pdm_x.as<float>();
+  a.periods = periods;
+  a.partial = ctx->partial.as<double>();
+  a.n = n;
+  a.np = np;
+  a.m0 = m0;
+  a.nsplit = nsplit;
+
+  PDC_CUDA(cudaEventRecord(ctx->ev_begin, st));
+  switch (threads) {
+    case 256: PDC_TRY(pdm_launch<256>(ctx, a, smem, blocks, st)); break;
+    case 128: PDC_TRY(pdm_launch<128>(ctx, a, smem, blocks, st)); break;
+    case 64: PDC_TRY(pdm_launch<64>(ctx, a, smem, blocks, st)); break;
+    default: PDC_TRY(pdm_launch<32>(ctx, a, smem, blocks, st)); break;
+  }
+  PDC_CUDA(cudaEventRecord(ctx->ev_end, st));
+  ctx->have_main_ev = true;
+
+  double* red_val = ctx->blockred.as<double>();
+  long long* red_idx = reinterpret_cast<long long*>(red_val + eblk);
+  pdm_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(a.partial, nsplit, m0, nc, np, theta_out, red_val, red_idx);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  if (argmin_out || min_out) {
+    argext_final_kernel<-1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmin_out, min_out);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  return PDC_OK;
+}
+
+}  // namespace pdc

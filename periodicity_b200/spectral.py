@@ -1,0 +1,158 @@
+"""Drop-in ``GLS`` backed by the sm_100a strip kernel.
+
+Same constructor, call signature, attributes and side effects as the reference
+class (``src/periodicity/spectral.py:43-204``); the difference is *how* the
+periodogram is evaluated.  The reference approximates the trigonometric sums
+with an FFT extirpolation (``_trig_sum``, ``spectral.py:11-40``); here the sums
+are evaluated exactly, by brute force, on a B200 through
+``libperiodicity_b200.so`` (``pdc_gls``), and the tau-offset algebra of
+``spectral.py:113-132`` runs on the device in float64.
+
+There is no CPU fallback: without the CUDA library / a B200 the call raises.
+"""
+import copy
+
+import numpy as np
+
+from . import _ffi
+from .core import FSeries, TSeries
+
+__all__ = ["GLS", "BGLST"]
+
+
+class GLS(object):
+    """Generalised Lomb-Scargle periodogram (Zechmeister & Kuerster 2009).
+
+    Parameters (identical to the reference, ``spectral.py:53-72``)
+    ----------
+    fmin, fmax : float, optional
+        Frequency range; defaults: half a cycle over the baseline, and the
+        pseudo-Nyquist frequency ``0.5 / median_dt``.
+    n : float, optional
+        Samples per peak: ``df = 1 / (baseline * n)`` (default 5).
+    psd : bool, optional
+        Leave the periodogram unnormalised.
+
+    Extra, keyword-only (not in the reference; defaults keep its behaviour)
+    ----------
+    device : int, optional
+        CUDA device ordinal (default: ``LOCAL_RANK`` or 0).
+    shard : bool, optional
+        If True and ``torch.distributed`` is initialised, shard the frequency
+        grid across ranks and all-gather power + argmax (``dist.gls_sharded``).
+    """
+
+    def __init__(self, fmin=None, fmax=None, n=5, psd=False, *, device=None, shard=False):
+        self.fmin = fmin
+        self.fmax = fmax
+        self.n = n
+        self.psd = psd
+        self.device = device
+        self.shard = shard
+
+    # -- helpers ---------------------------------------------------------------
+    def _grid(self, signal):
+        """(fmin, df, frequency) following ``spectral.py:88-98`` to the letter."""
+        df = 1.0 / signal.baseline / self.n
+        fmin = 0.5 * df if self.fmin is None else self.fmin
+        fmax = 0.5 / signal.median_dt if self.fmax is None else self.fmax
+        return fmin, df, np.arange(fmin, fmax + df, df)
+
+    def __call__(self, signal, err=None, fit_mean=True):
+        """Evaluate the periodogram of ``signal`` (``spectral.py:74-135``).
+
+        ``err`` are per-sample uncertainties (weights ``err**-2``);
+        ``fit_mean`` lets the mean float with the fit.
+        Returns an ``FSeries`` and sets ``frequency, err, signal, periodogram``.
+        """
+        if not isinstance(signal, TSeries):
+            signal = TSeries(values=signal)
+        fmin, df, self.frequency = self._grid(signal)
+        nf = self.frequency.size
+        if err is None:
+            err = np.ones_like(signal.values)
+            weights = None                      # uniform weights: unweighted kernel
+        else:
+            err = np.asarray(err)
+            weights = np.asarray(err, dtype=np.float64) ** -2.0
+        self.err = err
+        psd_scale = 0.5 * (np.asarray(err, dtype=np.float64) ** -2.0).sum() if self.psd else None
+        if self.shard:
+            from . import dist
+            power, self.argmax_index, self.max_power = dist.gls_sharded(
+                signal.time, signal.values, weights, fmin, df, nf, fit_mean, psd_scale, device=self.device)
+        else:
+            ctx = _ffi.default_context(self.device)
+            power, self.argmax_index, self.max_power = ctx.gls(
+                signal.time, signal.values, weights, fmin, df, nf, fit_mean=fit_mean, psd_scale=psd_scale)
+        self.signal = signal
+        self.periodogram = FSeries(self.frequency, power)
+        return self.periodogram
+
+    def copy(self):
+        return copy.deepcopy(self)
+
+    def bootstrap(self, n_bootstraps, random_seed=None, batch=256):
+        """Maximum power of ``n_bootstraps`` resamples (``spectral.py:140-152``).
+
+        The reference loops ``gls(bs_sample, err=bs_err).amax()``; here the
+        resamples (same times, resampled values and errors, drawn from the same
+        generator in the same order) go through the batched kernel
+        ``pdc_gls_batch`` keeping only each curve's maximum.
+        """
+        rng = np.random.default_rng(random_seed)
+        ndata = len(self.signal)
+        t = np.asarray(self.signal.time, dtype=np.float64)
+        values = np.asarray(self.signal.values, dtype=np.float64)
+        err = np.asarray(self.err, dtype=np.float64)
+        fmin, df, frequency = self._grid(self.signal)
+        nf = frequency.size
+        ctx = _ffi.default_context(self.device)
+        out = np.empty(n_bootstraps)
+        for a in range(0, n_bootstraps, batch):
+            b = min(n_bootstraps, a + batch)
+            idx = np.stack([rng.integers(0, ndata, ndata) for _ in range(a, b)])
+            yb = values[idx].ravel()
+            eb = err[idx]
+            wb = (eb ** -2.0).ravel()
+            offsets = np.arange(b - a + 1, dtype=np.int64) * ndata
+            psd_scale = 0.5 * (eb ** -2.0).sum(axis=1) if self.psd else None
+            _, _, mx = ctx.gls_batch(np.tile(t, b - a), yb, wb, offsets, fmin, df, nf, fit_mean=True,
+                                     psd_scale=psd_scale, want_power=False)
+            out[a:b] = mx
+        self.bs_replicates = out
+        return self.bs_replicates
+
+    def fap(self, power):
+        """False-alarm probability of ``power`` from the bootstrap replicates (``spectral.py:154-160``)."""
+        return np.mean(power < self.bs_replicates)
+
+    def fal(self, fap):
+        """Power level with false-alarm probability ``fap`` (``spectral.py:162-163``)."""
+        return np.quantile(self.bs_replicates, 1 - fap)
+
+    def window(self):
+        """Spectral window: periodogram of an all-ones signal without mean fit (``spectral.py:165-167``)."""
+        gls = self.copy()
+        return gls(0.0 * self.signal + 1.0, fit_mean=False)
+
+    def model(self, tf, f0):
+        """Best-fit offset + sinusoid at frequency ``f0`` evaluated at ``tf`` (``spectral.py:169-204``)."""
+        t = self.signal.time
+        sigma = np.asarray(self.err, dtype=np.float64)
+        w = sigma ** -2.0
+        y_mean = np.dot(self.signal.values, w) / w.sum()
+        resid = self.signal.values - y_mean
+
+        def design(times):
+            arg = 2 * np.pi * f0 * np.asarray(times)
+            return np.vstack([np.ones_like(arg), np.sin(arg), np.cos(arg)])
+
+        A = design(t) / sigma
+        theta = np.linalg.solve(A @ A.T, A @ (resid / sigma))
+        return TSeries(tf, y_mean + design(tf).T @ theta)
+
+
+class BGLST(object):
+    """Placeholder kept for API parity (empty in the reference too, ``spectral.py:207-208``)."""
+    pass
