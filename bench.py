@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- sample*frequency evaluations per second of the GLS / PDM hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  gls_c2 (default)  GLS, Kepler-like 65,000 points x 1e5 frequencies per GPU
+                    (BASELINE.json configs[1]).  With N GPUs the frequency grid is
+                    N x 1e5 long and sharded across ranks (weak scaling), followed by
+                    ONE all-gather of [power shard, local max, local argmax].
+  pdm_c3            PDM 1e5 points x 1e5 trial periods, nb=10, nc=2 (configs[2]);
+                    period grid sharded the same way.
+  gls_c5            GLS 1e6 points x (1e7/8 per GPU) frequencies (configs[4] per-GPU share).
+  gls_c4            batched GLS, 256 TESS-like curves x 20,000 points x 1e4 frequencies per GPU.
+
+Printed line (rank 0): metric/value/unit/... as the driver contract asks, plus
+  roofline      dominant kernel vs the FP32 issue roofline (the path is FP32-pipe bound, not
+                HBM or tensor bound): achieved = evals x 20 FLOP / kernel time
+                (CUDA events on the launching stream inside the library), peak = measured FFMA rate
+                (profiles/pipes_r01.json; MEASURED_PEAKS.json has no FP32 entry).
+  cpu_baseline  the oracle port of the reference algorithm timed on this box's host cores.
+  e2e           same metric through the host-pointer C-ABI call (H2D + kernels + D2H in the timed region).
+
+--impl reference times the reference's own CPU algorithm (numpy restatement in oracle/, the
+reference is pure Python and cannot be installed without xarray) on the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_EVAL_GLS = 20.0      # 12 FP32 instructions = 20 FLOP per sample*frequency
+OPS_PER_EVAL_PDM = 8.0        # 8 ops per sample*period
+FP32_PEAK_TFLOPS_MEASURED = 72.3   # profiles/pipes_r01.json: 36,172 GFFMA/s x 2
+PDM_PEAK_GEVALS_MEASURED = 1454.8  # profiles/pipes_r01.json: private-column smem RMW, sample updates/s
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic workloads (SURVEY.md section 8d recipes, fixed seeds)
+# ------------------------------------------------------------------------------------------
+def make_gls_c2(nf_total):
+    rng = np.random.default_rng(2)
+    n = 65_000
+    slots = np.sort(rng.choice(71_940, n, replace=False))
+    t = slots * (29.4244 / 1440.0) + rng.uniform(0, 1 / 1440.0, n)
+    df = 1 / (t[-1] - t[0]) / 5
+    fmin = 0.5 * df
+    fsig = fmin + 0.3137 * 100_000 * df
+    y = 1000 + np.sin(2 * np.pi * fsig * t + 0.3) + rng.standard_normal(n)
+    return dict(kind="gls", t=t, y=y, fmin=fmin, df=df, nf=nf_total,
+                name=f"GLS Kepler-like 65,000 points x {nf_total} frequencies (C2 per GPU)")
+
+
+def make_gls_c5(nf_total):
+    rng = np.random.default_rng(5)
+    n = 1_000_000
+    t = np.sort(rng.uniform(0, 1000.0, n))
+    df = 1 / (t[-1] - t[0]) / 5
+    fmin = 0.5 * df
+    y = 1000 + np.sin(2 * np.pi * 17.123 * t + 0.3) + rng.standard_normal(n)
+    return dict(kind="gls", t=t, y=y, fmin=fmin, df=df, nf=nf_total,
+                name=f"GLS 1e6 points x {nf_total} frequencies (C5 share)")
+
+
+def make_pdm_c3(np_total):
+    rng = np.random.default_rng(3)
+    n = 100_000
+    t = np.sort(rng.uniform(0, 1000.0, n))
+    x = 1000 + np.sin(2 * np.pi * t / 3.7) + 0.8 * np.sin(4 * np.pi * t / 3.7) + rng.standard_normal(n)
+    periods = np.linspace(1.0, 11.0, np_total)
+    return dict(kind="pdm", t=t, y=x, periods=periods, nb=10, nc=2, nf=np_total,
+                name=f"PDM 1e5 points x {np_total} trial periods, nb=10 nc=2 (C3)")
+
+
+def make_gls_c4(curves):
+    n, nf = 20_000, 10_000
+    ts, ys, fm, dfs = [], [], [], []
+    for b in range(curves):
+        rng = np.random.default_rng(4000 + b)
+        keep = rng.uniform(size=n + n // 50) > 0.01
+        tt = (np.arange(n + n // 50)[keep][:n]) * (2.0 / 1440.0) + rng.uniform(0, 0.2 / 1440.0, n)
+        P = rng.uniform(0.5, 10.0)
+        ys.append(1000 + np.sin(2 * np.pi * tt / P) + rng.standard_normal(n))
+        ts.append(tt)
+        d = 1 / (tt[-1] - tt[0]) / 5
+        dfs.append(d)
+        fm.append(0.5 * d)
+    return dict(kind="gls_batch", t=np.concatenate(ts), y=np.concatenate(ys),
+                offsets=np.arange(curves + 1, dtype=np.int64) * n, fmin=np.array(fm), df=np.array(dfs), nf=nf,
+                name=f"batched GLS {curves} TESS-like curves x 20,000 points x 1e4 frequencies (C4 share)")
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (NVML)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+            return
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle port of the reference's CPU algorithm)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_step(wl):
+    """One step of the reference's CPU path on (a bounded sample of) the workload.
+    Returns (evals processed, cores used, description of the sample)."""
+    from oracle import gls_numpy, pdm_numpy
+    if wl["kind"] == "gls":
+        # the reference's own algorithm: FFT extirpolation, single-threaded numpy (spectral.py:11-40)
+        gls_numpy.gls_power(wl["t"], wl["y"], None, wl["fmin"], wl["df"], wl["nf"], True, False)
+        return wl["t"].size * wl["nf"], 1, "full workload, reference FFT-extirpolation algorithm, numpy, 1 thread"
+    if wl["kind"] == "gls_batch":
+        B = min(len(wl["offsets"]) - 1, 64)
+        for b in range(B):
+            a, e = wl["offsets"][b], wl["offsets"][b + 1]
+            gls_numpy.gls_power(wl["t"][a:e], wl["y"][a:e], None, wl["fmin"][b], wl["df"][b], wl["nf"], True, False)
+        return int(wl["offsets"][B]) * wl["nf"], 1, f"first {B} curves, python loop (the reference has no batch API)"
+    cores = os.cpu_count() or 1
+    sample = wl["periods"][:: max(1, wl["periods"].size // (24 * cores))][: 24 * cores]
+    pdm_numpy.pdm_pool(wl["t"], wl["y"], sample, wl["nb"], wl["nc"], cores, sort=True)
+    return wl["t"].size * sample.size, cores, (f"{sample.size} of {wl['periods'].size} trial periods (strided), "
+                                               f"multiprocessing.Pool({cores}) as phase.py:185-186")
+
+
+def run_reference(args, wl, metric, unit):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        cpu_reference_step(wl)
+    t0 = time.perf_counter()
+    evals = 0
+    for _ in range(args.steps):
+        e, cores, desc = cpu_reference_step(wl)
+        evals += e
+    dt = time.perf_counter() - t0
+    value = evals / dt
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "note": "reference CPU algorithm (oracle port; the reference package "
+                   "needs xarray and cannot be installed here)"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c4"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    per_gpu = {"gls_c2": 100_000, "pdm_c3": 100_000, "gls_c5": 1_250_000, "gls_c4": 256}[args.workload]
+    total_units = per_gpu * max(world, 1)
+    if args.workload == "gls_c2":
+        wl = make_gls_c2(total_units)
+    elif args.workload == "gls_c5":
+        wl = make_gls_c5(total_units)
+    elif args.workload == "pdm_c3":
+        wl = make_pdm_c3(total_units)
+    else:
+        wl = make_gls_c4(total_units)
+    metric = "GLS sample*frequency evaluations per second" if wl["kind"] != "pdm" else \
+        "PDM sample*period evaluations per second"
+    unit = "evals/s"
+
+    if args.impl == "reference":
+        run_reference(args, wl, metric, unit)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from periodicity_b200 import _ffi
+    from periodicity_b200 import dist as pdist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = _ffi.default_context(local_rank)
+
+    # ---- device-resident inputs ------------------------------------------------------------
+    n = wl["t"].size
+    t_pin = torch.from_numpy(wl["t"]).pin_memory()
+    y_pin = torch.from_numpy(wl["y"]).pin_memory()
+    t_d = t_pin.to(dev)
+    y_d = y_pin.to(dev)
+    kind = wl["kind"]
+    if kind == "gls_batch":
+        B = len(wl["offsets"]) - 1
+        b0, b1 = pdist.batch_shard_bounds(B, rank, world)
+        off = wl["offsets"][b0:b1 + 1]
+        units_local = int(off[-1] - off[0]) * wl["nf"]
+        evals_total = int(wl["offsets"][-1]) * wl["nf"]
+        L = b1 - b0
+    else:
+        start, stop, L = pdist.shard_bounds(wl["nf"], rank, world)
+        units_local = n * (stop - start)
+        evals_total = n * wl["nf"]
+        if kind == "pdm":
+            p_d = torch.from_numpy(wl["periods"][start:stop].copy()).to(dev)
+
+    def step_device():
+        """One pass of the hot path with inputs resident in HBM; returns (values, best idx, best val)."""
+        if kind == "gls":
+            power, arg, mx = pdist.gls_torch(t_d, y_d, None, wl["fmin"], wl["df"], stop - start, j0=start, ctx=ctx)
+            garg = (arg + start).to(torch.float64).reshape(())
+            vals, bests, args_ = pdist.all_gather_packed(power, mx.reshape(()), garg, L)
+        elif kind == "pdm":
+            theta, arg, mn = pdist.pdm_torch(t_d, y_d, p_d, wl["nb"], wl["nc"], ctx=ctx)
+            garg = (arg + start).to(torch.float64).reshape(())
+            vals, bests, args_ = pdist.all_gather_packed(theta, mn.reshape(()), garg, L)
+        else:
+            a, e = int(off[0]), int(off[-1])
+            _, arg, mx = pdist.gls_batch_torch(t_d[a:e], y_d[a:e], None, off - off[0], wl["fmin"][b0:b1],
+                                               wl["df"][b0:b1], wl["nf"], want_power=False, ctx=ctx)
+            vals, bests, args_ = pdist.all_gather_packed(mx, mx.max(), arg.to(torch.float64).max(), L)
+        return vals, bests, args_
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = ctx.launch_count
+    kms0, kcnt0 = ctx.main_kernel_ms_total()
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()                      # evict L2 between timed iterations (not timed)
+        ev[k][0].record()
+        step_device()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    launches = ctx.launch_count - launches0
+    barrier()
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    kms1, kcnt1 = ctx.main_kernel_ms_total()
+    main_kernel_ms = (kms1 - kms0) / max(1, kcnt1 - kcnt0)   # average launch of the dominant kernel, timed region
+    if world > 1:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    value = evals_total / (ms_per_step * 1e-3)
+
+    # ---- e2e: host-pointer C-ABI call, pinned host inputs, H2D + D2H inside the timed region ---
+    th, yh = t_pin.numpy(), y_pin.numpy()
+
+    def step_e2e():
+        if kind == "gls":
+            p, a, m = ctx.gls(th, yh, None, wl["fmin"], wl["df"], stop - start, j0=start)
+            return p
+        if kind == "pdm":
+            p, a, m = ctx.pdm(th, yh, wl["periods"][start:stop], wl["nb"], wl["nc"])
+            return p
+        a_, e_ = int(off[0]), int(off[-1])
+        _, a, m = ctx.gls_batch(th[a_:e_], yh[a_:e_], None, off - off[0], wl["fmin"][b0:b1], wl["df"][b0:b1],
+                                wl["nf"], want_power=False)
+        return m
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = evals_total * args.steps / e2e_s
+    if kind == "gls_batch":
+        h2d = 2 * 8 * int(off[-1] - off[0])
+        d2h = out.nbytes * 2
+    else:
+        h2d = 2 * 8 * n + (8 * (stop - start) if kind == "pdm" else 0)
+        d2h = out.nbytes + 16
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------
+    if kind == "pdm":
+        ach = units_local / (main_kernel_ms * 1e-3) / 1e9
+        roof = {"bound": "smem", "kernel": "pdm_hist_kernel", "achieved": ach, "peak": PDM_PEAK_GEVALS_MEASURED,
+                "unit": "Gevals/s", "frac": ach / PDM_PEAK_GEVALS_MEASURED, "traffic": None,
+                "kernel_ms": main_kernel_ms,
+                "peak_source": "profiles/pipes_r01.json smem_private_rmw3 (3 LDS+3 FADD+3 STS per sample update); "
+                               "path is shared-memory/issue bound, not HBM or tensor bound"}
+    else:
+        ach = units_local * FLOP_PER_EVAL_GLS / (main_kernel_ms * 1e-3) / 1e12
+        roof = {"bound": "fp32", "kernel": "gls_strip_kernel", "achieved": ach, "peak": FP32_PEAK_TFLOPS_MEASURED,
+                "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS_MEASURED, "traffic": None,
+                "kernel_ms": main_kernel_ms, "flop_per_eval": FLOP_PER_EVAL_GLS,
+                "evals_per_s_kernel": units_local / (main_kernel_ms * 1e-3),
+                "peak_source": "profiles/pipes_r01.json ffma_shared_operands x2 FLOP (measured on this pool's B200; "
+                               "MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5)",
+                "hbm": {"achieved_gbs": (32.0 * n + 6 * 8 * 2 * (units_local / n)) / (main_kernel_ms * 1e-3) / 1e9,
+                        "peak_gbs": 6457.4, "note": "algorithmic bytes: 32 B/sample record + FP64 partial flush; "
+                                                     "the path is compute bound"}}
+
+    # ---- cpu baseline (rank 0, N=1 only) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        reps, evals = 0, 0
+        t0 = time.perf_counter()
+        while True:
+            e, cores, desc = cpu_reference_step(wl)
+            evals += e
+            reps += 1
+            if time.perf_counter() - t0 > 10.0 or reps >= 50:
+                break
+        dt = time.perf_counter() - t0
+        cpu = {"value": evals / dt, "unit": unit, "cores": cores, "kind": "port",
+               "sample": f"{desc}; {reps} repetition(s) in {dt:.1f} s", "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 sums, f64 phase/epilogue" if kind != "pdm" else "f64 phase, f32 histograms",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "units_per_gpu": per_gpu, "sharding": "frequency grid" if kind == "gls"
+                       else ("period grid" if kind == "pdm" else "light-curve batch"),
+                       "l2": "flushed between timed steps (256 MiB memset, not timed); per-step CUDA events summed",
+                       "collective": "one NCCL all-gather of [values, best, index] per step" if world > 1 else "none (1 GPU)"},
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_s / args.steps * 1e3, "api": "pdc_gls / pdc_pdm host-pointer C-ABI call (ctypes)"},
+            "gpu_launches": int(launches),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

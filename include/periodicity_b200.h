@@ -27,8 +27,10 @@
  *     pointers and are synchronous: inputs are copied to the device, results
  *     are back in the output buffers on return.
  *   - Device entry points (`*_dev`) take device pointers on the ctx's device,
- *     are ordered on `stream` (a cudaStream_t passed as void*; NULL = the ctx's
- *     own stream) and return without synchronising.
+ *     are ordered on `stream` (a cudaStream_t passed as void*; NULL is CUDA's
+ *     legacy default stream, as everywhere in CUDA -- it is what
+ *     torch.cuda.current_stream().cuda_stream yields by default; pass
+ *     PDC_STREAM_CTX to use the ctx's own stream) and return without synchronising.
  *   - All arrays are C-contiguous float64 (what TSeries.time / .values yield,
  *     core.py:60-66,479-481); FP32 is an internal detail of the kernels.
  *   - There is no CPU fallback: without a usable CUDA device the ctx cannot be
@@ -64,6 +66,9 @@ typedef enum pdc_status {
 #define PDC_GLS_PSD 2u      /* psd=True        (spectral.py:129-130): power *= psd_scale */
 
 typedef struct pdc_ctx pdc_ctx;
+
+/* `stream` value selecting the ctx's own non-blocking stream in the *_dev calls. */
+#define PDC_STREAM_CTX ((void*)(intptr_t)-1)
 
 PDC_API int pdc_version(void);
 PDC_API const char* pdc_last_error(void);
@@ -162,6 +167,12 @@ PDC_API int64_t pdc_ctx_launch_count(pdc_ctx* ctx);
  * recorded on the launching stream.  Synchronises on the end event.
  * Negative on error / if no call has been made. */
 PDC_API double pdc_ctx_last_main_kernel_ms(pdc_ctx* ctx);
+
+/* Cumulative duration in milliseconds of every dominant-kernel launch made
+ * through this ctx since creation; `count_out` (may be NULL) receives the number
+ * of launches.  Synchronises on the last recorded end event.  bench.py takes the
+ * difference across its timed region: average launch duration = d(ms) / d(count). */
+PDC_API double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libperiodicity_b200.so")
 PDC_OK, PDC_EINVAL, PDC_ECUDA, PDC_ENOMEM, PDC_ENODEVICE = range(5)
 GLS_FIT_MEAN = 1
 GLS_PSD = 2
+STREAM_CTX = ctypes.c_void_p(-1).value  # PDC_STREAM_CTX: the ctx's own stream (0/None = CUDA default stream)
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int64_p = ctypes.POINTER(ctypes.c_int64)
@@ -29,6 +30,7 @@ SIGNATURES = {
     "pdc_ctx_sm_count": (ctypes.c_int, [ctypes.c_void_p]),
     "pdc_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "pdc_ctx_last_main_kernel_ms": (ctypes.c_double, [ctypes.c_void_p]),
+    "pdc_ctx_main_kernel_ms_total": (ctypes.c_double, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "pdc_gls": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
@@ -126,6 +128,12 @@ class Context:
 
     def last_main_kernel_ms(self):
         return self._lib.pdc_ctx_last_main_kernel_ms(self._h)
+
+    def main_kernel_ms_total(self):
+        """(cumulative ms, launch count) of the dominant kernel since the ctx was created."""
+        cnt = ctypes.c_int64(0)
+        ms = self._lib.pdc_ctx_main_kernel_ms_total(self._h, ctypes.byref(cnt))
+        return ms, cnt.value
 
     def synchronize(self):
         _check(self._lib.pdc_ctx_synchronize(self._h))

@@ -117,40 +117,47 @@ class _Series(np.lib.mixins.NDArrayOperatorsMixin):
         return self._like(result)
 
     # -- NaN-aware reductions (core.py:202-262) -------------------------------
-    def argmax(self):
-        return int(np.nanargmax(self._values))
+    def _reduce(self, func, axis=None, out=None, **kw):
+        if axis not in (None, 0, -1) or out is not None:
+            raise ValueError("series are one-dimensional; only full reductions are supported")
+        kw.pop("keepdims", None)
+        result = func(self._values, **{k: v for k, v in kw.items() if v is not None})
+        return result.item() if hasattr(result, "item") else result
 
-    def argmin(self):
-        return int(np.nanargmin(self._values))
+    def argmax(self, **kw):
+        return int(self._reduce(np.nanargmax, **kw))
 
-    def amax(self):
-        return np.nanmax(self._values).item()
+    def argmin(self, **kw):
+        return int(self._reduce(np.nanargmin, **kw))
 
-    def amin(self):
-        return np.nanmin(self._values).item()
+    def amax(self, **kw):
+        return self._reduce(np.nanmax, **kw)
 
-    def max(self):
+    def amin(self, **kw):
+        return self._reduce(np.nanmin, **kw)
+
+    def max(self, **kw):
         i = self.argmax()
         return self[i:i + 1]
 
-    def min(self):
+    def min(self, **kw):
         i = self.argmin()
         return self[i:i + 1]
 
-    def mean(self):
-        return np.nanmean(self._values).item()
+    def mean(self, **kw):
+        return self._reduce(np.nanmean, **kw)
 
-    def median(self):
-        return np.nanmedian(self._values).item()
+    def median(self, **kw):
+        return self._reduce(np.nanmedian, **kw)
 
     def std(self, **kw):
-        return np.nanstd(self._values, **kw).item()
+        return self._reduce(np.nanstd, **kw)
 
     def var(self, **kw):
-        return np.nanvar(self._values, **kw).item()
+        return self._reduce(np.nanvar, **kw)
 
-    def sum(self):
-        return np.nansum(self._values).item()
+    def sum(self, **kw):
+        return self._reduce(np.nansum, **kw)
 
     def __getitem__(self, key):
         coord = self._coord[key]

@@ -83,6 +83,45 @@ void PinnedBuf::release() {
   cap = 0;
 }
 
+}  // namespace pdc
+
+int pdc_ctx::main_begin(cudaStream_t st) {
+  if (ev_pending.size() >= 1024) PDC_TRY(main_resolve());
+  if (ev_free.empty()) {
+    cudaEvent_t a, b;
+    PDC_CUDA(cudaEventCreate(&a));
+    PDC_CUDA(cudaEventCreate(&b));
+    ev_free.emplace_back(a, b);
+  }
+  ev_cur_begin = ev_free.back().first;
+  ev_cur_end = ev_free.back().second;
+  ev_free.pop_back();
+  PDC_CUDA(cudaEventRecord(ev_cur_begin, st));
+  return PDC_OK;
+}
+
+int pdc_ctx::main_end(cudaStream_t st) {
+  PDC_CUDA(cudaEventRecord(ev_cur_end, st));
+  ev_pending.emplace_back(ev_cur_begin, ev_cur_end);
+  return PDC_OK;
+}
+
+int pdc_ctx::main_resolve() {
+  for (auto& pr : ev_pending) {
+    PDC_CUDA(cudaEventSynchronize(pr.second));
+    float ms = 0.f;
+    PDC_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    main_ms_total += ms;
+    main_ms_last = ms;
+    main_count++;
+    ev_free.push_back(pr);
+  }
+  ev_pending.clear();
+  return PDC_OK;
+}
+
+namespace pdc {
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
@@ -134,13 +173,10 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  cudaError_t e2 = cudaEventCreate(&ctx->ev_begin);
-  cudaError_t e3 = cudaEventCreate(&ctx->ev_end);
   cudaError_t e4 = cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming);
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+  if (e1 != cudaSuccess || e4 != cudaSuccess) {
     pdc_ctx_destroy(ctx);
-    return cuda_fail(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4)),
-                     "stream/event creation", __FILE__, __LINE__);
+    return cuda_fail(e1 != cudaSuccess ? e1 : e4, "stream/event creation", __FILE__, __LINE__);
   }
   *out = ctx;
   return PDC_OK;
@@ -152,11 +188,11 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->in_a.release(); ctx->in_b.release(); ctx->in_c.release(); ctx->in_d.release();
   ctx->out_a.release(); ctx->out_small.release(); ctx->pin_small.release();
-  ctx->gls_curves.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release();
+  ctx->gls_curves.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release();
   ctx->partial.release(); ctx->blockred.release(); ctx->pin_meta.release();
   ctx->pdm_meta.release(); ctx->pdm_x.release();
-  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
-  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+  ctx->main_resolve();
+  for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -175,12 +211,18 @@ int pdc_ctx_sm_count(pdc_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
 int64_t pdc_ctx_launch_count(pdc_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 double pdc_ctx_last_main_kernel_ms(pdc_ctx* ctx) {
-  if (!ctx || !ctx->have_main_ev) return -1.0;
+  if (!ctx) return -1.0;
   DeviceGuard guard(ctx->device);
-  if (cudaEventSynchronize(ctx->ev_end) != cudaSuccess) return -1.0;
-  float ms = -1.f;
-  if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) != cudaSuccess) return -1.0;
-  return (double)ms;
+  if (ctx->main_resolve() != PDC_OK) return -1.0;
+  return ctx->main_ms_last;
+}
+
+double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out) {
+  if (!ctx) return -1.0;
+  DeviceGuard guard(ctx->device);
+  if (ctx->main_resolve() != PDC_OK) return -1.0;
+  if (count_out) *count_out = ctx->main_count;
+  return ctx->main_ms_total;
 }
 
 // ---------------------------------------------------------------------------
@@ -192,7 +234,7 @@ int pdc_gls_batch_dev(pdc_ctx* ctx, const double* t, const double* y, const doub
                       double* power_out, int64_t* argmax_out, double* max_out, void* stream) {
   if (!ctx || !t || !y || !offsets || !fmin || !df) { set_error("pdc_gls_batch_dev: NULL argument"); return PDC_EINVAL; }
   DeviceGuard guard(ctx->device);
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
   return gls_run(ctx, t, y, w, offsets, B, fmin, df, 0, nf, flags, psd_scale, power_out, argmax_out, max_out, st);
 }
 
@@ -203,7 +245,7 @@ int pdc_gls_dev(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   if (n < 1) { set_error("pdc_gls: n must be >= 1"); return PDC_EINVAL; }
   if (j0 < 0) { set_error("pdc_gls: j0 must be >= 0"); return PDC_EINVAL; }
   DeviceGuard guard(ctx->device);
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
   const int64_t offsets[2] = {0, n};
   return gls_run(ctx, t, y, w, offsets, 1, &fmin, &df, j0, nf, flags, &psd_scale, power_out, argmax_out, max_out, st);
 }
@@ -295,7 +337,7 @@ int pdc_pdm_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
                 double* theta_out, int64_t* argmin_out, double* min_out, void* stream) {
   if (!ctx || !t || !x || !periods || !theta_out) { set_error("pdc_pdm_dev: NULL argument"); return PDC_EINVAL; }
   DeviceGuard guard(ctx->device);
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
   return pdm_run(ctx, t, x, n, periods, np, nb, nc, theta_out, argmin_out, min_out, st);
 }
 

@@ -21,6 +21,7 @@
 //   gls_stats_kernel    per curve: t_min, sum w, weighted mean, YY      (FP64)
 //   gls_records_kernel  per sample: (t - t_min, frac(df (t - t_min))) as double2 and
 //                       (cos, sin of 2 pi df (t - t_min), y', w') as float4
+//   gls_lowfreq_kernel  FP64 direct sums for the few frequencies with < 1 cycle over the baseline
 //   gls_strip_kernel    the hot kernel: six FP32 sums per frequency
 //                       {C, S, YC, YS, CC, CS}, flushed to FP64 partials per tile
 //   gls_epilogue_kernel FP64: merge partials, tau-offset algebra
@@ -38,28 +39,42 @@ struct GlsCurve {
   double fmin, df;
   double psd_scale;
   // filled on the device by gls_stats_kernel
-  double tmin, wsum, ymean, yy, inv_rms;
+  double tmin, tmax, wsum, ymean, yy, inv_rms;
+  int low_begin, low_count;  // frequencies [low_begin, low_begin + low_count) of this call go through FP64
 };
 
 constexpr int GLS_TILE = 1024;  // samples per shared-memory tile == FP32 flush interval
+
+// Frequencies with |f| * (tmax - tmin) < GLS_LOW_CYCLES see less than one cycle over the
+// baseline: there CC - C^2 and SS - S^2 (spectral.py:125-127) cancel almost completely
+// (a slow cosine is nearly degenerate with the floating mean) and amplify FP32 rounding
+// by 1/var(cos) ~ 300x at f*T = 0.1.  Those few bins (at most GLS_NLOW_MAX per curve) are
+// evaluated by gls_lowfreq_kernel entirely in FP64.
+constexpr double GLS_LOW_CYCLES = 1.0;
+constexpr int GLS_NLOW_MAX = 16;
+constexpr int GLS_LOW_CHUNK = 4096;   // samples per block of gls_lowfreq_kernel
+constexpr int GLS_LOW_MAXCHUNKS = 256;
 
 // ---------------------------------------------------------------------------
 // per-curve statistics (one block per curve)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y,
-                 const double* __restrict__ w, GlsCurve* curves, unsigned flags) {
+                 const double* __restrict__ w, GlsCurve* curves, unsigned flags,
+                 long long j0, long long nf) {
   __shared__ double scratch[33];
   GlsCurve& cv = curves[blockIdx.x];
   const long long b = cv.begin, n = cv.n;
-  double tmin = INFINITY, sw = 0.0, swy = 0.0;
+  double tmin = INFINITY, tneg = INFINITY, sw = 0.0, swy = 0.0;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     double ti = t[b + i], yi = y[b + i], wi = w ? w[b + i] : 1.0;
     tmin = fmin(tmin, ti);
+    tneg = fmin(tneg, -ti);
     sw += wi;
     swy = fma(wi, yi, swy);
   }
   tmin = block_min(tmin, scratch);
+  const double tmax = -block_min(tneg, scratch);
   sw = block_sum(sw, scratch);
   swy = block_sum(swy, scratch);
   // spectral.py:102-108: w /= w.sum(); y = values - dot(w, values) if fit_mean
@@ -73,6 +88,24 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y,
   if (threadIdx.x == 0) {
     double yy = syy / sw;  // spectral.py:120  YY = dot(w, y**2)
     cv.tmin = tmin;
+    cv.tmax = tmax;
+    // low-frequency range: |fmin + (j0 + j) df| * T < GLS_LOW_CYCLES, j in [0, nf)
+    int lb = 0, lc = 0;
+    const double T = tmax - tmin;
+    if (T > 0.0 && cv.df > 0.0) {
+      const double flim = GLS_LOW_CYCLES / T;
+      double ja = ceil((-flim - cv.fmin) / cv.df - (double)j0);
+      double jb = floor((flim - cv.fmin) / cv.df - (double)j0);
+      if (ja < 0.0) ja = 0.0;
+      if (jb > (double)(nf - 1)) jb = (double)(nf - 1);
+      if (jb >= ja) {
+        double cnt = jb - ja + 1.0;
+        lb = (int)ja;
+        lc = cnt > (double)GLS_NLOW_MAX ? GLS_NLOW_MAX : (int)cnt;
+      }
+    }
+    cv.low_begin = lb;
+    cv.low_count = lc;
     cv.wsum = sw;
     cv.ymean = ymean;
     cv.yy = yy;
@@ -110,6 +143,49 @@ gls_records_kernel(const double* __restrict__ t, const double* __restrict__ y,
     }
     rec1[g] = make_double2(tt, b);
     rec2[g] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// FP64 evaluation of the (few) sub-cycle frequencies
+// ---------------------------------------------------------------------------
+// grid = (sample chunks, GLS_NLOW_MAX, curves); writes NORMALISED sums (weights sum to 1)
+// to lowsum[chunk][6][curve * GLS_NLOW_MAX + slot].
+__global__ void __launch_bounds__(256)
+gls_lowfreq_kernel(const double* __restrict__ t, const double* __restrict__ y,
+                   const double* __restrict__ w, const GlsCurve* __restrict__ curves,
+                   double* __restrict__ lowsum, long long j0, int B) {
+  __shared__ double scratch[33];
+  const int curve = blockIdx.z, slot = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const GlsCurve cv = curves[curve];
+  if (slot >= cv.low_count) return;  // block-uniform
+  const double f = cv.fmin + (double)(j0 + cv.low_begin + slot) * cv.df;
+  const long long per = (cv.n + nchunk - 1) / nchunk;
+  const long long sb = (long long)chunk * per;
+  const long long se = sb + per < cv.n ? sb + per : cv.n;
+  const double winv = 1.0 / cv.wsum;
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  for (long long i = sb + threadIdx.x; i < se; i += blockDim.x) {
+    const long long g = cv.begin + i;
+    const double ph = frac_of_product(f, t[g] - cv.tmin);
+    double sn, cs;
+    sincospi(2.0 * ph, &sn, &cs);
+    const double wi = (w ? w[g] : 1.0) * winv;
+    const double wy = wi * ((y[g] - cv.ymean) * cv.inv_rms);
+    const double wc = wi * cs;
+    a[0] += wc;
+    a[1] = fma(wi, sn, a[1]);
+    a[2] = fma(wy, cs, a[2]);
+    a[3] = fma(wy, sn, a[3]);
+    a[4] = fma(wc, cs, a[4]);
+    a[5] = fma(wc, sn, a[5]);
+  }
+  const long long cols = (long long)B * GLS_NLOW_MAX;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const double tot = block_sum(a[q], scratch);
+    if (threadIdx.x == 0)
+      lowsum[((long long)chunk * 6 + q) * cols + (long long)curve * GLS_NLOW_MAX + slot] = tot;
   }
 }
 
@@ -265,6 +341,7 @@ __device__ __forceinline__ double np_sign(double x) {
 
 __global__ void __launch_bounds__(256)
 gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restrict__ partial,
+                    const double* __restrict__ lowsum, int nlowchunk, int B,
                     int nsplit, long long nf, long long nf_tot, unsigned flags,
                     double* __restrict__ power_out, double* __restrict__ red_val,
                     long long* __restrict__ red_idx) {
@@ -277,14 +354,28 @@ gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restric
   long long idx = -1;
   if (j < nf) {
     double sums[6];
-    const double* p = partial + (long long)curve * nf + j;
+    double inv_n;
+    if (j >= cv.low_begin && j < cv.low_begin + cv.low_count) {
+      // sub-cycle frequency: FP64 sums from gls_lowfreq_kernel (already normalised)
+      const long long cols = (long long)B * GLS_NLOW_MAX;
+      const double* p = lowsum + (long long)curve * GLS_NLOW_MAX + (j - cv.low_begin);
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      double acc = 0.0;
-      for (int s = 0; s < nsplit; ++s) acc += p[((long long)s * 6 + q) * nf_tot];
-      sums[q] = acc;
+      for (int q = 0; q < 6; ++q) {
+        double acc = 0.0;
+        for (int c = 0; c < nlowchunk; ++c) acc += p[((long long)c * 6 + q) * cols];
+        sums[q] = acc;
+      }
+      inv_n = 1.0;
+    } else {
+      const double* p = partial + (long long)curve * nf + j;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double acc = 0.0;
+        for (int s = 0; s < nsplit; ++s) acc += p[((long long)s * 6 + q) * nf_tot];
+        sums[q] = acc;
+      }
+      inv_n = 1.0 / (double)cv.n;
     }
-    const double inv_n = 1.0 / (double)cv.n;
     const double C = sums[0] * inv_n, S = sums[1] * inv_n;
     const double Ch = sums[2] * inv_n, Sh = sums[3] * inv_n;
     // sum w cos(2x) = 2 sum w cos^2 x - 1,  sum w sin(2x) = 2 sum w sin x cos x   (sum w = 1)
@@ -399,6 +490,9 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   PDC_TRY(ctx->partial.reserve(sizeof(double) * 6 * nf_tot * nsplit));
   const int eblk = (int)((nf + 255) / 256);
   PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk * B));
+  long long nlowchunk = (nmax + GLS_LOW_CHUNK - 1) / GLS_LOW_CHUNK;
+  if (nlowchunk > GLS_LOW_MAXCHUNKS) nlowchunk = GLS_LOW_MAXCHUNKS;
+  PDC_TRY(ctx->gls_low.reserve(sizeof(double) * 6 * (size_t)nlowchunk * B * GLS_NLOW_MAX));
 
   GlsCurve* hc = ctx->pin_meta.as<GlsCurve>();
   const long long off0 = offsets_host[0];
@@ -408,7 +502,8 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     hc[b].fmin = fmin_host[b];
     hc[b].df = df_host[b];
     hc[b].psd_scale = psd_scale_host ? psd_scale_host[b] : 1.0;
-    hc[b].tmin = hc[b].wsum = hc[b].ymean = hc[b].yy = hc[b].inv_rms = 0.0;
+    hc[b].tmin = hc[b].tmax = hc[b].wsum = hc[b].ymean = hc[b].yy = hc[b].inv_rms = 0.0;
+    hc[b].low_begin = hc[b].low_count = 0;
   }
   GlsCurve* dc = ctx->gls_curves.as<GlsCurve>();
   PDC_CUDA(cudaMemcpyAsync(dc, hc, sizeof(GlsCurve) * B, cudaMemcpyHostToDevice, st));
@@ -418,7 +513,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   const double* yy = y + off0;
   const double* ww = w ? w + off0 : nullptr;
 
-  gls_stats_kernel<<<(unsigned)B, 1024, 0, st>>>(tt, yy, ww, dc, flags);
+  gls_stats_kernel<<<(unsigned)B, 1024, 0, st>>>(tt, yy, ww, dc, flags, (long long)j0, (long long)nf);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
 
@@ -427,6 +522,13 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     if (bx > 1024) bx = 1024;
     dim3 grid((unsigned)bx, (unsigned)B);
     gls_records_kernel<<<grid, 256, 0, st>>>(tt, yy, ww, dc, ctx->gls_rec1.as<double2>(), ctx->gls_rec2.as<float4>());
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+
+  {
+    dim3 grid((unsigned)nlowchunk, GLS_NLOW_MAX, (unsigned)B);
+    gls_lowfreq_kernel<<<grid, 256, 0, st>>>(tt, yy, ww, dc, ctx->gls_low.as<double>(), (long long)j0, (int)B);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -442,16 +544,16 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   a.nfb = (int)nfb;
   a.nsplit = nsplit;
 
-  PDC_CUDA(cudaEventRecord(ctx->ev_begin, st));
+  PDC_TRY(ctx->main_begin(st));
   PDC_TRY((launch_strip<K, THREADS, MINB>(ctx, a, w != nullptr, items, st)));
-  PDC_CUDA(cudaEventRecord(ctx->ev_end, st));
-  ctx->have_main_ev = true;
+  PDC_TRY(ctx->main_end(st));
 
   double* red_val = ctx->blockred.as<double>();
   long long* red_idx = reinterpret_cast<long long*>(red_val + (size_t)eblk * B);
   {
     dim3 grid((unsigned)eblk, (unsigned)B);
-    gls_epilogue_kernel<<<grid, 256, 0, st>>>(dc, a.partial, nsplit, nf, nf_tot, flags, power_out, red_val, red_idx);
+    gls_epilogue_kernel<<<grid, 256, 0, st>>>(dc, a.partial, ctx->gls_low.as<double>(), (int)nlowchunk, (int)B,
+                                              nsplit, nf, nf_tot, flags, power_out, red_val, red_idx);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <utility>
+#include <vector>
 
 #include "../../include/periodicity_b200.h"
 
@@ -49,10 +51,18 @@ struct pdc_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // around the dominant kernel
   cudaEvent_t ev_fence = nullptr;                     // caller-stream -> scratch reuse fence
-  bool have_main_ev = false;
   int64_t launches = 0;
+
+  // CUDA-event timing of the dominant kernel (GLS strip / PDM histogram), recorded on the
+  // launching stream; pairs are resolved lazily so recording never synchronises.
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+  cudaEvent_t ev_cur_begin = nullptr, ev_cur_end = nullptr;
+  double main_ms_total = 0.0, main_ms_last = -1.0;
+  int64_t main_count = 0;
+  int main_begin(cudaStream_t st);
+  int main_end(cudaStream_t st);
+  int main_resolve();
 
   // host-pointer entry points: device copies of the caller's arrays
   pdc::DevBuf in_a, in_b, in_c, in_d;
@@ -64,6 +74,7 @@ struct pdc_ctx {
   pdc::DevBuf gls_curves;      // GlsCurve[B]
   pdc::DevBuf gls_rec1;        // double2[n]  (t - tmin, frac(df (t - tmin)))
   pdc::DevBuf gls_rec2;        // float4[n]   (cos, sin of the per-index rotation, y or w*y, w)
+  pdc::DevBuf gls_low;         // float64 sums of the sub-cycle frequencies [chunk][6][B*16]
   pdc::DevBuf partial;         // float64 partial sums [nsplit][rows][units]
   pdc::DevBuf blockred;        // per-block (value, index) candidates
   pdc::PinnedBuf pin_meta;     // host staging for per-curve metadata

@@ -308,15 +308,14 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   a.m0 = m0;
   a.nsplit = nsplit;
 
-  PDC_CUDA(cudaEventRecord(ctx->ev_begin, st));
+  PDC_TRY(ctx->main_begin(st));
   switch (threads) {
     case 256: PDC_TRY(pdm_launch<256>(ctx, a, smem, blocks, st)); break;
     case 128: PDC_TRY(pdm_launch<128>(ctx, a, smem, blocks, st)); break;
     case 64: PDC_TRY(pdm_launch<64>(ctx, a, smem, blocks, st)); break;
     default: PDC_TRY(pdm_launch<32>(ctx, a, smem, blocks, st)); break;
   }
-  PDC_CUDA(cudaEventRecord(ctx->ev_end, st));
-  ctx->have_main_ev = true;
+  PDC_TRY(ctx->main_end(st));
 
   double* red_val = ctx->blockred.as<double>();
   long long* red_idx = reinterpret_cast<long long*>(red_val + eblk);

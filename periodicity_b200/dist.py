@@ -1,0 +1,209 @@
+"""Torch-tensor entry points and multi-GPU sharding (one process per GPU).
+
+The trial-frequency search partitions trivially: every
+frequency / trial period / light curve is independent.  Rank ``r`` of ``W``
+evaluates a contiguous, equally padded slice of the grid through the
+device-pointer C ABI (``pdc_gls_dev`` / ``pdc_pdm_dev``) and the ranks exchange
+ONE packed all-gather per call: ``[slice values (L doubles), local best value,
+local best global index]``; every rank then reduces the ``W`` (best, index)
+pairs, so all ranks end with the full periodogram and the global arg-extremum.
+``torch.distributed`` (NCCL over NVLink for CUDA tensors, gloo in the CPU tests)
+is plumbing only; there is no collective inside the hot kernels because the path
+has no exchange step.
+
+The reference's counterpart is the ``multiprocessing.Pool`` fan-out of
+``phase.py:185-186`` (and nothing for GLS).
+"""
+import math
+
+import numpy as np
+
+from . import _ffi
+
+
+def shard_bounds(n_units, rank, world):
+    """(start, stop, L): contiguous slice of rank ``rank`` and the padded slice length L."""
+    L = max(1, math.ceil(n_units / world))
+    start = min(n_units, rank * L)
+    stop = min(n_units, start + L)
+    return start, stop, L
+
+
+def reduce_best(best_vals, best_idx, sign):
+    """NaN-ignoring arg-extremum over per-rank candidates, first occurrence on ties.
+
+    ``sign=+1`` maximum (np.nanargmax, reference core.py:202-205), ``-1`` minimum.
+    Returns (index, value); (-1, nan) if there is no candidate."""
+    best_vals = np.asarray(best_vals, dtype=np.float64)
+    best_idx = np.asarray(best_idx, dtype=np.int64)
+    ok = (best_idx >= 0) & ~np.isnan(best_vals)
+    if not ok.any():
+        return -1, float("nan")
+    v = np.where(ok, best_vals, -np.inf if sign > 0 else np.inf)
+    target = v.max() if sign > 0 else v.min()
+    cand = best_idx[ok & (v == target)]
+    return int(cand.min()), float(target)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dist_info(group=None):
+    torch = _torch()
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 0, 1
+    return dist, dist.get_rank(group), dist.get_world_size(group)
+
+
+def all_gather_packed(local_vals, local_best, local_arg, L, group=None):
+    """All-gather ``[vals padded to L, best, arg]`` (float64 tensor on any device).
+
+    Returns (vals_all [W, L], best_all [W], arg_all [W]) as tensors on the input device."""
+    torch = _torch()
+    dist, rank, world = _dist_info(group)
+    packed = torch.full((L + 2,), float("nan"), dtype=torch.float64, device=local_vals.device)
+    packed[: local_vals.numel()] = local_vals
+    packed[L] = local_best
+    packed[L + 1] = local_arg
+    if dist is None or world == 1:
+        allp = packed.unsqueeze(0)
+    else:
+        allp = torch.empty((world, L + 2), dtype=torch.float64, device=local_vals.device)
+        dist.all_gather_into_tensor(allp.view(-1), packed, group=group)
+    return allp[:, :L], allp[:, L], allp[:, L + 1]
+
+
+# ---------------------------------------------------------------------------
+# torch-tensor entry points (single device, stream ordered, no host sync)
+# ---------------------------------------------------------------------------
+def gls_torch(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, j0=0, ctx=None):
+    """GLS power for CUDA float64 tensors; returns (power[nf], argmax[1] int64, max[1]) tensors."""
+    torch = _torch()
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise ValueError("t must be a contiguous CUDA float64 tensor")
+    ctx = ctx or _ffi.default_context(t.device.index)
+    y = y.contiguous()
+    w = None if w is None else w.contiguous()
+    power = torch.empty(int(nf), dtype=torch.float64, device=t.device)
+    arg = torch.empty(1, dtype=torch.int64, device=t.device)
+    mx = torch.empty(1, dtype=torch.float64, device=t.device)
+    flags = (_ffi.GLS_FIT_MEAN if fit_mean else 0) | (_ffi.GLS_PSD if psd_scale is not None else 0)
+    stream = torch.cuda.current_stream(t.device).cuda_stream
+    ctx.gls_dev(t.data_ptr(), y.data_ptr(), 0 if w is None else w.data_ptr(), t.numel(), fmin, df, j0, nf,
+                flags, 1.0 if psd_scale is None else psd_scale, power.data_ptr(), arg.data_ptr(),
+                mx.data_ptr(), stream)
+    return power, arg, mx
+
+
+def pdm_torch(t, x, periods, nb, nc, ctx=None):
+    """PDM theta for CUDA float64 tensors; returns (theta[np], argmin[1] int64, min[1]) tensors."""
+    torch = _torch()
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise ValueError("t must be a contiguous CUDA float64 tensor")
+    ctx = ctx or _ffi.default_context(t.device.index)
+    x = x.contiguous()
+    periods = periods.contiguous()
+    theta = torch.empty(periods.numel(), dtype=torch.float64, device=t.device)
+    arg = torch.empty(1, dtype=torch.int64, device=t.device)
+    mn = torch.empty(1, dtype=torch.float64, device=t.device)
+    stream = torch.cuda.current_stream(t.device).cuda_stream
+    ctx.pdm_dev(t.data_ptr(), x.data_ptr(), t.numel(), periods.data_ptr(), periods.numel(), nb, nc,
+                theta.data_ptr(), arg.data_ptr(), mn.data_ptr(), stream)
+    return theta, arg, mn
+
+
+def gls_batch_torch(t, y, w, offsets, fmin, df, nf, fit_mean=True, psd_scale=None, want_power=True, ctx=None):
+    """Batched GLS for CUDA tensors (curves back to back); offsets/fmin/df are host arrays."""
+    torch = _torch()
+    ctx = ctx or _ffi.default_context(t.device.index)
+    B = len(offsets) - 1
+    power = torch.empty((B, int(nf)), dtype=torch.float64, device=t.device) if want_power else None
+    arg = torch.empty(B, dtype=torch.int64, device=t.device)
+    mx = torch.empty(B, dtype=torch.float64, device=t.device)
+    flags = (_ffi.GLS_FIT_MEAN if fit_mean else 0) | (_ffi.GLS_PSD if psd_scale is not None else 0)
+    stream = torch.cuda.current_stream(t.device).cuda_stream
+    ctx.gls_batch_dev(t.data_ptr(), y.data_ptr(), 0 if w is None else w.data_ptr(), offsets, fmin, df, nf, flags,
+                      psd_scale, 0 if power is None else power.data_ptr(), arg.data_ptr(), mx.data_ptr(), stream)
+    return power, arg, mx
+
+
+# ---------------------------------------------------------------------------
+# sharded calls (numpy in, numpy out on every rank)
+# ---------------------------------------------------------------------------
+def _device_compute_gls(t, y, w, fmin, df, j0, n_local, fit_mean, psd_scale, device):
+    torch = _torch()
+    dev = torch.device("cuda", _ffi.default_context(device).device)
+    tt = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).to(dev, non_blocking=True)
+    yy = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64)).to(dev, non_blocking=True)
+    ww = None if w is None else torch.as_tensor(np.ascontiguousarray(w, dtype=np.float64)).to(dev, non_blocking=True)
+    power, arg, mx = gls_torch(tt, yy, ww, fmin, df, n_local, fit_mean, psd_scale, j0=j0,
+                               ctx=_ffi.default_context(device))
+    return power, arg, mx
+
+
+def gls_sharded(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, device=None, group=None, compute=None):
+    """Frequency-grid-sharded GLS.  Every rank passes the same inputs and gets the full result.
+
+    ``compute(t, y, w, fmin, df, j0, n_local, fit_mean, psd_scale, device)`` must return
+    float64 tensors ``(power[n_local], argmax[1] (local, int64), max[1])``; the default runs
+    ``pdc_gls_dev`` on this rank's GPU.  (The CPU gloo tests inject a stand-in.)
+    """
+    torch = _torch()
+    _, rank, world = _dist_info(group)
+    start, stop, L = shard_bounds(nf, rank, world)
+    compute = compute or _device_compute_gls
+    if stop > start:
+        power, arg, mx = compute(t, y, w, fmin, df, start, stop - start, fit_mean, psd_scale, device)
+        garg = torch.where(arg >= 0, arg + start, arg).to(torch.float64)
+        best = mx.reshape(())
+        garg = garg.reshape(())
+    else:
+        ref = compute(t, y, w, fmin, df, 0, 1, fit_mean, psd_scale, device)[0]  # keeps device/dtype
+        power = ref[:0]
+        best = torch.tensor(float("nan"), dtype=torch.float64, device=ref.device)
+        garg = torch.tensor(-1.0, dtype=torch.float64, device=ref.device)
+    vals, bests, args = all_gather_packed(power, best, garg, L, group)
+    full = vals.reshape(-1)[:nf].cpu().numpy()
+    idx, val = reduce_best(bests.cpu().numpy(), args.cpu().numpy().astype(np.int64), +1)
+    return full, idx, val
+
+
+def _device_compute_pdm(t, x, periods, nb, nc, device):
+    torch = _torch()
+    dev = torch.device("cuda", _ffi.default_context(device).device)
+    tt = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).to(dev, non_blocking=True)
+    xx = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(dev, non_blocking=True)
+    pp = torch.as_tensor(np.ascontiguousarray(periods, dtype=np.float64)).to(dev, non_blocking=True)
+    return pdm_torch(tt, xx, pp, nb, nc, ctx=_ffi.default_context(device))
+
+
+def pdm_sharded(t, x, periods, nb, nc, device=None, group=None, compute=None):
+    """Period-grid-sharded PDM; theta returned in the order of ``periods`` on every rank."""
+    torch = _torch()
+    _, rank, world = _dist_info(group)
+    periods = np.ascontiguousarray(periods, dtype=np.float64)
+    npd = periods.size
+    start, stop, L = shard_bounds(npd, rank, world)
+    compute = compute or _device_compute_pdm
+    if stop > start:
+        theta, arg, mn = compute(t, x, periods[start:stop], nb, nc, device)
+        garg = torch.where(arg >= 0, arg + start, arg).to(torch.float64).reshape(())
+        best = mn.reshape(())
+    else:
+        ref = compute(t, x, periods[:1], nb, nc, device)[0]
+        theta = ref[:0]
+        best = torch.tensor(float("nan"), dtype=torch.float64, device=ref.device)
+        garg = torch.tensor(-1.0, dtype=torch.float64, device=ref.device)
+    vals, bests, args = all_gather_packed(theta, best, garg, L, group)
+    full = vals.reshape(-1)[:npd].cpu().numpy()
+    idx, val = reduce_best(bests.cpu().numpy(), args.cpu().numpy().astype(np.int64), -1)
+    return full, idx, val
+
+
+def batch_shard_bounds(n_curves, rank, world):
+    """Contiguous group of light curves owned by ``rank`` (survey workload)."""
+    start, stop, _ = shard_bounds(n_curves, rank, world)
+    return start, stop

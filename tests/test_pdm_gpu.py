@@ -1,0 +1,131 @@
+"""GPU parity tests for PDM: CUDA path (through the C ABI) vs the oracle and the golden vectors.
+
+Tolerance: relative theta error <= 1e-5 and identical argmin.
+"""
+import numpy as np
+import pytest
+
+from conftest import PDM_CASES, PDM_KW, load_golden, opt
+from oracle import cport
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def synth(N, T, seed):
+    """SURVEY.md §8d C3 recipe."""
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(0, T, N))
+    x = 1000 + np.sin(2 * np.pi * t / 3.7) + 0.8 * np.sin(4 * np.pi * t / 3.7) + rng.standard_normal(N)
+    return t, x
+
+
+@pytest.mark.parametrize("case", PDM_CASES)
+def test_golden_cases_through_dropin_class(case):
+    from periodicity_b200 import PDM, TSeries
+    g = load_golden(case)
+    kw = {}
+    for k in PDM_KW:
+        if k in g and opt(g[k]) is not None:
+            v = opt(g[k])
+            kw[k] = int(v) if k in ("nb", "nc", "n_periods") else (bool(v) if k == "do_subharmonic" else v)
+    t = opt(g["t"])
+    sig = g["x"] if t is None else TSeries(t, g["x"])
+    pdm = PDM(**kw)
+    out = pdm(sig)
+    np.testing.assert_array_equal(pdm.periods, g["periods"])
+    np.testing.assert_array_equal(out.frequency, g["periodogram_frequency"])
+    np.testing.assert_allclose(out.values, g["periodogram_values"], rtol=TOL)
+    assert out.argmin() == np.nanargmin(g["periodogram_values"])
+
+
+def test_integer_times_rational_periods_bin_edges_exact(gpu_ctx):
+    """Samples exactly on bin edges (t integer, P 'nice'): must bin like the reference's >= / < tests."""
+    rng = np.random.default_rng(5)
+    t = np.arange(600.0)
+    x = np.sin(2 * np.pi * t / 12.0) + 0.3 * rng.standard_normal(600)
+    periods = np.array([2.0, 2.5, 4.0, 5.0, 8.0, 10.0, 12.0, 12.5, 16.0, 20.0, 25.0, 40.0, 3.0, 6.0, 7.0, 9.6])
+    for nb, nc in ((5, 2), (10, 2), (4, 1), (10, 3), (8, 4)):
+        th, am, mn = gpu_ctx.pdm(t, x, periods, nb, nc)
+        ref = cport.pdm(t, x, periods, nb, nc)
+        np.testing.assert_allclose(th, ref, rtol=2e-6)
+        assert am == np.nanargmin(ref)
+
+
+def test_c3_reduced_vs_c_oracle(gpu_ctx):
+    """BASELINE config C3 with 2,000 of the 1e5 trial periods (same N, nb, nc)."""
+    t, x = synth(100_000, 1000.0, 3)
+    periods = np.linspace(1.0, 11.0, 100_000)[::50]
+    th, am, mn = gpu_ctx.pdm(t, x, periods, 10, 2)
+    ref = cport.pdm(t, x, periods, 10, 2)
+    np.testing.assert_allclose(th, ref, rtol=TOL)
+    assert am == np.nanargmin(ref) and mn == th[am]
+
+
+def test_c3_full_size_properties(gpu_ctx):
+    """Full C3 (1e5 x 1e5): determinism, affine invariance, argmin vs oracle window."""
+    t, x = synth(100_000, 1000.0, 3)
+    periods = np.linspace(1.0, 11.0, 100_000)
+    th, am, mn = gpu_ctx.pdm(t, x, periods, 10, 2)
+    th2, am2, mn2 = gpu_ctx.pdm(t, x, periods, 10, 2)
+    np.testing.assert_array_equal(th, th2)
+    assert (am, mn) == (am2, mn2) and am == np.nanargmin(th)
+    th3, am3, _ = gpu_ctx.pdm(t, 2.5 * x - 40.0, periods, 10, 2)
+    assert am3 == am and np.max(np.abs(th3 - th) / th) <= 2e-6
+    lo, hi = max(0, am - 100), min(periods.size, am + 100)
+    ref = cport.pdm(t, x, periods[lo:hi], 10, 2)
+    np.testing.assert_allclose(th[lo:hi], ref, rtol=TOL)
+    assert lo + np.argmin(ref) == am
+    assert abs(periods[am] - 3.7) < 0.01 or abs(periods[am] - 7.4) < 0.02
+
+
+@pytest.mark.parametrize("nb,nc", [(1, 1), (2, 1), (50, 3), (100, 2), (13, 7)])
+def test_bin_geometries(gpu_ctx, nb, nc):
+    t, x = synth(5000, 200.0, 12)
+    periods = np.linspace(0.7, 9.0, 333)
+    th, am, _ = gpu_ctx.pdm(t, x, periods, nb, nc)
+    ref = cport.pdm(t, x, periods, nb, nc)
+    np.testing.assert_allclose(th, ref, rtol=TOL)
+    assert am == np.nanargmin(ref)
+
+
+def test_sparse_bins_and_negative_times(gpu_ctx):
+    t, x = synth(60, 30.0, 13)
+    t = t - 15.0
+    periods = np.linspace(0.9, 7.0, 101)
+    th, am, _ = gpu_ctx.pdm(t, x, periods, 10, 2)        # many bins have <= 1 sample and are dropped
+    ref = cport.pdm(t, x, periods, 10, 2)
+    np.testing.assert_allclose(th, ref, rtol=TOL)
+    assert am == np.nanargmin(ref)
+
+
+def test_few_periods_many_samples_uses_sample_split(gpu_ctx):
+    t, x = synth(300_000, 3000.0, 14)
+    periods = np.linspace(2.0, 9.0, 40)
+    th, am, _ = gpu_ctx.pdm(t, x, periods, 5, 2)
+    ref = cport.pdm(t, x, periods, 5, 2)
+    np.testing.assert_allclose(th, ref, rtol=TOL)
+    assert am == np.nanargmin(ref)
+
+
+def test_invalid_arguments_raise_value_error(gpu_ctx):
+    with pytest.raises(ValueError):
+        gpu_ctx.pdm(np.arange(5.0), np.arange(4.0), [1.0, 2.0], 5, 2)
+    with pytest.raises(ValueError):
+        gpu_ctx.pdm(np.arange(5.0), np.arange(5.0), [1.0], 0, 2)
+    with pytest.raises(ValueError):
+        gpu_ctx.pdm(np.arange(5.0), np.arange(5.0), [1.0], 10_000, 10)
+
+
+def test_torch_device_pointer_entry_matches_host_entry(gpu_ctx):
+    import torch
+    from periodicity_b200 import dist as pdist
+    t, x = synth(20_000, 500.0, 15)
+    periods = np.linspace(1.0, 11.0, 3000)
+    th, am, mn = gpu_ctx.pdm(t, x, periods, 10, 2)
+    td, ad, md = pdist.pdm_torch(torch.from_numpy(t).cuda(), torch.from_numpy(x).cuda(),
+                                 torch.from_numpy(periods).cuda(), 10, 2, ctx=gpu_ctx)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(td.cpu().numpy(), th)
+    assert int(ad.item()) == am and float(md.item()) == mn
