@@ -1,6 +1,7 @@
 // extern "C" surface of libperiodicity_b200.so (see include/periodicity_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -172,6 +173,7 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
   if (!ctx) { set_error("pdc_ctx_create: out of host memory"); return PDC_ENOMEM; }
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* g = getenv("PDC_GLS_GEOM")) ctx->gls_geom = atoi(g);
   cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   cudaError_t e4 = cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming);
   if (e1 != cudaSuccess || e4 != cudaSuccess) {

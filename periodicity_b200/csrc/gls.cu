@@ -217,8 +217,8 @@ __device__ __forceinline__ void gls_seed(double A, double b, double lKd, float& 
 template <int K, int THREADS, int MINB, bool WEIGHTED>
 __global__ void __launch_bounds__(THREADS, MINB)
 gls_strip_kernel(const GlsMainArgs a) {
-  __shared__ __align__(16) double2 s_ab[GLS_TILE];  // (phase at block base frequency, phase step per index)
-  __shared__ __align__(16) float4 s_r2[GLS_TILE];   // (cos, sin of the rotation, y' or w'y', w')
+  __shared__ __align__(16) double2 s_ab[GLS_TILE + 2];  // (phase at block base frequency, phase step per index)
+  __shared__ __align__(16) float4 s_r2[GLS_TILE + 2];   // (cos, sin of the rotation, y' or w'y', w'); +2 look-ahead pad
 
   const int item = blockIdx.x;
   const int split = item % a.nsplit;
@@ -242,6 +242,10 @@ gls_strip_kernel(const GlsMainArgs a) {
   double* pbase = a.partial + (long long)split * 6 * a.nf_tot + (long long)curve * a.nf + jB + lK;
   const long long jrem = a.nf - (jB + lK);  // strip entries with k < jrem are real frequencies
 
+  if (threadIdx.x < 2) {
+    s_ab[GLS_TILE + threadIdx.x] = make_double2(0.0, 0.0);
+    s_r2[GLS_TILE + threadIdx.x] = make_float4(1.f, 0.f, 0.f, 0.f);
+  }
   bool first = true;
   long long tile0 = sb;
   do {
@@ -259,49 +263,61 @@ gls_strip_kernel(const GlsMainArgs a) {
 #pragma unroll
     for (int k = 0; k < K; ++k) aC[k] = aS[k] = aYC[k] = aYS[k] = aCC[k] = aCS[k] = 0.f;
 
+    // One sample: K accumulations + K-1 rotations.  The sums are the per-frequency
+    // {C, S, YC, YS, CC, CS}; (c, s) enters as the exact seed at the strip's first frequency.
+    auto strip = [&](float c, float s, const float4 r2) {
+      const float cr = r2.x, sr = r2.y, yv = r2.z;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (WEIGHTED) {
+          const float wc = r2.w * c;
+          aC[k] += wc;
+          aS[k] = fmaf(r2.w, s, aS[k]);
+          aCC[k] = fmaf(wc, c, aCC[k]);
+          aCS[k] = fmaf(wc, s, aCS[k]);
+        } else {
+          aC[k] += c;
+          aS[k] += s;
+          aCC[k] = fmaf(c, c, aCC[k]);
+          aCS[k] = fmaf(c, s, aCS[k]);
+        }
+        aYC[k] = fmaf(yv, c, aYC[k]);
+        aYS[k] = fmaf(yv, s, aYS[k]);
+        if (k + 1 < K) {
+          const float c2 = fmaf(c, cr, -(s * sr));
+          const float s2 = fmaf(s, cr, c * sr);
+          c = c2;
+          s = s2;
+        }
+      }
+    };
+
     if (cnt > 0) {
-      float c, s;
-      float4 r2 = s_r2[0];
+      // Software pipeline, two samples per trip (ping-pong registers, no moves): the exact
+      // seed of the next sample is computed while the current strip runs.  The tile arrays
+      // carry two pad entries so the look-ahead never needs a bounds check.
+      float c0, s0, c1, s1;
+      float4 ra = s_r2[0], rb;
       {
         const double2 ab = s_ab[0];
-        gls_seed(ab.x, ab.y, lKd, c, s);
+        gls_seed(ab.x, ab.y, lKd, c0, s0);
       }
-      for (int i = 0; i < cnt; ++i) {
-        // software pipeline: seed of the next sample overlaps this sample's strip
-        const int in = i + 1 < cnt ? i + 1 : i;
-        const double2 abn = s_ab[in];
-        const float4 r2n = s_r2[in];
-        float cn_, sn_;
-        gls_seed(abn.x, abn.y, lKd, cn_, sn_);
-
-        const float cr = r2.x, sr = r2.y, yv = r2.z;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (WEIGHTED) {
-            const float wc = r2.w * c;
-            aC[k] += wc;
-            aS[k] = fmaf(r2.w, s, aS[k]);
-            aCC[k] = fmaf(wc, c, aCC[k]);
-            aCS[k] = fmaf(wc, s, aCS[k]);
-          } else {
-            aC[k] += c;
-            aS[k] += s;
-            aCC[k] = fmaf(c, c, aCC[k]);
-            aCS[k] = fmaf(c, s, aCS[k]);
-          }
-          aYC[k] = fmaf(yv, c, aYC[k]);
-          aYS[k] = fmaf(yv, s, aYS[k]);
-          if (k + 1 < K) {
-            const float c2 = fmaf(c, cr, -(s * sr));
-            const float s2 = fmaf(s, cr, c * sr);
-            c = c2;
-            s = s2;
-          }
+      int i = 0;
+      for (; i + 1 < cnt; i += 2) {
+        {
+          const double2 ab = s_ab[i + 1];
+          rb = s_r2[i + 1];
+          gls_seed(ab.x, ab.y, lKd, c1, s1);
         }
-        c = cn_;
-        s = sn_;
-        r2 = r2n;
+        strip(c0, s0, ra);
+        {
+          const double2 ab = s_ab[i + 2];
+          ra = s_r2[i + 2];
+          gls_seed(ab.x, ab.y, lKd, c0, s0);
+        }
+        strip(c1, s1, rb);
       }
+      if (i < cnt) strip(c0, s0, ra);
     }
 
     // flush this tile's FP32 sums into the FP64 partials this item owns
@@ -317,12 +333,14 @@ gls_strip_kernel(const GlsMainArgs a) {
           p[4 * a.nf_tot] = (double)aCC[k];
           p[5 * a.nf_tot] = (double)aCS[k];
         } else {
-          p[0] += (double)aC[k];
-          p[a.nf_tot] += (double)aS[k];
-          p[2 * a.nf_tot] += (double)aYC[k];
-          p[3 * a.nf_tot] += (double)aYS[k];
-          p[4 * a.nf_tot] += (double)aCC[k];
-          p[5 * a.nf_tot] += (double)aCS[k];
+          // RED.ADD.F64: no load latency to wait for.  Only this thread ever touches these
+          // addresses and its updates are issued in tile order, so the sum stays deterministic.
+          atomicAdd(p, (double)aC[k]);
+          atomicAdd(p + a.nf_tot, (double)aS[k]);
+          atomicAdd(p + 2 * a.nf_tot, (double)aYC[k]);
+          atomicAdd(p + 3 * a.nf_tot, (double)aYS[k]);
+          atomicAdd(p + 4 * a.nf_tot, (double)aCC[k]);
+          atomicAdd(p + 5 * a.nf_tot, (double)aCS[k]);
         }
       }
     }
@@ -414,18 +432,86 @@ gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restric
 // ---------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------
+// Strip-kernel geometries: K frequencies per thread, THREADS per block, MINB blocks per SM.
 struct GlsGeom {
   int K, threads, minb;
 };
+static const GlsGeom kGlsGeoms[] = {
+    {16, 256, 2},  // 0: 128 registers, 16 warps/SM
+    {8, 256, 4},   // 1:  64 registers, 32 warps/SM
+    {12, 128, 5},  // 2: 100 registers, 20 warps/SM
+    {10, 256, 3},  // 3:  85 registers, 24 warps/SM
+    {16, 128, 4},  // 4: 128 registers, 16 warps/SM, smaller blocks
+    {20, 128, 3},  // 5: 168 registers, 12 warps/SM
+    {24, 128, 2},  // 6: 255 registers,  8 warps/SM
+    {12, 256, 2},  // 7: 128 registers, 16 warps/SM
+    {16, 128, 3},  // 8: 168 registers, 12 warps/SM
+    {16, 128, 2},  // 9: 255 registers,  8 warps/SM
+    {16, 128, 1},  // 10: 4 warps/SM
+    {16, 64, 2},   // 11: 4 warps/SM
+    {16, 64, 4},   // 12: 8 warps/SM
+    {20, 128, 2},  // 13
+    {16, 256, 1},  // 14: 8 warps/SM, one block
+    {12, 128, 2},  // 15
+};
+constexpr int kGlsNumGeoms = sizeof(kGlsGeoms) / sizeof(kGlsGeoms[0]);
 
 template <int K, int THREADS, int MINB>
-static int launch_strip(pdc_ctx* ctx, const GlsMainArgs& a, bool weighted, long long items,
-                        cudaStream_t st) {
+static int strip_blocks_per_sm(bool weighted) {
+  int nb = 0;
+  cudaError_t e = weighted
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gls_strip_kernel<K, THREADS, MINB, true>, THREADS, 0)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gls_strip_kernel<K, THREADS, MINB, false>, THREADS, 0);
+  if (e != cudaSuccess) { cudaGetLastError(); return MINB; }
+  return nb > 0 ? nb : 1;
+}
+
+template <int K, int THREADS, int MINB>
+static int launch_strip_t(pdc_ctx* ctx, const GlsMainArgs& a, bool weighted, long long items,
+                          cudaStream_t st) {
   if (weighted) gls_strip_kernel<K, THREADS, MINB, true><<<(unsigned)items, THREADS, 0, st>>>(a);
   else gls_strip_kernel<K, THREADS, MINB, false><<<(unsigned)items, THREADS, 0, st>>>(a);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
   return PDC_OK;
+}
+
+#define PDC_GLS_GEOM_CASES(X) \
+  X(0, 16, 256, 2) X(1, 8, 256, 4) X(2, 12, 128, 5) X(3, 10, 256, 3) X(4, 16, 128, 4) X(5, 20, 128, 3) \
+  X(6, 24, 128, 2) X(7, 12, 256, 2) X(8, 16, 128, 3) X(9, 16, 128, 2) X(10, 16, 128, 1) X(11, 16, 64, 2) \
+  X(12, 16, 64, 4) X(13, 20, 128, 2) X(14, 16, 256, 1) X(15, 12, 128, 2)
+
+static int strip_occupancy(int geom, bool weighted) {
+  switch (geom) {
+#define X(i, k, t, m) case i: return strip_blocks_per_sm<k, t, m>(weighted);
+    PDC_GLS_GEOM_CASES(X)
+#undef X
+  }
+  return 1;
+}
+
+static int launch_strip(int geom, pdc_ctx* ctx, const GlsMainArgs& a, bool weighted, long long items,
+                        cudaStream_t st) {
+  switch (geom) {
+    case 0: return launch_strip_t<16, 256, 2>(ctx, a, weighted, items, st);
+    case 1: return launch_strip_t<8, 256, 4>(ctx, a, weighted, items, st);
+    case 2: return launch_strip_t<12, 128, 5>(ctx, a, weighted, items, st);
+    case 3: return launch_strip_t<10, 256, 3>(ctx, a, weighted, items, st);
+    case 4: return launch_strip_t<16, 128, 4>(ctx, a, weighted, items, st);
+    case 5: return launch_strip_t<20, 128, 3>(ctx, a, weighted, items, st);
+    case 6: return launch_strip_t<24, 128, 2>(ctx, a, weighted, items, st);
+    case 7: return launch_strip_t<12, 256, 2>(ctx, a, weighted, items, st);
+    case 8: return launch_strip_t<16, 128, 3>(ctx, a, weighted, items, st);
+    case 9: return launch_strip_t<16, 128, 2>(ctx, a, weighted, items, st);
+    case 10: return launch_strip_t<16, 128, 1>(ctx, a, weighted, items, st);
+    case 11: return launch_strip_t<16, 64, 2>(ctx, a, weighted, items, st);
+    case 12: return launch_strip_t<16, 64, 4>(ctx, a, weighted, items, st);
+    case 13: return launch_strip_t<20, 128, 2>(ctx, a, weighted, items, st);
+    case 14: return launch_strip_t<16, 256, 1>(ctx, a, weighted, items, st);
+    case 15: return launch_strip_t<12, 128, 2>(ctx, a, weighted, items, st);
+  }
+  set_error("bad strip geometry %d", geom);
+  return PDC_EINVAL;
 }
 
 // Pick the sample split so that (curves * frequency blocks * nsplit) work items
@@ -469,10 +555,14 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   const long long nf_tot = (long long)B * nf;
 
   // geometry of the hot kernel
-  constexpr int K = 16, THREADS = 256, MINB = 2;
+  int geom = ctx->gls_geom;
+  if (geom < 0 || geom >= kGlsNumGeoms) geom = 9;
+  const int K = kGlsGeoms[geom].K, THREADS = kGlsGeoms[geom].threads, MINB = kGlsGeoms[geom].minb;
   const long long fpb = (long long)K * THREADS;
   const long long nfb = (nf + fpb - 1) / fpb;
-  const long long resident = (long long)ctx->sm_count * MINB;
+  (void)MINB;
+  if (ctx->gls_occ[geom][w != nullptr] == 0) ctx->gls_occ[geom][w != nullptr] = strip_occupancy(geom, w != nullptr);
+  const long long resident = (long long)ctx->sm_count * ctx->gls_occ[geom][w != nullptr];
   const int nsplit = choose_nsplit((long long)B * nfb, nmax, resident);
   const long long items = (long long)B * nfb * nsplit;
   if (items > 0x7fffffffLL) { set_error("pdc_gls: problem too large for one call (%lld work items)", items); return PDC_EINVAL; }
@@ -545,7 +635,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   a.nsplit = nsplit;
 
   PDC_TRY(ctx->main_begin(st));
-  PDC_TRY((launch_strip<K, THREADS, MINB>(ctx, a, w != nullptr, items, st)));
+  PDC_TRY(launch_strip(geom, ctx, a, w != nullptr, items, st));
   PDC_TRY(ctx->main_end(st));
 
   double* red_val = ctx->blockred.as<double>();
