@@ -82,6 +82,34 @@ struct PdmArgs {
   int m0, nsplit;
 };
 
+// Fine-bin index of one sample for trial period P (rP = 1/P), plus an "ambiguity key":
+// key < PDM_AMBIG means phi*m0 is within 2^-20 of an integer and the bin has to be decided
+// against the reference's own thresholds (pdm_fix_bin).
+constexpr unsigned PDM_AMBIG = 2u << 12;
+
+__device__ __forceinline__ int pdm_bin(double tv, double P, double rP, double m0d, double& phi, unsigned& key) {
+  // correctly rounded t / P: q0 = t * (1/P), exact FMA residual, one correction (phase.py:131)
+  const double q0 = __dmul_rn(tv, rP);
+  const double r = __fma_rn(-q0, P, tv);
+  const double q1 = __fma_rn(r, rP, q0);
+  phi = __dadd_rn(q1, -floor(q1));                 // exact; == np.remainder(q1, 1)
+  const double u = __dmul_rn(phi, m0d);
+  const double v = __dadd_rn(u, 6442450944.0);     // 1.5 * 2^32: ulp(v) = 2^-20, low word = rint(u * 2^20)
+  const int lo = __double2loint(v);
+  key = (unsigned)(lo + 1) << 12;                  // fraction bits of u (+1 ulp), top-aligned
+  return lo >> 20;                                 // floor(u) unless ambiguous
+}
+
+__device__ __forceinline__ int pdm_fix_bin(int k, double phi, const double* s_thr, int m0) {
+  k = k < 0 ? 0 : (k > m0 - 1 ? m0 - 1 : k);
+  if (phi < s_thr[k]) --k;
+  else if (k < m0 - 1 && phi >= s_thr[k + 1]) ++k;
+  return k;
+}
+
+// Shared-memory layout: hist[bin][stat][THREADS] (stat = n, sum x', sum x'^2): a thread's
+// column is conflict free (bank = thread % 32 for every bin and stat) and the three
+// read-modify-writes of one sample differ by immediate offsets only.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 pdm_hist_kernel(const PdmArgs a) {
@@ -90,7 +118,7 @@ pdm_hist_kernel(const PdmArgs a) {
   double* s_t = reinterpret_cast<double*>(smem_raw);                 // [PDM_TILE]
   double* s_thr = s_t + PDM_TILE;                                    // [m0 + 1]  (padded to even)
   float* s_x = reinterpret_cast<float*>(s_thr + ((m0 + 2) & ~1));    // [PDM_TILE]
-  float* hist = s_x + PDM_TILE;                                      // [3][m0][THREADS]
+  float* hist = s_x + PDM_TILE;                                      // [m0][3][THREADS]
 
   const int split = blockIdx.x % a.nsplit;
   const long long pb = blockIdx.x / a.nsplit;
@@ -99,6 +127,7 @@ pdm_hist_kernel(const PdmArgs a) {
   const double P = valid ? a.periods[pi] : 1.0;
   const double rP = 1.0 / P;
   const double m0d = (double)m0;
+  const unsigned kmax = (unsigned)(m0 - 1);
 
   for (int k = threadIdx.x; k <= m0; k += THREADS) s_thr[k] = (double)k / m0d;  // phase.py:138-140
   for (int k = threadIdx.x; k < 3 * m0 * THREADS; k += THREADS) hist[k] = 0.f;
@@ -108,8 +137,15 @@ pdm_hist_kernel(const PdmArgs a) {
   const long long se = sb + per < a.n ? sb + per : a.n;
 
   float* col = hist + threadIdx.x;
-  const int stat_stride = m0 * THREADS;
   double* pcol = a.partial + (long long)split * 3 * m0 * a.np + pi;
+
+  auto update = [&](unsigned k, float xv) {
+    k = min(k, kmax);  // keeps NaN / phi == 1.0 inside the histogram
+    float* p = col + k * (3 * THREADS);
+    p[0] += 1.0f;
+    p[THREADS] += xv;
+    p[2 * THREADS] = fmaf(xv, xv, p[2 * THREADS]);
+  };
 
   bool first = true;
   int tiles_since_flush = 0;
@@ -124,44 +160,51 @@ pdm_hist_kernel(const PdmArgs a) {
     }
     __syncthreads();
 
-#pragma unroll 4
-    for (int i = 0; i < cnt; ++i) {
-      const double tv = s_t[i];
-      const float xv = s_x[i];
-      // correctly rounded t / P: q0 = t * (1/P), exact residual, one correction (phase.py:131)
-      const double q0 = __dmul_rn(tv, rP);
-      const double r = __fma_rn(-q0, P, tv);
-      const double q1 = __fma_rn(r, rP, q0);
-      const double phi = __dadd_rn(q1, -floor(q1));  // exact; == np.remainder(q1, 1)
-      const double u = __dmul_rn(phi, m0d);
-      const double v = __dadd_rn(u, 6755399441055744.0);  // low word = rint(u)
-      const double d = __dadd_rn(u, -__dadd_rn(v, -6755399441055744.0));
-      const int dhi = __double2hiint(d);
-      int k = __double2loint(v) + (dhi >> 31);  // floor(u)
-      if ((unsigned)(dhi << 1) < (unsigned)((1023 - 30) << 21)) {
-        // phi*m0 within 2^-30 of an integer: decide with the reference's own thresholds
-        k = k < 0 ? 0 : (k > m0 - 1 ? m0 - 1 : k);
-        if (phi < s_thr[k]) --k;
-        else if (k < m0 - 1 && phi >= s_thr[k + 1]) ++k;
+    int i = 0;
+    for (; i + 4 <= cnt; i += 4) {
+      // four independent phase computations (FP64 chains overlap), then four updates in order
+      const double2 ta = *reinterpret_cast<const double2*>(s_t + i);
+      const double2 tb = *reinterpret_cast<const double2*>(s_t + i + 2);
+      const float4 xv = *reinterpret_cast<const float4*>(s_x + i);
+      double f0, f1, f2, f3;
+      unsigned e0, e1, e2, e3;
+      int k0 = pdm_bin(ta.x, P, rP, m0d, f0, e0);
+      int k1 = pdm_bin(ta.y, P, rP, m0d, f1, e1);
+      int k2 = pdm_bin(tb.x, P, rP, m0d, f2, e2);
+      int k3 = pdm_bin(tb.y, P, rP, m0d, f3, e3);
+      if (min(min(e0, e1), min(e2, e3)) < PDM_AMBIG) {  // rare: a sample sits on a bin edge
+        if (e0 < PDM_AMBIG) k0 = pdm_fix_bin(k0, f0, s_thr, m0);
+        if (e1 < PDM_AMBIG) k1 = pdm_fix_bin(k1, f1, s_thr, m0);
+        if (e2 < PDM_AMBIG) k2 = pdm_fix_bin(k2, f2, s_thr, m0);
+        if (e3 < PDM_AMBIG) k3 = pdm_fix_bin(k3, f3, s_thr, m0);
       }
-      k = (int)min((unsigned)k, (unsigned)(m0 - 1));  // also keeps NaN / phi == 1.0 in range
-      float* p = col + k * THREADS;
-      p[0] += 1.0f;
-      p[stat_stride] += xv;
-      p[2 * stat_stride] = fmaf(xv, xv, p[2 * stat_stride]);
+      update((unsigned)k0, xv.x);
+      update((unsigned)k1, xv.y);
+      update((unsigned)k2, xv.z);
+      update((unsigned)k3, xv.w);
+    }
+    for (; i < cnt; ++i) {
+      double f0;
+      unsigned e0;
+      int k0 = pdm_bin(s_t[i], P, rP, m0d, f0, e0);
+      if (e0 < PDM_AMBIG) k0 = pdm_fix_bin(k0, f0, s_thr, m0);
+      update((unsigned)k0, s_x[i]);
     }
 
     tile0 += PDM_TILE;
     ++tiles_since_flush;
     if (tiles_since_flush == PDM_FLUSH_TILES || tile0 >= se) {
-      // merge this thread's FP32 column into the FP64 partials it owns
+      // merge this thread's FP32 column into the FP64 partials it owns ([stat][bin][period] rows)
       if (valid) {
-        for (int b = 0; b < 3 * m0; ++b) {
-          const double val = (double)col[b * THREADS];
-          double* g = pcol + (long long)b * a.np;
-          if (first) *g = val;
-          else *g += val;
-          col[b * THREADS] = 0.f;
+        for (int b = 0; b < m0; ++b) {
+#pragma unroll
+          for (int st = 0; st < 3; ++st) {
+            float* h = col + (b * 3 + st) * THREADS;
+            double* g = pcol + ((long long)st * m0 + b) * a.np;
+            if (first) *g = (double)*h;
+            else atomicAdd(g, (double)*h);  // RED: only this thread touches g; order is fixed
+            *h = 0.f;
+          }
         }
       }
       first = false;
