@@ -59,6 +59,18 @@ def make_gls_c2(nf_total):
                 name=f"GLS Kepler-like 65,000 points x {nf_total} frequencies (C2 per GPU)")
 
 
+def make_gls_c1(nf_total):
+    rng = np.random.default_rng(1)
+    n = 1000
+    t = np.sort(rng.uniform(0, 100.0, n))
+    df = 1 / (t[-1] - t[0]) / 5
+    fmin = 0.5 * df
+    fsig = fmin + 0.3137 * 10_000 * df
+    y = 1000 + np.sin(2 * np.pi * fsig * t + 0.3) + 0.5 * rng.standard_normal(n)
+    return dict(kind="gls", t=t, y=y, fmin=fmin, df=df, nf=nf_total,
+                name=f"GLS 1,000 points x {nf_total} frequencies (C1)")
+
+
 def make_gls_c5(nf_total):
     rng = np.random.default_rng(5)
     n = 1_000_000
@@ -211,7 +223,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c4"])
+    ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c1"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -220,12 +232,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    per_gpu = {"gls_c2": 100_000, "pdm_c3": 100_000, "gls_c5": 1_250_000, "gls_c4": 256}[args.workload]
+    per_gpu = {"gls_c2": 100_000, "pdm_c3": 100_000, "gls_c5": 1_250_000, "gls_c5_full": 10_000_000,
+               "gls_c4": 256, "gls_c1": 10_000}[args.workload]
     total_units = per_gpu * max(world, 1)
     if args.workload == "gls_c2":
         wl = make_gls_c2(total_units)
-    elif args.workload == "gls_c5":
+    elif args.workload in ("gls_c5", "gls_c5_full"):
         wl = make_gls_c5(total_units)
+    elif args.workload == "gls_c1":
+        wl = make_gls_c1(total_units)
     elif args.workload == "pdm_c3":
         wl = make_pdm_c3(total_units)
     else:
