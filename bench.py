@@ -43,6 +43,17 @@ FP32_PEAK_TFLOPS_MEASURED = 72.3   # profiles/pipes_r01.json: 36,172 GFFMA/s x 2
 PDM_PEAK_GEVALS_MEASURED = 1454.8  # profiles/pipes_r01.json: private-column smem RMW, sample updates/s
 
 
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_*.json); None if no capture exists."""
+    path = os.path.join(ROOT, "profiles", name)
+    try:
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------
 # synthetic workloads (SURVEY.md section 8d recipes, fixed seeds)
 # ------------------------------------------------------------------------------------------
@@ -377,14 +388,16 @@ def main():
     if kind == "pdm":
         ach = units_local / (main_kernel_ms * 1e-3) / 1e9
         roof = {"bound": "smem", "kernel": "pdm_hist_kernel", "achieved": ach, "peak": PDM_PEAK_GEVALS_MEASURED,
-                "unit": "Gevals/s", "frac": ach / PDM_PEAK_GEVALS_MEASURED, "traffic": None,
+                "unit": "Gevals/s", "frac": ach / PDM_PEAK_GEVALS_MEASURED,
+                "traffic": ncu_traffic("ncu_pdm_hist_c3_r01.json") if args.workload == "pdm_c3" and world == 1 else None,
                 "kernel_ms": main_kernel_ms,
                 "peak_source": "profiles/pipes_r01.json smem_private_rmw3 (3 LDS+3 FADD+3 STS per sample update); "
                                "path is shared-memory/issue bound, not HBM or tensor bound"}
     else:
         ach = units_local * FLOP_PER_EVAL_GLS / (main_kernel_ms * 1e-3) / 1e12
         roof = {"bound": "fp32", "kernel": "gls_strip_kernel", "achieved": ach, "peak": FP32_PEAK_TFLOPS_MEASURED,
-                "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS_MEASURED, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS_MEASURED,
+                "traffic": ncu_traffic("ncu_gls_strip_c2_r01.json") if args.workload == "gls_c2" and world == 1 else None,
                 "kernel_ms": main_kernel_ms, "flop_per_eval": FLOP_PER_EVAL_GLS,
                 "evals_per_s_kernel": units_local / (main_kernel_ms * 1e-3),
                 "peak_source": "profiles/pipes_r01.json ffma_shared_operands x2 FLOP (measured on this pool's B200; "
