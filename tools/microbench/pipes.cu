@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <string>
 #include <cuda_runtime.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -303,26 +304,40 @@ __global__ void __launch_bounds__(THREADS) k_smem_atomic(float* out, unsigned lo
   if (t == 123.456f) out[0] = t;
 }
 
-// ---- T14: GLS inner step, scalar: rotate (4) + 6 accumulations, 8 frequencies per thread
-KHEAD(k_gls_scalar) {
-  constexpr int K = 8;
+// ---- T14: GLS inner step, scalar: rotate (4) + 6 accumulations, K frequencies per thread.
+// SEED=1 adds the per-sample exact reseed (DFMA, DADD, I2F, FMUL, MUFU.SIN/COS) of the real kernel.
+template <int K, int SEED>
+__global__ void __launch_bounds__(THREADS) k_gls_scalar_t(float* out, unsigned long long* cyc, int iters, float seed) {
   float C[K], S[K], YC[K], YS[K], CC[K], CS[K];
 #pragma unroll
   for (int i = 0; i < K; ++i) C[i] = S[i] = YC[i] = YS[i] = CC[i] = CS[i] = 0.f;
   float c = 1.f, s = 0.f, cr = cosf(seed), sr = sinf(seed), y = seed;
+  double A = seed * 0.37, b = seed * 0.11, lk = (double)(threadIdx.x * K);
   KTIME_BEGIN
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
+      float cn0 = c, sn0 = s;
+      if (SEED) {
+        double ph = fma(lk, b, A);
+        double v = ph + 1572864.0;
+        int fx = __double2loint(v);
+        float x = (float)fx * 1.4629180792671596e-9f;
+        __sincosf(x, &sn0, &cn0);
+        A += 0.001;
+      }
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         C[i] += c; S[i] += s;
         YC[i] = fmaf(y, c, YC[i]); YS[i] = fmaf(y, s, YS[i]);
         CC[i] = fmaf(c, c, CC[i]); CS[i] = fmaf(c, s, CS[i]);
-        float cn = fmaf(c, cr, -(s * sr));
-        float sn = fmaf(s, cr, c * sr);
-        c = cn; s = sn;
+        if (i + 1 < K || !SEED) {
+          float cn = fmaf(c, cr, -(s * sr));
+          float sn = fmaf(s, cr, c * sr);
+          c = cn; s = sn;
+        }
       }
+      if (SEED) { c = cn0; s = sn0; }
       y += 0.001f;
     }
   }
@@ -330,6 +345,7 @@ KHEAD(k_gls_scalar) {
   float t = 0; for (int i = 0; i < K; ++i) t += C[i] + S[i] + YC[i] + YS[i] + CC[i] + CS[i];
   if (t == 123.456f) out[0] = t;
 }
+#define k_gls_scalar k_gls_scalar_t<8, 0>
 
 // ---- T15: GLS inner step, packed: two frequency strips per thread as f32x2 lanes
 KHEAD(k_gls_packed) {
@@ -388,6 +404,12 @@ int main(int argc, char** argv) {
     {"smem_private_rmw_v4",    k_smem_private_v4,16.0,     2, 4 * M0 * THREADS * sizeof(float), "sample-update"},
     {"smem_atomic_warp_hist",  k_smem_atomic,    16.0,     4, 0, "sample-update"},
     {"gls_step_scalar",        k_gls_scalar,     16.0,     4, 0, "eval"},
+    {"gls_step_scalar_k16",    k_gls_scalar_t<16, 0>, 32.0,  2, 0, "eval"},
+    {"gls_step_scalar_k16_occ3", k_gls_scalar_t<16, 0>, 32.0, 3, 0, "eval"},
+    {"gls_step_scalar_k8_seed",  k_gls_scalar_t<8, 1>, 16.0,  4, 0, "eval"},
+    {"gls_step_scalar_k16_seed", k_gls_scalar_t<16, 1>, 32.0, 2, 0, "eval"},
+    {"gls_step_scalar_k16_seed_128x3", k_gls_scalar_t<16, 1>, 32.0, 3, 0, "eval128"},
+    {"gls_step_scalar_k24_seed", k_gls_scalar_t<24, 1>, 48.0, 1, 0, "eval"},
     {"gls_step_packed",        k_gls_packed,     32.0,     2, 0, "eval"},
   };
   printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz_nominal\": %d, \"tests\": [\n", p.name, nsm, p.clockRate);
@@ -396,6 +418,8 @@ int main(int argc, char** argv) {
     Test& T = tests[t];
     if (T.smem) CK(cudaFuncSetAttribute(T.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.smem));
     int grid = nsm * T.bps;
+    int threads = THREADS;
+    if (std::string(T.unit) == "eval128") threads = 128;
     int its = iters;
     if (T.smem || t == 13) its = iters / 4 + 1;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -403,7 +427,7 @@ int main(int argc, char** argv) {
     for (int rep = 0; rep < 4; ++rep) {
       CK(cudaMemset(cyc, 0, 8));
       CK(cudaEventRecord(e0));
-      T.k<<<grid, THREADS, T.smem>>>(out, cyc, its, 1.0001f);
+      T.k<<<grid, threads, T.smem>>>(out, cyc, its, 1.0001f);
       CK(cudaEventRecord(e1));
       CK(cudaEventSynchronize(e1));
       CK(cudaGetLastError());
@@ -411,7 +435,7 @@ int main(int argc, char** argv) {
       unsigned long long c; CK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
       if (rep > 0 && ms < best_ms) { best_ms = ms; best_cyc = c; }
     }
-    double ops = T.ops_per_thread_iter * (double)its * THREADS * grid;
+    double ops = T.ops_per_thread_iter * (double)its * threads * grid;
     double per_clk_sm = ops / ((double)best_cyc * nsm);
     double gops = ops / (best_ms * 1e-3) / 1e9;
     double mhz = (double)best_cyc / (best_ms * 1e-3) / 1e6;
