@@ -517,11 +517,14 @@ static int launch_strip(int geom, pdc_ctx* ctx, const GlsMainArgs& a, bool weigh
 // Pick the sample split so that (curves * frequency blocks * nsplit) work items
 // fill whole waves of resident blocks.  Cost model: every wave costs the samples
 // of one item plus a fixed per-item overhead (staging, flush) worth ~48 samples.
-static int choose_nsplit(long long base_items, long long nmax, long long resident) {
+static int choose_nsplit(long long base_items, long long nmax, long long resident, long long plane_bytes) {
   if (base_items >= 24 * resident) return 1;
   long long cap = nmax / 256;
   if (cap < 1) cap = 1;
   if (cap > 4096) cap = 4096;
+  // every split owns one FP64 plane of partial sums: keep the scratch below 2 GiB
+  const long long mem_cap = ((long long)2 << 30) / (plane_bytes > 0 ? plane_bytes : 1);
+  if (cap > mem_cap) cap = mem_cap < 1 ? 1 : mem_cap;
   double best = 1e300;
   int best_s = 1;
   for (long long s = 1; s <= cap; ++s) {
@@ -563,7 +566,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   (void)MINB;
   if (ctx->gls_occ[geom][w != nullptr] == 0) ctx->gls_occ[geom][w != nullptr] = strip_occupancy(geom, w != nullptr);
   const long long resident = (long long)ctx->sm_count * ctx->gls_occ[geom][w != nullptr];
-  const int nsplit = choose_nsplit((long long)B * nfb, nmax, resident);
+  const int nsplit = choose_nsplit((long long)B * nfb, nmax, resident, (long long)sizeof(double) * 6 * nf_tot);
   const long long items = (long long)B * nfb * nsplit;
   if (items > 0x7fffffffLL) { set_error("pdc_gls: problem too large for one call (%lld work items)", items); return PDC_EINVAL; }
 

@@ -311,6 +311,8 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     long long cap = n / 512;
     if (cap < 1) cap = 1;
     if (cap > 1024) cap = 1024;
+    const long long mem_cap = ((long long)2 << 30) / ((long long)sizeof(double) * 3 * m0 * np);
+    if (cap > mem_cap) cap = mem_cap < 1 ? 1 : mem_cap;
     double best = 1e300;
     for (long long s = 1; s <= cap; ++s) {
       long long items = npb * s;

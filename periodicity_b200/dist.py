@@ -207,3 +207,56 @@ def batch_shard_bounds(n_curves, rank, world):
     """Contiguous group of light curves owned by ``rank`` (survey workload)."""
     start, stop, _ = shard_bounds(n_curves, rank, world)
     return start, stop
+
+
+def _device_compute_gls_batch(t, y, w, offsets, fmin, df, nf, fit_mean, psd_scale, want_power, device):
+    torch = _torch()
+    ctx = _ffi.default_context(device)
+    dev = torch.device("cuda", ctx.device)
+    a, e = int(offsets[0]), int(offsets[-1])
+    tt = torch.as_tensor(np.ascontiguousarray(t[a:e], dtype=np.float64)).to(dev, non_blocking=True)
+    yy = torch.as_tensor(np.ascontiguousarray(y[a:e], dtype=np.float64)).to(dev, non_blocking=True)
+    ww = None if w is None else torch.as_tensor(np.ascontiguousarray(w[a:e], dtype=np.float64)).to(dev, non_blocking=True)
+    return gls_batch_torch(tt, yy, ww, np.asarray(offsets) - a, fmin, df, nf, fit_mean, psd_scale, want_power, ctx=ctx)
+
+
+def gls_batch_sharded(t, y, w, offsets, fmin, df, nf, fit_mean=True, psd_scale=None, want_power=False,
+                      device=None, group=None, compute=None):
+    """Light-curve-batch-sharded GLS (survey workload).
+
+    Curves are split into contiguous groups, one per rank; each rank evaluates only its own curves
+    (no replication) and ONE all-gather returns every curve's (argmax, max) -- and the powers when
+    ``want_power`` -- to all ranks.  Returns ``(power [B, nf] or None, argmax [B], max [B])`` as numpy.
+    """
+    torch = _torch()
+    dist, rank, world = _dist_info(group)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    B = offsets.size - 1
+    fmin = np.ascontiguousarray(np.broadcast_to(fmin, (B,)), dtype=np.float64)
+    df = np.ascontiguousarray(np.broadcast_to(df, (B,)), dtype=np.float64)
+    if psd_scale is not None:
+        psd_scale = np.ascontiguousarray(np.broadcast_to(psd_scale, (B,)), dtype=np.float64)
+    b0, b1, L = shard_bounds(B, rank, world)
+    compute = compute or _device_compute_gls_batch
+    width = (nf if want_power else 0) + 2
+    if b1 > b0:
+        power, arg, mx = compute(t, y, w, offsets[b0:b1 + 1], fmin[b0:b1], df[b0:b1], nf, fit_mean,
+                                 None if psd_scale is None else psd_scale[b0:b1], want_power, device)
+        packed = torch.full((L, width), float("nan"), dtype=torch.float64, device=mx.device)
+        if want_power:
+            packed[: b1 - b0, :nf] = power
+        packed[: b1 - b0, width - 2] = mx
+        packed[: b1 - b0, width - 1] = arg.to(torch.float64)
+    else:
+        ref = compute(t, y, w, offsets[:2], fmin[:1], df[:1], nf, fit_mean,
+                      None if psd_scale is None else psd_scale[:1], False, device)[2]
+        packed = torch.full((L, width), float("nan"), dtype=torch.float64, device=ref.device)
+    if dist is None or world == 1:
+        allp = packed
+    else:
+        allp = torch.empty((world * L, width), dtype=torch.float64, device=packed.device)
+        dist.all_gather_into_tensor(allp.view(-1), packed.view(-1), group=group)
+    allp = allp[:B].cpu().numpy()
+    power = allp[:, :nf] if want_power else None
+    arg = np.where(np.isnan(allp[:, width - 1]), -1, allp[:, width - 1]).astype(np.int64)
+    return power, arg, allp[:, width - 2]

@@ -63,6 +63,25 @@ def _pdm_compute(t, x, periods, nb, nc, device):
     return torch.from_numpy(th), torch.tensor([int(np.nanargmin(th))]), torch.tensor([float(np.nanmin(th))], dtype=torch.float64)
 
 
+def _batch_compute(t, y, w, offsets, fmin, df, nf, fit_mean, psd_scale, want_power, device):
+    from oracle import cport
+    B = len(offsets) - 1
+    P = np.stack([cport.gls_exact(t[offsets[b]:offsets[b + 1]], y[offsets[b]:offsets[b + 1]], None, fmin[b], df[b], nf)
+                  for b in range(B)])
+    return (torch.from_numpy(P) if want_power else None, torch.from_numpy(np.nanargmax(P, axis=1)),
+            torch.from_numpy(np.nanmax(P, axis=1)))
+
+
+def _survey_inputs():
+    rng = np.random.default_rng(17)
+    sizes = [120, 80, 200, 150, 90]                       # 5 curves over 2 ranks: ragged, uneven split
+    ts = [np.sort(rng.uniform(0, 30, n)) for n in sizes]
+    ys = [np.sin(2 * np.pi * t / rng.uniform(1, 4)) + 0.3 * rng.standard_normal(t.size) for t in ts]
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    df = np.array([1 / (t[-1] - t[0]) / 5 for t in ts])
+    return ts, ys, offsets, 0.5 * df, df
+
+
 def _worker(rank, world, port, outdir):
     import sys
     sys.path.insert(0, ROOT)
@@ -78,8 +97,13 @@ def _worker(rank, world, port, outdir):
         power, idx, val = pdist.gls_sharded(t, y, None, 0.5 * df, df, nf, True, None, compute=_gls_compute)
         periods = np.linspace(0.3, 3.0, 77)
         theta, pidx, pval = pdist.pdm_sharded(t, y, periods, 5, 2, compute=_pdm_compute)
+        ts, ys, offsets, f0, dfs = _survey_inputs()
+        bp, barg, bmx = pdist.gls_batch_sharded(np.concatenate(ts), np.concatenate(ys), None, offsets, f0, dfs, 64,
+                                                want_power=True, compute=_batch_compute)
+        _, barg2, bmx2 = pdist.gls_batch_sharded(np.concatenate(ts), np.concatenate(ys), None, offsets, f0, dfs, 64,
+                                                 want_power=False, compute=_batch_compute)
         np.savez(os.path.join(outdir, f"rank{rank}.npz"), power=power, idx=idx, val=val, theta=theta,
-                 pidx=pidx, pval=pval)
+                 pidx=pidx, pval=pval, bp=bp, barg=barg, bmx=bmx, barg2=barg2, bmx2=bmx2)
     finally:
         dist.destroy_process_group()
 
@@ -102,3 +126,10 @@ def test_sharded_calls_world2_gloo(tmp_path):
         assert int(z["idx"]) == int(np.nanargmax(want)) and float(z["val"]) == float(np.nanmax(z["power"]))
         np.testing.assert_allclose(z["theta"], want_theta, rtol=1e-12)
         assert int(z["pidx"]) == int(np.nanargmin(want_theta))
+        # batch sharding: every rank ends with every curve's periodogram and peak
+        ts, ys, offsets, f0, dfs = _survey_inputs()
+        for b in range(5):
+            ref = cport.gls_exact(ts[b], ys[b], None, f0[b], dfs[b], 64)
+            np.testing.assert_allclose(z["bp"][b], ref, rtol=1e-12)
+            assert z["barg"][b] == z["barg2"][b] == np.nanargmax(ref)
+            assert z["bmx"][b] == z["bmx2"][b] == np.nanmax(z["bp"][b])

@@ -220,3 +220,53 @@ def test_bootstrap_on_gpu_matches_looped_calls():
         bs = rng2.integers(0, 120, 120)
         want.append(GLS(fmax=3.0)(TSeries(t, y[bs]), err=err[bs]).amax())
     np.testing.assert_allclose(reps, want, rtol=5e-6)
+
+
+def test_survey_api_matches_per_curve_class_calls():
+    from periodicity_b200 import GLS, TSeries
+    from periodicity_b200.survey import gls_survey
+    rng = np.random.default_rng(31)
+    sigs, errs, periods = [], [], []
+    for b in range(6):
+        n = int(rng.integers(300, 900))
+        t = np.sort(rng.uniform(0, 27.8, n))
+        P = rng.uniform(0.5, 10.0)
+        sigs.append(TSeries(t, 1000 + np.sin(2 * np.pi * t / P) + 0.5 * rng.standard_normal(n)))
+        errs.append(rng.uniform(0.4, 0.6, n))
+        periods.append(P)
+    for e in (None, errs):
+        out = gls_survey(sigs, errs=e, nf=2000, want_power=True)
+        for b, s in enumerate(sigs):
+            g = GLS(fmax=out["fmin"][b] + 1998.5 * out["df"][b])
+            ls = g(s, err=None if e is None else e[b])
+            assert ls.size == 2000
+            assert np.nanmax(np.abs(ls.values - out["power"][b])) <= 2e-6 * ls.amax()
+            assert ls.argmax() == out["argmax"][b]
+            assert abs(out["best_period"][b] - periods[b]) / periods[b] < 0.05
+
+
+def test_sharded_entry_points_single_rank(gpu_ctx):
+    """dist.gls_sharded / pdm_sharded / gls_batch_sharded with the real device compute (world size 1)."""
+    from periodicity_b200 import GLS, PDM, TSeries
+    from periodicity_b200 import dist as pdist
+    nf = 2500
+    t, y, fmin, df = synth(1500, 80.0, nf, 1.0, 41)
+    p, am, mx = gpu_ctx.gls(t, y, None, fmin, df, nf)
+    ps, ams, mxs = pdist.gls_sharded(t, y, None, fmin, df, nf, device=0)
+    np.testing.assert_array_equal(ps, p)
+    assert (ams, mxs) == (am, mx)
+    ls = GLS(fmin=fmin, fmax=fmin + (nf - 1.5) * df, shard=True)(TSeries(t, y))
+    np.testing.assert_array_equal(ls.values, p)
+    periods = np.linspace(0.5, 5.0, 700)
+    th, a2, m2 = gpu_ctx.pdm(t, y, periods, 5, 2)
+    ths, a2s, m2s = pdist.pdm_sharded(t, y, periods, 5, 2, device=0)
+    np.testing.assert_array_equal(ths, th)
+    assert (a2s, m2s) == (a2, m2)
+    pg = PDM(p_min=0.5, p_max=5.0, n_periods=700, shard=True)(TSeries(t, y))
+    np.testing.assert_array_equal(pg.values, th[::-1])
+    offsets = np.array([0, 400, 1500])
+    P, A, M = gpu_ctx.gls_batch(t, y, None, offsets, [fmin, fmin], [df, 2 * df], 300)
+    Ps, As, Ms = pdist.gls_batch_sharded(t, y, None, offsets, [fmin, fmin], [df, 2 * df], 300, want_power=True, device=0)
+    np.testing.assert_array_equal(Ps, P)
+    np.testing.assert_array_equal(As, A)
+    np.testing.assert_array_equal(Ms, M)
