@@ -54,6 +54,7 @@ struct pdc_ctx {
   cudaEvent_t ev_fence = nullptr;                     // caller-stream -> scratch reuse fence
   int64_t launches = 0;
   int gls_occ[32][2] = {};  // cached blocks/SM of each strip-kernel variant [geom][weighted]
+  int gls_nsplit_override = 0;
   int gls_geom = 9;  // index into kGlsGeoms (gls.cu); env PDC_GLS_GEOM overrides at ctx creation (tuning aid)
 
   // CUDA-event timing of the dominant kernel (GLS strip / PDM histogram), recorded on the
