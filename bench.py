@@ -178,6 +178,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu baseline (oracle port of the reference's CPU algorithm)
 # ------------------------------------------------------------------------------------------
+def _cpu_gls_one(job):
+    from oracle import gls_numpy
+    t, y, fmin, df, nf = job
+    return float(np.nanmax(gls_numpy.gls_power(t, y, None, fmin, df, nf, True, False)))
+
+
 def cpu_reference_step(wl):
     """One step of the reference's CPU path on (a bounded sample of) the workload.
     Returns (evals processed, cores used, description of the sample)."""
@@ -187,11 +193,16 @@ def cpu_reference_step(wl):
         gls_numpy.gls_power(wl["t"], wl["y"], None, wl["fmin"], wl["df"], wl["nf"], True, False)
         return wl["t"].size * wl["nf"], 1, "full workload, reference FFT-extirpolation algorithm, numpy, 1 thread"
     if wl["kind"] == "gls_batch":
-        B = min(len(wl["offsets"]) - 1, 64)
-        for b in range(B):
-            a, e = wl["offsets"][b], wl["offsets"][b + 1]
-            gls_numpy.gls_power(wl["t"][a:e], wl["y"][a:e], None, wl["fmin"][b], wl["df"][b], wl["nf"], True, False)
-        return int(wl["offsets"][B]) * wl["nf"], 1, f"first {B} curves, python loop (the reference has no batch API)"
+        # the reference has no batch API: a survey is a loop over curves; mapped over all host cores here
+        cores = os.cpu_count() or 1
+        B = min(len(wl["offsets"]) - 1, 8 * cores)
+        from multiprocessing import Pool
+        jobs = [(wl["t"][wl["offsets"][b]:wl["offsets"][b + 1]], wl["y"][wl["offsets"][b]:wl["offsets"][b + 1]],
+                 wl["fmin"][b], wl["df"][b], wl["nf"]) for b in range(B)]
+        with Pool(cores) as pool:
+            pool.map(_cpu_gls_one, jobs)
+        return int(wl["offsets"][B]) * wl["nf"], cores, (f"first {B} curves mapped over multiprocessing.Pool({cores}) "
+                                                         "(the reference has no batch API)")
     cores = os.cpu_count() or 1
     sample = wl["periods"][:: max(1, wl["periods"].size // (24 * cores))][: 24 * cores]
     pdm_numpy.pdm_pool(wl["t"], wl["y"], sample, wl["nb"], wl["nc"], cores, sort=True)

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <cmath>
 #include <string>
 #include <cuda_runtime.h>
 
@@ -347,6 +348,52 @@ __global__ void __launch_bounds__(THREADS) k_gls_scalar_t(float* out, unsigned l
 }
 #define k_gls_scalar k_gls_scalar_t<8, 0>
 
+// Same as k_gls_scalar_t<K, 1>, but the per-sample (cr, sr, y) come from constant memory with a
+// warp-uniform index, so ptxas keeps them in UNIFORM registers: FFMA/FMUL then read only two
+// operands from the vector register file.
+__constant__ float4 c_tab[256];
+template <int K>
+__global__ void __launch_bounds__(THREADS) k_gls_scalar_ur(float* out, unsigned long long* cyc, int iters, float seed) {
+  float C[K], S[K], YC[K], YS[K], CC[K], CS[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) C[i] = S[i] = YC[i] = YS[i] = CC[i] = CS[i] = 0.f;
+  float c = 1.f, s = 0.f;
+  double A = seed * 0.37, b = seed * 0.11, lk = (double)(threadIdx.x * K);
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float4 tb = c_tab[(it * 2 + r) & 255];
+      const float cr = tb.x, sr = tb.y, y = tb.z;
+      float cn0, sn0;
+      {
+        double ph = fma(lk, b, A);
+        double v = ph + 1572864.0;
+        int fx = __double2loint(v);
+        float x = (float)fx * 1.4629180792671596e-9f;
+        __sincosf(x, &sn0, &cn0);
+        A += 0.001;
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        C[i] += c; S[i] += s;
+        YC[i] = fmaf(y, c, YC[i]); YS[i] = fmaf(y, s, YS[i]);
+        CC[i] = fmaf(c, c, CC[i]); CS[i] = fmaf(c, s, CS[i]);
+        if (i + 1 < K) {
+          float cn = fmaf(c, cr, -(s * sr));
+          float sn = fmaf(s, cr, c * sr);
+          c = cn; s = sn;
+        }
+      }
+      c = cn0; s = sn0;
+    }
+  }
+  KTIME_END
+  float t = 0; for (int i = 0; i < K; ++i) t += C[i] + S[i] + YC[i] + YS[i] + CC[i] + CS[i];
+  if (t == 123.456f) out[0] = t;
+}
+
+
 // ---- T15: GLS inner step, packed: two frequency strips per thread as f32x2 lanes
 KHEAD(k_gls_packed) {
   constexpr int K = 8;
@@ -388,6 +435,11 @@ int main(int argc, char** argv) {
   float* out; unsigned long long* cyc;
   CK(cudaMalloc(&out, 64)); CK(cudaMalloc(&cyc, 8));
   int iters = argc > 1 ? atoi(argv[1]) : 2000;
+  {
+    float4 h[256];
+    for (int i = 0; i < 256; ++i) h[i] = make_float4(cosf(0.01f * i), sinf(0.01f * i), 0.5f + 0.001f * i, 1.f);
+    CK(cudaMemcpyToSymbol(c_tab, h, sizeof(h)));
+  }
   Test tests[] = {
     {"ffma_shared_operands",   k_ffma_shared,    8.0 * CH, 4, 0, "FFMA"},
     {"ffma_distinct_operands", k_ffma_distinct,  8.0 * CH, 4, 0, "FFMA"},
@@ -410,6 +462,8 @@ int main(int argc, char** argv) {
     {"gls_step_scalar_k16_seed", k_gls_scalar_t<16, 1>, 32.0, 2, 0, "eval"},
     {"gls_step_scalar_k16_seed_128x3", k_gls_scalar_t<16, 1>, 32.0, 3, 0, "eval128"},
     {"gls_step_scalar_k24_seed", k_gls_scalar_t<24, 1>, 48.0, 1, 0, "eval"},
+    {"gls_step_scalar_k16_seed_uniform", k_gls_scalar_ur<16>, 32.0, 2, 0, "eval"},
+    {"gls_step_scalar_k16_seed_uniform_128x3", k_gls_scalar_ur<16>, 32.0, 3, 0, "eval128"},
     {"gls_step_packed",        k_gls_packed,     32.0,     2, 0, "eval"},
   };
   printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz_nominal\": %d, \"tests\": [\n", p.name, nsm, p.clockRate);
