@@ -162,7 +162,7 @@ __device__ __forceinline__ double block_min(double v, double* scratch) {
 template <int SIGN>
 __device__ __forceinline__ bool better(double v, long long i, double bv, long long bi) {
   if (i < 0 || v != v) return false;
-  if (bi < 0) return true;
+  if (bi < 0 || bv != bv) return true;  // a NaN incumbent is no candidate
   if (SIGN > 0 ? (v > bv) : (v < bv)) return true;
   return v == bv && i < bi;
 }

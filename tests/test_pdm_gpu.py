@@ -129,3 +129,26 @@ def test_torch_device_pointer_entry_matches_host_entry(gpu_ctx):
     torch.cuda.synchronize()
     np.testing.assert_array_equal(td.cpu().numpy(), th)
     assert int(ad.item()) == am and float(md.item()) == mn
+
+
+def test_million_samples_crosses_flush_boundaries(gpu_ctx):
+    """1e6 samples per period thread: FP32 columns are merged into FP64 every 8192 samples."""
+    t, x = synth(1_000_000, 10_000.0, 16)
+    periods = np.linspace(2.0, 9.0, 600)
+    th, am, _ = gpu_ctx.pdm(t, x, periods, 10, 2)
+    sel = np.unique(np.concatenate([np.arange(0, 600, 60), np.arange(max(0, am - 3), min(600, am + 4))]))
+    ref = cport.pdm(t, x, periods[sel], 10, 2)
+    np.testing.assert_allclose(th[sel], ref, rtol=TOL)
+    assert sel[np.argmin(ref)] == am
+
+
+def test_outlier_heavy_values(gpu_ctx):
+    """Values with 1e3-sigma outliers and a large offset: centring/scaling before the FP32 cast must hold."""
+    t, x = synth(20_000, 300.0, 17)
+    x = x * 1e-3 + 5e6
+    x[::997] += 50.0
+    periods = np.linspace(1.0, 11.0, 400)
+    th, am, _ = gpu_ctx.pdm(t, x, periods, 10, 2)
+    ref = cport.pdm(t, x, periods, 10, 2)
+    np.testing.assert_allclose(th, ref, rtol=TOL)
+    assert am == np.nanargmin(ref)
