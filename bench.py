@@ -43,6 +43,16 @@ FP32_PEAK_TFLOPS_MEASURED = 72.3   # profiles/pipes_r01.json: 36,172 GFFMA/s x 2
 PDM_PEAK_GEVALS_MEASURED = 1454.8  # profiles/pipes_r01.json: private-column smem RMW, sample updates/s
 
 
+def measured_hbm_gbs():
+    """HBM copy bandwidth the driver measured on this pool (MEASURED_PEAKS.json); 6650 = the profiling
+    recipe's stated fallback if the file is absent."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
 def ncu_traffic(name):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture of this workload (profiles/ncu_*.json); None if no capture exists."""
@@ -414,8 +424,9 @@ def main():
                 "peak_source": "profiles/pipes_r01.json ffma_shared_operands x2 FLOP (measured on this pool's B200; "
                                "MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5)",
                 "hbm": {"achieved_gbs": (32.0 * n + 6 * 8 * 2 * (units_local / n)) / (main_kernel_ms * 1e-3) / 1e9,
-                        "peak_gbs": 6457.4, "note": "algorithmic bytes: 32 B/sample record + FP64 partial flush; "
-                                                     "the path is compute bound"}}
+                        "peak_gbs": measured_hbm_gbs()[0], "peak_source": measured_hbm_gbs()[1],
+                        "note": "algorithmic bytes: 32 B/sample record + FP64 partial flush; the path is "
+                                "compute bound, this line only shows how far from the HBM roofline it sits"}}
 
     # ---- cpu baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
