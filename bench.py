@@ -40,7 +40,7 @@ if ROOT not in sys.path:
 FLOP_PER_EVAL_GLS = 20.0      # 12 FP32 instructions = 20 FLOP per sample*frequency
 OPS_PER_EVAL_PDM = 8.0        # 8 ops per sample*period
 FP32_PEAK_TFLOPS_MEASURED = 72.3   # profiles/pipes_r01.json: 36,172 GFFMA/s x 2
-PDM_PEAK_GEVALS_MEASURED = 1454.8  # profiles/pipes_r01.json: private-column smem RMW, sample updates/s
+PDM_PEAK_GEVALS_MEASURED = 2256.3  # profiles/pipes_r01.json smem_private_rmw_f2: 64-bit private-column RMW, updates/s
 
 
 def measured_hbm_gbs():
@@ -412,8 +412,9 @@ def main():
                 "unit": "Gevals/s", "frac": ach / PDM_PEAK_GEVALS_MEASURED,
                 "traffic": ncu_traffic("ncu_pdm_hist_c3_r01.json") if args.workload == "pdm_c3" and world == 1 else None,
                 "kernel_ms": main_kernel_ms,
-                "peak_source": "profiles/pipes_r01.json smem_private_rmw3 (3 LDS+3 FADD+3 STS per sample update); "
-                               "path is shared-memory/issue bound, not HBM or tensor bound"}
+                "peak_source": "profiles/pipes_r01.json smem_private_rmw_f2 (one LDS.64 + 2 FADD + one STS.64 per sample "
+                               "update, the shared-memory floor of the kernel); path is shared-memory/issue bound, "
+                               "not HBM or tensor bound"}
     else:
         ach = units_local * FLOP_PER_EVAL_GLS / (main_kernel_ms * 1e-3) / 1e12
         roof = {"bound": "fp32", "kernel": "gls_strip_kernel", "achieved": ach, "peak": FP32_PEAK_TFLOPS_MEASURED,

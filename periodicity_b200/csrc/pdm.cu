@@ -8,11 +8,14 @@
 // and lies in exactly one FINE bin q, thr[q] <= phi < thr[q+1], thr[k] = k/m0
 // being the very float64 thresholds the reference compares against
 // (phase.py:138-140).  The reference's coarse bin k (phase.py:137-141) is the
-// circular union of fine bins k .. k+nc-1.  Per fine bin only (n, sum x', sum x'^2)
-// is needed, x' = (x - mean(x)) / std(x, ddof=1):
-//     theta = sum_{k good} (Q_k - S_k^2 / n_k) / (sum_{k good} n_k - M)
-// over the M coarse bins with n_k > 1 (phase.py:142-149; the division by
-// sigma^2 = var(x, ddof=1), phase.py:148,165, is folded into x').
+// circular union of fine bins k .. k+nc-1.  With x' = (x - mean(x)) / std(x, ddof=1)
+// (so that sum_i x'_i^2 = N - 1 and the division by sigma^2, phase.py:148,165, is folded in)
+// and every sample lying in exactly nc coarse bins,
+//     sum_{k good} (n_k - 1) s_k^2 = sum_k (Q_k - S_k^2 / n_k) = nc (N - 1) - sum_{k: n_k >= 1} S_k^2 / n_k,
+// because a bin with n_k = 1 has Q_k = S_k^2 (it contributes 0 whether it is dropped, phase.py:142,
+// or not) and an empty bin contributes nothing.  Hence only the count n and the sum S = sum x'
+// per fine bin are histogrammed -- no per-bin sum of squares -- and
+//     theta = [nc (N - 1) - sum_{n_k >= 1} S_k^2 / n_k] / sum_{n_k > 1} (n_k - 1)      (phase.py:145-149).
 // The argsort of phase.py:132-134 does not influence the result and is dropped.
 //
 // Mapping (north_star: "per-trial-period phase-bin variance histograms in shared
@@ -77,7 +80,7 @@ struct PdmArgs {
   const double* t;
   const float* xs;
   const double* periods;
-  double* partial;  // [nsplit][3*m0][np]
+  double* partial;  // [nsplit][2*m0][np]  rows: count per fine bin, then sum x' per fine bin
   long long n, np;
   int m0, nsplit;
 };
@@ -107,9 +110,8 @@ __device__ __forceinline__ int pdm_fix_bin(int k, double phi, const double* s_th
   return k;
 }
 
-// Shared-memory layout: hist[bin][stat][THREADS] (stat = n, sum x', sum x'^2): a thread's
-// column is conflict free (bank = thread % 32 for every bin and stat) and the three
-// read-modify-writes of one sample differ by immediate offsets only.
+// Shared-memory layout: hist[bin][THREADS] float2 = (count, sum x'): a thread's column is
+// conflict free and one sample costs one 64-bit read-modify-write.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 pdm_hist_kernel(const PdmArgs a) {
@@ -117,8 +119,8 @@ pdm_hist_kernel(const PdmArgs a) {
   const int m0 = a.m0;
   double* s_t = reinterpret_cast<double*>(smem_raw);                 // [PDM_TILE]
   double* s_thr = s_t + PDM_TILE;                                    // [m0 + 1]  (padded to even)
-  float* s_x = reinterpret_cast<float*>(s_thr + ((m0 + 2) & ~1));    // [PDM_TILE]
-  float* hist = s_x + PDM_TILE;                                      // [m0][3][THREADS]
+  float2* hist = reinterpret_cast<float2*>(s_thr + ((m0 + 2) & ~1)); // [m0][THREADS]
+  float* s_x = reinterpret_cast<float*>(hist + (size_t)m0 * THREADS); // [PDM_TILE]
 
   const int split = blockIdx.x % a.nsplit;
   const long long pb = blockIdx.x / a.nsplit;
@@ -130,21 +132,21 @@ pdm_hist_kernel(const PdmArgs a) {
   const unsigned kmax = (unsigned)(m0 - 1);
 
   for (int k = threadIdx.x; k <= m0; k += THREADS) s_thr[k] = (double)k / m0d;  // phase.py:138-140
-  for (int k = threadIdx.x; k < 3 * m0 * THREADS; k += THREADS) hist[k] = 0.f;
+  for (int k = threadIdx.x; k < m0 * THREADS; k += THREADS) hist[k] = make_float2(0.f, 0.f);
 
   const long long per = (a.n + a.nsplit - 1) / a.nsplit;
   const long long sb = (long long)split * per;
   const long long se = sb + per < a.n ? sb + per : a.n;
 
-  float* col = hist + threadIdx.x;
-  double* pcol = a.partial + (long long)split * 3 * m0 * a.np + pi;
+  float2* col = hist + threadIdx.x;
+  double* pcol = a.partial + (long long)split * 2 * m0 * a.np + pi;
 
   auto update = [&](unsigned k, float xv) {
     k = min(k, kmax);  // keeps NaN / phi == 1.0 inside the histogram
-    float* p = col + k * (3 * THREADS);
-    p[0] += 1.0f;
-    p[THREADS] += xv;
-    p[2 * THREADS] = fmaf(xv, xv, p[2 * THREADS]);
+    float2 h = col[k * THREADS];
+    h.x += 1.0f;
+    h.y += xv;
+    col[k * THREADS] = h;
   };
 
   bool first = true;
@@ -196,15 +198,18 @@ pdm_hist_kernel(const PdmArgs a) {
     if (tiles_since_flush == PDM_FLUSH_TILES || tile0 >= se) {
       // merge this thread's FP32 column into the FP64 partials it owns ([stat][bin][period] rows)
       if (valid) {
+        const long long stat = (long long)m0 * a.np;
         for (int b = 0; b < m0; ++b) {
-#pragma unroll
-          for (int st = 0; st < 3; ++st) {
-            float* h = col + (b * 3 + st) * THREADS;
-            double* g = pcol + ((long long)st * m0 + b) * a.np;
-            if (first) *g = (double)*h;
-            else atomicAdd(g, (double)*h);  // RED: only this thread touches g; order is fixed
-            *h = 0.f;
+          const float2 h = col[b * THREADS];
+          double* g = pcol + (long long)b * a.np;
+          if (first) {
+            g[0] = (double)h.x;
+            g[stat] = (double)h.y;
+          } else {  // RED.ADD.F64: only this thread touches g; order is fixed
+            atomicAdd(g, (double)h.x);
+            atomicAdd(g + stat, (double)h.y);
           }
+          col[b * THREADS] = make_float2(0.f, 0.f);
         }
       }
       first = false;
@@ -214,7 +219,7 @@ pdm_hist_kernel(const PdmArgs a) {
 }
 
 __global__ void __launch_bounds__(256)
-pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, long long np,
+pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, long long np, long long n,
                     double* __restrict__ theta_out, double* __restrict__ red_val,
                     long long* __restrict__ red_idx) {
   __shared__ double sv[32];
@@ -224,7 +229,7 @@ pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, lo
   long long idx = -1;
   if (pi < np) {
     // fold the sample splits into split 0 (this thread's own column only)
-    const long long rows = 3LL * m0;
+    const long long rows = 2LL * m0;
     for (long long b = 0; b < rows; ++b) {
       double acc = 0.0;
       for (int s = 0; s < nsplit; ++s) acc += partial[((long long)s * rows + b) * np + pi];
@@ -232,25 +237,20 @@ pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, lo
     }
     const double* pn = partial + pi;
     const double* p1 = pn + (long long)m0 * np;
-    const double* p2 = p1 + (long long)m0 * np;
-    double num = 0.0, ntot = 0.0;
-    int good = 0;
+    double sq = 0.0, den = 0.0;
     for (int k = 0; k < m0; ++k) {
-      double N = 0.0, S = 0.0, Q = 0.0;
+      double N = 0.0, S = 0.0;
       for (int c = 0; c < nc; ++c) {
         int q = k + c;
         if (q >= m0) q -= m0;
         N += pn[(long long)q * np];
         S += p1[(long long)q * np];
-        Q += p2[(long long)q * np];
       }
-      if (N > 1.0) {  // phase.py:142  mk.size > 1
-        num += Q - S * S / N;
-        ntot += N;
-        ++good;
-      }
+      if (N >= 1.0) sq += S * S / N;
+      if (N > 1.0) den += N - 1.0;  // phase.py:142,147: bins with <= 1 sample are dropped
     }
-    theta = num / (ntot - (double)good);  // phase.py:147-148 (sigma folded into x')
+    // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
+    theta = ((double)nc * (double)(n - 1) - sq) / den;
     theta_out[pi] = theta;
     idx = pi;
   }
@@ -263,7 +263,7 @@ pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, lo
 
 static size_t pdm_smem_bytes(int m0, int threads) {
   return sizeof(double) * (PDM_TILE + ((m0 + 2) & ~1)) + sizeof(float) * PDM_TILE +
-         sizeof(float) * 3 * (size_t)m0 * threads;
+         sizeof(float2) * (size_t)m0 * threads;
 }
 
 template <int THREADS>
@@ -285,7 +285,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   const size_t smem_max = 227 * 1024;
   if (m0l > 100000 || pdm_smem_bytes((int)m0l, 32) > smem_max) {
     set_error("pdc_pdm: nb*nc = %lld fine bins do not fit a shared-memory histogram (max %d)",
-              m0l, (int)((smem_max - 13 * 1024) / (12 * 32)));
+              m0l, (int)((smem_max - 13 * 1024) / (8 * 32)));
     return PDC_EINVAL;
   }
   const int m0 = (int)m0l;
@@ -311,13 +311,13 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     long long cap = n / 512;
     if (cap < 1) cap = 1;
     if (cap > 1024) cap = 1024;
-    const long long mem_cap = ((long long)2 << 30) / ((long long)sizeof(double) * 3 * m0 * np);
+    const long long mem_cap = ((long long)2 << 30) / ((long long)sizeof(double) * 2 * m0 * np);
     if (cap > mem_cap) cap = mem_cap < 1 ? 1 : mem_cap;
     double best = 1e300;
     for (long long s = 1; s <= cap; ++s) {
       long long items = npb * s;
       long long waves = (items + resident - 1) / resident;
-      double cost = (double)waves * ((double)((n + s - 1) / s) + 3.0 * m0 + 64.0);
+      double cost = (double)waves * ((double)((n + s - 1) / s) + 2.0 * m0 + 64.0);
       if (cost < best * 0.999) { best = cost; nsplit = (int)s; }
       if (items > 64 * resident) break;
     }
@@ -327,7 +327,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
 
   PDC_TRY(ctx->pdm_meta.reserve(sizeof(PdmMeta)));
   PDC_TRY(ctx->pdm_x.reserve(sizeof(float) * n));
-  PDC_TRY(ctx->partial.reserve(sizeof(double) * 3 * m0 * (size_t)np * nsplit));
+  PDC_TRY(ctx->partial.reserve(sizeof(double) * 2 * m0 * (size_t)np * nsplit));
   const int eblk = (int)((np + 255) / 256);
   PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk));
 
@@ -364,7 +364,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
 
   double* red_val = ctx->blockred.as<double>();
   long long* red_idx = reinterpret_cast<long long*>(red_val + eblk);
-  pdm_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(a.partial, nsplit, m0, nc, np, theta_out, red_val, red_idx);
+  pdm_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(a.partial, nsplit, m0, nc, np, (long long)n, theta_out, red_val, red_idx);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
   if (argmin_out || min_out) {

@@ -280,6 +280,32 @@ __global__ void __launch_bounds__(THREADS) k_smem_private_v4(float* out, unsigne
   if (t == 123.456f) out[0] = t;
 }
 
+// ---- T12b: private column of float2 (count, sum): one LDS.64 + 2 FADD + one STS.64 per sample update
+// (the shape pdm_hist_kernel uses since the per-bin sum of squares was eliminated algebraically)
+__global__ void __launch_bounds__(THREADS) k_smem_private_f2(float* out, unsigned long long* cyc, int iters, float seed) {
+  extern __shared__ float hist[];  // [M0][THREADS] float2
+  float2* h2 = reinterpret_cast<float2*>(hist);
+  for (int i = threadIdx.x; i < M0 * THREADS; i += THREADS) h2[i] = make_float2(0, 0);
+  __syncthreads();
+  unsigned s = threadIdx.x * 2654435761u + 12345u;
+  float v = seed;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      s = s * 1664525u + 1013904223u;
+      int q = (int)(((unsigned long long)(s >> 8) * M0) >> 24);
+      float2 h = h2[q * THREADS + threadIdx.x];
+      h.x += 1.0f; h.y += v;
+      h2[q * THREADS + threadIdx.x] = h;
+    }
+  }
+  KTIME_END
+  __syncthreads();
+  float t = 0; for (int i = 0; i < M0; ++i) { float2 h = h2[i * THREADS + threadIdx.x]; t += h.x + h.y; }
+  if (t == 123.456f) out[0] = t;
+}
+
 // ---- T13: shared-memory float atomics, one histogram per warp ([warp][3][M0]), 32 lanes contend
 __global__ void __launch_bounds__(THREADS) k_smem_atomic(float* out, unsigned long long* cyc, int iters, float seed) {
   __shared__ float hist[(THREADS / 32) * 3 * M0];
@@ -454,6 +480,7 @@ int main(int argc, char** argv) {
     {"i2f_s32",                k_i2f,            8.0 * CH, 4, 0, "I2F"},
     {"smem_private_rmw3",      k_smem_private,   16.0,     3, 3 * M0 * THREADS * sizeof(float), "sample-update"},
     {"smem_private_rmw_v4",    k_smem_private_v4,16.0,     2, 4 * M0 * THREADS * sizeof(float), "sample-update"},
+    {"smem_private_rmw_f2",    k_smem_private_f2,16.0,     4, 2 * M0 * THREADS * sizeof(float), "sample-update"},
     {"smem_atomic_warp_hist",  k_smem_atomic,    16.0,     4, 0, "sample-update"},
     {"gls_step_scalar",        k_gls_scalar,     16.0,     4, 0, "eval"},
     {"gls_step_scalar_k16",    k_gls_scalar_t<16, 0>, 32.0,  2, 0, "eval"},
@@ -475,7 +502,7 @@ int main(int argc, char** argv) {
     int threads = THREADS;
     if (std::string(T.unit) == "eval128") threads = 128;
     int its = iters;
-    if (T.smem || t == 13) its = iters / 4 + 1;
+    if (T.smem || std::string(T.name) == "smem_atomic_warp_hist") its = iters / 4 + 1;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     double best_ms = 1e30; unsigned long long best_cyc = 0;
     for (int rep = 0; rep < 4; ++rep) {
