@@ -158,6 +158,24 @@ PDC_API int pdc_pdm_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t 
                 const double* periods, int64_t np, int nb, int nc,
                 double* theta_out, int64_t* argmin_out, double* min_out, void* stream);
 
+/*
+ * The k highest local maxima of each row of a row-major float64 [rows, n] array
+ * (periodograms): what `FSeries.find_peaks()` + sorting by height gives
+ * (core.py:283-317,944-955 -> scipy.signal.find_peaks(values, prominence=0.0)):
+ * strict local maxima, the midpoint of flat tops, never the first or last sample,
+ * NaN never a peak; ties go to the lower index.
+ *
+ *   idx_out  int64[rows*k]    peak positions, highest first; -1 where a row has fewer than k peaks
+ *   val_out  float64[rows*k]  their values (NaN where idx is -1)
+ * k <= 64.  `pdc_peaks_topk` takes host pointers (the values are copied to the device),
+ * `pdc_peaks_topk_dev` device pointers, e.g. the power_out of pdc_gls_dev, so a 1e7-point
+ * periodogram never has to leave the GPU to find its peaks.
+ */
+PDC_API int pdc_peaks_topk(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k,
+                           int64_t* idx_out, double* val_out);
+PDC_API int pdc_peaks_topk_dev(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k,
+                               int64_t* idx_out, double* val_out, void* stream);
+
 /* Number of kernels this ctx has launched since creation (bench.py's
  * `gpu_launches` claim is the difference across the timed region). */
 PDC_API int64_t pdc_ctx_launch_count(pdc_ctx* ctx);

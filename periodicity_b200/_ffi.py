@@ -50,6 +50,10 @@ SIGNATURES = {
     "pdc_pdm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_peaks_topk": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_peaks_topk_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_pdm_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -195,6 +199,20 @@ class Context:
             _check(self._lib.pdc_pdm(self._h, _ptr(t), _ptr(x), t.size, _ptr(periods), periods.size,
                                      int(nb), int(nc), _ptr(theta), ctypes.addressof(arg), ctypes.addressof(mn)))
         return theta, arg.value, mn.value
+
+    def peaks_topk(self, values, k):
+        """(indices [rows, k], values [rows, k]) of the k highest local maxima of each row (host arrays)."""
+        v = np.atleast_2d(_f64(values))
+        rows, n = v.shape
+        idx = np.empty((rows, int(k)), dtype=np.int64)
+        val = np.empty((rows, int(k)), dtype=np.float64)
+        with self._lock:
+            _check(self._lib.pdc_peaks_topk(self._h, _ptr(v), rows, n, int(k), _ptr(idx), _ptr(val)))
+        return idx, val
+
+    def peaks_topk_dev(self, values_ptr, rows, n, k, idx_ptr, val_ptr, stream=0):
+        _check(self._lib.pdc_peaks_topk_dev(self._h, values_ptr, int(rows), int(n), int(k), idx_ptr, val_ptr,
+                                            stream or None))
 
     # ---- device-pointer entry points (raw addresses, stream ordered) ---------
     def gls_dev(self, t_ptr, y_ptr, w_ptr, n, fmin, df, j0, nf, flags, psd_scale, power_ptr, argmax_ptr,

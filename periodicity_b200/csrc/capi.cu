@@ -193,7 +193,7 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   ctx->out_a.release(); ctx->out_small.release(); ctx->pin_small.release();
   ctx->gls_curves.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release();
   ctx->partial.release(); ctx->blockred.release(); ctx->pin_meta.release();
-  ctx->pdm_meta.release(); ctx->pdm_x.release();
+  ctx->pdm_meta.release(); ctx->pdm_x.release(); ctx->peak_cand.release();
   ctx->main_resolve();
   for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);
@@ -369,6 +369,36 @@ int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
   const SmallRec* h = ctx->pin_small.as<SmallRec>();
   if (argmin_out) *argmin_out = h->arg;
   if (min_out) *min_out = h->val;
+  return PDC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// peaks
+// ---------------------------------------------------------------------------
+int pdc_peaks_topk_dev(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k,
+                       int64_t* idx_out, double* val_out, void* stream) {
+  if (!ctx || !values || !idx_out || !val_out) { set_error("pdc_peaks_topk_dev: NULL argument"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  return peaks_run(ctx, values, rows, n, k, idx_out, val_out, st);
+}
+
+int pdc_peaks_topk(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k,
+                   int64_t* idx_out, double* val_out) {
+  if (!ctx || !values || !idx_out || !val_out) { set_error("pdc_peaks_topk: NULL argument"); return PDC_EINVAL; }
+  if (rows < 1 || n < 1 || k < 1) { set_error("pdc_peaks_topk: empty input"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t nb = sizeof(double) * (size_t)rows * n, ob = (size_t)rows * k;
+  PDC_TRY(ctx->out_a.reserve(nb));
+  PDC_TRY(ctx->out_small.reserve(ob * (sizeof(double) + sizeof(int64_t))));
+  PDC_CUDA(cudaMemcpyAsync(ctx->out_a.p, values, nb, cudaMemcpyHostToDevice, st));
+  int64_t* d_idx = ctx->out_small.as<int64_t>();
+  double* d_val = reinterpret_cast<double*>(d_idx + ob);
+  PDC_TRY(peaks_run(ctx, ctx->out_a.as<double>(), rows, n, k, d_idx, d_val, st));
+  PDC_CUDA(cudaMemcpyAsync(idx_out, d_idx, ob * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaMemcpyAsync(val_out, d_val, ob * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaStreamSynchronize(st));
   return PDC_OK;
 }
 

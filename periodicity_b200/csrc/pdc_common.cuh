@@ -82,6 +82,8 @@ struct pdc_ctx {
   pdc::DevBuf blockred;        // per-block (value, index) candidates
   pdc::PinnedBuf pin_meta;     // host staging for per-curve metadata
 
+  pdc::DevBuf peak_cand;       // per-block peak candidates (peaks.cu)
+
   // PDM scratch
   pdc::DevBuf pdm_meta;        // PdmMeta
   pdc::DevBuf pdm_x;           // float[n] centred, unit-variance values
@@ -98,6 +100,9 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
 int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods,
             int64_t np, int nb, int nc, double* theta_out, int64_t* argmin_out, double* min_out,
             cudaStream_t stream);
+
+int peaks_run(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k, int64_t* idx_out,
+              double* val_out, cudaStream_t stream);
 
 // ---- small device helpers ---------------------------------------------------
 #ifdef __CUDACC__

@@ -92,6 +92,18 @@ class GLS(object):
     def copy(self):
         return copy.deepcopy(self)
 
+    def top_peaks(self, k=5):
+        """The ``k`` highest peaks of the last periodogram, found on the GPU (``pdc_peaks_topk``).
+
+        Same peak definition as ``self.periodogram.find_peaks()`` (``core.py:283-317``: local maxima,
+        edges excluded), so ``top_peaks(1)`` is ``periodogram.period_at_highest_peak`` without a host
+        pass over the whole grid.  Returns ``(frequency[k], power[k])``, NaN-padded if fewer peaks exist."""
+        ctx = _ffi.default_context(self.device)
+        idx, val = ctx.peaks_topk(self.periodogram.values, k)
+        idx, val = idx[0], val[0]
+        freq = np.where(idx >= 0, self.periodogram.frequency[np.maximum(idx, 0)], np.nan)
+        return freq, val
+
     def bootstrap(self, n_bootstraps, random_seed=None, batch=256):
         """Maximum power of ``n_bootstraps`` resamples (``spectral.py:140-152``).
 

@@ -16,7 +16,7 @@ __all__ = ["gls_survey"]
 
 
 def gls_survey(signals, errs=None, nf=10_000, n=5, fmin=None, psd=False, fit_mean=True, want_power=False,
-               device=None, shard=False):
+               device=None, shard=False, top_k=None):
     """GLS peak search over a list of light curves.
 
     signals : sequence of ``TSeries`` (or array-likes, coerced like ``spectral.py:86-87``)
@@ -24,8 +24,13 @@ def gls_survey(signals, errs=None, nf=10_000, n=5, fmin=None, psd=False, fit_mea
     nf      : number of trial frequencies per curve;  n : samples per peak (``GLS.n``)
     fmin    : optional common minimum frequency (default ``0.5*df`` per curve)
 
+    top_k   : if set, also return the ``top_k`` highest periodogram *peaks* (local maxima, as
+              ``FSeries.find_peaks`` defines them, ``core.py:283-317``) of every curve; the periodograms
+              stay on the GPU and only ``[B, top_k]`` indices and powers come back (``pdc_peaks_topk_dev``)
+
     Returns a dict with ``fmin, df`` (per curve), ``argmax, max_power, best_frequency,
-    best_period`` and, if ``want_power``, ``power`` of shape ``[len(signals), nf]``.
+    best_period`` and, if ``want_power``, ``power`` of shape ``[len(signals), nf]``; with ``top_k``
+    also ``peak_index, peak_power, peak_frequency`` of shape ``[len(signals), top_k]``.
     With ``shard=True`` (and ``torch.distributed`` initialised) the curves are split across
     ranks and every rank receives all results.
     """
@@ -50,7 +55,25 @@ def gls_survey(signals, errs=None, nf=10_000, n=5, fmin=None, psd=False, fit_mea
                               for b in range(B)])
     df = np.array([1.0 / s.baseline / n for s in sigs])
     f0 = 0.5 * df if fmin is None else np.full(B, float(fmin))
-    if shard:
+    peaks = None
+    if top_k is not None:
+        if shard:
+            raise ValueError("top_k and shard cannot be combined yet")
+        import torch
+        from . import dist
+        ctx = _ffi.default_context(device)
+        dev = torch.device("cuda", ctx.device)
+        td, yd = torch.from_numpy(t).to(dev), torch.from_numpy(y).to(dev)
+        wd = None if w is None else torch.from_numpy(w).to(dev)
+        pw, argd, mxd = dist.gls_batch_torch(td, yd, wd, offsets, f0, df, nf, fit_mean, psd_scale, True, ctx=ctx)
+        pidx = torch.empty((B, int(top_k)), dtype=torch.int64, device=dev)
+        pval = torch.empty((B, int(top_k)), dtype=torch.float64, device=dev)
+        ctx.peaks_topk_dev(pw.data_ptr(), B, nf, int(top_k), pidx.data_ptr(), pval.data_ptr(),
+                           torch.cuda.current_stream(dev).cuda_stream)
+        arg, mx = argd.cpu().numpy(), mxd.cpu().numpy()
+        power = pw.cpu().numpy() if want_power else None
+        peaks = (pidx.cpu().numpy(), pval.cpu().numpy())
+    elif shard:
         from . import dist
         power, arg, mx = dist.gls_batch_sharded(t, y, w, offsets, f0, df, nf, fit_mean, psd_scale, want_power,
                                                 device=device)
@@ -62,4 +85,7 @@ def gls_survey(signals, errs=None, nf=10_000, n=5, fmin=None, psd=False, fit_mea
            "best_period": 1.0 / best_f}
     if want_power:
         out["power"] = power
+    if peaks is not None:
+        out["peak_index"], out["peak_power"] = peaks
+        out["peak_frequency"] = np.where(peaks[0] >= 0, f0[:, None] + df[:, None] * peaks[0], np.nan)
     return out
