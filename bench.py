@@ -92,6 +92,19 @@ def make_gls_c1(nf_total):
                 name=f"GLS 1,000 points x {nf_total} frequencies (C1)")
 
 
+def make_gls_multi(series):
+    """C4-shaped survey sector whose light curves SHARE one time axis (pdc_gls_multi)."""
+    n, nf = 20_000, 10_000
+    rng = np.random.default_rng(4000)
+    keep = rng.uniform(size=n + n // 50) > 0.01
+    t = (np.arange(n + n // 50)[keep][:n]) * (2.0 / 1440.0) + rng.uniform(0, 0.2 / 1440.0, n)
+    P = rng.uniform(0.5, 10.0, series)
+    Y = 1000 + np.sin(2 * np.pi * t[None, :] / P[:, None]) + rng.standard_normal((series, n))
+    df = 1 / (t[-1] - t[0]) / 5
+    return dict(kind="gls_multi", t=t, y=Y, fmin=0.5 * df, df=df, nf=nf, S=series,
+                name=f"GLS {series} series on shared timestamps x 20,000 points x 1e4 frequencies (C4 shape)")
+
+
 def make_gls_c5(nf_total):
     rng = np.random.default_rng(5)
     n = 1_000_000
@@ -202,6 +215,14 @@ def cpu_reference_step(wl):
         # the reference's own algorithm: FFT extirpolation, single-threaded numpy (spectral.py:11-40)
         gls_numpy.gls_power(wl["t"], wl["y"], None, wl["fmin"], wl["df"], wl["nf"], True, False)
         return wl["t"].size * wl["nf"], 1, "full workload, reference FFT-extirpolation algorithm, numpy, 1 thread"
+    if wl["kind"] == "gls_multi":
+        cores = os.cpu_count() or 1
+        B = min(wl["S"], 8 * cores)
+        from multiprocessing import Pool
+        jobs = [(wl["t"], wl["y"][b], wl["fmin"], wl["df"], wl["nf"]) for b in range(B)]
+        with Pool(cores) as pool:
+            pool.map(_cpu_gls_one, jobs)
+        return wl["t"].size * B * wl["nf"], cores, f"first {B} series mapped over multiprocessing.Pool({cores})"
     if wl["kind"] == "gls_batch":
         # the reference has no batch API: a survey is a loop over curves; mapped over all host cores here
         cores = os.cpu_count() or 1
@@ -255,7 +276,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c1"])
+    ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c1", "gls_multi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -265,7 +286,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     per_gpu = {"gls_c2": 100_000, "pdm_c3": 100_000, "gls_c5": 1_250_000, "gls_c5_full": 10_000_000,
-               "gls_c4": 256, "gls_c1": 10_000}[args.workload]
+               "gls_c4": 256, "gls_c1": 10_000, "gls_multi": 256}[args.workload]
     total_units = per_gpu * max(world, 1)
     if args.workload == "gls_c2":
         wl = make_gls_c2(total_units)
@@ -273,6 +294,8 @@ def main():
         wl = make_gls_c5(total_units)
     elif args.workload == "gls_c1":
         wl = make_gls_c1(total_units)
+    elif args.workload == "gls_multi":
+        wl = make_gls_multi(total_units)
     elif args.workload == "pdm_c3":
         wl = make_pdm_c3(total_units)
     else:
@@ -299,11 +322,19 @@ def main():
     # ---- device-resident inputs ------------------------------------------------------------
     n = wl["t"].size
     t_pin = torch.from_numpy(wl["t"]).pin_memory()
-    y_pin = torch.from_numpy(wl["y"]).pin_memory()
+    y_pin = torch.from_numpy(np.ascontiguousarray(wl["y"])).pin_memory()
     t_d = t_pin.to(dev)
     y_d = y_pin.to(dev)
     kind = wl["kind"]
-    if kind == "gls_batch":
+    if kind == "gls_multi":
+        b0, b1 = pdist.batch_shard_bounds(wl["S"], rank, world)
+        units_local = n * wl["nf"] * (b1 - b0)
+        evals_total = n * wl["nf"] * wl["S"]
+        L = b1 - b0
+        ym_d = y_d[b0:b1].contiguous()
+        pm_arg = torch.empty(L, dtype=torch.int64, device=dev)
+        pm_max = torch.empty(L, dtype=torch.float64, device=dev)
+    elif kind == "gls_batch":
         B = len(wl["offsets"]) - 1
         b0, b1 = pdist.batch_shard_bounds(B, rank, world)
         off = wl["offsets"][b0:b1 + 1]
@@ -327,6 +358,11 @@ def main():
             theta, arg, mn = pdist.pdm_torch(t_d, y_d, p_d, wl["nb"], wl["nc"], ctx=ctx)
             garg = (arg + start).to(torch.float64).reshape(())
             vals, bests, args_ = pdist.all_gather_packed(theta, mn.reshape(()), garg, L)
+        elif kind == "gls_multi":
+            ctx._lib.pdc_gls_multi_dev(ctx._h, t_d.data_ptr(), ym_d.data_ptr(), None, n, L, float(wl["fmin"]),
+                                       float(wl["df"]), 0, wl["nf"], _ffi.GLS_FIT_MEAN, 1.0, None, pm_arg.data_ptr(),
+                                       pm_max.data_ptr(), torch.cuda.current_stream(dev).cuda_stream or None)
+            vals, bests, args_ = pdist.all_gather_packed(pm_max, pm_max.max(), pm_arg.to(torch.float64).max(), L)
         else:
             a, e = int(off[0]), int(off[-1])
             _, arg, mx = pdist.gls_batch_torch(t_d[a:e], y_d[a:e], None, off - off[0], wl["fmin"][b0:b1],
@@ -380,6 +416,9 @@ def main():
         if kind == "pdm":
             p, a, m = ctx.pdm(th, yh, wl["periods"][start:stop], wl["nb"], wl["nc"])
             return p
+        if kind == "gls_multi":
+            _, a, m = ctx.gls_multi(th, yh[b0:b1], None, wl["fmin"], wl["df"], wl["nf"], want_power=False)
+            return m
         a_, e_ = int(off[0]), int(off[-1])
         _, a, m = ctx.gls_batch(th[a_:e_], yh[a_:e_], None, off - off[0], wl["fmin"][b0:b1], wl["df"][b0:b1],
                                 wl["nf"], want_power=False)
@@ -398,7 +437,10 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_value = evals_total * args.steps / e2e_s
-    if kind == "gls_batch":
+    if kind == "gls_multi":
+        h2d = 8 * n * (1 + (b1 - b0))
+        d2h = out.nbytes * 2
+    elif kind == "gls_batch":
         h2d = 2 * 8 * int(off[-1] - off[0])
         d2h = out.nbytes * 2
     else:
@@ -421,6 +463,9 @@ def main():
                 "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS_MEASURED,
                 "traffic": ncu_traffic("ncu_gls_strip_c2_r01.json") if args.workload == "gls_c2" and world == 1 else None,
                 "kernel_ms": main_kernel_ms, "flop_per_eval": FLOP_PER_EVAL_GLS,
+                "note": ("shared-timestamp kernel: rotation and window sums are shared by 8 series, so the 20 FLOP "
+                         "per evaluation of the accounting figure are not all executed; frac > 1 is expected")
+                if kind == "gls_multi" else None,
                 "evals_per_s_kernel": units_local / (main_kernel_ms * 1e-3),
                 "peak_source": "profiles/pipes_r01.json ffma_shared_operands x2 FLOP (measured on this pool's B200; "
                                "MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5)",
@@ -452,6 +497,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["name"], "units_per_gpu": per_gpu, "sharding": "frequency grid" if kind == "gls"
                        else ("period grid" if kind == "pdm" else "light-curve batch"),
+                       "kernel": "glsm_strip_kernel" if kind == "gls_multi" else None,
                        "l2": "flushed between timed steps (256 MiB memset, not timed); per-step CUDA events summed",
                        "collective": "one NCCL all-gather of [values, best, index] per step" if world > 1 else "none (1 GPU)"},
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

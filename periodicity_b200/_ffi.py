@@ -47,6 +47,14 @@ SIGNATURES = {
                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_int64, ctypes.c_uint, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gls_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_int64, ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gls_multi_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
+                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_pdm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -184,6 +192,27 @@ class Context:
         with self._lock:
             _check(self._lib.pdc_gls_batch(self._h, _ptr(t), _ptr(y), _ptr(w), _ptr(offsets), B, _ptr(fmin),
                                            _ptr(df), nf, flags, _ptr(psd_scale), _ptr(power), _ptr(arg), _ptr(mx)))
+        return power, arg, mx
+
+    def gls_multi(self, t, Y, w, fmin, df, nf, fit_mean=True, psd_scale=None, j0=0, want_power=True):
+        """GLS of the rows of ``Y`` [S, n], all sampled at the common times ``t`` (``pdc_gls_multi``)."""
+        t = _f64(t)
+        Y = np.atleast_2d(_f64(Y))
+        if t.ndim != 1 or Y.shape[1] != t.size:
+            raise ValueError("Input arrays have incompatible lengths.")
+        if w is not None:
+            w = _f64(w)
+            if w.shape != t.shape:
+                raise ValueError("Input arrays have incompatible lengths.")
+        S, nf = Y.shape[0], int(nf)
+        flags = (GLS_FIT_MEAN if fit_mean else 0) | (GLS_PSD if psd_scale is not None else 0)
+        power = np.empty((S, nf), dtype=np.float64) if want_power else None
+        arg = np.empty(S, dtype=np.int64)
+        mx = np.empty(S, dtype=np.float64)
+        with self._lock:
+            _check(self._lib.pdc_gls_multi(self._h, _ptr(t), _ptr(Y), _ptr(w), t.size, S, float(fmin), float(df),
+                                           int(j0), nf, flags, float(psd_scale if psd_scale is not None else 1.0),
+                                           _ptr(power), _ptr(arg), _ptr(mx)))
         return power, arg, mx
 
     def pdm(self, t, x, periods, nb, nc):

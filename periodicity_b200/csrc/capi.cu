@@ -191,7 +191,7 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->in_a.release(); ctx->in_b.release(); ctx->in_c.release(); ctx->in_d.release();
   ctx->out_a.release(); ctx->out_small.release(); ctx->pin_small.release();
-  ctx->gls_curves.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release();
+  ctx->gls_curves.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->glsm_y.release();
   ctx->partial.release(); ctx->blockred.release(); ctx->pin_meta.release();
   ctx->pdm_meta.release(); ctx->pdm_x.release(); ctx->peak_cand.release();
   ctx->main_resolve();
@@ -330,6 +330,53 @@ int pdc_gls_batch(pdc_ctx* ctx, const double* t, const double* y, const double* 
   if (!ctx || !t || !y || !offsets || !fmin || !df) { set_error("pdc_gls_batch: NULL argument"); return PDC_EINVAL; }
   DeviceGuard guard(ctx->device);
   return gls_host_common(ctx, t, y, w, offsets, B, fmin, df, 0, nf, flags, psd_scale, power_out, argmax_out, max_out);
+}
+
+int pdc_gls_multi_dev(pdc_ctx* ctx, const double* t, const double* Y, const double* w, int64_t n, int64_t S,
+                      double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,
+                      double* power_out, int64_t* argmax_out, double* max_out, void* stream) {
+  if (!ctx || !t || !Y) { set_error("pdc_gls_multi_dev: NULL argument"); return PDC_EINVAL; }
+  if (j0 < 0) { set_error("pdc_gls_multi: j0 must be >= 0"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  return glsm_run(ctx, t, Y, w, n, S, fmin, df, j0, nf, flags, psd_scale, power_out, argmax_out, max_out, st);
+}
+
+int pdc_gls_multi(pdc_ctx* ctx, const double* t, const double* Y, const double* w, int64_t n, int64_t S,
+                  double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,
+                  double* power_out, int64_t* argmax_out, double* max_out) {
+  if (!ctx || !t || !Y) { set_error("pdc_gls_multi: NULL argument"); return PDC_EINVAL; }
+  if (n < 1 || S < 1 || nf < 1) { set_error("pdc_gls_multi: need n, S, nf >= 1"); return PDC_EINVAL; }
+  if (j0 < 0) { set_error("pdc_gls_multi: j0 must be >= 0"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t tb = sizeof(double) * (size_t)n, yb = tb * (size_t)S;
+  PDC_TRY(ctx->in_a.reserve(tb));
+  PDC_TRY(ctx->in_b.reserve(yb));
+  if (w) PDC_TRY(ctx->in_c.reserve(tb));
+  if (power_out) PDC_TRY(ctx->out_a.reserve(sizeof(double) * (size_t)nf * S));
+  PDC_TRY(ctx->out_small.reserve((sizeof(long long) + sizeof(double)) * (size_t)S));
+  PDC_TRY(ctx->pin_small.reserve((sizeof(long long) + sizeof(double)) * (size_t)S));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_a.p, t, tb, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_b.p, Y, yb, cudaMemcpyHostToDevice, st));
+  if (w) PDC_CUDA(cudaMemcpyAsync(ctx->in_c.p, w, tb, cudaMemcpyHostToDevice, st));
+  long long* d_arg = ctx->out_small.as<long long>();
+  double* d_val = reinterpret_cast<double*>(d_arg + S);
+  PDC_TRY(glsm_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), w ? ctx->in_c.as<double>() : nullptr, n, S,
+                   fmin, df, j0, nf, flags, psd_scale, power_out ? ctx->out_a.as<double>() : nullptr,
+                   (int64_t*)d_arg, d_val, st));
+  if (power_out)
+    PDC_CUDA(cudaMemcpyAsync(power_out, ctx->out_a.p, sizeof(double) * (size_t)nf * S, cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, ctx->out_small.p, (sizeof(long long) + sizeof(double)) * (size_t)S,
+                           cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaStreamSynchronize(st));
+  const long long* h_arg = ctx->pin_small.as<long long>();
+  const double* h_val = reinterpret_cast<const double*>(h_arg + S);
+  for (int64_t s = 0; s < S; ++s) {
+    if (argmax_out) argmax_out[s] = h_arg[s];
+    if (max_out) max_out[s] = h_val[s];
+  }
+  return PDC_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -30,30 +30,9 @@
 //
 // Algorithmic work of the hot kernel: per sample*frequency evaluation
 // 4 FP32 instructions for the rotation + 6 for the sums (7 with weights).
-#include "pdc_common.cuh"
+#include "gls_common.cuh"
 
 namespace pdc {
-
-struct GlsCurve {
-  long long begin, n;
-  double fmin, df;
-  double psd_scale;
-  // filled on the device by gls_stats_kernel
-  double tmin, tmax, wsum, ymean, yy, inv_rms;
-  int low_begin, low_count;  // frequencies [low_begin, low_begin + low_count) of this call go through FP64
-};
-
-constexpr int GLS_TILE = 1024;  // samples per shared-memory tile == FP32 flush interval
-
-// Frequencies with |f| * (tmax - tmin) < GLS_LOW_CYCLES see less than one cycle over the
-// baseline: there CC - C^2 and SS - S^2 (spectral.py:125-127) cancel almost completely
-// (a slow cosine is nearly degenerate with the floating mean) and amplify FP32 rounding
-// by 1/var(cos) ~ 300x at f*T = 0.1.  Those few bins (at most GLS_NLOW_MAX per curve) are
-// evaluated by gls_lowfreq_kernel entirely in FP64.
-constexpr double GLS_LOW_CYCLES = 1.0;
-constexpr int GLS_NLOW_MAX = 16;
-constexpr int GLS_LOW_CHUNK = 4096;   // samples per block of gls_lowfreq_kernel
-constexpr int GLS_LOW_MAXCHUNKS = 256;
 
 // ---------------------------------------------------------------------------
 // per-curve statistics (one block per curve)
@@ -89,21 +68,8 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y,
     double yy = syy / sw;  // spectral.py:120  YY = dot(w, y**2)
     cv.tmin = tmin;
     cv.tmax = tmax;
-    // low-frequency range: |fmin + (j0 + j) df| * T < GLS_LOW_CYCLES, j in [0, nf)
-    int lb = 0, lc = 0;
-    const double T = tmax - tmin;
-    if (T > 0.0 && cv.df > 0.0) {
-      const double flim = GLS_LOW_CYCLES / T;
-      double ja = ceil((-flim - cv.fmin) / cv.df - (double)j0);
-      double jb = floor((flim - cv.fmin) / cv.df - (double)j0);
-      if (ja < 0.0) ja = 0.0;
-      if (jb > (double)(nf - 1)) jb = (double)(nf - 1);
-      if (jb >= ja) {
-        double cnt = jb - ja + 1.0;
-        lb = (int)ja;
-        lc = cnt > (double)GLS_NLOW_MAX ? GLS_NLOW_MAX : (int)cnt;
-      }
-    }
+    int lb, lc;
+    gls_low_range(cv.fmin, cv.df, j0, nf, tmax - tmin, lb, lc);
     cv.low_begin = lb;
     cv.low_count = lc;
     cv.wsum = sw;
@@ -203,16 +169,6 @@ struct GlsMainArgs {
   int nfb;            // frequency blocks per curve
   int nsplit;         // sample splits per curve
 };
-
-// Exact seed: phase = A + lK*b cycles (FP64), reduced mod 1 by a magic-number add
-// whose low mantissa word is the fraction in units of 2^-32 cycle, then MUFU sin/cos.
-__device__ __forceinline__ void gls_seed(double A, double b, double lKd, float& c, float& s) {
-  const double ph = __fma_rn(lKd, b, A);
-  const double v = __dadd_rn(ph, 1572864.0);  // 1.5 * 2^20: ulp(v) = 2^-32
-  const int fx = __double2loint(v);           // two's-complement fraction, [-0.5, 0.5) cycle
-  const float x = (float)fx * 1.4629180792671596e-9f;  // 2 pi / 2^32 -> radians in [-pi, pi)
-  __sincosf(x, &s, &c);
-}
 
 template <int K, int THREADS, int MINB, bool WEIGHTED>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -352,11 +308,6 @@ gls_strip_kernel(const GlsMainArgs a) {
 // ---------------------------------------------------------------------------
 // FP64 epilogue: spectral.py:113-132 per frequency + block argmax
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double np_sign(double x) {
-  if (x != x) return x;
-  return (double)((x > 0.0) - (x < 0.0));
-}
-
 __global__ void __launch_bounds__(256)
 gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restrict__ partial,
                     const double* __restrict__ lowsum, int nlowchunk, int B,
@@ -394,31 +345,7 @@ gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restric
       }
       inv_n = 1.0 / (double)cv.n;
     }
-    const double C = sums[0] * inv_n, S = sums[1] * inv_n;
-    const double Ch = sums[2] * inv_n, Sh = sums[3] * inv_n;
-    // sum w cos(2x) = 2 sum w cos^2 x - 1,  sum w sin(2x) = 2 sum w sin x cos x   (sum w = 1)
-    const double C2 = 2.0 * sums[4] * inv_n - 1.0, S2 = 2.0 * sums[5] * inv_n;
-    const bool fit_mean = flags & PDC_GLS_FIT_MEAN;
-    double tan2;
-    if (fit_mean) tan2 = (S2 - 2.0 * S * C) / (C2 - (C * C - S * S));  // spectral.py:113
-    else tan2 = S2 / C2;                                               // spectral.py:115
-    const double hyp = sqrt(1.0 + tan2 * tan2);
-    const double S2w = tan2 / hyp;
-    const double C2w = 1.0 / hyp;
-    const double Cw = sqrt(0.5) * sqrt(1.0 + C2w);
-    const double Sw = sqrt(0.5) * np_sign(S2w) * sqrt(1.0 - C2w);
-    const double YC = Ch * Cw + Sh * Sw;
-    const double YS = Sh * Cw - Ch * Sw;
-    double CC = 0.5 * (1.0 + C2 * C2w + S2 * S2w);
-    double SS = 0.5 * (1.0 - C2 * C2w - S2 * S2w);
-    if (fit_mean) {
-      const double a1 = C * Cw + S * Sw, a2 = S * Cw - C * Sw;
-      CC -= a1 * a1;
-      SS -= a2 * a2;
-    }
-    power = YC * YC / CC + YS * YS / SS;  // spectral.py:128 (y was pre-scaled: YY == 1)
-    if (flags & PDC_GLS_PSD) power *= cv.yy * cv.psd_scale;  // spectral.py:130
-    else if (!(cv.yy > 0.0)) power = nan("");               // spectral.py:132 with YY == 0
+    power = gls_power_from_sums(sums, inv_n, flags, cv.yy, cv.psd_scale);
     if (power_out) power_out[(long long)curve * nf + j] = power;
     idx = j;
   }

@@ -1,0 +1,102 @@
+// Device code shared by the GLS kernels (gls.cu: one series per curve; glsm.cu: many series on
+// common sampling times).
+#pragma once
+
+#include "pdc_common.cuh"
+
+namespace pdc {
+
+struct GlsCurve {
+  long long begin, n;
+  double fmin, df;
+  double psd_scale;
+  // filled on the device by gls_stats_kernel
+  double tmin, tmax, wsum, ymean, yy, inv_rms;
+  int low_begin, low_count;  // frequencies [low_begin, low_begin + low_count) of this call go through FP64
+};
+
+constexpr int GLS_TILE = 1024;  // samples per shared-memory tile == FP32 flush interval
+
+// Frequencies with |f| * (tmax - tmin) < GLS_LOW_CYCLES see less than one cycle over the
+// baseline: there CC - C^2 and SS - S^2 (spectral.py:125-127) cancel almost completely
+// (a slow cosine is nearly degenerate with the floating mean) and amplify FP32 rounding
+// by 1/var(cos) ~ 300x at f*T = 0.1.  Those few bins (at most GLS_NLOW_MAX per curve) are
+// evaluated by gls_lowfreq_kernel entirely in FP64.
+constexpr double GLS_LOW_CYCLES = 1.0;
+constexpr int GLS_NLOW_MAX = 16;
+constexpr int GLS_LOW_CHUNK = 4096;   // samples per block of gls_lowfreq_kernel
+constexpr int GLS_LOW_MAXCHUNKS = 256;
+
+
+#ifdef __CUDACC__
+
+// Exact seed: phase = A + lK*b cycles (FP64), reduced mod 1 by a magic-number add
+// whose low mantissa word is the fraction in units of 2^-32 cycle, then MUFU sin/cos.
+__device__ __forceinline__ void gls_seed(double A, double b, double lKd, float& c, float& s) {
+  const double ph = __fma_rn(lKd, b, A);
+  const double v = __dadd_rn(ph, 1572864.0);  // 1.5 * 2^20: ulp(v) = 2^-32
+  const int fx = __double2loint(v);           // two's-complement fraction, [-0.5, 0.5) cycle
+  const float x = (float)fx * 1.4629180792671596e-9f;  // 2 pi / 2^32 -> radians in [-pi, pi)
+  __sincosf(x, &s, &c);
+}
+
+__device__ __forceinline__ double np_sign(double x) {
+  if (x != x) return x;
+  return (double)((x > 0.0) - (x < 0.0));
+}
+
+// Low-frequency range of a call: indices j in [0, nf) with |fmin + (j0 + j) df| * T < GLS_LOW_CYCLES.
+__device__ __forceinline__ void gls_low_range(double fmin, double df, long long j0, long long nf, double T,
+                                              int& low_begin, int& low_count) {
+  low_begin = 0;
+  low_count = 0;
+  if (T > 0.0 && df > 0.0) {
+    const double flim = GLS_LOW_CYCLES / T;
+    double ja = ceil((-flim - fmin) / df - (double)j0);
+    double jb = floor((flim - fmin) / df - (double)j0);
+    if (ja < 0.0) ja = 0.0;
+    if (jb > (double)(nf - 1)) jb = (double)(nf - 1);
+    if (jb >= ja) {
+      const double cnt = jb - ja + 1.0;
+      low_begin = (int)ja;
+      low_count = cnt > (double)GLS_NLOW_MAX ? GLS_NLOW_MAX : (int)cnt;
+    }
+  }
+}
+
+// FP64 epilogue for one frequency: spectral.py:113-132 literally.
+//   sums = {sum w c, sum w s, sum w y c, sum w y s, sum w c^2, sum w c s} * (1 / inv_n)
+// y was pre-scaled to unit weighted RMS, so YY == 1 (spectral.py:120,132).
+__device__ __forceinline__ double gls_power_from_sums(const double* sums, double inv_n, unsigned flags,
+                                                      double yy, double psd_scale) {
+  const double C = sums[0] * inv_n, S = sums[1] * inv_n;
+  const double Ch = sums[2] * inv_n, Sh = sums[3] * inv_n;
+  // sum w cos(2x) = 2 sum w cos^2 x - 1,  sum w sin(2x) = 2 sum w sin x cos x   (sum w = 1)
+  const double C2 = 2.0 * sums[4] * inv_n - 1.0, S2 = 2.0 * sums[5] * inv_n;
+  const bool fit_mean = flags & PDC_GLS_FIT_MEAN;
+  double tan2;
+  if (fit_mean) tan2 = (S2 - 2.0 * S * C) / (C2 - (C * C - S * S));  // spectral.py:113
+  else tan2 = S2 / C2;                                               // spectral.py:115
+  const double hyp = sqrt(1.0 + tan2 * tan2);
+  const double S2w = tan2 / hyp;
+  const double C2w = 1.0 / hyp;
+  const double Cw = sqrt(0.5) * sqrt(1.0 + C2w);
+  const double Sw = sqrt(0.5) * np_sign(S2w) * sqrt(1.0 - C2w);
+  const double YC = Ch * Cw + Sh * Sw;
+  const double YS = Sh * Cw - Ch * Sw;
+  double CC = 0.5 * (1.0 + C2 * C2w + S2 * S2w);
+  double SS = 0.5 * (1.0 - C2 * C2w - S2 * S2w);
+  if (fit_mean) {
+    const double a1 = C * Cw + S * Sw, a2 = S * Cw - C * Sw;
+    CC -= a1 * a1;
+    SS -= a2 * a2;
+  }
+  double power = YC * YC / CC + YS * YS / SS;          // spectral.py:128
+  if (flags & PDC_GLS_PSD) power *= yy * psd_scale;    // spectral.py:130
+  else if (!(yy > 0.0)) power = nan("");              // spectral.py:132 with YY == 0
+  return power;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace pdc

@@ -77,6 +77,8 @@ struct pdc_ctx {
   pdc::DevBuf gls_curves;      // GlsCurve[B]
   pdc::DevBuf gls_rec1;        // double2[n]  (t - tmin, frac(df (t - tmin)))
   pdc::DevBuf gls_rec2;        // float4[n]   (cos, sin of the per-index rotation, y or w*y, w)
+  pdc::DevBuf glsm_y;          // float [groups][n][R]: scaled values of the shared-time series (glsm.cu)
+  int glsm_occ[2] = {0, 0};    // cached blocks/SM of glsm_strip_kernel [weighted]
   pdc::DevBuf gls_low;         // float64 sums of the sub-cycle frequencies [chunk][6][B*16]
   pdc::DevBuf partial;         // float64 partial sums [nsplit][rows][units]
   pdc::DevBuf blockred;        // per-block (value, index) candidates
@@ -96,6 +98,10 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
             const int64_t* offsets_host, int64_t B, const double* fmin_host, const double* df_host,
             int64_t j0, int64_t nf, unsigned flags, const double* psd_scale_host,
             double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t stream);
+
+int glsm_run(pdc_ctx* ctx, const double* t, const double* Y, const double* w, int64_t n, int64_t S,
+             double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,
+             double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t stream);
 
 int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods,
             int64_t np, int nb, int nc, double* theta_out, int64_t* argmin_out, double* min_out,

@@ -109,8 +109,9 @@ class GLS(object):
 
         The reference loops ``gls(bs_sample, err=bs_err).amax()``; here the
         resamples (same times, resampled values and errors, drawn from the same
-        generator in the same order) go through the batched kernel
-        ``pdc_gls_batch`` keeping only each curve's maximum.
+        generator in the same order) go through the batched kernels keeping only
+        each curve's maximum: ``pdc_gls_multi`` (shared times and weights) when the
+        errors are uniform, ``pdc_gls_batch`` otherwise.
         """
         rng = np.random.default_rng(random_seed)
         ndata = len(self.signal)
@@ -121,16 +122,23 @@ class GLS(object):
         nf = frequency.size
         ctx = _ffi.default_context(self.device)
         out = np.empty(n_bootstraps)
+        uniform = bool(np.all(err == err.flat[0]))   # err=None in the original call: every replicate has equal weights
         for a in range(0, n_bootstraps, batch):
             b = min(n_bootstraps, a + batch)
             idx = np.stack([rng.integers(0, ndata, ndata) for _ in range(a, b)])
-            yb = values[idx].ravel()
-            eb = err[idx]
-            wb = (eb ** -2.0).ravel()
-            offsets = np.arange(b - a + 1, dtype=np.int64) * ndata
-            psd_scale = 0.5 * (eb ** -2.0).sum(axis=1) if self.psd else None
-            _, _, mx = ctx.gls_batch(np.tile(t, b - a), yb, wb, offsets, fmin, df, nf, fit_mean=True,
-                                     psd_scale=psd_scale, want_power=False)
+            if uniform:
+                # same times, same (uniform) weights: rotation and window sums are shared (pdc_gls_multi)
+                psd_scale = 0.5 * (err ** -2.0).sum() if self.psd else None
+                _, _, mx = ctx.gls_multi(t, values[idx], None, fmin, df, nf, fit_mean=True, psd_scale=psd_scale,
+                                         want_power=False)
+            else:
+                yb = values[idx].ravel()
+                eb = err[idx]
+                wb = (eb ** -2.0).ravel()
+                offsets = np.arange(b - a + 1, dtype=np.int64) * ndata
+                psd_scale = 0.5 * (eb ** -2.0).sum(axis=1) if self.psd else None
+                _, _, mx = ctx.gls_batch(np.tile(t, b - a), yb, wb, offsets, fmin, df, nf, fit_mean=True,
+                                         psd_scale=psd_scale, want_power=False)
             out[a:b] = mx
         self.bs_replicates = out
         return self.bs_replicates

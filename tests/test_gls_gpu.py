@@ -324,3 +324,56 @@ def test_million_point_curve_window_vs_oracle(gpu_ctx):
     big = ref >= 1e-2 * np.nanmax(p)
     assert np.max(np.abs(p[sel][big] - ref[big]) / ref[big]) <= TOL
     assert sel[np.argmax(ref)] == am
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("S", [1, 5, 8, 19])
+def test_shared_time_multi_series_matches_single_calls(gpu_ctx, S, weighted):
+    """pdc_gls_multi (series on common timestamps) == pdc_gls per series == formula oracle."""
+    rng = np.random.default_rng(100 + S)
+    n, nf = 1777, 2100
+    t = np.sort(rng.uniform(0, 90, n))
+    df = 1 / (t[-1] - t[0]) / 5
+    fmin = 0.5 * df
+    Y = np.stack([50 * s + np.sin(2 * np.pi * t / rng.uniform(0.7, 9)) * rng.uniform(0.5, 3) +
+                  rng.standard_normal(n) for s in range(S)])
+    err = rng.uniform(0.5, 1.5, n) if weighted else None
+    w = None if err is None else err ** -2.0
+    P, A, M = gpu_ctx.gls_multi(t, Y, w, fmin, df, nf)
+    _, A2, M2 = gpu_ctx.gls_multi(t, Y, w, fmin, df, nf, want_power=False)
+    np.testing.assert_array_equal(A, A2)
+    np.testing.assert_array_equal(M, M2)
+    for s in range(S):
+        ref = cport.gls_exact(t, Y[s], err, fmin, df, nf)
+        assert_power_close(P[s], ref)
+        assert A[s] == np.nanargmax(ref) and M[s] == np.nanmax(P[s])
+        p1, a1, _ = gpu_ctx.gls(t, Y[s], w, fmin, df, nf)
+        assert a1 == A[s] and np.nanmax(np.abs(p1 - P[s])) <= 2e-6 * M[s]
+
+
+def test_shared_time_multi_series_shard_offset_and_psd(gpu_ctx):
+    rng = np.random.default_rng(77)
+    n, nf = 900, 1500
+    t = np.sort(rng.uniform(0, 40, n))
+    df = 1 / (t[-1] - t[0]) / 5
+    Y = np.stack([np.sin(2 * np.pi * t / 3.3) + 0.5 * rng.standard_normal(n) for _ in range(3)])
+    err = rng.uniform(0.2, 0.4, n)
+    w = err ** -2.0
+    P, A, M = gpu_ctx.gls_multi(t, Y, w, 0.5 * df, df, nf - 700, j0=700, psd_scale=0.5 * w.sum())
+    for s in range(3):
+        ref = cport.gls_exact(t, Y[s], err, 0.5 * df, df, nf - 700, True, psd=True, j0=700)
+        assert_power_close(P[s], ref)
+        assert A[s] == np.nanargmax(ref)
+
+
+def test_bootstrap_uniform_errors_uses_shared_time_kernel():
+    from periodicity_b200 import GLS, TSeries
+    rng = np.random.default_rng(5)
+    t = np.sort(rng.uniform(0, 30, 400))
+    y = np.sin(2 * np.pi * t / 2.0) + 0.5 * rng.standard_normal(400)
+    gls = GLS(fmax=3.0)
+    gls(TSeries(t, y))
+    reps = gls.bootstrap(10, random_seed=9, batch=4)
+    rng2 = np.random.default_rng(9)
+    want = [GLS(fmax=3.0)(TSeries(t, y[rng2.integers(0, 400, 400)])).amax() for _ in range(10)]
+    np.testing.assert_allclose(reps, want, rtol=5e-6)

@@ -33,6 +33,11 @@ class OracleContext:
         return (np.stack([o[0] for o in out]) if want_power else None,
                 np.array([o[1] for o in out]), np.array([o[2] for o in out]))
 
+    def gls_multi(self, t, Y, w, fmin, df, nf, fit_mean=True, psd_scale=None, j0=0, want_power=True):
+        out = [self.gls(t, y, w, fmin, df, nf, fit_mean, psd_scale, j0) for y in np.atleast_2d(Y)]
+        return (np.stack([o[0] for o in out]) if want_power else None,
+                np.array([o[1] for o in out]), np.array([o[2] for o in out]))
+
     def pdm(self, t, x, periods, nb, nc):
         th = cport.pdm(t, x, periods, nb, nc)
         return th, int(np.nanargmin(th)), float(np.nanmin(th))
@@ -99,6 +104,13 @@ def test_gls_window_bootstrap_model_copy():
         want.append(GLS(fmax=2.0)(TSeries(t, y[bs]), err=err[bs]).amax())
     np.testing.assert_allclose(reps, want, rtol=1e-12)
     assert 0.0 <= gls.fap(ls.amax()) <= 1.0 and gls.fal(0.5) == np.quantile(reps, 0.5)
+    # err=None: uniform weights -> the shared-time path (pdc_gls_multi) must give the reference loop too
+    gu = GLS(fmax=2.0)
+    gu(TSeries(t, y))
+    repsu = gu.bootstrap(4, random_seed=11, batch=3)
+    rng3 = np.random.default_rng(11)
+    wantu = [GLS(fmax=2.0)(TSeries(t, y[rng3.integers(0, 80, 80)])).amax() for _ in range(4)]
+    np.testing.assert_allclose(repsu, wantu, rtol=1e-12)
     fit = gls.model(t, 1 / 2.5)                                  # spectral.py:169-204
     assert np.sqrt(np.mean((fit.values - y) ** 2)) < 0.2
     assert gls.copy() is not gls and gls.copy().fmax == 2.0
