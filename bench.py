@@ -515,6 +515,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         reps, evals = 0, 0
+        cpu_reference_step(wl)             # untimed warm-up (imports, worker start-up, calibration)
         t0 = time.perf_counter()
         while True:
             e, cores, desc = cpu_reference_step(wl)
