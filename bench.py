@@ -389,10 +389,14 @@ def main():
         """One pass of the hot path with inputs resident in HBM; returns (values, best idx, best val)."""
         if kind == "gls":
             power, arg, mx = pdist.gls_torch(t_d, y_d, None, wl["fmin"], wl["df"], stop - start, j0=start, ctx=ctx)
+            if world == 1:
+                return power, mx, arg          # one GPU: nothing to exchange
             garg = (arg + start).to(torch.float64).reshape(())
             vals, bests, args_ = pdist.all_gather_packed(power, mx.reshape(()), garg, L)
         elif kind == "pdm":
             theta, arg, mn = pdist.pdm_torch(t_d, y_d, p_d, wl["nb"], wl["nc"], ctx=ctx)
+            if world == 1:
+                return theta, mn, arg
             garg = (arg + start).to(torch.float64).reshape(())
             vals, bests, args_ = pdist.all_gather_packed(theta, mn.reshape(()), garg, L)
         elif kind == "gls_multi":

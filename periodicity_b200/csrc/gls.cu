@@ -380,6 +380,7 @@ static const GlsGeom kGlsGeoms[] = {
     {20, 128, 2},  // 13
     {16, 256, 1},  // 14: 8 warps/SM, one block
     {12, 128, 2},  // 15
+    {8, 64, 8},    // 16: small problems -- 512 frequencies per block so that tiny grids still fill the SMs
 };
 constexpr int kGlsNumGeoms = sizeof(kGlsGeoms) / sizeof(kGlsGeoms[0]);
 
@@ -406,7 +407,7 @@ static int launch_strip_t(pdc_ctx* ctx, const GlsMainArgs& a, bool weighted, lon
 #define PDC_GLS_GEOM_CASES(X) \
   X(0, 16, 256, 2) X(1, 8, 256, 4) X(2, 12, 128, 5) X(3, 10, 256, 3) X(4, 16, 128, 4) X(5, 20, 128, 3) \
   X(6, 24, 128, 2) X(7, 12, 256, 2) X(8, 16, 128, 3) X(9, 16, 128, 2) X(10, 16, 128, 1) X(11, 16, 64, 2) \
-  X(12, 16, 64, 4) X(13, 20, 128, 2) X(14, 16, 256, 1) X(15, 12, 128, 2)
+  X(12, 16, 64, 4) X(13, 20, 128, 2) X(14, 16, 256, 1) X(15, 12, 128, 2) X(16, 8, 64, 8)
 
 static int strip_occupancy(int geom, bool weighted) {
   switch (geom) {
@@ -436,6 +437,7 @@ static int launch_strip(int geom, pdc_ctx* ctx, const GlsMainArgs& a, bool weigh
     case 13: return launch_strip_t<20, 128, 2>(ctx, a, weighted, items, st);
     case 14: return launch_strip_t<16, 256, 1>(ctx, a, weighted, items, st);
     case 15: return launch_strip_t<12, 128, 2>(ctx, a, weighted, items, st);
+    case 16: return launch_strip_t<8, 64, 8>(ctx, a, weighted, items, st);
   }
   set_error("bad strip geometry %d", geom);
   return PDC_EINVAL;
@@ -444,9 +446,10 @@ static int launch_strip(int geom, pdc_ctx* ctx, const GlsMainArgs& a, bool weigh
 // Pick the sample split so that (curves * frequency blocks * nsplit) work items
 // fill whole waves of resident blocks.  Cost model: every wave costs the samples
 // of one item plus a fixed per-item overhead (staging, flush) worth ~48 samples.
-static int choose_nsplit(long long base_items, long long nmax, long long resident, long long plane_bytes) {
+static int choose_nsplit(long long base_items, long long nmax, long long resident, long long plane_bytes,
+                         int min_samples) {
   if (base_items >= 24 * resident) return 1;
-  long long cap = nmax / 256;
+  long long cap = nmax / min_samples;
   if (cap < 1) cap = 1;
   if (cap > 4096) cap = 4096;
   // every split owns one FP64 plane of partial sums: keep the scratch below 2 GiB
@@ -488,13 +491,20 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   // geometry of the hot kernel
   int geom = ctx->gls_geom;
   if (geom < 0 || geom >= kGlsNumGeoms) geom = 9;
+  if (!ctx->gls_geom_forced) {
+    // tiny problems: with 2048 frequencies per block the grid cannot fill 148 SMs even after
+    // splitting the sample axis; use 512-frequency blocks of 64 threads instead
+    const long long big_items = (long long)B * ((nf + 2047) / 2048) * (nmax / 256 > 0 ? nmax / 256 : 1);
+    if (big_items < 2LL * ctx->sm_count) geom = 16;
+  }
   const int K = kGlsGeoms[geom].K, THREADS = kGlsGeoms[geom].threads, MINB = kGlsGeoms[geom].minb;
   const long long fpb = (long long)K * THREADS;
   const long long nfb = (nf + fpb - 1) / fpb;
   (void)MINB;
   if (ctx->gls_occ[geom][w != nullptr] == 0) ctx->gls_occ[geom][w != nullptr] = strip_occupancy(geom, w != nullptr);
   const long long resident = (long long)ctx->sm_count * ctx->gls_occ[geom][w != nullptr];
-  int nsplit = choose_nsplit((long long)B * nfb, nmax, resident, (long long)sizeof(double) * 6 * nf_tot);
+  int nsplit = choose_nsplit((long long)B * nfb, nmax, resident, (long long)sizeof(double) * 6 * nf_tot,
+                             geom == 16 ? 96 : 256);
   if (ctx->gls_nsplit_override > 0) nsplit = ctx->gls_nsplit_override;  // tuning aid (env PDC_GLS_NSPLIT)
   const long long items = (long long)B * nfb * nsplit;
   if (items > 0x7fffffffLL) { set_error("pdc_gls: problem too large for one call (%lld work items)", items); return PDC_EINVAL; }
