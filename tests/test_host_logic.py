@@ -38,6 +38,17 @@ class OracleContext:
         return (np.stack([o[0] for o in out]) if want_power else None,
                 np.array([o[1] for o in out]), np.array([o[2] for o in out]))
 
+    def peaks_topk(self, values, k):
+        from scipy.signal import find_peaks
+        v = np.atleast_2d(values)
+        idx = np.full((v.shape[0], k), -1, dtype=np.int64)
+        val = np.full((v.shape[0], k), np.nan)
+        for r, row in enumerate(v):
+            pk, _ = find_peaks(row, prominence=0.0)
+            top = pk[np.lexsort((pk, -row[pk]))][:k]
+            idx[r, :top.size], val[r, :top.size] = top, row[top]
+        return idx, val
+
     def pdm(self, t, x, periods, nb, nc):
         th = cport.pdm(t, x, periods, nb, nc)
         return th, int(np.nanargmin(th)), float(np.nanmin(th))
@@ -139,3 +150,32 @@ def test_pdm_front_end_matches_reference(case):
     assert pdm.t is pdm.signal.time and pdm.x is pdm.signal.values
     assert pdm._pdm(pdm.periods[3]) == pytest.approx(
         cport.pdm(pdm.t, pdm.x, pdm.periods[3:4], pdm.nb, pdm.nc)[0], rel=1e-13)
+
+
+def test_survey_front_end_and_top_peaks():
+    from periodicity_b200.survey import gls_survey
+    rng = np.random.default_rng(8)
+    sigs, errs = [], []
+    for b in range(3):
+        n = 150 + 40 * b
+        t = np.sort(rng.uniform(0, 25, n))
+        sigs.append(TSeries(t, np.sin(2 * np.pi * t / (1.5 + b)) + 0.2 * rng.standard_normal(n)))
+        errs.append(rng.uniform(0.1, 0.3, n))
+    out = gls_survey(sigs, errs=errs, nf=400, want_power=True)
+    for b, s in enumerate(sigs):
+        df = 1.0 / s.baseline / 5                                   # spectral.py:88
+        assert out["df"][b] == df and out["fmin"][b] == 0.5 * df    # spectral.py:89-90
+        ref = cport.gls_exact(s.time, s.values, errs[b], 0.5 * df, df, 400)
+        np.testing.assert_allclose(out["power"][b], ref, rtol=1e-12)
+        assert out["argmax"][b] == np.nanargmax(ref)
+        assert out["best_period"][b] == 1.0 / (0.5 * df + df * np.nanargmax(ref))
+        assert abs(out["best_period"][b] - (1.5 + b)) < 0.1
+    with pytest.raises(ValueError):
+        gls_survey([], nf=10)
+    with pytest.raises(ValueError):
+        gls_survey(sigs, errs=errs[:2], nf=10)
+    gls = GLS(fmax=2.0)
+    ls = gls(sigs[0])
+    f, p = gls.top_peaks(3)
+    assert 1.0 / f[0] == ls.period_at_highest_peak
+    np.testing.assert_array_equal(1.0 / f, ls.psort_by_peak()[:3])
