@@ -31,6 +31,8 @@
  *     legacy default stream, as everywhere in CUDA -- it is what
  *     torch.cuda.current_stream().cuda_stream yields by default; pass
  *     PDC_STREAM_CTX to use the ctx's own stream) and return without synchronising.
+ *     Calls on one ctx share its scratch buffers: each call is ordered (by a CUDA
+ *     event) after the previous call on the same ctx, whatever streams they use.
  *   - All arrays are C-contiguous float64 (what TSeries.time / .values yield,
  *     core.py:60-66,479-481); FP32 is an internal detail of the kernels.
  *   - There is no CPU fallback: without a usable CUDA device the ctx cannot be

@@ -86,6 +86,16 @@ void PinnedBuf::release() {
 
 }  // namespace pdc
 
+int pdc_ctx::scratch_acquire(cudaStream_t st) {
+  PDC_CUDA(cudaStreamWaitEvent(st, ev_done, 0));  // no-op until the event has been recorded once
+  return PDC_OK;
+}
+
+int pdc_ctx::scratch_release(cudaStream_t st) {
+  PDC_CUDA(cudaEventRecord(ev_done, st));
+  return PDC_OK;
+}
+
 int pdc_ctx::main_begin(cudaStream_t st) {
   if (ev_pending.size() >= 1024) PDC_TRY(main_resolve());
   if (ev_free.empty()) {
@@ -177,6 +187,7 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
   if (const char* g = getenv("PDC_GLS_NSPLIT")) ctx->gls_nsplit_override = atoi(g);
   cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   cudaError_t e4 = cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming);
+  if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
   if (e1 != cudaSuccess || e4 != cudaSuccess) {
     pdc_ctx_destroy(ctx);
     return cuda_fail(e1 != cudaSuccess ? e1 : e4, "stream/event creation", __FILE__, __LINE__);
@@ -197,6 +208,7 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   ctx->main_resolve();
   for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);
+  if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return PDC_OK;

@@ -52,6 +52,10 @@ struct pdc_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_fence = nullptr;                     // caller-stream -> scratch reuse fence
+  cudaEvent_t ev_done = nullptr;                      // end of the previous call: the scratch buffers are shared, so
+                                                      // a call on another stream first waits for it (scratch_acquire)
+  int scratch_acquire(cudaStream_t st);               // order `st` after the previous call on this ctx
+  int scratch_release(cudaStream_t st);               // mark the end of this call
   int64_t launches = 0;
   int gls_occ[32][2] = {};  // cached blocks/SM of each strip-kernel variant [geom][weighted]
   int gls_nsplit_override = 0;

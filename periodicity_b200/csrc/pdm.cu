@@ -325,6 +325,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   const long long blocks = npb * nsplit;
   if (blocks > 0x7fffffffLL) { set_error("pdc_pdm: problem too large for one call"); return PDC_EINVAL; }
 
+  PDC_TRY(ctx->scratch_acquire(st));
   PDC_TRY(ctx->pdm_meta.reserve(sizeof(PdmMeta)));
   PDC_TRY(ctx->pdm_x.reserve(sizeof(float) * n));
   PDC_TRY(ctx->partial.reserve(sizeof(double) * 2 * m0 * (size_t)np * nsplit));
@@ -372,6 +373,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
+  PDC_TRY(ctx->scratch_release(st));
   return PDC_OK;
 }
 

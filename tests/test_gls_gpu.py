@@ -377,3 +377,28 @@ def test_bootstrap_uniform_errors_uses_shared_time_kernel():
     rng2 = np.random.default_rng(9)
     want = [GLS(fmax=3.0)(TSeries(t, y[rng2.integers(0, 400, 400)])).amax() for _ in range(10)]
     np.testing.assert_allclose(reps, want, rtol=5e-6)
+
+
+def test_calls_on_different_streams_share_a_ctx_safely(gpu_ctx):
+    """A ctx's scratch is shared: calls issued on different CUDA streams must still be ordered."""
+    import torch
+    from periodicity_b200 import dist as pdist
+    nf = 20_000
+    t, y, fmin, df = synth(20_000, 400.0, nf, 1.0, 61)
+    t2, y2, fmin2, df2 = synth(15_000, 300.0, nf, 1.0, 62)
+    want1 = gpu_ctx.gls(t, y, None, fmin, df, nf)[0]
+    want2 = gpu_ctx.gls(t2, y2, None, fmin2, df2, nf)[0]
+    d = [torch.from_numpy(a).cuda() for a in (t, y, t2, y2)]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(3):
+        with torch.cuda.stream(s1):
+            p1 = pdist.gls_torch(d[0], d[1], None, fmin, df, nf, ctx=gpu_ctx)[0]
+        with torch.cuda.stream(s2):
+            p2 = pdist.gls_torch(d[2], d[3], None, fmin2, df2, nf, ctx=gpu_ctx)[0]
+        outs.append((p1, p2))
+    torch.cuda.synchronize()
+    for p1, p2 in outs:
+        np.testing.assert_array_equal(p1.cpu().numpy(), want1)
+        np.testing.assert_array_equal(p2.cpu().numpy(), want2)
