@@ -97,15 +97,15 @@ gls_records_kernel(const double* __restrict__ t, const double* __restrict__ y,
     sincospi(2.0 * b, &sb, &cb);
     const double yv = (y[g] - cv.ymean) * cv.inv_rms;  // unit weighted RMS before the FP32 cast
     float4 r;
-    r.x = (float)cb;
-    r.y = (float)sb;
+    rec_set(r, rec_slot(REC_CR), (float)cb);
+    rec_set(r, rec_slot(REC_SR), (float)sb);
     if (w) {
       const double wn = w[g] * wscale;
-      r.z = (float)(wn * yv);
-      r.w = (float)wn;
+      rec_set(r, rec_slot(REC_Y), (float)(wn * yv));
+      rec_set(r, rec_slot(REC_W), (float)wn);
     } else {
-      r.z = (float)yv;
-      r.w = 1.0f;
+      rec_set(r, rec_slot(REC_Y), (float)yv);
+      rec_set(r, rec_slot(REC_W), 1.0f);
     }
     rec1[g] = make_double2(tt, b);
     rec2[g] = r;
@@ -200,7 +200,7 @@ gls_strip_kernel(const GlsMainArgs a) {
 
   if (threadIdx.x < 2) {
     s_ab[GLS_TILE + threadIdx.x] = make_double2(0.0, 0.0);
-    s_r2[GLS_TILE + threadIdx.x] = make_float4(1.f, 0.f, 0.f, 0.f);
+    s_r2[GLS_TILE + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   bool first = true;
   long long tile0 = sb;
@@ -222,13 +222,15 @@ gls_strip_kernel(const GlsMainArgs a) {
     // One sample: K accumulations + K-1 rotations.  The sums are the per-frequency
     // {C, S, YC, YS, CC, CS}; (c, s) enters as the exact seed at the strip's first frequency.
     auto strip = [&](float c, float s, const float4 r2) {
-      const float cr = r2.x, sr = r2.y, yv = r2.z;
+      const float cr = rec_get(r2, rec_slot(REC_CR)), sr = rec_get(r2, rec_slot(REC_SR));
+      const float yv = rec_get(r2, rec_slot(REC_Y)), wv = rec_get(r2, rec_slot(REC_W));
+      (void)wv;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         if (WEIGHTED) {
-          const float wc = r2.w * c;
+          const float wc = wv * c;
           aC[k] += wc;
-          aS[k] = fmaf(r2.w, s, aS[k]);
+          aS[k] = fmaf(wv, s, aS[k]);
           aCC[k] = fmaf(wc, c, aCC[k]);
           aCS[k] = fmaf(wc, s, aCS[k]);
         } else {
@@ -409,6 +411,11 @@ static int launch_strip_t(pdc_ctx* ctx, const GlsMainArgs& a, bool weighted, lon
   X(6, 24, 128, 2) X(7, 12, 256, 2) X(8, 16, 128, 3) X(9, 16, 128, 2) X(10, 16, 128, 1) X(11, 16, 64, 2) \
   X(12, 16, 64, 4) X(13, 20, 128, 2) X(14, 16, 256, 1) X(15, 12, 128, 2) X(16, 8, 64, 8)
 
+#ifdef PDC_ONLY_DEFAULT_GEOM
+#undef PDC_GLS_GEOM_CASES
+#define PDC_GLS_GEOM_CASES(X) X(9, 16, 128, 2)
+#endif
+
 static int strip_occupancy(int geom, bool weighted) {
   switch (geom) {
 #define X(i, k, t, m) case i: return strip_blocks_per_sm<k, t, m>(weighted);
@@ -421,23 +428,9 @@ static int strip_occupancy(int geom, bool weighted) {
 static int launch_strip(int geom, pdc_ctx* ctx, const GlsMainArgs& a, bool weighted, long long items,
                         cudaStream_t st) {
   switch (geom) {
-    case 0: return launch_strip_t<16, 256, 2>(ctx, a, weighted, items, st);
-    case 1: return launch_strip_t<8, 256, 4>(ctx, a, weighted, items, st);
-    case 2: return launch_strip_t<12, 128, 5>(ctx, a, weighted, items, st);
-    case 3: return launch_strip_t<10, 256, 3>(ctx, a, weighted, items, st);
-    case 4: return launch_strip_t<16, 128, 4>(ctx, a, weighted, items, st);
-    case 5: return launch_strip_t<20, 128, 3>(ctx, a, weighted, items, st);
-    case 6: return launch_strip_t<24, 128, 2>(ctx, a, weighted, items, st);
-    case 7: return launch_strip_t<12, 256, 2>(ctx, a, weighted, items, st);
-    case 8: return launch_strip_t<16, 128, 3>(ctx, a, weighted, items, st);
-    case 9: return launch_strip_t<16, 128, 2>(ctx, a, weighted, items, st);
-    case 10: return launch_strip_t<16, 128, 1>(ctx, a, weighted, items, st);
-    case 11: return launch_strip_t<16, 64, 2>(ctx, a, weighted, items, st);
-    case 12: return launch_strip_t<16, 64, 4>(ctx, a, weighted, items, st);
-    case 13: return launch_strip_t<20, 128, 2>(ctx, a, weighted, items, st);
-    case 14: return launch_strip_t<16, 256, 1>(ctx, a, weighted, items, st);
-    case 15: return launch_strip_t<12, 128, 2>(ctx, a, weighted, items, st);
-    case 16: return launch_strip_t<8, 64, 8>(ctx, a, weighted, items, st);
+#define X(i, k, t, m) case i: return launch_strip_t<k, t, m>(ctx, a, weighted, items, st);
+    PDC_GLS_GEOM_CASES(X)
+#undef X
   }
   set_error("bad strip geometry %d", geom);
   return PDC_EINVAL;

@@ -15,6 +15,30 @@ struct GlsCurve {
   int low_begin, low_count;  // frequencies [low_begin, low_begin + low_count) of this call go through FP64
 };
 
+// Order of (cos, sin, y', w') inside the float4 sample record.  The record is loaded with one
+// LDS.128, which pins its four components to register banks 0..3 (the register file behaves as
+// 4 banks, reg % 4, one read per bank per cycle -- tools/bank_model.py reproduces ncu's issue
+// utilisation from the SASS with exactly that model); the order decides which components collide
+// with the rotating (c, s) state.
+#ifndef PDC_REC_CODE
+#define PDC_REC_CODE 123  /* decimal digits = float4 slot of cos, sin, y', w' (0123 = x, y, z, w) */
+#endif
+__host__ __device__ constexpr int rec_slot(int which) {
+  constexpr int order[4] = {(PDC_REC_CODE / 1000) % 10, (PDC_REC_CODE / 100) % 10, (PDC_REC_CODE / 10) % 10,
+                            PDC_REC_CODE % 10};
+  return order[which];
+}
+__host__ __device__ __forceinline__ float rec_get(const float4& r, int slot) {
+  return slot == 0 ? r.x : (slot == 1 ? r.y : (slot == 2 ? r.z : r.w));
+}
+__host__ __device__ __forceinline__ void rec_set(float4& r, int slot, float v) {
+  if (slot == 0) r.x = v;
+  else if (slot == 1) r.y = v;
+  else if (slot == 2) r.z = v;
+  else r.w = v;
+}
+constexpr int REC_CR = 0, REC_SR = 1, REC_Y = 2, REC_W = 3;
+
 constexpr int GLS_TILE = 1024;  // samples per shared-memory tile == FP32 flush interval
 
 // Frequencies with |f| * (tmax - tmin) < GLS_LOW_CYCLES see less than one cycle over the
