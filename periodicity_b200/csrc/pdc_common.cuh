@@ -60,7 +60,7 @@ struct pdc_ctx {
   int gls_occ[32][2] = {};  // cached blocks/SM of each strip-kernel variant [geom][weighted]
   int gls_nsplit_override = 0;
   bool gls_geom_forced = false;  // PDC_GLS_GEOM given: no automatic small-problem geometry
-  int gls_geom = 9;  // index into kGlsGeoms (gls.cu); env PDC_GLS_GEOM overrides at ctx creation (tuning aid)
+  int gls_geom = 0;  // index into kGlsGeoms (gls.cu); env PDC_GLS_GEOM overrides at ctx creation (tuning aid)
 
   // CUDA-event timing of the dominant kernel (GLS strip / PDM histogram), recorded on the
   // launching stream; pairs are resolved lazily so recording never synchronises.
