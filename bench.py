@@ -315,6 +315,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c1", "gls_multi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1, single-curve GLS: 'p2p' = all-gather fused into the epilogue kernel over NVLink peer "
+                         "memory (pdc_gls_dev_fanout), 'nccl' = one ncclAllGather after the kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -388,6 +391,9 @@ def main():
     def step_device():
         """One pass of the hot path with inputs resident in HBM; returns (values, best idx, best val)."""
         if kind == "gls":
+            if world > 1 and gather_mode[0] == "p2p":
+                power, best = pdist.gls_sharded_p2p_torch(t_d, y_d, None, wl["fmin"], wl["df"], wl["nf"], ctx=ctx)
+                return power, best[:, 0], best[:, 1]
             power, arg, mx = pdist.gls_torch(t_d, y_d, None, wl["fmin"], wl["df"], stop - start, j0=start, ctx=ctx)
             if world == 1:
                 return power, mx, arg          # one GPU: nothing to exchange
@@ -410,6 +416,19 @@ def main():
                                                wl["df"][b0:b1], wl["nf"], want_power=False, ctx=ctx)
             vals, bests, args_ = pdist.all_gather_packed(mx, mx.max(), arg.to(torch.float64).max(), L)
         return vals, bests, args_
+
+    gather_mode = [args.gather if (world > 1 and kind == "gls") else "nccl"]
+    if gather_mode[0] == "p2p":
+        try:                               # symmetric-memory rendezvous is collective: every rank tries, all agree
+            step_device()
+            torch.cuda.synchronize()
+            okflag = torch.ones(1, device=dev)
+        except Exception as exc:           # noqa: BLE001 -- transport set-up failed: fall back to the NCCL all-gather
+            print(f"[bench] p2p gather unavailable on rank {rank}: {exc}", file=sys.stderr)
+            okflag = torch.zeros(1, device=dev)
+        dist.all_reduce(okflag, op=dist.ReduceOp.MIN)
+        if okflag.item() < 1:
+            gather_mode[0] = "nccl"
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
@@ -541,7 +560,11 @@ def main():
                        else ("period grid" if kind == "pdm" else "light-curve batch"),
                        "kernel": "glsm_strip_kernel" if kind == "gls_multi" else None,
                        "l2": "flushed between timed steps (256 MiB memset, not timed); per-step CUDA events summed",
-                       "collective": "one NCCL all-gather of [values, best, index] per step" if world > 1 else "none (1 GPU)"},
+                       "collective": ("none (1 GPU)" if world == 1 else
+                                      ("all-gather fused into the epilogue kernel: stores to every rank's symmetric "
+                                       "buffer over NVLink peer memory + 2 device barriers (no NCCL call)"
+                                       if gather_mode[0] == "p2p" else
+                                       "one NCCL all-gather of [values, best, index] per step"))},
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s / args.steps * 1e3, "api": "pdc_gls / pdc_pdm host-pointer C-ABI call (ctypes)"},

@@ -119,6 +119,31 @@ PDC_API int pdc_gls_dev(pdc_ctx* ctx, const double* t, const double* y, const do
                 double* power_out, int64_t* argmax_out, double* max_out, void* stream);
 
 /*
+ * Frequency-grid-sharded GLS with the all-gather FUSED into the epilogue: rank `rank` of `world`
+ * evaluates frequencies [j0, j0 + nf) like pdc_gls_dev, and its epilogue kernel stores every power
+ * value straight into ALL ranks' result buffers through NVLink peer mappings (one coalesced 8-byte
+ * store per destination), and its arg-max kernel stores (max, global argmax) into slot `rank` of
+ * every rank's candidate table.  No NCCL call, no staging buffer: the "collective" is part of
+ * the kernel that produces the data.  The caller provides buffers mapped into this process for
+ * every rank (e.g. torch.distributed._symmetric_memory: `handle.buffer_ptrs`) and must separate
+ * successive calls with a cross-rank barrier (`handle.barrier()`), see periodicity_b200/dist.py.
+ *
+ *   power[r]  base of rank r's full-grid power array (float64[nf_total]); element j0 + j is written
+ *   best[r]   rank r's candidate table (float64[2*world]); elements 2*rank, 2*rank+1 are written
+ */
+#define PDC_MAX_PEERS 16
+typedef struct pdc_fanout {
+  int32_t world;
+  int32_t rank;
+  double* power[PDC_MAX_PEERS];
+  double* best[PDC_MAX_PEERS];
+} pdc_fanout;
+
+PDC_API int pdc_gls_dev_fanout(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+                               double fmin, double df, int64_t j0, int64_t nf, unsigned flags,
+                               double psd_scale, const pdc_fanout* dst, void* stream);
+
+/*
  * Batched GLS: B independent light curves stored back to back
  * (curve b = samples offsets[b] .. offsets[b+1]-1), each with its own grid
  * origin fmin[b] and spacing df[b] but a common number of frequencies nf

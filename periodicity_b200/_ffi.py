@@ -17,6 +17,15 @@ GLS_FIT_MEAN = 1
 GLS_PSD = 2
 STREAM_CTX = ctypes.c_void_p(-1).value  # PDC_STREAM_CTX: the ctx's own stream (0/None = CUDA default stream)
 
+MAX_PEERS = 16
+
+
+class Fanout(ctypes.Structure):
+    """``pdc_fanout``: per-rank destination buffers of the fused epilogue + all-gather."""
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("power", ctypes.c_void_p * MAX_PEERS), ("best", ctypes.c_void_p * MAX_PEERS)]
+
+
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int64_p = ctypes.POINTER(ctypes.c_int64)
 
@@ -39,6 +48,10 @@ SIGNATURES = {
                                    ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                    ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gls_dev_fanout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
+                                          ctypes.POINTER(Fanout), ctypes.c_void_p]),
     "pdc_gls_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int64, ctypes.c_uint, ctypes.c_void_p,
@@ -249,6 +262,11 @@ class Context:
         _check(self._lib.pdc_gls_dev(self._h, t_ptr, y_ptr, w_ptr or None, int(n), float(fmin), float(df),
                                      int(j0), int(nf), int(flags), float(psd_scale), power_ptr or None,
                                      argmax_ptr or None, max_ptr or None, stream or None))
+
+    def gls_dev_fanout(self, t_ptr, y_ptr, w_ptr, n, fmin, df, j0, nf, flags, psd_scale, fanout, stream=0):
+        _check(self._lib.pdc_gls_dev_fanout(self._h, t_ptr, y_ptr, w_ptr or None, int(n), float(fmin), float(df),
+                                            int(j0), int(nf), int(flags), float(psd_scale), ctypes.byref(fanout),
+                                            stream or None))
 
     def gls_batch_dev(self, t_ptr, y_ptr, w_ptr, offsets, fmin, df, nf, flags, psd_scale, power_ptr,
                       argmax_ptr, max_ptr, stream=0):

@@ -265,6 +265,20 @@ int pdc_gls_dev(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   return gls_run(ctx, t, y, w, offsets, 1, &fmin, &df, j0, nf, flags, &psd_scale, power_out, argmax_out, max_out, st);
 }
 
+int pdc_gls_dev_fanout(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+                       double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,
+                       const pdc_fanout* dst, void* stream) {
+  if (!ctx || !t || !y || !dst) { set_error("pdc_gls_dev_fanout: NULL argument"); return PDC_EINVAL; }
+  if (n < 1) { set_error("pdc_gls: n must be >= 1"); return PDC_EINVAL; }
+  if (j0 < 0) { set_error("pdc_gls: j0 must be >= 0"); return PDC_EINVAL; }
+  for (int r = 0; r < dst->world && r < PDC_MAX_PEERS; ++r)
+    if (!dst->power[r] || !dst->best[r]) { set_error("pdc_gls_dev_fanout: NULL destination for rank %d", r); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  const int64_t offsets[2] = {0, n};
+  return gls_run(ctx, t, y, w, offsets, 1, &fmin, &df, j0, nf, flags, &psd_scale, nullptr, nullptr, nullptr, st, dst);
+}
+
 struct SmallRec {
   long long arg;
   double val;

@@ -315,7 +315,7 @@ gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restric
                     const double* __restrict__ lowsum, int nlowchunk, int B,
                     int nsplit, long long nf, long long nf_tot, unsigned flags,
                     double* __restrict__ power_out, double* __restrict__ red_val,
-                    long long* __restrict__ red_idx) {
+                    long long* __restrict__ red_idx, const pdc_fanout fan, long long fan_offset) {
   __shared__ double sv[32];
   __shared__ long long si[32];
   const int curve = blockIdx.y;
@@ -349,12 +349,39 @@ gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restric
     }
     power = gls_power_from_sums(sums, inv_n, flags, cv.yy, cv.psd_scale);
     if (power_out) power_out[(long long)curve * nf + j] = power;
+    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
+    for (int r = 0; r < fan.world; ++r) fan.power[r][fan_offset + j] = power;
     idx = j;
   }
   block_argext<+1>(power, idx, sv, si);
   if (threadIdx.x == 0) {
     red_val[(long long)curve * gridDim.x + blockIdx.x] = power;
     red_idx[(long long)curve * gridDim.x + blockIdx.x] = idx;
+  }
+}
+
+// Final arg-max of a shard, published to every rank: slot `rank` of each candidate table gets
+// (max, global index as double).
+__global__ void __launch_bounds__(256)
+gls_best_fanout_kernel(const double* __restrict__ red_val, const long long* __restrict__ red_idx, int nblk,
+                       const pdc_fanout fan, long long offset) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  double bv = 0.0;
+  long long bi = -1;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+    const double v = red_val[k];
+    const long long i = red_idx[k];
+    if (better<+1>(v, i, bv, bi)) { bv = v; bi = i; }
+  }
+  block_argext<+1>(bv, bi, sv, si);
+  if (threadIdx.x == 0) {
+    const double val = bi >= 0 ? bv : nan("");
+    const double arg = bi >= 0 ? (double)(bi + offset) : -1.0;
+    for (int r = 0; r < fan.world; ++r) {
+      fan.best[r][2 * fan.rank] = val;
+      fan.best[r][2 * fan.rank + 1] = arg;
+    }
   }
 }
 
@@ -452,7 +479,13 @@ static int choose_nsplit(long long base_items, long long nmax, long long residen
 int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
             const int64_t* offsets_host, int64_t B, const double* fmin_host, const double* df_host,
             int64_t j0, int64_t nf, unsigned flags, const double* psd_scale_host,
-            double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t st) {
+            double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t st,
+            const pdc_fanout* fanout) {
+  if (fanout && (B != 1 || fanout->world < 1 || fanout->world > PDC_MAX_PEERS || fanout->rank < 0 ||
+                 fanout->rank >= fanout->world)) {
+    set_error("pdc_gls_dev_fanout: needs one curve and 1 <= world <= %d", PDC_MAX_PEERS);
+    return PDC_EINVAL;
+  }
   if (B <= 0 || nf <= 0) { set_error("pdc_gls: need at least one curve and one frequency"); return PDC_EINVAL; }
   const long long ntot = offsets_host[B] - offsets_host[0];
   long long nmax = 0;
@@ -566,12 +599,20 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   long long* red_idx = reinterpret_cast<long long*>(red_val + (size_t)eblk * B);
   {
     dim3 grid((unsigned)eblk, (unsigned)B);
+    pdc_fanout fan;
+    if (fanout) fan = *fanout;
+    else fan.world = 0;
     gls_epilogue_kernel<<<grid, 256, 0, st>>>(dc, a.partial, ctx->gls_low.as<double>(), (int)nlowchunk, (int)B,
-                                              nsplit, nf, nf_tot, flags, power_out, red_val, red_idx);
+                                              nsplit, nf, nf_tot, flags, power_out, red_val, red_idx, fan,
+                                              (long long)j0);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  if (argmax_out || max_out) {
+  if (fanout) {
+    gls_best_fanout_kernel<<<1, 256, 0, st>>>(red_val, red_idx, eblk, *fanout, (long long)j0);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  } else if (argmax_out || max_out) {
     argext_final_kernel<+1><<<(unsigned)B, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmax_out, max_out);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;

@@ -102,7 +102,8 @@ namespace pdc {
 int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
             const int64_t* offsets_host, int64_t B, const double* fmin_host, const double* df_host,
             int64_t j0, int64_t nf, unsigned flags, const double* psd_scale_host,
-            double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t stream);
+            double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t stream,
+            const pdc_fanout* fanout = nullptr);
 
 int glsm_run(pdc_ctx* ctx, const double* t, const double* Y, const double* w, int64_t n, int64_t S,
              double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,

@@ -260,3 +260,76 @@ def gls_batch_sharded(t, y, w, offsets, fmin, df, nf, fit_mean=True, psd_scale=N
     power = allp[:, :nf] if want_power else None
     arg = np.where(np.isnan(allp[:, width - 1]), -1, allp[:, width - 1]).astype(np.int64)
     return power, arg, allp[:, width - 2]
+
+
+# ---------------------------------------------------------------------------
+# fused epilogue + all-gather over NVLink peer memory (no NCCL call on the data path)
+# ---------------------------------------------------------------------------
+_symm_cache = {}
+
+
+def _symm_buffer(n_doubles, device, group):
+    """Symmetric float64 buffer of ``n_doubles`` on every rank, mapped into every process
+    (torch.distributed._symmetric_memory); cached per (size, device)."""
+    torch = _torch()
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    key = (int(n_doubles), str(device))
+    ent = _symm_cache.get(key)
+    if ent is None:
+        buf = symm_mem.empty(int(n_doubles), dtype=torch.float64, device=device)
+        hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        ent = (buf, hdl)
+        _symm_cache[key] = ent
+    return ent
+
+
+def gls_sharded_p2p_torch(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, ctx=None, group=None):
+    """Frequency-grid-sharded GLS for CUDA tensors with the all-gather fused into the epilogue kernel.
+
+    Every rank evaluates its slice; the epilogue stores each power value directly into the symmetric
+    result buffer of ALL ranks through NVLink peer mappings (``pdc_gls_dev_fanout``), so when the
+    kernel ends the "all-gather" has already happened.  Two device-side barriers on the current
+    stream (``handle.barrier``) order successive calls.  Returns views ``(power[nf], best[W, 2])``
+    of this rank's symmetric buffer (valid until the next call) -- ``best[r] = (max, global argmax)``
+    of rank r's slice."""
+    torch = _torch()
+    dist, rank, world = _dist_info(group)
+    if dist is None or world < 2:
+        raise RuntimeError("gls_sharded_p2p_torch needs an initialised process group with >= 2 ranks")
+    if world > _ffi.MAX_PEERS:
+        raise ValueError(f"at most {_ffi.MAX_PEERS} ranks")
+    ctx = ctx or _ffi.default_context(t.device.index)
+    buf, hdl = _symm_buffer(int(nf) + 2 * world, t.device, group)
+    start, stop, _ = shard_bounds(nf, rank, world)
+    fan = _ffi.Fanout()
+    fan.world, fan.rank = world, rank
+    ptrs = hdl.buffer_ptrs
+    for r in range(world):
+        fan.power[r] = int(ptrs[r])
+        fan.best[r] = int(ptrs[r]) + 8 * int(nf)
+    flags = (_ffi.GLS_FIT_MEAN if fit_mean else 0) | (_ffi.GLS_PSD if psd_scale is not None else 0)
+    stream = torch.cuda.current_stream(t.device).cuda_stream
+    hdl.barrier(channel=0)        # every rank has finished READING the previous result
+    if stop > start:
+        ctx.gls_dev_fanout(t.data_ptr(), y.data_ptr(), 0 if w is None else w.data_ptr(), t.numel(), fmin, df,
+                           start, stop - start, flags, 1.0 if psd_scale is None else psd_scale, fan, stream)
+    else:
+        buf[int(nf) + 2 * rank: int(nf) + 2 * rank + 2] = torch.tensor([float("nan"), -1.0], dtype=torch.float64,
+                                                                        device=t.device)
+    hdl.barrier(channel=1)        # every rank's stores have landed everywhere
+    return buf[: int(nf)], buf[int(nf):].view(world, 2)
+
+
+def gls_sharded_p2p(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, device=None, group=None):
+    """numpy in / numpy out wrapper of :func:`gls_sharded_p2p_torch` (same return as ``gls_sharded``)."""
+    torch = _torch()
+    ctx = _ffi.default_context(device)
+    dev = torch.device("cuda", ctx.device)
+    tt = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).to(dev)
+    yy = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64)).to(dev)
+    ww = None if w is None else torch.as_tensor(np.ascontiguousarray(w, dtype=np.float64)).to(dev)
+    power, best = gls_sharded_p2p_torch(tt, yy, ww, fmin, df, nf, fit_mean, psd_scale, ctx=ctx, group=group)
+    best = best.cpu().numpy()
+    idx, val = reduce_best(best[:, 0], best[:, 1].astype(np.int64), +1)
+    return power.cpu().numpy(), idx, val

@@ -39,7 +39,9 @@ class GLS(object):
         CUDA device ordinal (default: ``LOCAL_RANK`` or 0).
     shard : bool, optional
         If True and ``torch.distributed`` is initialised, shard the frequency
-        grid across ranks and all-gather power + argmax (``dist.gls_sharded``).
+        grid across ranks and all-gather power + argmax (``dist.gls_sharded``, one NCCL
+        all-gather).  ``shard="p2p"`` uses ``dist.gls_sharded_p2p`` instead: the epilogue kernel
+        stores its results directly into every rank's buffer over NVLink (no NCCL call).
     """
 
     def __init__(self, fmin=None, fmax=None, n=5, psd=False, *, device=None, shard=False):
@@ -79,7 +81,8 @@ class GLS(object):
         psd_scale = 0.5 * (np.asarray(err, dtype=np.float64) ** -2.0).sum() if self.psd else None
         if self.shard:
             from . import dist
-            power, self.argmax_index, self.max_power = dist.gls_sharded(
+            sharded = dist.gls_sharded_p2p if self.shard == "p2p" else dist.gls_sharded
+            power, self.argmax_index, self.max_power = sharded(
                 signal.time, signal.values, weights, fmin, df, nf, fit_mean, psd_scale, device=self.device)
         else:
             ctx = _ffi.default_context(self.device)
