@@ -316,7 +316,7 @@ def main():
     ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c1", "gls_multi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1, single-curve GLS: 'p2p' = all-gather fused into the epilogue kernel over NVLink peer "
+                    help="N>1, GLS / PDM grids: 'p2p' = all-gather fused into the epilogue kernel over NVLink peer "
                          "memory (pdc_gls_dev_fanout), 'nccl' = one ncclAllGather after the kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -387,6 +387,7 @@ def main():
         evals_total = n * wl["nf"]
         if kind == "pdm":
             p_d = torch.from_numpy(wl["periods"][start:stop].copy()).to(dev)
+            pfull_d = torch.from_numpy(wl["periods"]).to(dev)
 
     def step_device():
         """One pass of the hot path with inputs resident in HBM; returns (values, best idx, best val)."""
@@ -400,6 +401,9 @@ def main():
             garg = (arg + start).to(torch.float64).reshape(())
             vals, bests, args_ = pdist.all_gather_packed(power, mx.reshape(()), garg, L)
         elif kind == "pdm":
+            if world > 1 and gather_mode[0] == "p2p":
+                theta, best = pdist.pdm_sharded_p2p_torch(t_d, y_d, pfull_d, wl["nb"], wl["nc"], ctx=ctx)
+                return theta, best[:, 0], best[:, 1]
             theta, arg, mn = pdist.pdm_torch(t_d, y_d, p_d, wl["nb"], wl["nc"], ctx=ctx)
             if world == 1:
                 return theta, mn, arg
@@ -417,7 +421,7 @@ def main():
             vals, bests, args_ = pdist.all_gather_packed(mx, mx.max(), arg.to(torch.float64).max(), L)
         return vals, bests, args_
 
-    gather_mode = [args.gather if (world > 1 and kind == "gls") else "nccl"]
+    gather_mode = [args.gather if (world > 1 and kind in ("gls", "pdm")) else "nccl"]
     if gather_mode[0] == "p2p":
         try:                               # symmetric-memory rendezvous is collective: every rank tries, all agree
             step_device()

@@ -224,6 +224,13 @@ PDC_API int pdc_peaks_topk(pdc_ctx* ctx, const double* values, int64_t rows, int
 PDC_API int pdc_peaks_topk_dev(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k,
                                int64_t* idx_out, double* val_out, void* stream);
 
+/* Period-grid-sharded PDM with the all-gather fused into the epilogue (see pdc_gls_dev_fanout):
+ * this rank evaluates `periods[0..np)`, which are elements [offset, offset + np) of the full period
+ * grid; theta goes to power[r][offset + i] and (min, global argmin) to best[r][2*rank..] of every rank. */
+PDC_API int pdc_pdm_dev_fanout(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+                               const double* periods, int64_t np, int nb, int nc, int64_t offset,
+                               const pdc_fanout* dst, void* stream);
+
 /* Number of kernels this ctx has launched since creation (bench.py's
  * `gpu_launches` claim is the difference across the timed region). */
 PDC_API int64_t pdc_ctx_launch_count(pdc_ctx* ctx);

@@ -75,6 +75,9 @@ SIGNATURES = {
                                       ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_peaks_topk_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_pdm_dev_fanout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                          ctypes.POINTER(Fanout), ctypes.c_void_p]),
     "pdc_pdm_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -267,6 +270,10 @@ class Context:
         _check(self._lib.pdc_gls_dev_fanout(self._h, t_ptr, y_ptr, w_ptr or None, int(n), float(fmin), float(df),
                                             int(j0), int(nf), int(flags), float(psd_scale), ctypes.byref(fanout),
                                             stream or None))
+
+    def pdm_dev_fanout(self, t_ptr, x_ptr, n, periods_ptr, np_, nb, nc, offset, fanout, stream=0):
+        _check(self._lib.pdc_pdm_dev_fanout(self._h, t_ptr, x_ptr, int(n), periods_ptr, int(np_), int(nb), int(nc),
+                                            int(offset), ctypes.byref(fanout), stream or None))
 
     def gls_batch_dev(self, t_ptr, y_ptr, w_ptr, offsets, fmin, df, nf, flags, psd_scale, power_ptr,
                       argmax_ptr, max_ptr, stream=0):

@@ -417,6 +417,17 @@ int pdc_pdm_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
   return pdm_run(ctx, t, x, n, periods, np, nb, nc, theta_out, argmin_out, min_out, st);
 }
 
+int pdc_pdm_dev_fanout(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods,
+                       int64_t np, int nb, int nc, int64_t offset, const pdc_fanout* dst, void* stream) {
+  if (!ctx || !t || !x || !periods || !dst) { set_error("pdc_pdm_dev_fanout: NULL argument"); return PDC_EINVAL; }
+  if (offset < 0) { set_error("pdc_pdm_dev_fanout: offset must be >= 0"); return PDC_EINVAL; }
+  for (int r = 0; r < dst->world && r < PDC_MAX_PEERS; ++r)
+    if (!dst->power[r] || !dst->best[r]) { set_error("pdc_pdm_dev_fanout: NULL destination for rank %d", r); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  return pdm_run(ctx, t, x, n, periods, np, nb, nc, nullptr, nullptr, nullptr, st, dst, offset);
+}
+
 int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
             const double* periods, int64_t np, int nb, int nc,
             double* theta_out, int64_t* argmin_out, double* min_out) {

@@ -360,31 +360,6 @@ gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restric
   }
 }
 
-// Final arg-max of a shard, published to every rank: slot `rank` of each candidate table gets
-// (max, global index as double).
-__global__ void __launch_bounds__(256)
-gls_best_fanout_kernel(const double* __restrict__ red_val, const long long* __restrict__ red_idx, int nblk,
-                       const pdc_fanout fan, long long offset) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  double bv = 0.0;
-  long long bi = -1;
-  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
-    const double v = red_val[k];
-    const long long i = red_idx[k];
-    if (better<+1>(v, i, bv, bi)) { bv = v; bi = i; }
-  }
-  block_argext<+1>(bv, bi, sv, si);
-  if (threadIdx.x == 0) {
-    const double val = bi >= 0 ? bv : nan("");
-    const double arg = bi >= 0 ? (double)(bi + offset) : -1.0;
-    for (int r = 0; r < fan.world; ++r) {
-      fan.best[r][2 * fan.rank] = val;
-      fan.best[r][2 * fan.rank + 1] = arg;
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------
@@ -609,7 +584,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     ctx->launches++;
   }
   if (fanout) {
-    gls_best_fanout_kernel<<<1, 256, 0, st>>>(red_val, red_idx, eblk, *fanout, (long long)j0);
+    best_fanout_kernel<+1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, *fanout, (long long)j0);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   } else if (argmax_out || max_out) {

@@ -221,7 +221,7 @@ pdm_hist_kernel(const PdmArgs a) {
 __global__ void __launch_bounds__(256)
 pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, long long np, long long n,
                     double* __restrict__ theta_out, double* __restrict__ red_val,
-                    long long* __restrict__ red_idx) {
+                    long long* __restrict__ red_idx, const pdc_fanout fan, long long fan_offset) {
   __shared__ double sv[32];
   __shared__ long long si[32];
   const long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -251,7 +251,9 @@ pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, lo
     }
     // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
     theta = ((double)nc * (double)(n - 1) - sq) / den;
-    theta_out[pi] = theta;
+    if (theta_out) theta_out[pi] = theta;
+    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
+    for (int r = 0; r < fan.world; ++r) fan.power[r][fan_offset + pi] = theta;
     idx = pi;
   }
   block_argext<-1>(theta, idx, sv, si);
@@ -277,7 +279,12 @@ static int pdm_launch(pdc_ctx* ctx, const PdmArgs& a, size_t smem, long long blo
 
 int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods,
             int64_t np, int nb, int nc, double* theta_out, int64_t* argmin_out, double* min_out,
-            cudaStream_t st) {
+            cudaStream_t st, const pdc_fanout* fanout, int64_t fan_offset) {
+  if (fanout && (fanout->world < 1 || fanout->world > PDC_MAX_PEERS || fanout->rank < 0 ||
+                 fanout->rank >= fanout->world)) {
+    set_error("pdc_pdm_dev_fanout: needs 1 <= world <= %d", PDC_MAX_PEERS);
+    return PDC_EINVAL;
+  }
   if (n < 2) { set_error("pdc_pdm: need at least 2 samples"); return PDC_EINVAL; }
   if (np < 1) { set_error("pdc_pdm: need at least one trial period"); return PDC_EINVAL; }
   if (nb < 1 || nc < 1) { set_error("pdc_pdm: nb and nc must be >= 1"); return PDC_EINVAL; }
@@ -365,10 +372,18 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
 
   double* red_val = ctx->blockred.as<double>();
   long long* red_idx = reinterpret_cast<long long*>(red_val + eblk);
-  pdm_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(a.partial, nsplit, m0, nc, np, (long long)n, theta_out, red_val, red_idx);
+  pdc_fanout fan;
+  if (fanout) fan = *fanout;
+  else fan.world = 0;
+  pdm_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(a.partial, nsplit, m0, nc, np, (long long)n, theta_out, red_val,
+                                                      red_idx, fan, (long long)fan_offset);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
-  if (argmin_out || min_out) {
+  if (fanout) {
+    best_fanout_kernel<-1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, *fanout, (long long)fan_offset);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  } else if (argmin_out || min_out) {
     argext_final_kernel<-1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmin_out, min_out);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;

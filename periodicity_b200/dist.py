@@ -302,12 +302,7 @@ def gls_sharded_p2p_torch(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, 
     ctx = ctx or _ffi.default_context(t.device.index)
     buf, hdl = _symm_buffer(int(nf) + 2 * world, t.device, group)
     start, stop, _ = shard_bounds(nf, rank, world)
-    fan = _ffi.Fanout()
-    fan.world, fan.rank = world, rank
-    ptrs = hdl.buffer_ptrs
-    for r in range(world):
-        fan.power[r] = int(ptrs[r])
-        fan.best[r] = int(ptrs[r]) + 8 * int(nf)
+    fan = _fanout_struct(hdl, nf, world, rank)
     flags = (_ffi.GLS_FIT_MEAN if fit_mean else 0) | (_ffi.GLS_PSD if psd_scale is not None else 0)
     stream = torch.cuda.current_stream(t.device).cuda_stream
     hdl.barrier(channel=0)        # every rank has finished READING the previous result
@@ -319,6 +314,54 @@ def gls_sharded_p2p_torch(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, 
                                                                         device=t.device)
     hdl.barrier(channel=1)        # every rank's stores have landed everywhere
     return buf[: int(nf)], buf[int(nf):].view(world, 2)
+
+
+def _fanout_struct(hdl, n_values, world, rank):
+    fan = _ffi.Fanout()
+    fan.world, fan.rank = world, rank
+    ptrs = hdl.buffer_ptrs
+    for r in range(world):
+        fan.power[r] = int(ptrs[r])
+        fan.best[r] = int(ptrs[r]) + 8 * int(n_values)
+    return fan
+
+
+def pdm_sharded_p2p_torch(t, x, periods, nb, nc, ctx=None, group=None):
+    """Period-grid-sharded PDM for CUDA tensors, all-gather fused into the epilogue (``pdc_pdm_dev_fanout``).
+    ``periods`` is the FULL grid (CUDA tensor) on every rank.  Returns views ``(theta[np], best[W, 2])``."""
+    torch = _torch()
+    dist, rank, world = _dist_info(group)
+    if dist is None or world < 2:
+        raise RuntimeError("pdm_sharded_p2p_torch needs an initialised process group with >= 2 ranks")
+    ctx = ctx or _ffi.default_context(t.device.index)
+    npd = periods.numel()
+    buf, hdl = _symm_buffer(npd + 2 * world, t.device, group)
+    start, stop, _ = shard_bounds(npd, rank, world)
+    fan = _fanout_struct(hdl, npd, world, rank)
+    stream = torch.cuda.current_stream(t.device).cuda_stream
+    hdl.barrier(channel=0)
+    if stop > start:
+        ctx.pdm_dev_fanout(t.data_ptr(), x.data_ptr(), t.numel(), periods.data_ptr() + 8 * start, stop - start,
+                           nb, nc, start, fan, stream)
+    else:
+        buf[npd + 2 * rank: npd + 2 * rank + 2] = torch.tensor([float("nan"), -1.0], dtype=torch.float64,
+                                                              device=t.device)
+    hdl.barrier(channel=1)
+    return buf[:npd], buf[npd:].view(world, 2)
+
+
+def pdm_sharded_p2p(t, x, periods, nb, nc, device=None, group=None):
+    """numpy in / numpy out wrapper of :func:`pdm_sharded_p2p_torch` (same return as ``pdm_sharded``)."""
+    torch = _torch()
+    ctx = _ffi.default_context(device)
+    dev = torch.device("cuda", ctx.device)
+    tt = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).to(dev)
+    xx = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    pp = torch.as_tensor(np.ascontiguousarray(periods, dtype=np.float64)).to(dev)
+    theta, best = pdm_sharded_p2p_torch(tt, xx, pp, nb, nc, ctx=ctx, group=group)
+    best = best.cpu().numpy()
+    idx, val = reduce_best(best[:, 0], best[:, 1].astype(np.int64), -1)
+    return theta.cpu().numpy(), idx, val
 
 
 def gls_sharded_p2p(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, device=None, group=None):

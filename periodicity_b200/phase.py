@@ -32,7 +32,8 @@ class PDM(object):
     cores : ignored (kept for signature compatibility)
 
     Extra, keyword-only: ``device`` (CUDA ordinal), ``shard`` (split the period
-    grid across ``torch.distributed`` ranks, ``dist.pdm_sharded``).
+    grid across ``torch.distributed`` ranks, ``dist.pdm_sharded``; ``shard="p2p"`` fuses the
+    all-gather into the epilogue kernel over NVLink peer memory, ``dist.pdm_sharded_p2p``).
     """
 
     def __init__(self, nb=5, nc=2, p_min=None, p_max=None, n_periods=1000, oversample=1,
@@ -52,7 +53,8 @@ class PDM(object):
         """theta for each period, in the order given (replaces the Pool map of ``phase.py:185-187``)."""
         if self.shard:
             from . import dist
-            theta, self.argmin_index, self.min_theta = dist.pdm_sharded(
+            sharded = dist.pdm_sharded_p2p if self.shard == "p2p" else dist.pdm_sharded
+            theta, self.argmin_index, self.min_theta = sharded(
                 self.t, self.x, periods, self.nb, self.nc, device=self.device)
         else:
             ctx = _ffi.default_context(self.device)

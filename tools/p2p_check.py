@@ -25,6 +25,12 @@ p2, idx2, val2 = pdist.gls_sharded_p2p(t, 2 * y + 1, None, fmin, df, nf, device=
 ok = ok and idx2 == ridx and np.nanmax(np.abs(p2 - ref)) < 2e-6 * rval
 ls = GLS(fmin=fmin, fmax=fmin + (nf - 1.5) * df, shard="p2p", device=local)(TSeries(t, y))
 ok = ok and np.array_equal(ls.values, ref)
+# PDM: period grid sharded, fused gather vs NCCL gather
+periods = np.linspace(1.0, 11.0, 20_001)
+x = np.sin(2 * np.pi * t / 3.7) + rng.standard_normal(n)
+th_ref, ai_ref, av_ref = pdist.pdm_sharded(t, x, periods, 10, 2, device=local)
+th, ai, av = pdist.pdm_sharded_p2p(t, x, periods, 10, 2, device=local)
+ok = ok and np.array_equal(th, th_ref) and ai == ai_ref and av == av_ref
 # timing: NCCL all-gather path vs fused path, device resident
 td, yd = torch.from_numpy(t).to(dev), torch.from_numpy(y).to(dev)
 start, stop, L = pdist.shard_bounds(nf, rank, world)
