@@ -36,34 +36,49 @@
 // Kernels: pdm_stats_kernel (mean, 1/std), pdm_center_kernel (x' as float),
 // pdm_hist_kernel (hot), pdm_epilogue_kernel (FP64 theta + block argmin),
 // argext_final_kernel<-1>.
+#include <type_traits>
+
 #include "pdc_common.cuh"
 
 namespace pdc {
 
 struct PdmMeta {
   double mean, inv_sd;
+  double q_binned;  // sum of x'^2 over the samples with a finite time stamp (== N - 1 when all are)
+  int bad;          // some t or x is NaN / inf: the histogram kernel then runs its guarded variant
 };
 
 constexpr int PDM_TILE = 1024;        // samples per shared-memory tile
 constexpr int PDM_FLUSH_TILES = 8;    // FP32 histograms are merged into FP64 every 8192 samples
 
 __global__ void __launch_bounds__(1024)
-pdm_stats_kernel(const double* __restrict__ x, long long n, PdmMeta* meta) {
+pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmMeta* meta) {
   __shared__ double scratch[33];
   double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  int bad = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    s += x[i];
+    bad |= !isfinite(x[i]) || !isfinite(t[i]);
+  }
+  bad = __syncthreads_or(bad);
   s = block_sum(s, scratch);
   const double mean = s / (double)n;
-  double q = 0.0;
+  double q = 0.0, qb = 0.0;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     double d = x[i] - mean;
     q = fma(d, d, q);
+    if (bad && isfinite(t[i])) qb = fma(d, d, qb);
   }
   q = block_sum(q, scratch);
+  qb = block_sum(qb, scratch);
   if (threadIdx.x == 0) {
     const double var = q / (double)(n - 1);  // phase.py:165  np.var(values, ddof=1)
     meta->mean = mean;
     meta->inv_sd = 1.0 / sqrt(var);
+    // a sample whose phase is NaN fails every mask of phase.py:138-140 and is in no bin, but still
+    // counts in sigma^2: the epilogue then needs sum x'^2 over the binned samples only
+    meta->q_binned = bad ? qb / var : (double)(n - 1);
+    meta->bad = bad;
   }
 }
 
@@ -80,6 +95,7 @@ struct PdmArgs {
   const double* t;
   const float* xs;
   const double* periods;
+  const PdmMeta* meta;
   double* partial;  // [nsplit][2*m0][np]  rows: count per fine bin, then sum x' per fine bin
   long long n, np;
   int m0, nsplit;
@@ -96,8 +112,8 @@ __device__ __forceinline__ int pdm_bin(double tv, double P, double rP, double m0
   const double r = __fma_rn(-q0, P, tv);
   const double q1 = __fma_rn(r, rP, q0);
   phi = __dadd_rn(q1, -floor(q1));                 // exact; == np.remainder(q1, 1)
-  const double u = __dmul_rn(phi, m0d);
-  const double v = __dadd_rn(u, 6442450944.0);     // 1.5 * 2^32: ulp(v) = 2^-20, low word = rint(u * 2^20)
+  // phi * m0 + 1.5 * 2^32 in ONE rounding: ulp = 2^-20, low word = rint(phi * m0 * 2^20)
+  const double v = __fma_rn(phi, m0d, 6442450944.0);
   const int lo = __double2loint(v);
   key = (unsigned)(lo + 1) << 12;                  // fraction bits of u (+1 ulp), top-aligned
   return lo >> 20;                                 // floor(u) unless ambiguous
@@ -126,8 +142,10 @@ pdm_hist_kernel(const PdmArgs a) {
   const long long pb = blockIdx.x / a.nsplit;
   const long long pi = pb * THREADS + threadIdx.x;
   const bool valid = pi < a.np;
-  const double P = valid ? a.periods[pi] : 1.0;
+  double P = valid ? a.periods[pi] : 1.0;
+  if (!isfinite(1.0 / P) || !isfinite(P)) P = 1.0;  // invalid trial period: theta is set to NaN by the epilogue
   const double rP = 1.0 / P;
+  const bool clamp_bins = a.meta->bad != 0;        // block-uniform
   const double m0d = (double)m0;
   const unsigned kmax = (unsigned)(m0 - 1);
 
@@ -141,27 +159,20 @@ pdm_hist_kernel(const PdmArgs a) {
   float2* col = hist + threadIdx.x;
   double* pcol = a.partial + (long long)split * 2 * m0 * a.np + pi;
 
-  auto update = [&](unsigned k, float xv) {
-    k = min(k, kmax);  // keeps NaN / phi == 1.0 inside the histogram
+  // With finite inputs the bin index is always in range (phi == 1.0 is caught by the ambiguity test and
+  // fixed by pdm_fix_bin), so the guard is compiled in only for the SAFE variant used when some
+  // sample is NaN / inf: a NaN phase is in no bin (every comparison of phase.py:138-140 is false).
+  auto update = [&](auto safe, unsigned k, double phi, float xv) {
+    if (decltype(safe)::value) {
+      if (!(phi == phi)) return;
+      k = min(k, kmax);
+    }
     float2 h = col[k * THREADS];
     h.x += 1.0f;
     h.y += xv;
     col[k * THREADS] = h;
   };
-
-  bool first = true;
-  int tiles_since_flush = 0;
-  long long tile0 = sb;
-  do {
-    long long left = se - tile0;
-    const int cnt = left <= 0 ? 0 : (left < PDM_TILE ? (int)left : PDM_TILE);
-    __syncthreads();
-    for (int i = threadIdx.x; i < cnt; i += THREADS) {
-      s_t[i] = a.t[tile0 + i];
-      s_x[i] = a.xs[tile0 + i];
-    }
-    __syncthreads();
-
+  auto tile_loop = [&](auto safe, int cnt) {
     int i = 0;
     for (; i + 4 <= cnt; i += 4) {
       // four independent phase computations (FP64 chains overlap), then four updates in order
@@ -180,18 +191,35 @@ pdm_hist_kernel(const PdmArgs a) {
         if (e2 < PDM_AMBIG) k2 = pdm_fix_bin(k2, f2, s_thr, m0);
         if (e3 < PDM_AMBIG) k3 = pdm_fix_bin(k3, f3, s_thr, m0);
       }
-      update((unsigned)k0, xv.x);
-      update((unsigned)k1, xv.y);
-      update((unsigned)k2, xv.z);
-      update((unsigned)k3, xv.w);
+      update(safe, (unsigned)k0, f0, xv.x);
+      update(safe, (unsigned)k1, f1, xv.y);
+      update(safe, (unsigned)k2, f2, xv.z);
+      update(safe, (unsigned)k3, f3, xv.w);
     }
     for (; i < cnt; ++i) {
       double f0;
       unsigned e0;
       int k0 = pdm_bin(s_t[i], P, rP, m0d, f0, e0);
       if (e0 < PDM_AMBIG) k0 = pdm_fix_bin(k0, f0, s_thr, m0);
-      update((unsigned)k0, s_x[i]);
+      update(safe, (unsigned)k0, f0, s_x[i]);
     }
+  };
+
+  bool first = true;
+  int tiles_since_flush = 0;
+  long long tile0 = sb;
+  do {
+    long long left = se - tile0;
+    const int cnt = left <= 0 ? 0 : (left < PDM_TILE ? (int)left : PDM_TILE);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += THREADS) {
+      s_t[i] = a.t[tile0 + i];
+      s_x[i] = a.xs[tile0 + i];
+    }
+    __syncthreads();
+
+    if (clamp_bins) tile_loop(std::true_type{}, cnt);
+    else tile_loop(std::false_type{}, cnt);
 
     tile0 += PDM_TILE;
     ++tiles_since_flush;
@@ -219,7 +247,8 @@ pdm_hist_kernel(const PdmArgs a) {
 }
 
 __global__ void __launch_bounds__(256)
-pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, long long np, long long n,
+pdm_epilogue_kernel(double* __restrict__ partial, const double* __restrict__ periods,
+                    const PdmMeta* __restrict__ meta, int nsplit, int m0, int nc, long long np,
                     double* __restrict__ theta_out, double* __restrict__ red_val,
                     long long* __restrict__ red_idx, const pdc_fanout fan, long long fan_offset) {
   __shared__ double sv[32];
@@ -250,7 +279,10 @@ pdm_epilogue_kernel(double* __restrict__ partial, int nsplit, int m0, int nc, lo
       if (N > 1.0) den += N - 1.0;  // phase.py:142,147: bins with <= 1 sample are dropped
     }
     // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
-    theta = ((double)nc * (double)(n - 1) - sq) / den;
+    theta = ((double)nc * meta->q_binned - sq) / den;
+    const double P = periods[pi];
+    if (isinf(P)) theta = 1.0;  // every phase is 0: one populated fine bin holding all samples
+    else if (!isfinite(1.0 / P) || P != P) theta = nan("");  // period 0, denormal or NaN: phases are inf / NaN
     if (theta_out) theta_out[pi] = theta;
     // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
     for (int r = 0; r < fan.world; ++r) fan.power[r][fan_offset + pi] = theta;
@@ -340,7 +372,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk));
 
   PdmMeta* meta = ctx->pdm_meta.as<PdmMeta>();
-  pdm_stats_kernel<<<1, 1024, 0, st>>>(x, n, meta);
+  pdm_stats_kernel<<<1, 1024, 0, st>>>(t, x, n, meta);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
   {
@@ -355,6 +387,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   a.t = t;
   a.xs = ctx->pdm_x.as<float>();
   a.periods = periods;
+  a.meta = meta;
   a.partial = ctx->partial.as<double>();
   a.n = n;
   a.np = np;
@@ -375,8 +408,8 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   pdc_fanout fan;
   if (fanout) fan = *fanout;
   else fan.world = 0;
-  pdm_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(a.partial, nsplit, m0, nc, np, (long long)n, theta_out, red_val,
-                                                      red_idx, fan, (long long)fan_offset);
+  pdm_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(a.partial, periods, meta, nsplit, m0, nc, np, theta_out,
+                                                      red_val, red_idx, fan, (long long)fan_offset);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
   if (fanout) {

@@ -152,3 +152,37 @@ def test_outlier_heavy_values(gpu_ctx):
     ref = cport.pdm(t, x, periods, 10, 2)
     np.testing.assert_allclose(th, ref, rtol=TOL)
     assert am == np.nanargmin(ref)
+
+
+def test_degenerate_trial_periods_follow_the_reference_classes(gpu_ctx):
+    """P = 0 / denormal / NaN give NaN (phases are inf or NaN, phase.py:131), P = inf gives 1, P < 0 works."""
+    t, x = synth(3000, 100.0, 18)
+    periods = np.array([0.0, 1.0, np.inf, np.nan, 2.0, 1e-320, -3.0, 3.7])
+    th, am, mn = gpu_ctx.pdm(t, x, periods, 5, 2)
+    with np.errstate(all="ignore"):
+        ref = cport.pdm(t, x, periods, 5, 2)
+    np.testing.assert_array_equal(np.isnan(th), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(th[ok], ref[ok], rtol=TOL)
+    assert am == np.nanargmin(ref) and mn == th[am]
+
+
+def test_non_finite_samples_do_not_corrupt_memory(gpu_ctx):
+    """NaN / inf time stamps are in no bin (every mask of phase.py:138-140 is false); NaN values poison
+    sigma and hence every theta (phase.py:165).  Either way the guarded kernel variant runs."""
+    t, x = synth(20_000, 300.0, 19)
+    periods = np.linspace(1.0, 11.0, 700)
+    base, _, _ = gpu_ctx.pdm(t, x, periods, 10, 2)
+    tb = t.copy()
+    tb[[5, 777, 19_999]] = [np.nan, np.inf, -np.inf]
+    th, am, _ = gpu_ctx.pdm(tb, x, periods, 10, 2)
+    with np.errstate(all="ignore"):
+        ref = cport.pdm(tb, x, periods, 10, 2)
+    np.testing.assert_allclose(th, ref, rtol=TOL)
+    assert am == np.nanargmin(ref)
+    xb = x.copy()
+    xb[123] = np.nan
+    th, am, _ = gpu_ctx.pdm(t, xb, periods, 10, 2)
+    assert np.isnan(th).all()
+    again, _, _ = gpu_ctx.pdm(t, x, periods, 10, 2)      # the ctx is still healthy and deterministic
+    np.testing.assert_array_equal(again, base)
