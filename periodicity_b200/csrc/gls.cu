@@ -30,7 +30,24 @@
 //
 // Algorithmic work of the hot kernel: per sample*frequency evaluation
 // 4 FP32 instructions for the rotation + 6 for the sums (7 with weights).
+#include <type_traits>
+
 #include "gls_common.cuh"
+
+// Three-term strip: source order of the eight statements of one (sample, frequency) step.  ptxas
+// derives its register allocation and schedule from it, and on B200 the resulting register-file
+// operand conflicts ("dispatch" stalls) move the kernel time between 1.90 and 2.47 ms on the C2
+// shape.  The default is the best of ~250 orders timed on B200 for BOTH the plain and the weighted
+// kernel (tools/build_variants.sh + tools/tune_strip.py; profiles/tune_strip_r01.txt).
+#ifndef PDC_TT_ORDER
+#define PDC_TT_ORDER ST_CC ST_YC ST_RC ST_YS ST_RS ST_S ST_CS ST_C
+#endif
+#ifndef PDC_TT_ORDER_W  /* weighted kernel (all eight statements are FFMA) */
+#define PDC_TT_ORDER_W PDC_TT_ORDER
+#endif
+#ifndef PDC_GEOM0_K
+#define PDC_GEOM0_K 16  /* strip length of the default geometry */
+#endif
 
 namespace pdc {
 
@@ -40,7 +57,7 @@ namespace pdc {
 __global__ void __launch_bounds__(1024)
 gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y,
                  const double* __restrict__ w, GlsCurve* curves, unsigned flags,
-                 long long j0, long long nf) {
+                 long long j0, long long nf, int allow_three_term) {
   __shared__ double scratch[33];
   GlsCurve& cv = curves[blockIdx.x];
   const long long b = cv.begin, n = cv.n;
@@ -76,6 +93,10 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y,
     cv.ymean = ymean;
     cv.yy = yy;
     cv.inv_rms = yy > 0.0 ? rsqrt(yy) : 0.0;
+    const double span = cv.df * (tmax - tmin);  // turns swept by the per-index step angle over the samples
+    const bool tt = allow_three_term && cv.df > 0.0 && span <= GLS_TT_MAX_SPAN;
+    cv.three_term = tt;
+    cv.gamma = tt ? 0.25 - 0.5 * span : 0.0;
   }
 }
 
@@ -92,14 +113,22 @@ gls_records_kernel(const double* __restrict__ t, const double* __restrict__ y,
        i += (long long)gridDim.x * blockDim.x) {
     const long long g = cv.begin + i;
     const double tt = t[g] - cv.tmin;  // power is shift invariant; the reference shifts too (spectral.py:19-21)
-    const double b = frac_of_product(cv.df, tt);
+    // step of the phase per frequency index, in turns.  gamma is the same for every sample of the
+    // curve, i.e. a per-frequency phase origin, which the power does not depend on (the tau offset
+    // of spectral.py:113-119 absorbs it).
+    const double b = frac_of_product(cv.df, tt) + cv.gamma;
     double sb, cb;
     sincospi(2.0 * b, &sb, &cb);
     const double yv = (y[g] - cv.ymean) * cv.inv_rms;  // unit weighted RMS before the FP32 cast
     float4 r;
     rec_set(r, rec_slot(REC_CR), (float)cb);
     rec_set(r, rec_slot(REC_SR), (float)sb);
-    if (w) {
+    if (w && cv.three_term) {
+      // the three-term strip carries (sqrt(w') cos, sqrt(w') sin): every sum is then one FFMA
+      const double sw = sqrt(w[g] * wscale);
+      rec_set(r, rec_slot(REC_Y), (float)(sw * yv));
+      rec_set(r, rec_slot(REC_W), (float)sw);
+    } else if (w) {
       const double wn = w[g] * wscale;
       rec_set(r, rec_slot(REC_Y), (float)(wn * yv));
       rec_set(r, rec_slot(REC_W), (float)wn);
@@ -194,6 +223,9 @@ gls_strip_kernel(const GlsMainArgs a) {
   const double fB = fmin + (double)(a.j0 + jB) * df;  // spectral.py:36: f = fmin + df * arange(nf)
   const int lK = threadIdx.x * K;
   const double lKd = (double)lK;
+  const bool three_term = cvp->three_term != 0;  // block-uniform
+  double gB = (double)(a.j0 + jB) * cvp->gamma;  // phase origin of the block's first frequency (turns)
+  gB -= floor(gB);
 
   double* pbase = a.partial + (long long)split * 6 * a.nf_tot + (long long)curve * a.nf + jB + lK;
   const long long jrem = a.nf - (jB + lK);  // strip entries with k < jrem are real frequencies
@@ -210,7 +242,7 @@ gls_strip_kernel(const GlsMainArgs a) {
     __syncthreads();  // previous tile fully consumed
     for (int i = threadIdx.x; i < cnt; i += THREADS) {
       const double2 r1 = a.rec1[cbegin + tile0 + i];
-      s_ab[i] = make_double2(frac_of_product(fB, r1.x), r1.y);
+      s_ab[i] = make_double2(frac_of_product(fB, r1.x) + gB, r1.y);
       s_r2[i] = a.rec2[cbegin + tile0 + i];
     }
     __syncthreads();
@@ -219,41 +251,91 @@ gls_strip_kernel(const GlsMainArgs a) {
 #pragma unroll
     for (int k = 0; k < K; ++k) aC[k] = aS[k] = aYC[k] = aYS[k] = aCC[k] = aCS[k] = 0.f;
 
-    // One sample: K accumulations + K-1 rotations.  The sums are the per-frequency
-    // {C, S, YC, YS, CC, CS}; (c, s) enters as the exact seed at the strip's first frequency.
-    auto strip = [&](float c, float s, const float4 r2) {
+    // One sample: K accumulations and K-1 steps along the frequency axis.  The sums are the
+    // per-frequency {C, S, YC, YS, CC, CS}; (c, s) enters as the exact seed at the strip's first
+    // frequency.  Two forms of the step (block-uniform choice, GlsCurve::three_term):
+    //  * rotation        (c, s) <- (c cr - s sr, s cr + c sr)                  2 FMUL + 2 FFMA
+    //  * three-term      c[k+1] = 2 cr c[k] - c[k-1], same for s               2 FFMA
+    //    (Chebyshev recurrence; rounding errors grow by 1/|sin step|, bounded because the step
+    //    angles were centred on a quarter turn by GlsCurve::gamma).  Being linear, it also carries
+    //    a factor sqrt(w') for free, which turns every weighted sum into a single FFMA.
+    auto accumulate = [&](int k, float c, float s, float yv, float wv) {  // rotation form
+      if (WEIGHTED) {
+        const float wc = wv * c;
+        aC[k] += wc;
+        aS[k] = fmaf(wv, s, aS[k]);
+        aCC[k] = fmaf(wc, c, aCC[k]);
+        aCS[k] = fmaf(wc, s, aCS[k]);
+      } else {
+        aC[k] += c;
+        aS[k] += s;
+        aCC[k] = fmaf(c, c, aCC[k]);
+        aCS[k] = fmaf(c, s, aCS[k]);
+      }
+      aYC[k] = fmaf(yv, c, aYC[k]);
+      aYS[k] = fmaf(yv, s, aYS[k]);
+    };
+    auto strip = [&](auto tt_tag, float c, float s, const float4 r2) {
+      constexpr bool TT = decltype(tt_tag)::value;
       const float cr = rec_get(r2, rec_slot(REC_CR)), sr = rec_get(r2, rec_slot(REC_SR));
       const float yv = rec_get(r2, rec_slot(REC_Y)), wv = rec_get(r2, rec_slot(REC_W));
       (void)wv;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if (WEIGHTED) {
-          const float wc = wv * c;
-          aC[k] += wc;
-          aS[k] = fmaf(wv, s, aS[k]);
-          aCC[k] = fmaf(wc, c, aCC[k]);
-          aCS[k] = fmaf(wc, s, aCS[k]);
-        } else {
-          aC[k] += c;
-          aS[k] += s;
-          aCC[k] = fmaf(c, c, aCC[k]);
-          aCS[k] = fmaf(c, s, aCS[k]);
+      if (TT) {
+        if (WEIGHTED) {  // (c, s) carry sqrt(w'); the record holds yv = sqrt(w') y', wv = sqrt(w')
+          c *= wv;
+          s *= wv;
         }
-        aYC[k] = fmaf(yv, c, aYC[k]);
-        aYS[k] = fmaf(yv, s, aYS[k]);
-        if (k + 1 < K) {
-          const float c2 = fmaf(c, cr, -(s * sr));
-          const float s2 = fmaf(s, cr, c * sr);
-          c = c2;
-          s = s2;
+        const float tc = cr + cr;
+        float cp = c, sp = s;                       // index k - 1
+        c = fmaf(cp, cr, -(sp * sr));               // index 1 by one rotation
+        s = fmaf(sp, cr, cp * sr);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float cc = k == 0 ? cp : c, ss = k == 0 ? sp : s;
+          float cn = 0.f, sn = 0.f;
+          const bool step = k >= 1 && k + 1 < K;
+#define ST_C  if (WEIGHTED) aC[k] = fmaf(cc, wv, aC[k]); else aC[k] += cc;
+#define ST_S  if (WEIGHTED) aS[k] = fmaf(ss, wv, aS[k]); else aS[k] += ss;
+#define ST_YC aYC[k] = fmaf(cc, yv, aYC[k]);
+#define ST_YS aYS[k] = fmaf(ss, yv, aYS[k]);
+#define ST_CC aCC[k] = fmaf(cc, cc, aCC[k]);
+#define ST_CS aCS[k] = fmaf(ss, cc, aCS[k]);
+#define ST_RC if (step) cn = fmaf(c, tc, -cp);
+#define ST_RS if (step) sn = fmaf(s, tc, -sp);
+          if (WEIGHTED) { PDC_TT_ORDER_W } else { PDC_TT_ORDER }
+#undef ST_C
+#undef ST_S
+#undef ST_YC
+#undef ST_YS
+#undef ST_CC
+#undef ST_CS
+#undef ST_RC
+#undef ST_RS
+          if (step) {
+            cp = c;
+            sp = s;
+            c = cn;
+            s = sn;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          accumulate(k, c, s, yv, wv);
+          if (k + 1 < K) {
+            const float c2 = fmaf(c, cr, -(s * sr));
+            const float s2 = fmaf(s, cr, c * sr);
+            c = c2;
+            s = s2;
+          }
         }
       }
     };
 
-    if (cnt > 0) {
-      // Software pipeline, two samples per trip (ping-pong registers, no moves): the exact
-      // seed of the next sample is computed while the current strip runs.  The tile arrays
-      // carry two pad entries so the look-ahead never needs a bounds check.
+    // Software pipeline, two samples per trip (ping-pong registers, no moves): the exact
+    // seed of the next sample is computed while the current strip runs.  The tile arrays
+    // carry two pad entries so the look-ahead never needs a bounds check.
+    auto run_tile = [&](auto tt_tag) {
       float c0, s0, c1, s1;
       float4 ra = s_r2[0], rb;
       {
@@ -267,15 +349,19 @@ gls_strip_kernel(const GlsMainArgs a) {
           rb = s_r2[i + 1];
           gls_seed(ab.x, ab.y, lKd, c1, s1);
         }
-        strip(c0, s0, ra);
+        strip(tt_tag, c0, s0, ra);
         {
           const double2 ab = s_ab[i + 2];
           ra = s_r2[i + 2];
           gls_seed(ab.x, ab.y, lKd, c0, s0);
         }
-        strip(c1, s1, rb);
+        strip(tt_tag, c1, s1, rb);
       }
-      if (i < cnt) strip(c0, s0, ra);
+      if (i < cnt) strip(tt_tag, c0, s0, ra);
+    };
+    if (cnt > 0) {
+      if (three_term) run_tile(std::true_type{});
+      else run_tile(std::false_type{});
     }
 
     // flush this tile's FP32 sums into the FP64 partials this item owns
@@ -368,7 +454,7 @@ struct GlsGeom {
   int K, threads, minb;
 };
 static const GlsGeom kGlsGeoms[] = {
-    {16, 128, 2},  // 0: default -- 142 registers, 3 blocks/SM; best of the 16 geometries tried in round 1
+    {PDC_GEOM0_K, 128, 2},  // 0: default -- 142 registers, 3 blocks/SM; best of the 16 geometries tried in round 1
     {8, 64, 8},    // 1: small problems -- 512 frequencies per block so that tiny grids still fill the SMs
     {16, 128, 4},  // 2: capped at 128 registers (4 blocks/SM): ~4 % slower, more bank conflicts
     {20, 128, 2},  // 3: longer strips: fewer seeds per evaluation, ~2 % slower overall
@@ -398,11 +484,11 @@ static int launch_strip_t(pdc_ctx* ctx, const GlsMainArgs& a, bool weighted, lon
 }
 
 #define PDC_GLS_GEOM_CASES(X) \
-  X(0, 16, 128, 2) X(1, 8, 64, 8) X(2, 16, 128, 4) X(3, 20, 128, 2) X(4, 12, 128, 2) X(5, 8, 256, 4)
+  X(0, PDC_GEOM0_K, 128, 2) X(1, 8, 64, 8) X(2, 16, 128, 4) X(3, 20, 128, 2) X(4, 12, 128, 2) X(5, 8, 256, 4)
 
 #ifdef PDC_ONLY_DEFAULT_GEOM
 #undef PDC_GLS_GEOM_CASES
-#define PDC_GLS_GEOM_CASES(X) X(0, 16, 128, 2)
+#define PDC_GLS_GEOM_CASES(X) X(0, PDC_GEOM0_K, 128, 2)
 #endif
 
 static int strip_occupancy(int geom, bool weighted) {
@@ -526,6 +612,8 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     hc[b].psd_scale = psd_scale_host ? psd_scale_host[b] : 1.0;
     hc[b].tmin = hc[b].tmax = hc[b].wsum = hc[b].ymean = hc[b].yy = hc[b].inv_rms = 0.0;
     hc[b].low_begin = hc[b].low_count = 0;
+    hc[b].gamma = 0.0;
+    hc[b].three_term = hc[b].pad_ = 0;
   }
   GlsCurve* dc = ctx->gls_curves.as<GlsCurve>();
   PDC_CUDA(cudaMemcpyAsync(dc, hc, sizeof(GlsCurve) * B, cudaMemcpyHostToDevice, st));
@@ -535,7 +623,8 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   const double* yy = y + off0;
   const double* ww = w ? w + off0 : nullptr;
 
-  gls_stats_kernel<<<(unsigned)B, 1024, 0, st>>>(tt, yy, ww, dc, flags, (long long)j0, (long long)nf);
+  gls_stats_kernel<<<(unsigned)B, 1024, 0, st>>>(tt, yy, ww, dc, flags, (long long)j0, (long long)nf,
+                                                 ctx->gls_three_term ? 1 : 0);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
 

@@ -13,6 +13,11 @@ struct GlsCurve {
   // filled on the device by gls_stats_kernel
   double tmin, tmax, wsum, ymean, yy, inv_rms;
   int low_begin, low_count;  // frequencies [low_begin, low_begin + low_count) of this call go through FP64
+  // Three-term recurrence (see gls.cu): per-frequency-index phase offset in cycles that centres the
+  // per-sample step angles 2 pi (df (t - tmin) + gamma) on a quarter turn; three_term == 0 when the step
+  // angles span too much of the circle and the strip kernel has to use the plain rotation.
+  double gamma;
+  int three_term, pad_;
 };
 
 // Order of (cos, sin, y', w') inside the float4 sample record.  The record is loaded with one
@@ -40,6 +45,11 @@ __host__ __device__ __forceinline__ void rec_set(float4& r, int slot, float v) {
 constexpr int REC_CR = 0, REC_SR = 1, REC_Y = 2, REC_W = 3;
 
 constexpr int GLS_TILE = 1024;  // samples per shared-memory tile == FP32 flush interval
+
+// The three-term recurrence c[k+1] = 2 cos(d) c[k] - c[k-1] amplifies rounding errors by 1 / |sin d|;
+// it is used when every step angle d_i can be brought within +-GLS_TT_MAX_SPAN/2 turns of a quarter
+// turn (|sin d| >= 0.48), i.e. when df * (tmax - tmin) <= GLS_TT_MAX_SPAN (n >= 3 samples per peak).
+constexpr double GLS_TT_MAX_SPAN = 0.34;
 
 // Frequencies with |f| * (tmax - tmin) < GLS_LOW_CYCLES see less than one cycle over the
 // baseline: there CC - C^2 and SS - S^2 (spectral.py:125-127) cancel almost completely

@@ -60,6 +60,7 @@ struct pdc_ctx {
   int gls_occ[32][2] = {};  // cached blocks/SM of each strip-kernel variant [geom][weighted]
   int gls_nsplit_override = 0;
   bool gls_geom_forced = false;  // PDC_GLS_GEOM given: no automatic small-problem geometry
+  bool gls_three_term = true;  // env PDC_GLS_THREE_TERM=0 forces the rotation form of the strip step (tuning aid)
   int gls_geom = 0;  // index into kGlsGeoms (gls.cu); env PDC_GLS_GEOM overrides at ctx creation (tuning aid)
 
   // CUDA-event timing of the dominant kernel (GLS strip / PDM histogram), recorded on the

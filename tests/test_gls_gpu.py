@@ -402,3 +402,48 @@ def test_calls_on_different_streams_share_a_ctx_safely(gpu_ctx):
     for p1, p2 in outs:
         np.testing.assert_array_equal(p1.cpu().numpy(), want1)
         np.testing.assert_array_equal(p2.cpu().numpy(), want2)
+
+
+@pytest.mark.parametrize("n_per_peak,weighted", [(1.0, False), (2.0, True), (2.9, False), (3.0, True), (3.1, False),
+                                                 (10.0, True), (40.0, False)])
+def test_grid_density_selects_strip_step_form(gpu_ctx, n_per_peak, weighted):
+    """df * baseline <= 0.34 turns uses the three-term recurrence along the frequency axis, coarser grids
+    (n < 3 samples per peak, spectral.py:88) the plain rotation: both against the formula oracle."""
+    N, nf = 3000, 6000
+    rng = np.random.default_rng(21)
+    t = np.sort(rng.uniform(0, 50.0, N))
+    df = 1 / (t[-1] - t[0]) / n_per_peak
+    fmin = 0.5 * df
+    y = 3 + np.sin(2 * np.pi * (fmin + 0.41 * nf * df) * t) + 0.7 * rng.standard_normal(N)
+    err = rng.uniform(0.5, 1.5, N) if weighted else None
+    p, am, _ = gpu_ctx.gls(t, y, None if err is None else err ** -2.0, fmin, df, nf)
+    ref = cport.gls_exact(t, y, err, fmin, df, nf, True)
+    assert_power_close(p, ref)
+    assert am == np.nanargmax(ref)
+
+
+def test_three_term_and_rotation_forms_agree(monkeypatch):
+    """PDC_GLS_THREE_TERM=0 (read at ctx creation) forces the rotation form: same periodogram within tolerance."""
+    from periodicity_b200 import _ffi
+    t, y, fmin, df = synth(20_000, 400.0, 30_000, 1.0, 22)
+    w = np.random.default_rng(23).uniform(0.5, 2.0, t.size)
+    a = _ffi.Context(0)
+    monkeypatch.setenv("PDC_GLS_THREE_TERM", "0")
+    b = _ffi.Context(0)
+    for ww in (None, w):
+        pa, ia, _ = a.gls(t, y, ww, fmin, df, 30_000)
+        pb, ib, _ = b.gls(t, y, ww, fmin, df, 30_000)
+        assert ia == ib
+        assert np.max(np.abs(pa - pb)) <= 2e-6 * np.max(pb)
+    lo = ia - 200
+    ref = cport.gls_exact(t, y, None if ww is None else ww ** -0.5, fmin + lo * df, df, 400, True)
+    assert_power_close(pa[lo:lo + 400], ref)
+
+
+def test_grid_crossing_zero_frequency(gpu_ctx):
+    """Negative and sub-cycle frequencies in one grid (three-term form, FP64 low-frequency bins)."""
+    t, y, fmin, df = synth(2000, 80.0, 4000, 0.5, 24)
+    p2, am2, _ = gpu_ctx.gls(t, y, None, -1000.25 * df, df, 4000)
+    ref2 = cport.gls_exact(t, y, None, -1000.25 * df, df, 4000, True)
+    assert_power_close(p2, ref2)
+    assert am2 == np.nanargmax(ref2)
