@@ -40,6 +40,11 @@ if ROOT not in sys.path:
 FLOP_PER_EVAL_GLS = 20.0      # 12 FP32 instructions = 20 FLOP per sample*frequency
 OPS_PER_EVAL_PDM = 8.0        # 8 ops per sample*period
 FP32_PEAK_TFLOPS_MEASURED = 72.3   # profiles/pipes_r01.json: 36,172 GFFMA/s x 2
+FP32_PEAK_GINSTR_MEASURED = 36172.0  # same measurement as thread-instructions/s (125 per clk per SM)
+# what gls_strip_kernel<16,128> executes in its three-term form (SASS hot loop: 282 instructions per
+# 2 samples x 16 frequencies; 6 FFMA + 2 FADD per evaluation): the 20 FLOP of the accounting figure are NOT all executed
+GLS_EXECUTED_INSTR_PER_EVAL = 282.0 / 32.0
+GLS_EXECUTED_FLOP_PER_EVAL = 14.0
 PDM_PEAK_GEVALS_MEASURED = 2256.3  # profiles/pipes_r01.json smem_private_rmw_f2: 64-bit private-column RMW, updates/s
 
 
@@ -531,6 +536,13 @@ def main():
                          "per evaluation of the accounting figure are not all executed; frac > 1 is expected")
                 if kind == "gls_multi" else None,
                 "evals_per_s_kernel": units_local / (main_kernel_ms * 1e-3),
+                "executed": None if kind == "gls_multi" else {
+                    "instr_per_eval": GLS_EXECUTED_INSTR_PER_EVAL, "flop_per_eval": GLS_EXECUTED_FLOP_PER_EVAL,
+                    "issue_frac": units_local * GLS_EXECUTED_INSTR_PER_EVAL / (main_kernel_ms * 1e-3) / 1e9
+                    / FP32_PEAK_GINSTR_MEASURED,
+                    "note": "three-term recurrence along the frequency axis: 8 FP32 instructions per evaluation "
+                            "instead of the 12 of SURVEY 8d's accounting figure; `frac` stays on the 20-FLOP figure "
+                            "as SURVEY 8d prescribes, issue_frac = executed instructions / measured FP32 issue peak"},
                 "peak_source": "profiles/pipes_r01.json ffma_shared_operands x2 FLOP (measured on this pool's B200; "
                                "MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5)",
                 "hbm": {"achieved_gbs": (32.0 * n + 6 * 8 * 2 * (units_local / n)) / (main_kernel_ms * 1e-3) / 1e9,

@@ -45,6 +45,7 @@ namespace pdc {
 struct PdmMeta {
   double mean, inv_sd;
   double q_binned;  // sum of x'^2 over the samples with a finite time stamp (== N - 1 when all are)
+  double t_absmax;  // max |t| over the finite time stamps: decides whether the 32-bit fixed-point phase is usable
   int bad;          // some t or x is NaN / inf: the histogram kernel then runs its guarded variant
 };
 
@@ -54,14 +55,16 @@ constexpr int PDM_FLUSH_TILES = 8;    // FP32 histograms are merged into FP64 ev
 __global__ void __launch_bounds__(1024)
 pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmMeta* meta) {
   __shared__ double scratch[33];
-  double s = 0.0;
+  double s = 0.0, tneg = 0.0;
   int bad = 0;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     s += x[i];
     bad |= !isfinite(x[i]) || !isfinite(t[i]);
+    if (isfinite(t[i])) tneg = fmin(tneg, -fabs(t[i]));
   }
   bad = __syncthreads_or(bad);
   s = block_sum(s, scratch);
+  const double tabs = -block_min(tneg, scratch);
   const double mean = s / (double)n;
   double q = 0.0, qb = 0.0;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
@@ -79,6 +82,7 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
     // counts in sigma^2: the epilogue then needs sum x'^2 over the binned samples only
     meta->q_binned = bad ? qb / var : (double)(n - 1);
     meta->bad = bad;
+    meta->t_absmax = tabs;
   }
 }
 
@@ -124,6 +128,23 @@ __device__ __forceinline__ int pdm_fix_bin(int k, double phi, const double* s_th
   if (phi < s_thr[k]) --k;
   else if (k < m0 - 1 && phi >= s_thr[k + 1]) ++k;
   return k;
+}
+
+// Fast path: |t / P| < 2^19 for every sample.  fma(t, 1/P, 1.5 * 2^20) leaves frac(t / P) in units of 2^-32
+// turn in the low mantissa word (one DFMA, as in the GLS seed), a 32 x 32 -> 64 bit multiply by m0
+// then gives the fine bin (high word) and the position inside the bin (low word).  The fixed-point
+// phase is within 2^-32 + |t/P| 2^-52 of the reference's (t / P) % 1, so the bin can differ only
+// if the phase lies within PDM_FAST_GUARD * 2^-32 of a bin edge: those samples (about m0 * 4e-9 of
+// them) are re-binned by the exact path below.
+constexpr double PDM_FAST_MAGIC = 1572864.0;   // 1.5 * 2^20
+constexpr double PDM_FAST_LIMIT = 262144.0;    // |t / P| < 2^18 keeps the sum inside [2^20, 2^21)
+constexpr unsigned PDM_FAST_GUARD = 4u;
+
+__device__ __forceinline__ unsigned pdm_bin_fast(double tv, double rP, unsigned m0u, unsigned guard, unsigned& edge) {
+  const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, PDM_FAST_MAGIC));
+  const unsigned long long w = (unsigned long long)u * m0u;
+  edge = ((unsigned)w + guard) < 2u * guard ? 1u : 0u;   // within guard of either edge of the bin
+  return (unsigned)(w >> 32);
 }
 
 // Shared-memory layout: hist[bin][THREADS] float2 = (count, sum x'): a thread's column is
@@ -172,6 +193,52 @@ pdm_hist_kernel(const PdmArgs a) {
     h.y += xv;
     col[k * THREADS] = h;
   };
+  // warp-uniform: every period of this warp keeps |t / P| small enough for the fixed-point phase
+  const bool fast = __all_sync(0xffffffffu, fabs(rP) * a.meta->t_absmax < PDM_FAST_LIMIT) != 0;
+  const unsigned m0u = (unsigned)m0, guard = PDM_FAST_GUARD * m0u;
+  auto exact_bin = [&](double tv, double& phi) {
+    unsigned e;
+    int k = pdm_bin(tv, P, rP, m0d, phi, e);
+    if (e < PDM_AMBIG) k = pdm_fix_bin(k, phi, s_thr, m0);
+    return (unsigned)k;
+  };
+  auto tile_loop_fast = [&](auto safe, int cnt) {
+    constexpr bool SAFE = decltype(safe)::value;
+    int i = 0;
+    for (; i + 4 <= cnt; i += 4) {
+      const double2 ta = *reinterpret_cast<const double2*>(s_t + i);
+      const double2 tb = *reinterpret_cast<const double2*>(s_t + i + 2);
+      const float4 xv = *reinterpret_cast<const float4*>(s_x + i);
+      unsigned e0, e1, e2, e3;
+      unsigned k0 = pdm_bin_fast(ta.x, rP, m0u, guard, e0);
+      unsigned k1 = pdm_bin_fast(ta.y, rP, m0u, guard, e1);
+      unsigned k2 = pdm_bin_fast(tb.x, rP, m0u, guard, e2);
+      unsigned k3 = pdm_bin_fast(tb.y, rP, m0u, guard, e3);
+      double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;   // only the guarded variant looks at them (NaN = skip)
+      if (SAFE) {
+        f0 = ta.x - ta.x; f1 = ta.y - ta.y; f2 = tb.x - tb.x; f3 = tb.y - tb.y;   // NaN for NaN / inf stamps
+      }
+      if (e0 | e1 | e2 | e3) {  // rare: a sample sits on a bin edge
+        double ph;
+        if (e0) k0 = exact_bin(ta.x, ph);
+        if (e1) k1 = exact_bin(ta.y, ph);
+        if (e2) k2 = exact_bin(tb.x, ph);
+        if (e3) k3 = exact_bin(tb.y, ph);
+      }
+      update(safe, k0, f0, xv.x);
+      update(safe, k1, f1, xv.y);
+      update(safe, k2, f2, xv.z);
+      update(safe, k3, f3, xv.w);
+    }
+    for (; i < cnt; ++i) {
+      unsigned e0;
+      const double tv = s_t[i];
+      unsigned k0 = pdm_bin_fast(tv, rP, m0u, guard, e0);
+      double ph;
+      if (e0) k0 = exact_bin(tv, ph);
+      update(safe, k0, SAFE ? tv - tv : 0.0, s_x[i]);
+    }
+  };
   auto tile_loop = [&](auto safe, int cnt) {
     int i = 0;
     for (; i + 4 <= cnt; i += 4) {
@@ -218,8 +285,13 @@ pdm_hist_kernel(const PdmArgs a) {
     }
     __syncthreads();
 
-    if (clamp_bins) tile_loop(std::true_type{}, cnt);
-    else tile_loop(std::false_type{}, cnt);
+    if (fast) {
+      if (clamp_bins) tile_loop_fast(std::true_type{}, cnt);
+      else tile_loop_fast(std::false_type{}, cnt);
+    } else {
+      if (clamp_bins) tile_loop(std::true_type{}, cnt);
+      else tile_loop(std::false_type{}, cnt);
+    }
 
     tile0 += PDM_TILE;
     ++tiles_since_flush;
