@@ -8,6 +8,8 @@
  *              `GLS.__call__`          (src/periodicity/spectral.py:109-132)
  *   pdc_pdm*   replaces `pool.map(self._pdm, self.periods)` in `PDM.__call__`
  *                                      (src/periodicity/phase.py:185-187,128-149)
+ *   pdc_stringlength*  replaces `pool.map(self._stringlength, periods)` in
+ *              `StringLength.__call__` (src/periodicity/phase.py:68-70,45-51)
  *
  * Everything before those lines (signal coercion, grid derivation, weight
  * normalisation) and after them (FSeries wrap, sub-harmonic averaging) stays in
@@ -205,6 +207,26 @@ PDC_API int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
 PDC_API int pdc_pdm_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
                 const double* periods, int64_t np, int nb, int nc,
                 double* theta_out, int64_t* argmin_out, double* min_out, void* stream);
+
+/*
+ * String Length (Dworetsky 1983): `StringLength._stringlength` (phase.py:45-51) for each trial
+ * period, replacing `pool.map(self._stringlength, periods)` (phase.py:68-70).
+ *
+ *   t         float64[n]   sample times
+ *   m         float64[n]   the scaled signal `self.m` of phase.py:64-65 (computed by the caller)
+ *   periods   float64[np]  trial periods (phase.py:67; any order, all != 0)
+ *   ell_out   float64[np]  string length in the order of `periods`:
+ *               phi = (t / P) % 1, samples stably sorted by phi (core.py:543-544,473-477),
+ *               sum_j hypot(m[j+1] - m[j], phi[j+1] - phi[j]) with indices mod n (np.roll)
+ *   argmin_out / min_out   shortest string (NaN ignored, first occurrence).  May be NULL.
+ */
+PDC_API int pdc_stringlength(pdc_ctx* ctx, const double* t, const double* m, int64_t n,
+                             const double* periods, int64_t np,
+                             double* ell_out, int64_t* argmin_out, double* min_out);
+
+PDC_API int pdc_stringlength_dev(pdc_ctx* ctx, const double* t, const double* m, int64_t n,
+                                 const double* periods, int64_t np,
+                                 double* ell_out, int64_t* argmin_out, double* min_out, void* stream);
 
 /*
  * The k highest local maxima of each row of a row-major float64 [rows, n] array

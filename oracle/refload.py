@@ -10,7 +10,8 @@ xarray, which is not installed).  ``spectral.py`` and ``phase.py`` only need
 numpy plus ``TSeries`` / ``FSeries`` from ``.core`` (``spectral.py:1-5``,
 ``phase.py:1-5``), so they are executed as-is with ``periodicity.core`` seeded
 by the numpy-only stand-in below, which carries exactly the attributes the two
-files touch: ``time, values, size, baseline, median_dt, __len__, copy``
+files touch: ``time, values, size, baseline, median_dt, __len__, copy`` (+ ``fold, max, min`` and scalar
+arithmetic for ``StringLength``, see the note in the class)
 (``core.py:60-66,94-99,144-145,460-511``) and ``frequency, values``
 (``core.py:859-889``).
 """
@@ -67,6 +68,26 @@ class _StubTSeries:
         return _StubTSeries(self.time, self.values + k, assume_sorted=True)
 
     __radd__ = __add__
+
+    # --- what StringLength touches (phase.py:45-51,64-66) -------------------------------------
+    # core.py:543-544; the constructor re-sorts by phase (core.py:473-477)
+    def fold(self, period, t0=0):
+        return _StubTSeries(((self.time - t0) / period) % 1, self.values)
+
+    # ASSUMPTION: scalar extrema.  The reference's Signal.max() returns a one-sample series
+    # (core.py:217-220) that `signal - signal.max()` cannot broadcast (core.py:175-178); scalars are
+    # what phase.py:64-65 needs to mean anything.
+    def max(self):
+        return np.nanmax(self.values)
+
+    def min(self):
+        return np.nanmin(self.values)
+
+    def __sub__(self, k):
+        return _StubTSeries(self.time, self.values - k, assume_sorted=True)
+
+    def __truediv__(self, k):
+        return _StubTSeries(self.time, self.values / k, assume_sorted=True)
 
 
 class _StubFSeries:

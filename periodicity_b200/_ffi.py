@@ -71,6 +71,12 @@ SIGNATURES = {
     "pdc_pdm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_stringlength": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p]),
+    "pdc_stringlength_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                            ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_peaks_topk": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_peaks_topk_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
@@ -244,6 +250,25 @@ class Context:
             _check(self._lib.pdc_pdm(self._h, _ptr(t), _ptr(x), t.size, _ptr(periods), periods.size,
                                      int(nb), int(nc), _ptr(theta), ctypes.addressof(arg), ctypes.addressof(mn)))
         return theta, arg.value, mn.value
+
+    def stringlength(self, t, m, periods):
+        """String length of the scaled signal ``m`` for each trial period (host arrays)."""
+        t = _f64(t)
+        m = _f64(m)
+        periods = _f64(periods)
+        if t.ndim != 1 or t.shape != m.shape:
+            raise ValueError("Input arrays have incompatible lengths.")
+        ell = np.empty(periods.size, dtype=np.float64)
+        arg = ctypes.c_int64(-1)
+        mn = ctypes.c_double(float("nan"))
+        with self._lock:
+            _check(self._lib.pdc_stringlength(self._h, _ptr(t), _ptr(m), t.size, _ptr(periods), periods.size,
+                                              _ptr(ell), ctypes.addressof(arg), ctypes.addressof(mn)))
+        return ell, arg.value, mn.value
+
+    def stringlength_dev(self, t_ptr, m_ptr, n, periods_ptr, np_, ell_ptr, argmin_ptr, min_ptr, stream=0):
+        _check(self._lib.pdc_stringlength_dev(self._h, t_ptr, m_ptr, int(n), periods_ptr, int(np_), ell_ptr,
+                                              argmin_ptr or None, min_ptr or None, stream or None))
 
     def peaks_topk(self, values, k):
         """(indices [rows, k], values [rows, k]) of the k highest local maxima of each row (host arrays)."""

@@ -458,6 +458,44 @@ int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
 }
 
 // ---------------------------------------------------------------------------
+// string length
+// ---------------------------------------------------------------------------
+int pdc_stringlength_dev(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const double* periods,
+                         int64_t np, double* ell_out, int64_t* argmin_out, double* min_out, void* stream) {
+  if (!ctx || !t || !m || !periods || !ell_out) { set_error("pdc_stringlength_dev: NULL argument"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  return strlen_run(ctx, t, m, n, periods, np, ell_out, argmin_out, min_out, st);
+}
+
+int pdc_stringlength(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const double* periods,
+                     int64_t np, double* ell_out, int64_t* argmin_out, double* min_out) {
+  if (!ctx || !t || !m || !periods || !ell_out) { set_error("pdc_stringlength: NULL argument"); return PDC_EINVAL; }
+  if (n < 1 || np < 1) { set_error("pdc_stringlength: need n >= 1 samples and np >= 1 periods"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  PDC_TRY(ctx->in_a.reserve(sizeof(double) * (size_t)n));
+  PDC_TRY(ctx->in_b.reserve(sizeof(double) * (size_t)n));
+  PDC_TRY(ctx->in_d.reserve(sizeof(double) * (size_t)np));
+  PDC_TRY(ctx->out_a.reserve(sizeof(double) * (size_t)np));
+  PDC_TRY(ctx->out_small.reserve(sizeof(SmallRec)));
+  PDC_TRY(ctx->pin_small.reserve(sizeof(SmallRec)));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_a.p, t, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_b.p, m, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_d.p, periods, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, st));
+  SmallRec* d_rec = ctx->out_small.as<SmallRec>();
+  PDC_TRY(strlen_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), n, ctx->in_d.as<double>(), np,
+                     ctx->out_a.as<double>(), (int64_t*)&d_rec->arg, &d_rec->val, st));
+  PDC_CUDA(cudaMemcpyAsync(ell_out, ctx->out_a.p, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, d_rec, sizeof(SmallRec), cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaStreamSynchronize(st));
+  const SmallRec* h = ctx->pin_small.as<SmallRec>();
+  if (argmin_out) *argmin_out = h->arg;
+  if (min_out) *min_out = h->val;
+  return PDC_OK;
+}
+
+// ---------------------------------------------------------------------------
 // peaks
 // ---------------------------------------------------------------------------
 int pdc_peaks_topk_dev(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k,

@@ -114,6 +114,9 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
             int64_t np, int nb, int nc, double* theta_out, int64_t* argmin_out, double* min_out,
             cudaStream_t stream, const pdc_fanout* fanout = nullptr, int64_t fan_offset = 0);
 
+int strlen_run(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const double* periods, int64_t np,
+               double* ell_out, int64_t* argmin_out, double* min_out, cudaStream_t stream);
+
 int peaks_run(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k, int64_t* idx_out,
               double* val_out, cudaStream_t stream);
 

@@ -1,4 +1,4 @@
-"""Drop-in ``PDM`` backed by the sm_100a phase-bin histogram kernel.
+"""Drop-in ``PDM`` and ``StringLength`` backed by sm_100a kernels (phase-bin histograms; per-period sort).
 
 Same constructor, call signature, attributes and side effects as the reference
 class (``src/periodicity/phase.py:75-195``).  The reference fans
@@ -13,7 +13,57 @@ import numpy as np
 from . import _ffi
 from .core import FSeries, TSeries
 
-__all__ = ["PDM"]
+__all__ = ["StringLength", "PDM"]
+
+
+class StringLength(object):
+    """String Length (Dworetsky 1983): same constructor and call signature as the reference class
+    (``src/periodicity/phase.py:18-72``); ``cores`` is accepted and ignored.
+
+    The reference fans ``self._stringlength(period)`` out over a ``multiprocessing.Pool``
+    (``phase.py:68-70``); here all trial periods go to a B200 in one ``pdc_stringlength`` call (one
+    thread block per period: fold, sort by phase, sum the segment lengths).
+
+    Semantics note.  ``phase.py:65`` scales the signal with ``signal - signal.max()``.  In the reference's
+    own ``core.py`` ``Signal.max()`` returns a ONE-SAMPLE series (``core.py:217-220``), and the subtraction
+    of two series of different length is refused by xarray's exact join (``core.py:175-178``), so the
+    reference class cannot complete a call as shipped and has no test (``tests/test_phase.py`` is empty).
+    This class implements what the line states -- scale the values to [-0.25, 0.25] with the scalar
+    maximum and minimum (NaN-ignoring, as ``amax``/``amin`` are, ``core.py:212-215``) -- and everything
+    after it literally: ``periods = 1 / linspace(n_periods*df, df, n_periods)``, ``df = dphi / baseline``;
+    per period ``phi = (t / P) % 1``, stable sort by ``phi``, closed-polygon length with ``np.roll``.
+    """
+
+    def __init__(self, dphi=0.1, n_periods=1000, cores=None, *, device=None):
+        self.dphi = dphi
+        self.n_periods = n_periods
+        self.cores = cores
+        self.device = device
+
+    def _ell(self, periods):
+        ctx = _ffi.default_context(self.device)
+        ell, self.argmin_index, self.min_length = ctx.stringlength(self.m.time, self.m.values, periods)
+        return ell
+
+    def _stringlength(self, period):
+        """String length for a single trial period (``phase.py:45-51``)."""
+        return float(self._ell(np.array([period], dtype=np.float64))[0])
+
+    def __call__(self, signal):
+        """String length on the reference's period grid as an ``FSeries`` over ``1/P`` (``phase.py:53-72``);
+        sets ``signal, m, periodogram``."""
+        if not isinstance(signal, TSeries):
+            signal = TSeries(values=signal)
+        self.signal = signal
+        # scale signal to range from -0.25 to +0.25 (phase.py:64-65)
+        vmax = np.nanmax(signal.values)
+        vmin = np.nanmin(signal.values)
+        self.m = TSeries(signal.time, (signal.values - vmax) / (2 * (vmax - vmin)) + 0.25, assume_sorted=True)
+        df = self.dphi / signal.baseline
+        periods = 1 / np.linspace(self.n_periods * df, df, self.n_periods)
+        ell = self._ell(periods)
+        self.periodogram = FSeries(1 / periods, ell)
+        return self.periodogram
 
 
 class PDM(object):

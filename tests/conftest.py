@@ -37,6 +37,7 @@ GLS_CASES = ["gls_sine100", "gls_c1_small", "gls_err", "gls_nofitmean", "gls_psd
 PDM_CASES = ["pdm_basic", "pdm_negative_t_nc3", "pdm_sparse", "pdm_integer_t_ties", "pdm_subharmonic",
              "pdm_nc1", "pdm_defaults"]
 PDM_KW = ["nb", "nc", "p_min", "p_max", "n_periods", "do_subharmonic"]
+SL_CASES = ["sl_basic", "sl_sparse_negative_t", "sl_integer_t_ties", "sl_3000"]
 
 
 @pytest.fixture(scope="session")

@@ -142,6 +142,27 @@ def main():
     run_pdm("pdm_nc1", t5, x5, nb=7, nc=1, p_min=2.0, p_max=20.0, n_periods=90)
     run_pdm("pdm_defaults", t, x, n_periods=64)
 
+    # ---- String Length ----------------------------------------------------------
+    # phase.py:18-72 executed unmodified; the stand-in core's max()/min() return scalars (see oracle/refload.py:
+    # with the reference's own core.py the scaling line phase.py:65 cannot run)
+    def run_sl(name, t, x, **kw):
+        sig = refload.TSeries(t, x) if t is not None else x
+        s_ = phase.StringLength(cores=2, **kw)
+        out = s_(sig)
+        save(name, t=NONE if t is None else t, x=x, m=np.array(s_.m.values),
+             periodogram_frequency=np.array(out.frequency), periodogram_values=np.array(out.values), **kw)
+
+    rng = np.random.default_rng(6)
+    t = np.sort(rng.uniform(0, 60, 300))
+    x = 12.0 + 0.4 * np.sin(2 * np.pi * t / 4.3) + 0.05 * rng.standard_normal(300)
+    run_sl("sl_basic", t, x, dphi=0.1, n_periods=400)
+    run_sl("sl_sparse_negative_t", t[::7] - 30.0, x[::7], dphi=0.25, n_periods=150)
+    xi = np.round(np.sin(2 * np.pi * np.arange(120) / 8.0), 3)       # integer times: many equal phases (ties)
+    run_sl("sl_integer_t_ties", None, xi, dphi=0.5, n_periods=60)
+    t3 = np.sort(rng.uniform(0, 300, 3000))
+    x3 = np.sin(2 * np.pi * t3 / 11.7) ** 3 + 0.1 * rng.standard_normal(3000)
+    run_sl("sl_3000", t3, x3, dphi=0.1, n_periods=100)
+
 
 if __name__ == "__main__":
     main()

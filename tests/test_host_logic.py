@@ -9,9 +9,9 @@ evaluates the oracle, so these tests run without a GPU.
 import numpy as np
 import pytest
 
-from conftest import GLS_CASES, PDM_CASES, PDM_KW, load_golden, opt
-from oracle import cport
-from periodicity_b200 import GLS, PDM, FSeries, TSeries, _ffi
+from conftest import GLS_CASES, PDM_CASES, PDM_KW, SL_CASES, load_golden, opt
+from oracle import cport, stringlength_numpy
+from periodicity_b200 import GLS, PDM, FSeries, StringLength, TSeries, _ffi
 
 
 class OracleContext:
@@ -52,6 +52,10 @@ class OracleContext:
     def pdm(self, t, x, periods, nb, nc):
         th = cport.pdm(t, x, periods, nb, nc)
         return th, int(np.nanargmin(th)), float(np.nanmin(th))
+
+    def stringlength(self, t, m, periods):
+        ell = stringlength_numpy.string_lengths(np.asarray(t, dtype=np.float64), np.asarray(m), periods)
+        return ell, int(np.nanargmin(ell)), float(np.nanmin(ell))
 
 
 @pytest.fixture(autouse=True)
@@ -179,3 +183,16 @@ def test_survey_front_end_and_top_peaks():
     f, p = gls.top_peaks(3)
     assert 1.0 / f[0] == ls.period_at_highest_peak
     np.testing.assert_array_equal(1.0 / f, ls.psort_by_peak()[:3])
+
+
+@pytest.mark.parametrize("case", SL_CASES)
+def test_stringlength_front_end_matches_reference(case):
+    g = load_golden(case)
+    sl = StringLength(dphi=float(g["dphi"]), n_periods=int(g["n_periods"]), cores=2)
+    out = sl(_signal(g, "x"))
+    np.testing.assert_array_equal(sl.m.values, g["m"])                          # phase.py:64-65
+    np.testing.assert_array_equal(out.frequency, g["periodogram_frequency"])    # phase.py:66-67,71
+    np.testing.assert_allclose(out.values, g["periodogram_values"], rtol=1e-13)
+    assert out is sl.periodogram and sl.signal.size == g["x"].size
+    p = 1 / out.frequency[5]
+    assert sl._stringlength(p) == pytest.approx(out.values[5], rel=1e-13)

@@ -6,8 +6,8 @@ Fixtures: tests/golden/*.npz, written by tests/golden/make_golden.py from
 import numpy as np
 import pytest
 
-from conftest import GLS_CASES, PDM_CASES, PDM_KW, load_golden, opt
-from oracle import cport, gls_numpy, pdm_numpy
+from conftest import GLS_CASES, PDM_CASES, PDM_KW, SL_CASES, load_golden, opt
+from oracle import cport, gls_numpy, pdm_numpy, stringlength_numpy
 
 
 def _gls_inputs(g):
@@ -114,3 +114,16 @@ def test_pdm_restatements_match_reference(case, impl):
     np.testing.assert_allclose((1 / periods)[order], g["periodogram_frequency"], rtol=0, atol=0)
     np.testing.assert_allclose(theta[order], g["periodogram_values"], rtol=1e-11, atol=0)
     assert np.nanargmin(theta[order]) == np.nanargmin(g["periodogram_values"])
+
+
+@pytest.mark.parametrize("case", SL_CASES)
+def test_stringlength_restatement_matches_reference_code(case):
+    """phase.py:18-72 executed unmodified behind the stand-in core (scalar max()/min(), see oracle/refload.py)."""
+    g = load_golden(case)
+    x = g["x"]
+    t = opt(g["t"])
+    t = np.arange(len(x), dtype=np.float64) if t is None else t
+    periods, ell = stringlength_numpy.stringlength(t, x, dphi=float(g["dphi"]), n_periods=int(g["n_periods"]))
+    np.testing.assert_array_equal(stringlength_numpy.scale(x), g["m"])
+    np.testing.assert_array_equal((1 / periods)[::-1], g["periodogram_frequency"])     # FSeries re-sorts (core.py:877-881)
+    np.testing.assert_allclose(ell[::-1], g["periodogram_values"], rtol=1e-13)
