@@ -131,6 +131,18 @@ def make_pdm_c3(np_total):
                 name=f"PDM 1e5 points x {np_total} trial periods, nb=10 nc=2 (C3)")
 
 
+def make_sl(np_total):
+    """String Length on a sparse light curve (the method's use case; SURVEY 8f row 2 has no BASELINE config)."""
+    from oracle import stringlength_numpy
+    rng = np.random.default_rng(7)
+    n = 2000
+    t = np.sort(rng.uniform(0, 1000.0, n))
+    x = 12.0 + 0.4 * np.sin(2 * np.pi * t / 4.3) + 0.05 * rng.standard_normal(n)
+    periods = stringlength_numpy.period_grid(t, dphi=0.1, n_periods=np_total)
+    return dict(kind="sl", t=t, y=stringlength_numpy.scale(x), periods=periods, nf=np_total,
+                name=f"String Length 2,000 points x {np_total} trial periods (phase.py:18-72)")
+
+
 def make_gls_c4(curves):
     n, nf = 20_000, 10_000
     ts, ys, fm, dfs = [], [], [], []
@@ -213,8 +225,10 @@ def _pool(cores):
     """One worker pool for the whole run (its start-up is not part of any timed step)."""
     global _POOL
     if _POOL is None:
+        import atexit
         from multiprocessing import Pool
         _POOL = Pool(cores)
+        atexit.register(_POOL.terminate)
     return _POOL
 
 
@@ -251,6 +265,11 @@ def _cpu_gls_one(job):
     return float(np.nanmax(gls_numpy.gls_power(t, y, None, fmin, df, nf, True, False)))
 
 
+def _cpu_sl_chunk(t, m, periods):
+    from oracle import stringlength_numpy
+    return stringlength_numpy.string_lengths(t, m, periods)
+
+
 def cpu_reference_step(wl):
     """One step of the reference's CPU path on (a bounded sample of) the workload.
     Returns (evals processed, cores used, description of the sample)."""
@@ -277,6 +296,11 @@ def cpu_reference_step(wl):
                                                         f"{used} core(s) (faster of in-process / Pool({cores}); the "
                                                         "reference has no batch API)")
     cores = os.cpu_count() or 1
+    if wl["kind"] == "sl":
+        sample = wl["periods"][:: max(1, wl["periods"].size // (512 * cores))][: 512 * cores]
+        _pool(cores).starmap(_cpu_sl_chunk, [(wl["t"], wl["y"], c) for c in np.array_split(sample, cores)])
+        return wl["t"].size * sample.size, cores, (f"{sample.size} of {wl['periods'].size} trial periods (strided), "
+                                                   f"multiprocessing.Pool({cores}) as phase.py:68-70")
     sample = wl["periods"][:: max(1, wl["periods"].size // (24 * cores))][: 24 * cores]
     pdm_numpy.pdm_pool(wl["t"], wl["y"], sample, wl["nb"], wl["nc"], cores, sort=True)
     return wl["t"].size * sample.size, cores, (f"{sample.size} of {wl['periods'].size} trial periods (strided), "
@@ -339,7 +363,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c1", "gls_multi"])
+    ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c1", "gls_multi", "sl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1, GLS / PDM grids: 'p2p' = all-gather fused into the epilogue kernel over NVLink peer "
@@ -352,7 +376,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     per_gpu = {"gls_c2": 100_000, "pdm_c3": 100_000, "gls_c5": 1_250_000, "gls_c5_full": 10_000_000,
-               "gls_c4": 256, "gls_c1": 10_000, "gls_multi": 256}[args.workload]
+               "gls_c4": 256, "gls_c1": 10_000, "gls_multi": 256, "sl": 100_000}[args.workload]
     total_units = per_gpu * max(world, 1)
     if args.workload == "gls_c2":
         wl = make_gls_c2(total_units)
@@ -364,10 +388,13 @@ def main():
         wl = make_gls_multi(total_units)
     elif args.workload == "pdm_c3":
         wl = make_pdm_c3(total_units)
+    elif args.workload == "sl":
+        wl = make_sl(total_units)
     else:
         wl = make_gls_c4(total_units)
-    metric = "GLS sample*frequency evaluations per second" if wl["kind"] != "pdm" else \
-        "PDM sample*period evaluations per second"
+    metric = {"pdm": "PDM sample*period evaluations per second",
+              "sl": "String Length sample*period evaluations per second"}.get(
+                  wl["kind"], "GLS sample*frequency evaluations per second")
     unit = "evals/s"
 
     if args.impl == "reference":
@@ -411,7 +438,7 @@ def main():
         start, stop, L = pdist.shard_bounds(wl["nf"], rank, world)
         units_local = n * (stop - start)
         evals_total = n * wl["nf"]
-        if kind == "pdm":
+        if kind in ("pdm", "sl"):
             p_d = torch.from_numpy(wl["periods"][start:stop].copy()).to(dev)
             pfull_d = torch.from_numpy(wl["periods"]).to(dev)
 
@@ -435,6 +462,12 @@ def main():
                 return theta, mn, arg
             garg = (arg + start).to(torch.float64).reshape(())
             vals, bests, args_ = pdist.all_gather_packed(theta, mn.reshape(()), garg, L)
+        elif kind == "sl":
+            ell, arg, mn = pdist.stringlength_torch(t_d, y_d, p_d, ctx=ctx)
+            if world == 1:
+                return ell, mn, arg
+            garg = (arg + start).to(torch.float64).reshape(())
+            vals, bests, args_ = pdist.all_gather_packed(ell, mn.reshape(()), garg, L)
         elif kind == "gls_multi":
             ctx._lib.pdc_gls_multi_dev(ctx._h, t_d.data_ptr(), ym_d.data_ptr(), None, n, L, float(wl["fmin"]),
                                        float(wl["df"]), 0, wl["nf"], _ffi.GLS_FIT_MEAN, 1.0, None, pm_arg.data_ptr(),
@@ -506,6 +539,9 @@ def main():
         if kind == "pdm":
             p, a, m = ctx.pdm(th, yh, wl["periods"][start:stop], wl["nb"], wl["nc"])
             return p
+        if kind == "sl":
+            p, a, m = ctx.stringlength(th, yh, wl["periods"][start:stop])
+            return p
         if kind == "gls_multi":
             _, a, m = ctx.gls_multi(th, yh[b0:b1], None, wl["fmin"], wl["df"], wl["nf"], want_power=False)
             return m
@@ -534,11 +570,24 @@ def main():
         h2d = 2 * 8 * int(off[-1] - off[0])
         d2h = out.nbytes * 2
     else:
-        h2d = 2 * 8 * n + (8 * (stop - start) if kind == "pdm" else 0)
+        h2d = 2 * 8 * n + (8 * (stop - start) if kind in ("pdm", "sl") else 0)
         d2h = out.nbytes + 16
 
     # ---- roofline of the dominant kernel ----------------------------------------------------
-    if kind == "pdm":
+    if kind == "sl":
+        # bitonic network: log2(Np)(log2(Np)+1)/2 stages, each reading and (worst case) writing every 12-byte
+        # (key, index) record once = the algorithmic shared-memory traffic of the chosen algorithm
+        npad = 1 << (n - 1).bit_length()
+        lg = npad.bit_length() - 1
+        smem_bytes = (stop - start) * (lg * (lg + 1) // 2) * npad * 12.0 * 2
+        ach = smem_bytes / (main_kernel_ms * 1e-3) / 1e9
+        peak = 148 * 128 * 1.965                    # 128 B/clk/SM shared-memory bandwidth at 1.965 GHz, GB/s
+        roof = {"bound": "smem", "kernel": "sl_kernel", "achieved": ach, "peak": peak, "unit": "GB/s (shared memory)",
+                "frac": ach / peak, "traffic": None, "kernel_ms": main_kernel_ms,
+                "evals_per_s_kernel": units_local / (main_kernel_ms * 1e-3),
+                "peak_source": "nominal 128 B/clk/SM x 148 SMs x 1.965 GHz (shared-memory bandwidth; the sort never "
+                               "leaves the SM, HBM traffic is 16 B/sample per block)"}
+    elif kind == "pdm":
         ach = units_local / (main_kernel_ms * 1e-3) / 1e9
         roof = {"bound": "smem", "kernel": "pdm_hist_kernel", "achieved": ach, "peak": PDM_PEAK_GEVALS_MEASURED,
                 "unit": "Gevals/s", "frac": ach / PDM_PEAK_GEVALS_MEASURED,
@@ -591,10 +640,10 @@ def main():
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 sums, f64 phase/epilogue" if kind != "pdm" else "f64 phase, f32 histograms",
+            "vs_baseline": None, "dtype": {"pdm": "f64 phase, f32 histograms", "sl": "f64"}.get(kind, "f32 sums, f64 phase/epilogue"),
             "data": "synthetic",
             "config": {"workload": wl["name"], "units_per_gpu": per_gpu, "sharding": "frequency grid" if kind == "gls"
-                       else ("period grid" if kind == "pdm" else "light-curve batch"),
+                       else ("period grid" if kind in ("pdm", "sl") else "light-curve batch"),
                        "kernel": "glsm_strip_kernel" if kind == "gls_multi" else None,
                        "l2": "flushed between timed steps (256 MiB memset, not timed); per-step CUDA events summed",
                        "collective": ("none (1 GPU)" if world == 1 else

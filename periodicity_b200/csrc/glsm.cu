@@ -6,14 +6,17 @@
 // time axis the rotation exp(2 pi i f_j t_i) and the window sums {C, S, CC, CS} (they depend on
 // t and w only) are common to all series; only YC_s = sum w y_s cos and YS_s = sum w y_s sin
 // differ.  A thread therefore owns K consecutive frequencies of R series at once:
-//   per (sample, frequency): 4 FP32 instr rotation + 4 (5 weighted) window + 2R for the R series
-//   = (8 + 2R)/R instructions per series-evaluation: 3.0 at R = 8 instead of 10 in gls_strip_kernel.
+//   per (sample, frequency): 2 FP32 instr for the step (three-term form, see gls.cu; 4 in the rotation
+//   form) + 2R for the R series, and only in the first group of series 4 (5 weighted) for the window
+//   sums = (2 + 2R)/R instructions per series-evaluation: 2.25 at R = 8 instead of 8 in gls_strip_kernel.
 // Everything else -- exact FP64 seeding per strip, FP32 tile sums flushed to FP64 partials, FP64
 // sub-cycle bins, FP64 epilogue (spectral.py:113-132), NaN-aware argmax -- is as in gls.cu.
 //
 // Kernels: glsm_stats_kernel (per series: mean, YY; shared: t range, sum w),
 // glsm_records_kernel (shared rotation records + per-series scaled values, group-interleaved),
 // glsm_lowfreq_kernel (FP64), glsm_strip_kernel (hot), glsm_epilogue_kernel, argext_final_kernel.
+#include <type_traits>
+
 #include "gls_common.cuh"
 
 namespace pdc {
@@ -23,6 +26,8 @@ struct GlsmShared {  // one per call
   double fmin, df, psd_scale;
   double tmin, tmax, wsum;
   int low_begin, low_count;
+  double gamma;    // per-frequency-index phase origin of the three-term step (see gls.cu / GlsCurve)
+  int three_term, pad_;
 };
 
 struct GlsmSeries {  // one per series
@@ -34,7 +39,8 @@ constexpr int GLSM_TILE = 512;
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 glsm_stats_kernel(const double* __restrict__ t, const double* __restrict__ Y, const double* __restrict__ w,
-                  GlsmShared* sh, GlsmSeries* series, unsigned flags, long long j0, long long nf) {
+                  GlsmShared* sh, GlsmSeries* series, unsigned flags, long long j0, long long nf,
+                  int allow_three_term) {
   __shared__ double scratch[33];
   const long long n = sh->n;
   const double* y = Y + (long long)blockIdx.x * n;
@@ -70,6 +76,10 @@ glsm_stats_kernel(const double* __restrict__ t, const double* __restrict__ Y, co
       gls_low_range(sh->fmin, sh->df, j0, nf, tmax - tmin, lb, lc);
       sh->low_begin = lb;
       sh->low_count = lc;
+      const double span = sh->df * (tmax - tmin);
+      const bool tt = allow_three_term && sh->df > 0.0 && span <= GLS_TT_MAX_SPAN;
+      sh->three_term = tt;
+      sh->gamma = tt ? 0.25 - 0.5 * span : 0.0;
     }
   }
 }
@@ -89,7 +99,7 @@ glsm_records_kernel(const double* __restrict__ t, const double* __restrict__ Y, 
     const double wn = w ? w[i] * wscale : 1.0;
     if (g == 0) {
       const double tt = t[i] - sh.tmin;
-      const double b = frac_of_product(sh.df, tt);
+      const double b = frac_of_product(sh.df, tt) + sh.gamma;
       double sb, cb;
       sincospi(2.0 * b, &sb, &cb);
       rec1[i] = make_double2(tt, b);
@@ -204,6 +214,9 @@ glsm_strip_kernel(const GlsmArgs a) {
   const int lK = threadIdx.x * K;
   const double lKd = (double)lK;
   const long long jrem = a.nf - (jB + lK);
+  const bool three_term = a.sh->three_term != 0;  // block-uniform
+  double gB = (double)(a.j0 + jB) * a.sh->gamma;   // phase origin of the block's first frequency (turns)
+  gB -= floor(gB);
 
   double* pwin = a.win + (long long)split * 4 * a.nf + jB + lK;
   double* pys = a.ys + ((long long)split * 2 * a.S_pad + (long long)g * R) * a.nf + jB + lK;
@@ -223,7 +236,7 @@ glsm_strip_kernel(const GlsmArgs a) {
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += THREADS) {
       const double2 r1 = a.rec1[tile0 + i];
-      s_ab[i] = make_double2(frac_of_product(fB, r1.x), r1.y);
+      s_ab[i] = make_double2(frac_of_product(fB, r1.x) + gB, r1.y);
       s_rot[i] = a.rot[tile0 + i];
     }
     {
@@ -241,21 +254,29 @@ glsm_strip_kernel(const GlsmArgs a) {
       for (int r = 0; r < R; ++r) aYC[r][k] = aYS[r][k] = 0.f;
     }
 
-    auto strip = [&](float c, float s, const float4 rt, const float* yv) {
+    // One sample: K accumulations and K-1 steps along the frequency axis (rotation or three-term
+    // form, as in gls_strip_kernel).  The window sums {C, S, CC, CS} are the same in every group of
+    // series: only group 0 (WIN) spends instructions on them.
+    auto strip = [&](auto win_tag, auto tt_tag, float c, float s, const float4 rt, const float* yv) {
+      constexpr bool WIN = decltype(win_tag)::value, TT = decltype(tt_tag)::value;
       const float cr = rt.x, sr = rt.y;
+      const float tc = cr + cr;
+      float cp = 0.f, sp = 0.f;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        if (WEIGHTED) {
-          const float wc = rt.z * c;
-          aC[k] += wc;
-          aS[k] = fmaf(rt.z, s, aS[k]);
-          aCC[k] = fmaf(wc, c, aCC[k]);
-          aCS[k] = fmaf(wc, s, aCS[k]);
-        } else {
-          aC[k] += c;
-          aS[k] += s;
-          aCC[k] = fmaf(c, c, aCC[k]);
-          aCS[k] = fmaf(c, s, aCS[k]);
+        if (WIN) {
+          if (WEIGHTED) {
+            const float wc = rt.z * c;
+            aC[k] += wc;
+            aS[k] = fmaf(rt.z, s, aS[k]);
+            aCC[k] = fmaf(wc, c, aCC[k]);
+            aCS[k] = fmaf(wc, s, aCS[k]);
+          } else {
+            aC[k] += c;
+            aS[k] += s;
+            aCC[k] = fmaf(c, c, aCC[k]);
+            aCS[k] = fmaf(c, s, aCS[k]);
+          }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -263,15 +284,23 @@ glsm_strip_kernel(const GlsmArgs a) {
           aYS[r][k] = fmaf(yv[r], s, aYS[r][k]);
         }
         if (k + 1 < K) {
-          const float c2 = fmaf(c, cr, -(s * sr));
-          const float s2 = fmaf(s, cr, c * sr);
+          float c2, s2;
+          if (TT && k >= 1) {  // c[k+1] = 2 cos(d) c[k] - c[k-1]
+            c2 = fmaf(tc, c, -cp);
+            s2 = fmaf(tc, s, -sp);
+          } else {
+            c2 = fmaf(c, cr, -(s * sr));
+            s2 = fmaf(s, cr, c * sr);
+          }
+          cp = c;
+          sp = s;
           c = c2;
           s = s2;
         }
       }
     };
 
-    if (cnt > 0) {
+    auto run_tile = [&](auto win_tag, auto tt_tag) {
       float c0, s0, c1, s1;
       {
         const double2 ab = s_ab[0];
@@ -289,9 +318,18 @@ glsm_strip_kernel(const GlsmArgs a) {
           const float4 v = yp[q];
           yv[4 * q] = v.x; yv[4 * q + 1] = v.y; yv[4 * q + 2] = v.z; yv[4 * q + 3] = v.w;
         }
-        strip(c0, s0, s_rot[i], yv);
+        strip(win_tag, tt_tag, c0, s0, s_rot[i], yv);
         c0 = c1;
         s0 = s1;
+      }
+    };
+    if (cnt > 0) {
+      if (g == 0) {
+        if (three_term) run_tile(std::true_type{}, std::true_type{});
+        else run_tile(std::true_type{}, std::false_type{});
+      } else {
+        if (three_term) run_tile(std::false_type{}, std::true_type{});
+        else run_tile(std::false_type{}, std::false_type{});
       }
     }
 
@@ -445,12 +483,14 @@ int glsm_run(pdc_ctx* ctx, const double* t, const double* Y, const double* w, in
   GlsmShared* hs = ctx->pin_meta.as<GlsmShared>();
   hs->n = n; hs->fmin = fmin; hs->df = df; hs->psd_scale = psd_scale;
   hs->tmin = hs->tmax = hs->wsum = 0.0; hs->low_begin = hs->low_count = 0;
+  hs->gamma = 0.0; hs->three_term = hs->pad_ = 0;
   GlsmShared* dsh = ctx->gls_curves.as<GlsmShared>();
   GlsmSeries* dser = reinterpret_cast<GlsmSeries*>(dsh + 1);
   PDC_CUDA(cudaMemcpyAsync(dsh, hs, sizeof(GlsmShared), cudaMemcpyHostToDevice, st));
   PDC_CUDA(cudaEventRecord(ctx->ev_fence, st));
 
-  glsm_stats_kernel<<<(unsigned)S, 1024, 0, st>>>(t, Y, w, dsh, dser, flags, (long long)j0, (long long)nf);
+  glsm_stats_kernel<<<(unsigned)S, 1024, 0, st>>>(t, Y, w, dsh, dser, flags, (long long)j0, (long long)nf,
+                                                  ctx->gls_three_term ? 1 : 0);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
   {
