@@ -10,7 +10,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libperiodicity_b200.so")
+# PERIODICITY_B200_LIB: explicit path of the shared object (tuning builds, tools/tune_strip.py); default = in-tree build
+LIB_PATH = os.environ.get("PERIODICITY_B200_LIB") or os.path.join(_HERE, "lib", "libperiodicity_b200.so")
 
 PDC_OK, PDC_EINVAL, PDC_ECUDA, PDC_ENOMEM, PDC_ENODEVICE = range(5)
 GLS_FIT_MEAN = 1

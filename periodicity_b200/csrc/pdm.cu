@@ -46,9 +46,13 @@ struct PdmMeta {
   double mean, inv_sd;
   double q_binned;  // sum of x'^2 over the samples with a finite time stamp (== N - 1 when all are)
   double t_absmax;  // max |t| over the finite time stamps: decides whether the 32-bit fixed-point phase is usable
+  int pack_q;       // >= 0: x' is also provided as 2^23 + rint(x' 2^pack_q) for the packed 32-bit histogram; -1: not usable
   int bad;          // some t or x is NaN / inf: the histogram kernel then runs its guarded variant
 };
 
+constexpr int PDM_PACK_FLUSH = 256;   // samples between flushes of the packed 32-bit columns into the float2 columns
+constexpr int PDM_PACK_MIN_Q = 11;    // coarsest usable quantisation of x' (2^-11 sigma)
+constexpr int PDM_PACK_MIN_N = 4096;  // shorter curves keep the FP32 columns (they are accurate to 1e-7 there)
 constexpr int PDM_TILE = 1024;        // samples per shared-memory tile
 constexpr int PDM_FLUSH_TILES = 8;    // FP32 histograms are merged into FP64 every 8192 samples
 
@@ -66,14 +70,16 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
   s = block_sum(s, scratch);
   const double tabs = -block_min(tneg, scratch);
   const double mean = s / (double)n;
-  double q = 0.0, qb = 0.0;
+  double q = 0.0, qb = 0.0, dneg = 0.0;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     double d = x[i] - mean;
     q = fma(d, d, q);
+    dneg = fmin(dneg, -fabs(d));
     if (bad && isfinite(t[i])) qb = fma(d, d, qb);
   }
   q = block_sum(q, scratch);
   qb = block_sum(qb, scratch);
+  const double dmax = -block_min(dneg, scratch);
   if (threadIdx.x == 0) {
     const double var = q / (double)(n - 1);  // phase.py:165  np.var(values, ddof=1)
     meta->mean = mean;
@@ -83,21 +89,40 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
     meta->q_binned = bad ? qb / var : (double)(n - 1);
     meta->bad = bad;
     meta->t_absmax = tabs;
+    // Packed first-level histogram (pdm_hist_kernel): one 32-bit word per (bin, period) holds the count in
+    // its top 9 bits and sum rint(x' 2^q) in the low 23 (two's complement) for at most PDM_PACK_FLUSH samples,
+    // so 256 * max|x'| * 2^q must stay below 2^22.  Worth it only if the quantisation step 2^-q is fine
+    // enough (q >= PDM_PACK_MIN_Q: relative theta error ~ 0.4 * 2^-q / sqrt(nc N) / theta) and the curve is long.
+    int pq = -1;
+    const double xmax = dmax / sqrt(var);
+    if (!bad && xmax > 0.0 && isfinite(xmax) && n >= PDM_PACK_MIN_N) {
+      pq = (int)floor(log2(16000.0 / xmax));
+      if (pq > 20) pq = 20;
+      if (pq < PDM_PACK_MIN_Q) pq = -1;
+    }
+    meta->pack_q = pq;
   }
 }
 
 __global__ void __launch_bounds__(256)
 pdm_center_kernel(const double* __restrict__ x, long long n, const PdmMeta* __restrict__ meta,
-                  float* __restrict__ xs) {
+                  float* __restrict__ xs, unsigned* __restrict__ xq) {
   const double mean = meta->mean, inv_sd = meta->inv_sd;
+  const int pq = meta->pack_q;
+  const double scale = pq >= 0 ? (double)(1u << pq) : 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    xs[i] = (float)((x[i] - mean) * inv_sd);
+       i += (long long)gridDim.x * blockDim.x) {
+    const double v = (x[i] - mean) * inv_sd;
+    xs[i] = (float)v;
+    // one add per sample updates count and sum: 2^23 (count field) + signed fixed-point x'
+    if (pq >= 0) xq[i] = (1u << 23) + (unsigned)(int)rint(v * scale);
+  }
 }
 
 struct PdmArgs {
   const double* t;
   const float* xs;
+  const unsigned* xq;   // packed increments (valid if meta->pack_q >= 0)
   const double* periods;
   const PdmMeta* meta;
   double* partial;  // [nsplit][2*m0][np]  rows: count per fine bin, then sum x' per fine bin
@@ -147,6 +172,18 @@ __device__ __forceinline__ unsigned pdm_bin_fast(double tv, double rP, unsigned 
   return (unsigned)(w >> 32);
 }
 
+// Same with the guard folded into the magic constant: the phase is shifted up by PDM_FAST_GUARD units of
+// 2^-32 turn (exact: ulp of the sum is 2^-32), so `pos` = position inside the bin + guard, and
+// pos < 2 guard  <=>  the unshifted phase is within guard of a bin edge (then the bin index may be off by
+// one and the caller re-bins exactly); otherwise the shift cannot have carried into the bin index.
+constexpr double PDM_FAST_MAGIC_G = PDM_FAST_MAGIC + PDM_FAST_GUARD * (1.0 / 4294967296.0);
+__device__ __forceinline__ unsigned pdm_bin_fast_g(double tv, double rP, unsigned m0u, unsigned& pos) {
+  const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, PDM_FAST_MAGIC_G));
+  const unsigned long long w = (unsigned long long)u * m0u;
+  pos = (unsigned)w;
+  return (unsigned)(w >> 32);
+}
+
 // Shared-memory layout: hist[bin][THREADS] float2 = (count, sum x'): a thread's column is
 // conflict free and one sample costs one 64-bit read-modify-write.
 template <int THREADS>
@@ -157,7 +194,8 @@ pdm_hist_kernel(const PdmArgs a) {
   double* s_t = reinterpret_cast<double*>(smem_raw);                 // [PDM_TILE]
   double* s_thr = s_t + PDM_TILE;                                    // [m0 + 1]  (padded to even)
   float2* hist = reinterpret_cast<float2*>(s_thr + ((m0 + 2) & ~1)); // [m0][THREADS]
-  float* s_x = reinterpret_cast<float*>(hist + (size_t)m0 * THREADS); // [PDM_TILE]
+  float* s_x = reinterpret_cast<float*>(hist + (size_t)m0 * THREADS); // [PDM_TILE]  (x' as float, or packed increments)
+  unsigned* hist32 = reinterpret_cast<unsigned*>(s_x + PDM_TILE);     // [m0][THREADS] packed first-level columns
 
   const int split = blockIdx.x % a.nsplit;
   const long long pb = blockIdx.x / a.nsplit;
@@ -171,7 +209,10 @@ pdm_hist_kernel(const PdmArgs a) {
   const unsigned kmax = (unsigned)(m0 - 1);
 
   for (int k = threadIdx.x; k <= m0; k += THREADS) s_thr[k] = (double)k / m0d;  // phase.py:138-140
-  for (int k = threadIdx.x; k < m0 * THREADS; k += THREADS) hist[k] = make_float2(0.f, 0.f);
+  for (int k = threadIdx.x; k < m0 * THREADS; k += THREADS) {
+    hist[k] = make_float2(0.f, 0.f);
+    hist32[k] = 0u;
+  }
 
   const long long per = (a.n + a.nsplit - 1) / a.nsplit;
   const long long sb = (long long)split * per;
@@ -193,14 +234,87 @@ pdm_hist_kernel(const PdmArgs a) {
     h.y += xv;
     col[k * THREADS] = h;
   };
-  // warp-uniform: every period of this warp keeps |t / P| small enough for the fixed-point phase
-  const bool fast = __all_sync(0xffffffffu, fabs(rP) * a.meta->t_absmax < PDM_FAST_LIMIT) != 0;
+  // block-uniform: every period of this block keeps |t / P| small enough for the fixed-point phase
+  const bool fast = __syncthreads_and(fabs(rP) * a.meta->t_absmax < PDM_FAST_LIMIT) != 0;
+  const int pack_q = a.meta->pack_q;
+  const bool packed = fast && !clamp_bins && pack_q >= 0;   // block-uniform
+  const float unpack = packed ? 1.0f / (float)(1u << pack_q) : 0.f;
+  unsigned* col32 = hist32 + threadIdx.x;
+  const unsigned* s_xq = reinterpret_cast<const unsigned*>(s_x);
   const unsigned m0u = (unsigned)m0, guard = PDM_FAST_GUARD * m0u;
   auto exact_bin = [&](double tv, double& phi) {
     unsigned e;
     int k = pdm_bin(tv, P, rP, m0d, phi, e);
     if (e < PDM_AMBIG) k = pdm_fix_bin(k, phi, s_thr, m0);
     return (unsigned)k;
+  };
+  // Packed path: the private column is a 32-bit word per bin, (count << 23) + sum of fixed-point x', so one
+  // sample costs one LDS.32 + IADD + STS.32 (2 shared-memory wavefronts per warp instead of 4); every
+  // PDM_PACK_FLUSH samples the words are unpacked into the float2 columns.
+  auto flush32 = [&]() {
+    for (int b = 0; b < m0; ++b) {
+      const unsigned w = col32[b * THREADS];
+      const int sfix = ((int)(w << 9)) >> 9;               // low 23 bits, sign extended
+      const unsigned cnt = (w - (unsigned)sfix) >> 23;
+      float2 h = col[b * THREADS];
+      h.x += (float)cnt;
+      h.y = fmaf((float)sfix, unpack, h.y);
+      col[b * THREADS] = h;
+      col32[b * THREADS] = 0u;
+    }
+  };
+#ifndef PDM_PACK_ATOMIC
+#define PDM_PACK_ATOMIC 1
+#endif
+  // The column is private, so the integer add needs no atomicity -- but a native shared-memory integer
+  // atomic without a return value (ATOMS.ADD) is ONE fire-and-forget instruction instead of the dependent
+  // LDS -> IADD -> STS chain, and same-bin updates of consecutive samples stay ordered in the memory pipe.
+  auto add32 = [&](unsigned k, unsigned inc) {
+#if PDM_PACK_ATOMIC
+    atomicAdd(col32 + k * THREADS, inc);
+#else
+    col32[k * THREADS] += inc;
+#endif
+  };
+  auto tile_loop_packed = [&](int cnt) {
+    const unsigned guard2 = 2u * guard;
+    for (int c0 = 0; c0 < cnt; c0 += PDM_PACK_FLUSH) {
+      const int c1 = c0 + PDM_PACK_FLUSH < cnt ? c0 + PDM_PACK_FLUSH : cnt;
+      int i = c0;
+      for (; i + 4 <= c1; i += 4) {
+        const double2 ta = *reinterpret_cast<const double2*>(s_t + i);
+        const double2 tb = *reinterpret_cast<const double2*>(s_t + i + 2);
+        const uint4 xv = *reinterpret_cast<const uint4*>(s_xq + i);
+        unsigned p0, p1, p2, p3;
+        unsigned k0 = pdm_bin_fast_g(ta.x, rP, m0u, p0);
+        unsigned k1 = pdm_bin_fast_g(ta.y, rP, m0u, p1);
+        unsigned k2 = pdm_bin_fast_g(tb.x, rP, m0u, p2);
+        unsigned k3 = pdm_bin_fast_g(tb.y, rP, m0u, p3);
+        if (min(min(p0, p1), min(p2, p3)) < guard2) {  // rare: a sample sits on a bin edge
+          double ph;
+          if (p0 < guard2) k0 = exact_bin(ta.x, ph);
+          if (p1 < guard2) k1 = exact_bin(ta.y, ph);
+          if (p2 < guard2) k2 = exact_bin(tb.x, ph);
+          if (p3 < guard2) k3 = exact_bin(tb.y, ph);
+        }
+        add32(k0, xv.x);
+        add32(k1, xv.y);
+        add32(k2, xv.z);
+        add32(k3, xv.w);
+      }
+      for (; i < c1; ++i) {
+        unsigned p0;
+        const double tv = s_t[i];
+        unsigned k0 = pdm_bin_fast_g(tv, rP, m0u, p0);
+        double ph;
+        if (p0 < guard2) k0 = exact_bin(tv, ph);
+        add32(k0, s_xq[i]);
+      }
+#if PDM_PACK_ATOMIC
+      __syncwarp();
+#endif
+      flush32();
+    }
   };
   auto tile_loop_fast = [&](auto safe, int cnt) {
     constexpr bool SAFE = decltype(safe)::value;
@@ -281,11 +395,14 @@ pdm_hist_kernel(const PdmArgs a) {
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += THREADS) {
       s_t[i] = a.t[tile0 + i];
-      s_x[i] = a.xs[tile0 + i];
+      if (packed) reinterpret_cast<unsigned*>(s_x)[i] = a.xq[tile0 + i];
+      else s_x[i] = a.xs[tile0 + i];
     }
     __syncthreads();
 
-    if (fast) {
+    if (packed) {
+      tile_loop_packed(cnt);
+    } else if (fast) {
       if (clamp_bins) tile_loop_fast(std::true_type{}, cnt);
       else tile_loop_fast(std::false_type{}, cnt);
     } else {
@@ -369,7 +486,7 @@ pdm_epilogue_kernel(double* __restrict__ partial, const double* __restrict__ per
 
 static size_t pdm_smem_bytes(int m0, int threads) {
   return sizeof(double) * (PDM_TILE + ((m0 + 2) & ~1)) + sizeof(float) * PDM_TILE +
-         sizeof(float2) * (size_t)m0 * threads;
+         (sizeof(float2) + sizeof(unsigned)) * (size_t)m0 * threads;
 }
 
 template <int THREADS>
@@ -396,7 +513,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   const size_t smem_max = 227 * 1024;
   if (m0l > 100000 || pdm_smem_bytes((int)m0l, 32) > smem_max) {
     set_error("pdc_pdm: nb*nc = %lld fine bins do not fit a shared-memory histogram (max %d)",
-              m0l, (int)((smem_max - 13 * 1024) / (8 * 32)));
+              m0l, (int)((smem_max - 13 * 1024) / (12 * 32)));
     return PDC_EINVAL;
   }
   const int m0 = (int)m0l;
@@ -438,7 +555,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
 
   PDC_TRY(ctx->scratch_acquire(st));
   PDC_TRY(ctx->pdm_meta.reserve(sizeof(PdmMeta)));
-  PDC_TRY(ctx->pdm_x.reserve(sizeof(float) * n));
+  PDC_TRY(ctx->pdm_x.reserve((sizeof(float) + sizeof(unsigned)) * (size_t)n));
   PDC_TRY(ctx->partial.reserve(sizeof(double) * 2 * m0 * (size_t)np * nsplit));
   const int eblk = (int)((np + 255) / 256);
   PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk));
@@ -450,7 +567,8 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   {
     long long bx = (n + 255) / 256;
     if (bx > 2048) bx = 2048;
-    pdm_center_kernel<<<(unsigned)bx, 256, 0, st>>>(x, n, meta, ctx->pdm_x.as<float>());
+    pdm_center_kernel<<<(unsigned)bx, 256, 0, st>>>(x, n, meta, ctx->pdm_x.as<float>(),
+                                                    reinterpret_cast<unsigned*>(ctx->pdm_x.as<float>() + n));
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -458,6 +576,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   PdmArgs a;
   a.t = t;
   a.xs = ctx->pdm_x.as<float>();
+  a.xq = reinterpret_cast<const unsigned*>(ctx->pdm_x.as<float>() + n);
   a.periods = periods;
   a.meta = meta;
   a.partial = ctx->partial.as<double>();

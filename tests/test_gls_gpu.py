@@ -447,3 +447,52 @@ def test_grid_crossing_zero_frequency(gpu_ctx):
     ref2 = cport.gls_exact(t, y, None, -1000.25 * df, df, 4000, True)
     assert_power_close(p2, ref2)
     assert am2 == np.nanargmax(ref2)
+
+
+def test_batch_mixes_step_forms_per_curve(gpu_ctx):
+    """One batch whose curves have different grid densities: the strip kernel picks the three-term or the
+    rotation step per curve (block-uniform), weighted and unweighted."""
+    rng = np.random.default_rng(31)
+    sizes = [900, 1500, 700, 1200]
+    dens = [5.0, 1.5, 3.0, 2.0]          # samples per peak: 5 and 3 -> three-term, 1.5 and 2 -> rotation
+    nf = 1500
+    ts, ys, ws, fm, dfs = [], [], [], [], []
+    for n, d_ in zip(sizes, dens):
+        t = np.sort(rng.uniform(0, 40.0, n))
+        d = 1 / (t[-1] - t[0]) / d_
+        ts.append(t)
+        ys.append(2 + np.sin(2 * np.pi * (0.5 * d + 0.37 * nf * d) * t) + rng.standard_normal(n))
+        ws.append(rng.uniform(0.5, 2, n))
+        dfs.append(d)
+        fm.append(0.5 * d)
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    T, Y, W = np.concatenate(ts), np.concatenate(ys), np.concatenate(ws)
+    for w_all, w_list in ((None, [None] * 4), (W, ws)):
+        P, A, M = gpu_ctx.gls_batch(T, Y, w_all, offsets, fm, dfs, nf)
+        for b in range(4):
+            err = None if w_list[b] is None else w_list[b] ** -0.5
+            ref = cport.gls_exact(ts[b], ys[b], err, fm[b], dfs[b], nf)
+            assert_power_close(P[b], ref)
+            assert A[b] == np.nanargmax(ref)
+            single, a1, _ = gpu_ctx.gls(ts[b], ys[b], w_list[b], fm[b], dfs[b], nf)
+            assert np.max(np.abs(single - P[b])) <= 2e-6 * np.max(single)   # same kernel, different sample split
+            assert a1 == A[b]
+
+
+def test_shared_time_multi_series_coarse_grid_uses_rotation(gpu_ctx):
+    """pdc_gls_multi with n = 2 samples per peak (rotation form) and 20 series (three groups: window sums come
+    from the first group only)."""
+    rng = np.random.default_rng(32)
+    n, S, nf = 1500, 20, 2000
+    t = np.sort(rng.uniform(0, 30.0, n))
+    for dens in (2.0, 5.0):
+        df = 1 / (t[-1] - t[0]) / dens
+        fmin = 0.5 * df
+        Y = 1 + np.sin(2 * np.pi * t[None, :] / rng.uniform(0.3, 3.0, S)[:, None]) + rng.standard_normal((S, n))
+        w = rng.uniform(0.5, 2.0, n)
+        for ww in (None, w):
+            P, A, M = gpu_ctx.gls_multi(t, Y, ww, fmin, df, nf)
+            for s in (0, 7, 8, 19):
+                ref = cport.gls_exact(t, Y[s], None if ww is None else ww ** -0.5, fmin, df, nf)
+                assert_power_close(P[s], ref)
+                assert A[s] == np.nanargmax(ref)
