@@ -45,7 +45,7 @@ FP32_PEAK_GINSTR_MEASURED = 36172.0  # same measurement as thread-instructions/s
 # 2 samples x 16 frequencies; 6 FFMA + 2 FADD per evaluation): the 20 FLOP of the accounting figure are NOT all executed
 GLS_EXECUTED_INSTR_PER_EVAL = 282.0 / 32.0
 GLS_EXECUTED_FLOP_PER_EVAL = 14.0
-PDM_PEAK_GEVALS_MEASURED = 2256.3  # profiles/pipes_r01.json smem_private_rmw_f2: 64-bit private-column RMW, updates/s
+PDM_PEAK_GEVALS_MEASURED = 3841.3  # profiles/pipes_r01.json smem_private_u32_atoms: private-column ATOMS.ADD, updates/s
 
 
 def measured_hbm_gbs():
@@ -593,9 +593,9 @@ def main():
                 "unit": "Gevals/s", "frac": ach / PDM_PEAK_GEVALS_MEASURED,
                 "traffic": ncu_traffic("ncu_pdm_hist_c3_r01.json") if args.workload == "pdm_c3" and world == 1 else None,
                 "kernel_ms": main_kernel_ms,
-                "peak_source": "profiles/pipes_r01.json smem_private_rmw_f2 (one LDS.64 + 2 FADD + one STS.64 per sample "
-                               "update, the shared-memory floor of the kernel); path is shared-memory/issue bound, "
-                               "not HBM or tensor bound"}
+                "peak_source": "profiles/pipes_r01.json smem_private_u32_atoms (one shared-memory ATOMS.ADD on a private "
+                               "32-bit column word per sample update, 13.7 per clk per SM: the floor of the "
+                               "kernel's histogram update); path is shared-memory/issue bound, not HBM or tensor bound"}
     else:
         ach = units_local * FLOP_PER_EVAL_GLS / (main_kernel_ms * 1e-3) / 1e12
         roof = {"bound": "fp32", "kernel": "gls_strip_kernel", "achieved": ach, "peak": FP32_PEAK_TFLOPS_MEASURED,

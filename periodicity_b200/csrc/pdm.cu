@@ -19,13 +19,20 @@
 // The argsort of phase.py:132-134 does not influence the result and is dropped.
 //
 // Mapping (north_star: "per-trial-period phase-bin variance histograms in shared
-// memory"): one thread owns one trial period and a PRIVATE histogram column in
-// shared memory, hist[stat][bin][thread] -- bank = thread % 32 whatever the bin,
-// so the read-modify-write is conflict free and needs no atomics.  On sm_100a a
-// shared-memory float atomicAdd is a CAS loop (ATOMS.CAST.SPIN); measured
-// (profiles/pipes_r01.json) the private-column update sustains 5.07 sample
-// updates/clk/SM against 0.96 for warp-shared atomic histograms, so the
-// atomic-free mapping is the one kept (SURVEY.md §7 hard part 8 allows either).
+// memory with warp-aggregated atomics"): one thread owns one trial period and a PRIVATE
+// histogram column in shared memory, hist[bin][thread] -- bank = thread % 32 whatever the
+// bin, so updates are conflict free and nothing needs aggregating.  Two levels:
+//   level 1  one 32-bit word per bin, (count << 23) + sum rint(x' 2^q): one sample is ONE native
+//            shared-memory integer atomic without return value (ATOMS.ADD, fire-and-forget; the
+//            column is private, the atomic is used for its single-instruction read-modify-write,
+//            measured 13.7 updates/clk/SM against 9.5 for LDS + IADD + STS, profiles/pipes_r01.json);
+//   level 2  float2 (count, sum x') per bin, fed from level 1 every 256 samples, merged into the
+//            FP64 partials in global memory every 8192 samples.
+// Level 1 needs 256 max|x'| 2^q < 2^22 with a fine enough step 2^-q (q >= 11) and is skipped for
+// short curves, non-finite samples or huge |t / P|: then samples go straight to level 2
+// (one LDS.64 + 2 FADD + STS.64).  A shared-memory FLOAT atomicAdd is a CAS loop on sm_100a
+// (ATOMS.CAST.SPIN, 0.96 updates/clk/SM for warp-shared histograms) and so is a 64-bit integer
+// one, which is why the packed word is 32 bits wide.
 //
 // Bin fidelity: t/P is the correctly rounded quotient (one Newton correction of
 // t * (1/P) with the exact FMA residual), phi = q - floor(q) is exact, and the
@@ -33,7 +40,7 @@
 // 2^-30 of an integer, so ties on bin edges (integer times, rational periods)
 // fall exactly where the reference puts them.
 //
-// Kernels: pdm_stats_kernel (mean, 1/std), pdm_center_kernel (x' as float),
+// Kernels: pdm_stats_kernel (mean, 1/std, packing exponent), pdm_center_kernel (x' as float and as packed increment),
 // pdm_hist_kernel (hot), pdm_epilogue_kernel (FP64 theta + block argmin),
 // argext_final_kernel<-1>.
 #include <type_traits>
@@ -276,40 +283,49 @@ pdm_hist_kernel(const PdmArgs a) {
     col32[k * THREADS] += inc;
 #endif
   };
+  // One sample of the packed path with the edge test (tail of a chunk, and the rare slow trips).
+  auto packed_one = [&](int i, unsigned guard2) {
+    unsigned p0;
+    const double tv = s_t[i];
+    unsigned k0 = pdm_bin_fast_g(tv, rP, m0u, p0);
+    double ph;
+    if (p0 < guard2) k0 = exact_bin(tv, ph);
+    add32(k0, s_xq[i]);
+  };
   auto tile_loop_packed = [&](int cnt) {
+    constexpr int U = 8;  // samples per trip: eight independent DFMA -> IMAD.WIDE chains, one edge test
     const unsigned guard2 = 2u * guard;
     for (int c0 = 0; c0 < cnt; c0 += PDM_PACK_FLUSH) {
       const int c1 = c0 + PDM_PACK_FLUSH < cnt ? c0 + PDM_PACK_FLUSH : cnt;
       int i = c0;
-      for (; i + 4 <= c1; i += 4) {
-        const double2 ta = *reinterpret_cast<const double2*>(s_t + i);
-        const double2 tb = *reinterpret_cast<const double2*>(s_t + i + 2);
-        const uint4 xv = *reinterpret_cast<const uint4*>(s_xq + i);
-        unsigned p0, p1, p2, p3;
-        unsigned k0 = pdm_bin_fast_g(ta.x, rP, m0u, p0);
-        unsigned k1 = pdm_bin_fast_g(ta.y, rP, m0u, p1);
-        unsigned k2 = pdm_bin_fast_g(tb.x, rP, m0u, p2);
-        unsigned k3 = pdm_bin_fast_g(tb.y, rP, m0u, p3);
-        if (min(min(p0, p1), min(p2, p3)) < guard2) {  // rare: a sample sits on a bin edge
-          double ph;
-          if (p0 < guard2) k0 = exact_bin(ta.x, ph);
-          if (p1 < guard2) k1 = exact_bin(ta.y, ph);
-          if (p2 < guard2) k2 = exact_bin(tb.x, ph);
-          if (p3 < guard2) k3 = exact_bin(tb.y, ph);
+      for (; i + U <= c1; i += U) {
+        double tv[U];
+        unsigned xv[U], k[U], pos[U];
+#pragma unroll
+        for (int u = 0; u < U; u += 2) {
+          const double2 tt = *reinterpret_cast<const double2*>(s_t + i + u);
+          tv[u] = tt.x;
+          tv[u + 1] = tt.y;
         }
-        add32(k0, xv.x);
-        add32(k1, xv.y);
-        add32(k2, xv.z);
-        add32(k3, xv.w);
+#pragma unroll
+        for (int u = 0; u < U; u += 4) {
+          const uint4 xx = *reinterpret_cast<const uint4*>(s_xq + i + u);
+          xv[u] = xx.x; xv[u + 1] = xx.y; xv[u + 2] = xx.z; xv[u + 3] = xx.w;
+        }
+        unsigned pmin = 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          k[u] = pdm_bin_fast_g(tv[u], rP, m0u, pos[u]);
+          pmin = min(pmin, pos[u]);
+        }
+        if (pmin < guard2) {  // rare (about m0 * U * 4e-9 of the trips): some sample sits on a bin edge
+          for (int u = 0; u < U; ++u) packed_one(i + u, guard2);
+          continue;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) add32(k[u], xv[u]);
       }
-      for (; i < c1; ++i) {
-        unsigned p0;
-        const double tv = s_t[i];
-        unsigned k0 = pdm_bin_fast_g(tv, rP, m0u, p0);
-        double ph;
-        if (p0 < guard2) k0 = exact_bin(tv, ph);
-        add32(k0, s_xq[i]);
-      }
+      for (; i < c1; ++i) packed_one(i, guard2);
 #if PDM_PACK_ATOMIC
       __syncwarp();
 #endif

@@ -306,6 +306,34 @@ __global__ void __launch_bounds__(THREADS) k_smem_private_f2(float* out, unsigne
   if (t == 123.456f) out[0] = t;
 }
 
+// ---- T12c/d: private column of packed 32-bit words (count << 23 + fixed-point sum), the first-level histogram
+// of pdm_hist_kernel: ATOMIC = native shared-memory integer atomic without return (ATOMS.ADD), else LDS + IADD + STS.
+template <bool ATOMIC>
+__global__ void __launch_bounds__(THREADS) k_smem_private_u32(float* out, unsigned long long* cyc, int iters, float seed) {
+  extern __shared__ float hist[];  // [M0][THREADS] unsigned
+  unsigned* h1 = reinterpret_cast<unsigned*>(hist);
+  for (int i = threadIdx.x; i < M0 * THREADS; i += THREADS) h1[i] = 0u;
+  __syncthreads();
+  unsigned s = threadIdx.x * 2654435761u + 12345u;
+  const unsigned inc = (1u << 23) + (unsigned)(int)seed;
+  KTIME_BEGIN
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      s = s * 1664525u + 1013904223u;
+      int q = (int)(((unsigned long long)(s >> 8) * M0) >> 24);
+      if (ATOMIC) atomicAdd(h1 + q * THREADS + threadIdx.x, inc);
+      else h1[q * THREADS + threadIdx.x] += inc;
+    }
+    if ((it & 15) == 15)  // keep the count field from overflowing (256 updates between resets)
+      for (int i = 0; i < M0; ++i) h1[i * THREADS + threadIdx.x] &= 0x7fffffu;
+  }
+  KTIME_END
+  __syncthreads();
+  unsigned t = 0; for (int i = 0; i < M0; ++i) t += h1[i * THREADS + threadIdx.x];
+  if (t == 123456789u) out[0] = (float)t;
+}
+
 // ---- T13: shared-memory float atomics, one histogram per warp ([warp][3][M0]), 32 lanes contend
 __global__ void __launch_bounds__(THREADS) k_smem_atomic(float* out, unsigned long long* cyc, int iters, float seed) {
   __shared__ float hist[(THREADS / 32) * 3 * M0];
@@ -481,6 +509,8 @@ int main(int argc, char** argv) {
     {"smem_private_rmw3",      k_smem_private,   16.0,     3, 3 * M0 * THREADS * sizeof(float), "sample-update"},
     {"smem_private_rmw_v4",    k_smem_private_v4,16.0,     2, 4 * M0 * THREADS * sizeof(float), "sample-update"},
     {"smem_private_rmw_f2",    k_smem_private_f2,16.0,     4, 2 * M0 * THREADS * sizeof(float), "sample-update"},
+    {"smem_private_u32_atoms", k_smem_private_u32<true>, 16.0, 4, sizeof(unsigned) * M0 * THREADS, "sample-update"},
+    {"smem_private_u32_rmw", k_smem_private_u32<false>, 16.0, 4, sizeof(unsigned) * M0 * THREADS, "sample-update"},
     {"smem_atomic_warp_hist",  k_smem_atomic,    16.0,     4, 0, "sample-update"},
     {"gls_step_scalar",        k_gls_scalar,     16.0,     4, 0, "eval"},
     {"gls_step_scalar_k16",    k_gls_scalar_t<16, 0>, 32.0,  2, 0, "eval"},
