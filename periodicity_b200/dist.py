@@ -220,6 +220,24 @@ def pdm_sharded(t, x, periods, nb, nc, device=None, group=None, compute=None):
     return full, idx, val
 
 
+def _device_compute_sl(t, m, periods, device):
+    torch = _torch()
+    dev = torch.device("cuda", _ffi.default_context(device).device)
+    tt = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).to(dev, non_blocking=True)
+    mm = torch.as_tensor(np.ascontiguousarray(m, dtype=np.float64)).to(dev, non_blocking=True)
+    pp = torch.as_tensor(np.ascontiguousarray(periods, dtype=np.float64)).to(dev, non_blocking=True)
+    return stringlength_torch(tt, mm, pp, ctx=_ffi.default_context(device))
+
+
+def stringlength_sharded(t, m, periods, device=None, group=None, compute=None):
+    """Period-grid-sharded String Length (trial periods are independent): every rank evaluates a
+    contiguous slice and one all-gather of ``[lengths, local min, local argmin]`` gives every rank the whole
+    periodogram, in the order of ``periods``."""
+    compute = compute or _device_compute_sl
+    return pdm_sharded(t, m, periods, None, None, device=device, group=group,
+                       compute=lambda t_, m_, p_, nb_, nc_, dev_: compute(t_, m_, p_, dev_))
+
+
 def batch_shard_bounds(n_curves, rank, world):
     """Contiguous group of light curves owned by ``rank`` (survey workload)."""
     start, stop, _ = shard_bounds(n_curves, rank, world)

@@ -34,15 +34,21 @@ class StringLength(object):
     per period ``phi = (t / P) % 1``, stable sort by ``phi``, closed-polygon length with ``np.roll``.
     """
 
-    def __init__(self, dphi=0.1, n_periods=1000, cores=None, *, device=None):
+    def __init__(self, dphi=0.1, n_periods=1000, cores=None, *, device=None, shard=False):
         self.dphi = dphi
         self.n_periods = n_periods
         self.cores = cores
         self.device = device
+        self.shard = shard      # split the period grid across torch.distributed ranks (dist.stringlength_sharded)
 
     def _ell(self, periods):
-        ctx = _ffi.default_context(self.device)
-        ell, self.argmin_index, self.min_length = ctx.stringlength(self.m.time, self.m.values, periods)
+        if self.shard:
+            from . import dist
+            ell, self.argmin_index, self.min_length = dist.stringlength_sharded(
+                self.m.time, self.m.values, periods, device=self.device)
+        else:
+            ctx = _ffi.default_context(self.device)
+            ell, self.argmin_index, self.min_length = ctx.stringlength(self.m.time, self.m.values, periods)
         return ell
 
     def _stringlength(self, period):

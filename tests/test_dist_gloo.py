@@ -63,6 +63,12 @@ def _pdm_compute(t, x, periods, nb, nc, device):
     return torch.from_numpy(th), torch.tensor([int(np.nanargmin(th))]), torch.tensor([float(np.nanmin(th))], dtype=torch.float64)
 
 
+def _sl_compute(t, m, periods, device):
+    from oracle import stringlength_numpy
+    ell = stringlength_numpy.string_lengths(np.asarray(t), np.asarray(m), periods)
+    return torch.from_numpy(ell), torch.tensor([int(np.nanargmin(ell))]), torch.tensor([float(np.nanmin(ell))], dtype=torch.float64)
+
+
 def _batch_compute(t, y, w, offsets, fmin, df, nf, fit_mean, psd_scale, want_power, device):
     from oracle import cport
     B = len(offsets) - 1
@@ -97,13 +103,15 @@ def _worker(rank, world, port, outdir):
         power, idx, val = pdist.gls_sharded(t, y, None, 0.5 * df, df, nf, True, None, compute=_gls_compute)
         periods = np.linspace(0.3, 3.0, 77)
         theta, pidx, pval = pdist.pdm_sharded(t, y, periods, 5, 2, compute=_pdm_compute)
+        from oracle import stringlength_numpy
+        ell, lidx, lval = pdist.stringlength_sharded(t, stringlength_numpy.scale(y), periods, compute=_sl_compute)
         ts, ys, offsets, f0, dfs = _survey_inputs()
         bp, barg, bmx = pdist.gls_batch_sharded(np.concatenate(ts), np.concatenate(ys), None, offsets, f0, dfs, 64,
                                                 want_power=True, compute=_batch_compute)
         _, barg2, bmx2 = pdist.gls_batch_sharded(np.concatenate(ts), np.concatenate(ys), None, offsets, f0, dfs, 64,
                                                  want_power=False, compute=_batch_compute)
         np.savez(os.path.join(outdir, f"rank{rank}.npz"), power=power, idx=idx, val=val, theta=theta,
-                 pidx=pidx, pval=pval, bp=bp, barg=barg, bmx=bmx, barg2=barg2, bmx2=bmx2)
+                 pidx=pidx, pval=pval, ell=ell, lidx=lidx, lval=lval, bp=bp, barg=barg, bmx=bmx, barg2=barg2, bmx2=bmx2)
     finally:
         dist.destroy_process_group()
 
@@ -119,6 +127,8 @@ def test_sharded_calls_world2_gloo(tmp_path):
     df = 1 / (t[-1] - t[0]) / 5
     want = cport.gls_exact(t, y, None, 0.5 * df, df, 501)
     want_theta = cport.pdm(t, y, np.linspace(0.3, 3.0, 77), 5, 2)
+    from oracle import stringlength_numpy
+    want_ell = stringlength_numpy.string_lengths(t, stringlength_numpy.scale(y), np.linspace(0.3, 3.0, 77))
     for r in range(world):
         z = np.load(tmp_path / f"rank{r}.npz")
         # every rank ends with the full periodogram and the global peak
@@ -126,6 +136,8 @@ def test_sharded_calls_world2_gloo(tmp_path):
         assert int(z["idx"]) == int(np.nanargmax(want)) and float(z["val"]) == float(np.nanmax(z["power"]))
         np.testing.assert_allclose(z["theta"], want_theta, rtol=1e-12)
         assert int(z["pidx"]) == int(np.nanargmin(want_theta))
+        np.testing.assert_array_equal(z["ell"], want_ell)
+        assert int(z["lidx"]) == int(np.nanargmin(want_ell)) and float(z["lval"]) == float(np.nanmin(want_ell))
         # batch sharding: every rank ends with every curve's periodogram and peak
         ts, ys, offsets, f0, dfs = _survey_inputs()
         for b in range(5):
