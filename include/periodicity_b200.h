@@ -246,6 +246,21 @@ PDC_API int pdc_peaks_topk(pdc_ctx* ctx, const double* values, int64_t rows, int
 PDC_API int pdc_peaks_topk_dev(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k,
                                int64_t* idx_out, double* val_out, void* stream);
 
+/*
+ * Half-maximum crossings of given peaks, the index arithmetic of `FSeries.periods_at_half_max`
+ * (core.py:957-972): for peak p of row r, level = v[p] - height / 2 and d = v - level, where
+ * height = v[p], or height[r, j] if `height` (float64[rows, k], e.g. prominences, core.py:960-963) is not NULL;
+ *   left_out   last  j <= p - 2 with signbit(d[j]) != signbit(d[j + 1])   (core.py:967; -1 if none)
+ *   right_out  first j >= p     with signbit(d[j]) != signbit(d[j + 1])   (core.py:968; -1 if none)
+ * `peak_idx` is int64[rows, k] (e.g. the idx_out of pdc_peaks_topk; entries < 0 give -1, -1).
+ * The `_dev` twin takes device pointers for all four arrays.
+ */
+PDC_API int pdc_peaks_halfmax(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k,
+                              const int64_t* peak_idx, const double* height, int64_t* left_out, int64_t* right_out);
+PDC_API int pdc_peaks_halfmax_dev(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k,
+                                  const int64_t* peak_idx, const double* height, int64_t* left_out,
+                                  int64_t* right_out, void* stream);
+
 /* Period-grid-sharded PDM with the all-gather fused into the epilogue (see pdc_gls_dev_fanout):
  * this rank evaluates `periods[0..np)`, which are elements [offset, offset + np) of the full period
  * grid; theta goes to power[r][offset + i] and (min, global argmin) to best[r][2*rank..] of every rank. */

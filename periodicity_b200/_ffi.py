@@ -80,6 +80,11 @@ SIGNATURES = {
                                             ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_peaks_topk": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_peaks_halfmax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_peaks_halfmax_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_peaks_topk_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_pdm_dev_fanout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
@@ -251,6 +256,22 @@ class Context:
             _check(self._lib.pdc_pdm(self._h, _ptr(t), _ptr(x), t.size, _ptr(periods), periods.size,
                                      int(nb), int(nc), _ptr(theta), ctypes.addressof(arg), ctypes.addressof(mn)))
         return theta, arg.value, mn.value
+
+    def peaks_halfmax(self, values, peak_idx, height=None):
+        """Indices (left, right) of the half-maximum crossings around each given peak of each row (host arrays);
+        ``height`` defaults to the peak values (``use_prominence=False`` of ``periods_at_half_max``)."""
+        v = np.atleast_2d(_f64(values))
+        rows, n = v.shape
+        idx = np.ascontiguousarray(np.atleast_2d(peak_idx), dtype=np.int64)
+        if idx.shape[0] != rows:
+            raise ValueError("peak_idx must have one row per row of values")
+        k = idx.shape[1]
+        h = None if height is None else np.ascontiguousarray(np.atleast_2d(_f64(height)))
+        left = np.empty((rows, k), dtype=np.int64)
+        right = np.empty((rows, k), dtype=np.int64)
+        with self._lock:
+            _check(self._lib.pdc_peaks_halfmax(self._h, _ptr(v), rows, n, k, _ptr(idx), _ptr(h), _ptr(left), _ptr(right)))
+        return left, right
 
     def stringlength(self, t, m, periods):
         """String length of the scaled signal ``m`` for each trial period (host arrays)."""

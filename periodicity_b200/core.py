@@ -182,6 +182,16 @@ class _Series(np.lib.mixins.NDArrayOperatorsMixin):
         peaks.attrs.update(res)
         return peaks
 
+    def find_zero_crossings(self, height=None, delta=0.0):
+        """Indices ``j`` with a sign change between samples ``j`` and ``j + 1`` (``core.py:341-367``); with
+        ``height`` the near-zero minima of ``|values|`` instead, as the reference does."""
+        if height is None:
+            (ind,) = np.where(np.diff(np.signbit(self._values)))
+            return ind
+        from scipy import signal as _signal
+        ind, _ = _signal.find_peaks(-np.abs(self._values), height=-height, prominence=delta)
+        return ind
+
     def __repr__(self):
         return (f"<{type(self).__name__} ({self._coord_name}: {self.size})>\n"
                 f"{self._coord_name}: {self._coord!r}\nvalues: {self._values!r}")
@@ -285,3 +295,18 @@ class FSeries(_Series):
     def period_at_highest_prominence(self):
         peaks = self.find_peaks()
         return peaks.period[np.nanargmax(peaks.attrs["prominences"])]
+
+    def periods_at_half_max(self, peak_order=1, use_prominence=False):
+        """``(lower, upper)`` periods where the periodogram falls to half the height (or half the prominence) of
+        its ``peak_order``-th highest peak (``core.py:957-972``).  The level is ``values[peak] - height / 2`` as a
+        scalar: the reference builds it as a one-sample series, which its own exact-join arithmetic cannot
+        subtract from the slices (same defect as ``phase.py:65``); the index arithmetic is the reference's."""
+        peaks = self.find_peaks()
+        indices = peaks.attrs["indices"]
+        heights = peaks.attrs["prominences"] if use_prominence else peaks.values
+        jmax = heights.argsort()[-peak_order]
+        idmax = indices[jmax]
+        half = self._values[idmax] - heights[jmax] / 2
+        hi = (self[:idmax] - half).find_zero_crossings()[-1]
+        lo = (self[idmax:] - half).find_zero_crossings()[0]
+        return self[idmax:].period[lo], self[:idmax].period[hi]

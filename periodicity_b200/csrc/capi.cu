@@ -525,4 +525,35 @@ int pdc_peaks_topk(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, 
   return PDC_OK;
 }
 
+int pdc_peaks_halfmax_dev(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k, const int64_t* peak_idx,
+                          const double* height, int64_t* left_out, int64_t* right_out, void* stream) {
+  if (!ctx || !values || !peak_idx || !left_out || !right_out) { set_error("pdc_peaks_halfmax_dev: NULL argument"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  return peaks_halfmax_run(ctx, values, rows, n, k, peak_idx, height, left_out, right_out, st);
+}
+
+int pdc_peaks_halfmax(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k, const int64_t* peak_idx,
+                      const double* height, int64_t* left_out, int64_t* right_out) {
+  if (!ctx || !values || !peak_idx || !left_out || !right_out) { set_error("pdc_peaks_halfmax: NULL argument"); return PDC_EINVAL; }
+  if (rows < 1 || n < 1 || k < 1) { set_error("pdc_peaks_halfmax: empty input"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t nb = sizeof(double) * (size_t)rows * n, ob = (size_t)rows * k;
+  PDC_TRY(ctx->out_a.reserve(nb));
+  PDC_TRY(ctx->out_small.reserve(ob * (3 * sizeof(int64_t) + sizeof(double))));
+  int64_t* d_idx = ctx->out_small.as<int64_t>();
+  int64_t* d_left = d_idx + ob;
+  int64_t* d_right = d_left + ob;
+  double* d_h = reinterpret_cast<double*>(d_right + ob);
+  PDC_CUDA(cudaMemcpyAsync(ctx->out_a.p, values, nb, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(d_idx, peak_idx, ob * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (height) PDC_CUDA(cudaMemcpyAsync(d_h, height, ob * sizeof(double), cudaMemcpyHostToDevice, st));
+  PDC_TRY(peaks_halfmax_run(ctx, ctx->out_a.as<double>(), rows, n, k, d_idx, height ? d_h : nullptr, d_left, d_right, st));
+  PDC_CUDA(cudaMemcpyAsync(left_out, d_left, ob * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaMemcpyAsync(right_out, d_right, ob * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  PDC_CUDA(cudaStreamSynchronize(st));
+  return PDC_OK;
+}
+
 }  // extern "C"

@@ -120,6 +120,9 @@ int strlen_run(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const 
 int peaks_run(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k, int64_t* idx_out,
               double* val_out, cudaStream_t stream);
 
+int peaks_halfmax_run(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k, const int64_t* peak_idx,
+                      const double* height, int64_t* left_out, int64_t* right_out, cudaStream_t stream);
+
 // ---- small device helpers ---------------------------------------------------
 #ifdef __CUDACC__
 

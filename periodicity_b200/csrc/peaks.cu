@@ -93,6 +93,61 @@ peaks_merge_kernel(double* __restrict__ cand_v, long long* __restrict__ cand_i, 
               out_v + (long long)row * k, out_i + (long long)row * k, sv, si, &win);
 }
 
+// Half-maximum crossings of given peaks: `FSeries.periods_at_half_max` (reference core.py:957-972).
+// For a peak at index p the level is half = v[p] - height / 2 with height = v[p] (or the caller's per-peak
+// height, e.g. the prominence: use_prominence=True, core.py:960-963); d[j] = v[j] - half.
+//   left  = the LAST  j in [0, p - 2]      with signbit(d[j]) != signbit(d[j + 1])  (core.py:967, find_zero_crossings :362)
+//   right = the FIRST j in [p, n - 2]      with signbit(d[j]) != signbit(d[j + 1])  (core.py:968)
+// -1 if there is none.  One warp per peak scans outwards 32 samples at a time.
+__device__ __forceinline__ bool sl_signbit(double x) { return (__double2hiint(x) >> 31) != 0; }
+
+__global__ void __launch_bounds__(128)
+peaks_halfmax_kernel(const double* __restrict__ values, long long n, int k, const long long* __restrict__ peak_idx,
+                     const double* __restrict__ height, long long total, long long* __restrict__ left_out,
+                     long long* __restrict__ right_out) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= total) return;
+  const long long row = w / k;
+  const double* v = values + row * n;
+  const long long p = peak_idx[w];
+  long long left = -1, right = -1;
+  if (p >= 0 && p < n) {
+    const double half = v[p] - (height ? height[w] : v[p]) / 2;
+    // rightwards: pairs (j, j + 1), j = p .. n - 2
+    for (long long j0 = p; j0 <= n - 2; j0 += 32) {
+      const long long j = j0 + lane;
+      const bool hit = j <= n - 2 && sl_signbit(v[j] - half) != sl_signbit(v[j + 1] - half);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) { right = j0 + (__ffs(m) - 1); break; }
+    }
+    // leftwards: pairs (j, j + 1), j = p - 2 .. 0
+    for (long long j0 = p - 2; j0 >= 0; j0 -= 32) {
+      const long long j = j0 - lane;
+      const bool hit = j >= 0 && sl_signbit(v[j] - half) != sl_signbit(v[j + 1] - half);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) { left = j0 - (__ffs(m) - 1); break; }
+    }
+  }
+  if (lane == 0) {
+    left_out[w] = left;
+    right_out[w] = right;
+  }
+}
+
+int peaks_halfmax_run(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k, const int64_t* peak_idx,
+                      const double* height, int64_t* left_out, int64_t* right_out, cudaStream_t st) {
+  if (rows < 1 || n < 1 || k < 1) { set_error("pdc_peaks_halfmax: empty input"); return PDC_EINVAL; }
+  const long long total = (long long)rows * k;
+  const long long blocks = (total * 32 + 127) / 128;
+  if (blocks > 0x7fffffffLL) { set_error("pdc_peaks_halfmax: too many peaks for one call"); return PDC_EINVAL; }
+  peaks_halfmax_kernel<<<(unsigned)blocks, 128, 0, st>>>(values, (long long)n, k, (const long long*)peak_idx, height,
+                                                         total, (long long*)left_out, (long long*)right_out);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return PDC_OK;
+}
+
 int peaks_run(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k, int64_t* idx_out,
               double* val_out, cudaStream_t st) {
   if (rows < 1 || n < 1) { set_error("pdc_peaks_topk: empty input"); return PDC_EINVAL; }

@@ -107,6 +107,22 @@ class GLS(object):
         freq = np.where(idx >= 0, self.periodogram.frequency[np.maximum(idx, 0)], np.nan)
         return freq, val
 
+    def top_peak_widths(self, k=5):
+        """Half-maximum period intervals of the ``k`` highest peaks, found on the GPU (``pdc_peaks_topk`` +
+        ``pdc_peaks_halfmax``): row ``j`` is what ``periodogram.periods_at_half_max(peak_order=j + 1)`` returns
+        (``core.py:957-972``).  Returns ``(frequency[k], power[k], lower_period[k], upper_period[k])``; NaN where a
+        peak or a crossing does not exist."""
+        ctx = _ffi.default_context(self.device)
+        pg = self.periodogram
+        idx, val = ctx.peaks_topk(pg.values, k)
+        left, right = ctx.peaks_halfmax(pg.values, idx)
+        idx, val, left, right = idx[0], val[0], left[0], right[0]
+        period = pg.period
+        freq = np.where(idx >= 0, pg.frequency[np.maximum(idx, 0)], np.nan)
+        lower = np.where(right >= 0, period[np.maximum(right, 0)], np.nan)   # crossing on the high-frequency side
+        upper = np.where(left >= 0, period[np.maximum(left, 0)], np.nan)
+        return freq, val, lower, upper
+
     def bootstrap(self, n_bootstraps, random_seed=None, batch=256):
         """Maximum power of ``n_bootstraps`` resamples (``spectral.py:140-152``).
 

@@ -76,3 +76,20 @@ def test_fseries_nan_aware_reductions_and_peaks():
     assert list(peaks.attrs["indices"]) == [1, 4]
     with pytest.raises(ValueError):
         FSeries([1.0, 2.0], [1.0])
+
+
+def test_periods_at_half_max_and_zero_crossings():
+    """core.py:341-367,957-972 with a scalar half-maximum level (see the method's docstring)."""
+    f = np.linspace(0.01, 2.0, 4000)
+    v = np.exp(-0.5 * ((f - 0.7) / 0.01) ** 2) + 0.6 * np.exp(-0.5 * ((f - 1.3) / 0.02) ** 2)
+    pg = FSeries(f, v)
+    lower, upper = pg.periods_at_half_max()
+    fwhm = 2 * np.sqrt(2 * np.log(2)) * 0.01
+    assert lower < 1 / 0.7 < upper
+    assert abs((1 / lower - 1 / upper) - fwhm) < 3 * (f[1] - f[0])
+    lo2, up2 = pg.periods_at_half_max(peak_order=2)
+    assert lo2 < 1 / 1.3 < up2
+    lo3, up3 = pg.periods_at_half_max(peak_order=1, use_prominence=True)
+    assert (lo3, up3) == (lower, upper)                      # isolated peak on a zero floor: prominence == height
+    zc = (pg - 0.5).find_zero_crossings()
+    assert zc.size == 4 and np.all(np.diff(np.signbit(v - 0.5))[zc])

@@ -77,3 +77,47 @@ def test_gls_top_peaks_and_survey_topk(gpu_ctx):
         np.testing.assert_array_equal(out["peak_index"][b], ri)
         np.testing.assert_array_equal(out["peak_power"][b], rv)
         assert out["peak_index"][b][0] == out["argmax"][b] or out["max_power"][b] >= rv[0]
+
+
+def _halfmax_numpy(v, p, height=None):
+    half = v[p] - (v[p] if height is None else height) / 2
+    d = v - half
+    ch = np.where(np.diff(np.signbit(d)))[0]
+    left = ch[ch <= p - 2]
+    right = ch[ch >= p]
+    return (left[-1] if left.size else -1), (right[0] if right.size else -1)
+
+
+def test_halfmax_crossings_match_numpy(gpu_ctx):
+    rng = np.random.default_rng(41)
+    rows, n, k = 5, 30_000, 12
+    v = np.abs(rng.standard_normal((rows, n))).cumsum(axis=1)
+    v = np.sin(v / 40.0) ** 2 * rng.uniform(0.5, 2.0, (rows, 1)) + 0.01 * rng.standard_normal((rows, n))
+    idx, val = gpu_ctx.peaks_topk(v, k)
+    left, right = gpu_ctx.peaks_halfmax(v, idx)
+    prom = rng.uniform(0.1, 1.0, idx.shape) * val
+    left_p, right_p = gpu_ctx.peaks_halfmax(v, idx, prom)
+    for r in range(rows):
+        for j in range(k):
+            assert (left[r, j], right[r, j]) == _halfmax_numpy(v[r], idx[r, j])
+            assert (left_p[r, j], right_p[r, j]) == _halfmax_numpy(v[r], idx[r, j], prom[r, j])
+    # peaks next to the borders, missing peaks, no crossing at all
+    w = np.array([[0.0, 1.0, 0.9, 0.95, 0.2, 0.1, 3.0, 2.9]])
+    pk = np.array([[1, 6, -1, 3]])
+    l2, r2 = gpu_ctx.peaks_halfmax(w, pk)
+    want = [_halfmax_numpy(w[0], p) if p >= 0 else (-1, -1) for p in pk[0]]
+    assert [(a, b) for a, b in zip(l2[0], r2[0])] == want
+
+
+def test_top_peak_widths_match_container_method():
+    from periodicity_b200 import GLS, TSeries
+    rng = np.random.default_rng(42)
+    t = np.sort(rng.uniform(0, 200, 1500))
+    y = np.sin(2 * np.pi * t / 7.3) + 0.5 * np.sin(2 * np.pi * t / 2.9) + 0.2 * rng.standard_normal(1500)
+    gls = GLS(fmax=1.0)
+    pg = gls(TSeries(t, y))
+    freq, power, lower, upper = gls.top_peak_widths(4)
+    for j in range(4):
+        lo, up = pg.periods_at_half_max(peak_order=j + 1)
+        assert (lower[j], upper[j]) == (lo, up)
+    assert abs(1 / freq[0] - 7.3) < 0.1 and lower[0] < 7.3 < upper[0]
