@@ -40,7 +40,7 @@
 // 2^-30 of an integer, so ties on bin edges (integer times, rational periods)
 // fall exactly where the reference puts them.
 //
-// Kernels: pdm_stats_kernel (mean, 1/std, packing exponent), pdm_center_kernel (x' as float and as packed increment),
+// Kernels: pdm_stats{1,2,3}_kernel (mean, 1/std, packing exponent; multi-block), pdm_center_kernel (x' as float and as packed increment),
 // pdm_hist_kernel (hot), pdm_epilogue_kernel (FP64 theta + block argmin),
 // argext_final_kernel<-1>.
 #include <type_traits>
@@ -63,23 +63,58 @@ constexpr int PDM_PACK_MIN_N = 4096;  // shorter curves keep the FP32 columns (t
 constexpr int PDM_TILE = 1024;        // samples per shared-memory tile
 constexpr int PDM_FLUSH_TILES = 8;    // FP32 histograms are merged into FP64 every 8192 samples
 
-__global__ void __launch_bounds__(1024)
-pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmMeta* meta) {
+// Statistics in three small launches so that a long curve is read by many SMs (one block would take ~100 us
+// for 1e5 samples): per-block partials in a fixed layout, reduced by every consumer in the same order, so the
+// result is deterministic.
+struct PdmPart {
+  double s, tabs, q, qb, dmax;
+  int bad, pad_;
+};
+constexpr int PDM_STATS_THREADS = 256;
+constexpr int PDM_STATS_MAXBLK = 128;
+
+// pass 1: sum x, max |t| over finite stamps, any non-finite sample
+__global__ void __launch_bounds__(PDM_STATS_THREADS)
+pdm_stats1_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmPart* part) {
   __shared__ double scratch[33];
   double s = 0.0, tneg = 0.0;
   int bad = 0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    s += x[i];
-    bad |= !isfinite(x[i]) || !isfinite(t[i]);
-    if (isfinite(t[i])) tneg = fmin(tneg, -fabs(t[i]));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double xi = x[i], ti = t[i];
+    s += xi;
+    bad |= !isfinite(xi) || !isfinite(ti);
+    if (isfinite(ti)) tneg = fmin(tneg, -fabs(ti));
   }
   bad = __syncthreads_or(bad);
   s = block_sum(s, scratch);
   const double tabs = -block_min(tneg, scratch);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x].s = s;
+    part[blockIdx.x].tabs = tabs;
+    part[blockIdx.x].bad = bad;
+  }
+}
+
+__device__ __forceinline__ void pdm_reduce_pass1(const PdmPart* part, int nblk, double& s, double& tabs, int& bad) {
+  s = 0.0; tabs = 0.0; bad = 0;
+  for (int b = 0; b < nblk; ++b) {  // same order in every block
+    s += part[b].s;
+    tabs = fmax(tabs, part[b].tabs);
+    bad |= part[b].bad;
+  }
+}
+
+// pass 2: sum (x - mean)^2 (all samples, and those with a finite stamp), max |x - mean|
+__global__ void __launch_bounds__(PDM_STATS_THREADS)
+pdm_stats2_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmPart* part) {
+  __shared__ double scratch[33];
+  double s, tabs;
+  int bad;
+  pdm_reduce_pass1(part, gridDim.x, s, tabs, bad);
   const double mean = s / (double)n;
   double q = 0.0, qb = 0.0, dneg = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    double d = x[i] - mean;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double d = x[i] - mean;
     q = fma(d, d, q);
     dneg = fmin(dneg, -fabs(d));
     if (bad && isfinite(t[i])) qb = fma(d, d, qb);
@@ -88,6 +123,25 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
   qb = block_sum(qb, scratch);
   const double dmax = -block_min(dneg, scratch);
   if (threadIdx.x == 0) {
+    part[blockIdx.x].q = q;
+    part[blockIdx.x].qb = qb;
+    part[blockIdx.x].dmax = dmax;
+  }
+}
+
+__global__ void pdm_stats3_kernel(const PdmPart* __restrict__ part, int nblk, long long n, PdmMeta* meta) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s, tabs;
+  int bad;
+  pdm_reduce_pass1(part, nblk, s, tabs, bad);
+  double q = 0.0, qb = 0.0, dmax = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    q += part[b].q;
+    qb += part[b].qb;
+    dmax = fmax(dmax, part[b].dmax);
+  }
+  const double mean = s / (double)n;
+  {
     const double var = q / (double)(n - 1);  // phase.py:165  np.var(values, ddof=1)
     meta->mean = mean;
     meta->inv_sd = 1.0 / sqrt(var);
@@ -464,10 +518,12 @@ pdm_epilogue_kernel(double* __restrict__ partial, const double* __restrict__ per
   if (pi < np) {
     // fold the sample splits into split 0 (this thread's own column only)
     const long long rows = 2LL * m0;
-    for (long long b = 0; b < rows; ++b) {
-      double acc = 0.0;
-      for (int s = 0; s < nsplit; ++s) acc += partial[((long long)s * rows + b) * np + pi];
-      partial[b * np + pi] = acc;
+    if (nsplit > 1) {
+      for (long long b = 0; b < rows; ++b) {
+        double acc = 0.0;
+        for (int s = 0; s < nsplit; ++s) acc += partial[((long long)s * rows + b) * np + pi];
+        partial[b * np + pi] = acc;
+      }
     }
     const double* pn = partial + pi;
     const double* p1 = pn + (long long)m0 * np;
@@ -570,16 +626,25 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   if (blocks > 0x7fffffffLL) { set_error("pdc_pdm: problem too large for one call"); return PDC_EINVAL; }
 
   PDC_TRY(ctx->scratch_acquire(st));
-  PDC_TRY(ctx->pdm_meta.reserve(sizeof(PdmMeta)));
+  PDC_TRY(ctx->pdm_meta.reserve(sizeof(PdmMeta) + 16 + sizeof(PdmPart) * PDM_STATS_MAXBLK));
   PDC_TRY(ctx->pdm_x.reserve((sizeof(float) + sizeof(unsigned)) * (size_t)n));
   PDC_TRY(ctx->partial.reserve(sizeof(double) * 2 * m0 * (size_t)np * nsplit));
   const int eblk = (int)((np + 255) / 256);
   PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk));
 
   PdmMeta* meta = ctx->pdm_meta.as<PdmMeta>();
-  pdm_stats_kernel<<<1, 1024, 0, st>>>(t, x, n, meta);
-  PDC_CUDA(cudaGetLastError());
-  ctx->launches++;
+  {
+    PdmPart* part = reinterpret_cast<PdmPart*>(reinterpret_cast<char*>(meta) + ((sizeof(PdmMeta) + 15) & ~(size_t)15));
+    long long sblk = (n + 8 * PDM_STATS_THREADS - 1) / (8 * PDM_STATS_THREADS);
+    if (sblk > PDM_STATS_MAXBLK) sblk = PDM_STATS_MAXBLK;
+    pdm_stats1_kernel<<<(unsigned)sblk, PDM_STATS_THREADS, 0, st>>>(t, x, n, part);
+    PDC_CUDA(cudaGetLastError());
+    pdm_stats2_kernel<<<(unsigned)sblk, PDM_STATS_THREADS, 0, st>>>(t, x, n, part);
+    PDC_CUDA(cudaGetLastError());
+    pdm_stats3_kernel<<<1, 32, 0, st>>>(part, (int)sblk, n, meta);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches += 3;
+  }
   {
     long long bx = (n + 255) / 256;
     if (bx > 2048) bx = 2048;
