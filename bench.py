@@ -591,7 +591,7 @@ def main():
         ach = units_local / (main_kernel_ms * 1e-3) / 1e9
         roof = {"bound": "smem", "kernel": "pdm_hist_kernel", "achieved": ach, "peak": PDM_PEAK_GEVALS_MEASURED,
                 "unit": "Gevals/s", "frac": ach / PDM_PEAK_GEVALS_MEASURED,
-                "traffic": ncu_traffic("ncu_pdm_hist_c3_r01.json") if args.workload == "pdm_c3" and world == 1 else None,
+                "traffic": ncu_traffic("ncu_pdm_hist_r01c.json") if args.workload == "pdm_c3" and world == 1 else None,
                 "kernel_ms": main_kernel_ms,
                 "peak_source": "profiles/pipes_r01.json smem_private_u32_atoms (one shared-memory ATOMS.ADD on a private "
                                "32-bit column word per sample update, 13.7 per clk per SM: the floor of the "
@@ -600,7 +600,7 @@ def main():
         ach = units_local * FLOP_PER_EVAL_GLS / (main_kernel_ms * 1e-3) / 1e12
         roof = {"bound": "fp32", "kernel": "gls_strip_kernel", "achieved": ach, "peak": FP32_PEAK_TFLOPS_MEASURED,
                 "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS_MEASURED,
-                "traffic": ncu_traffic("ncu_gls_strip_c2_r01.json") if args.workload == "gls_c2" and world == 1 else None,
+                "traffic": ncu_traffic("ncu_gls_strip_r01c.json") if args.workload == "gls_c2" and world == 1 else None,
                 "kernel_ms": main_kernel_ms, "flop_per_eval": FLOP_PER_EVAL_GLS,
                 "note": ("shared-timestamp kernel: rotation and window sums are shared by 8 series, so the 20 FLOP "
                          "per evaluation of the accounting figure are not all executed; frac > 1 is expected")
