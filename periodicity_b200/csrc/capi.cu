@@ -202,7 +202,8 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   DeviceGuard guard(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->in_a.release(); ctx->in_b.release(); ctx->in_c.release(); ctx->in_d.release();
-  ctx->out_a.release(); ctx->out_small.release(); ctx->pin_small.release();
+  ctx->out_a.release(); ctx->out_small.release(); ctx->pin_small.release(); ctx->pin_out.release();
+  for (auto& e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   ctx->gls_curves.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->glsm_y.release();
   ctx->partial.release(); ctx->blockred.release(); ctx->pin_meta.release();
   ctx->pdm_meta.release(); ctx->pdm_x.release(); ctx->peak_cand.release();
@@ -285,6 +286,37 @@ struct SmallRec {
   double val;
 };
 
+// Device -> caller's host buffer.  A cudaMemcpyAsync into pageable memory is staged by the driver at ~10 GB/s
+// (0.8 MB periodogram: 86 us); going through our own pinned buffer in a few chunks, each copied out by the CPU
+// while the next one is in flight, takes about half of that.  Returns with the data in `dst`.
+static int staged_d2h(pdc_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes < ((size_t)128 << 10) || bytes > ((size_t)256 << 20)) {
+    PDC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    PDC_CUDA(cudaStreamSynchronize(st));
+    return PDC_OK;
+  }
+  PDC_TRY(ctx->pin_out.reserve(bytes));
+  int nchunk = (int)(bytes / ((size_t)256 << 10));
+  if (nchunk < 2) nchunk = 2;
+  if (nchunk > 8) nchunk = 8;
+  const size_t step = ((bytes / nchunk) + 4095) & ~(size_t)4095;
+  char* pin = ctx->pin_out.as<char>();
+  int used = 0;
+  for (size_t off = 0; off < bytes; off += step, ++used) {
+    const size_t len = off + step < bytes ? step : bytes - off;
+    if (!ctx->ev_chunk[used]) PDC_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[used], cudaEventDisableTiming));
+    PDC_CUDA(cudaMemcpyAsync(pin + off, (const char*)src + off, len, cudaMemcpyDeviceToHost, st));
+    PDC_CUDA(cudaEventRecord(ctx->ev_chunk[used], st));
+  }
+  int c = 0;
+  for (size_t off = 0; off < bytes; off += step, ++c) {
+    const size_t len = off + step < bytes ? step : bytes - off;
+    PDC_CUDA(cudaEventSynchronize(ctx->ev_chunk[c]));
+    memcpy((char*)dst + off, pin + off, len);
+  }
+  return PDC_OK;
+}
+
 static int gls_host_common(pdc_ctx* ctx, const double* t, const double* y, const double* w,
                            const int64_t* offsets, int64_t B, const double* fmin, const double* df,
                            int64_t j0, int64_t nf, unsigned flags, const double* psd_scale,
@@ -325,10 +357,9 @@ static int gls_host_common(pdc_ctx* ctx, const double* t, const double* y, const
                    power_out ? ctx->out_a.as<double>() : nullptr, (int64_t*)d_arg, d_val, st);
   delete[] heap_off;
   PDC_TRY(rc);
-  if (power_out)
-    PDC_CUDA(cudaMemcpyAsync(power_out, ctx->out_a.p, sizeof(double) * (size_t)nf * B, cudaMemcpyDeviceToHost, st));
   PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, ctx->out_small.p, (sizeof(long long) + sizeof(double)) * (size_t)B,
                            cudaMemcpyDeviceToHost, st));
+  if (power_out) PDC_TRY(staged_d2h(ctx, power_out, ctx->out_a.p, sizeof(double) * (size_t)nf * B, st));
   PDC_CUDA(cudaStreamSynchronize(st));
   const long long* h_arg = ctx->pin_small.as<long long>();
   const double* h_val = reinterpret_cast<const double*>(h_arg + B);
@@ -392,10 +423,9 @@ int pdc_gls_multi(pdc_ctx* ctx, const double* t, const double* Y, const double* 
   PDC_TRY(glsm_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), w ? ctx->in_c.as<double>() : nullptr, n, S,
                    fmin, df, j0, nf, flags, psd_scale, power_out ? ctx->out_a.as<double>() : nullptr,
                    (int64_t*)d_arg, d_val, st));
-  if (power_out)
-    PDC_CUDA(cudaMemcpyAsync(power_out, ctx->out_a.p, sizeof(double) * (size_t)nf * S, cudaMemcpyDeviceToHost, st));
   PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, ctx->out_small.p, (sizeof(long long) + sizeof(double)) * (size_t)S,
                            cudaMemcpyDeviceToHost, st));
+  if (power_out) PDC_TRY(staged_d2h(ctx, power_out, ctx->out_a.p, sizeof(double) * (size_t)nf * S, st));
   PDC_CUDA(cudaStreamSynchronize(st));
   const long long* h_arg = ctx->pin_small.as<long long>();
   const double* h_val = reinterpret_cast<const double*>(h_arg + S);
@@ -448,8 +478,8 @@ int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
   SmallRec* d_rec = ctx->out_small.as<SmallRec>();
   PDC_TRY(pdm_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), n, ctx->in_d.as<double>(), np, nb, nc,
                   ctx->out_a.as<double>(), (int64_t*)&d_rec->arg, &d_rec->val, st));
-  PDC_CUDA(cudaMemcpyAsync(theta_out, ctx->out_a.p, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, st));
   PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, d_rec, sizeof(SmallRec), cudaMemcpyDeviceToHost, st));
+  PDC_TRY(staged_d2h(ctx, theta_out, ctx->out_a.p, sizeof(double) * (size_t)np, st));
   PDC_CUDA(cudaStreamSynchronize(st));
   const SmallRec* h = ctx->pin_small.as<SmallRec>();
   if (argmin_out) *argmin_out = h->arg;
@@ -486,8 +516,8 @@ int pdc_stringlength(pdc_ctx* ctx, const double* t, const double* m, int64_t n, 
   SmallRec* d_rec = ctx->out_small.as<SmallRec>();
   PDC_TRY(strlen_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), n, ctx->in_d.as<double>(), np,
                      ctx->out_a.as<double>(), (int64_t*)&d_rec->arg, &d_rec->val, st));
-  PDC_CUDA(cudaMemcpyAsync(ell_out, ctx->out_a.p, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, st));
   PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, d_rec, sizeof(SmallRec), cudaMemcpyDeviceToHost, st));
+  PDC_TRY(staged_d2h(ctx, ell_out, ctx->out_a.p, sizeof(double) * (size_t)np, st));
   PDC_CUDA(cudaStreamSynchronize(st));
   const SmallRec* h = ctx->pin_small.as<SmallRec>();
   if (argmin_out) *argmin_out = h->arg;

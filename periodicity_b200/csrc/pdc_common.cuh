@@ -78,6 +78,8 @@ struct pdc_ctx {
   pdc::DevBuf out_a;           // power / theta
   pdc::DevBuf out_small;       // argmax/max records
   pdc::PinnedBuf pin_small;    // pinned landing zone for the small records
+  pdc::PinnedBuf pin_out;      // pinned staging of large results on their way to the caller's (pageable) buffer
+  cudaEvent_t ev_chunk[8] = {};
 
   // GLS scratch
   pdc::DevBuf gls_curves;      // GlsCurve[B]
