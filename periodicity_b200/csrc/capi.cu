@@ -204,7 +204,7 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   ctx->in_a.release(); ctx->in_b.release(); ctx->in_c.release(); ctx->in_d.release();
   ctx->out_a.release(); ctx->out_small.release(); ctx->pin_small.release(); ctx->pin_out.release();
   for (auto& e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
-  ctx->gls_curves.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->glsm_y.release();
+  ctx->gls_curves.release(); ctx->gls_part.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->glsm_y.release();
   ctx->partial.release(); ctx->blockred.release(); ctx->pin_meta.release();
   ctx->pdm_meta.release(); ctx->pdm_x.release(); ctx->peak_cand.release();
   ctx->main_resolve();

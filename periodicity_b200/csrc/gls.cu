@@ -18,7 +18,7 @@
 // MUFU sin/cos) and rotates K-1 times in FP32.  "K" = strip length = reseed period.
 //
 // Kernels (launch order):
-//   gls_stats_kernel    per curve: t_min, sum w, weighted mean, YY      (FP64)
+//   gls_stats{1,2,3}_kernel  per curve: t_min, sum w, weighted mean, YY  (FP64, multi-block partials)
 //   gls_records_kernel  per sample: (t - t_min, frac(df (t - t_min))) as double2 and
 //                       (cos, sin of 2 pi df (t - t_min), y', w') as float4
 //   gls_lowfreq_kernel  FP64 direct sums for the few frequencies with < 1 cycle over the baseline
@@ -52,17 +52,23 @@
 namespace pdc {
 
 // ---------------------------------------------------------------------------
-// per-curve statistics (one block per curve)
+// per-curve statistics: grid (G, B).  A long single curve is read by G blocks (one block would need
+// ~30 us for 65,000 samples), a batch uses G = 1; partials live in a fixed layout and every consumer
+// reduces them in the same order, so the result does not depend on scheduling.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y,
-                 const double* __restrict__ w, GlsCurve* curves, unsigned flags,
-                 long long j0, long long nf, int allow_three_term) {
+struct GlsPart {
+  double tmin, tneg, sw, swy, syy;
+};
+constexpr int GLS_STATS_THREADS = 256;
+
+__global__ void __launch_bounds__(GLS_STATS_THREADS)
+gls_stats1_kernel(const double* __restrict__ t, const double* __restrict__ y,
+                  const double* __restrict__ w, const GlsCurve* __restrict__ curves, GlsPart* __restrict__ part) {
   __shared__ double scratch[33];
-  GlsCurve& cv = curves[blockIdx.x];
+  const GlsCurve& cv = curves[blockIdx.y];
   const long long b = cv.begin, n = cv.n;
   double tmin = INFINITY, tneg = INFINITY, sw = 0.0, swy = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double ti = t[b + i], yi = y[b + i], wi = w ? w[b + i] : 1.0;
     tmin = fmin(tmin, ti);
     tneg = fmin(tneg, -ti);
@@ -70,18 +76,63 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y,
     swy = fma(wi, yi, swy);
   }
   tmin = block_min(tmin, scratch);
-  const double tmax = -block_min(tneg, scratch);
+  tneg = block_min(tneg, scratch);
   sw = block_sum(sw, scratch);
   swy = block_sum(swy, scratch);
+  if (threadIdx.x == 0) {
+    GlsPart& p = part[(long long)blockIdx.y * gridDim.x + blockIdx.x];
+    p.tmin = tmin;
+    p.tneg = tneg;
+    p.sw = sw;
+    p.swy = swy;
+  }
+}
+
+__device__ __forceinline__ void gls_reduce_pass1(const GlsPart* p, int g, double& tmin, double& tneg, double& sw,
+                                                 double& swy) {
+  tmin = INFINITY; tneg = INFINITY; sw = 0.0; swy = 0.0;
+  for (int k = 0; k < g; ++k) {  // same order everywhere
+    tmin = fmin(tmin, p[k].tmin);
+    tneg = fmin(tneg, p[k].tneg);
+    sw += p[k].sw;
+    swy += p[k].swy;
+  }
+}
+
+__global__ void __launch_bounds__(GLS_STATS_THREADS)
+gls_stats2_kernel(const double* __restrict__ y, const double* __restrict__ w, const GlsCurve* __restrict__ curves,
+                  GlsPart* __restrict__ part, unsigned flags) {
+  __shared__ double scratch[33];
+  const GlsCurve& cv = curves[blockIdx.y];
+  const long long b = cv.begin, n = cv.n;
+  GlsPart* p = part + (long long)blockIdx.y * gridDim.x;
+  double tmin, tneg, sw, swy;
+  gls_reduce_pass1(p, gridDim.x, tmin, tneg, sw, swy);
   // spectral.py:102-108: w /= w.sum(); y = values - dot(w, values) if fit_mean
   const double ymean = (flags & PDC_GLS_FIT_MEAN) ? swy / sw : 0.0;
   double syy = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double d = y[b + i] - ymean, wi = w ? w[b + i] : 1.0;
     syy = fma(wi * d, d, syy);
   }
   syy = block_sum(syy, scratch);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) p[blockIdx.x].syy = syy;
+}
+
+__global__ void __launch_bounds__(64)
+gls_stats3_kernel(GlsCurve* curves, const GlsPart* __restrict__ part, int g, int B, unsigned flags,
+                  long long j0, long long nf, int allow_three_term) {
+  const int curve = blockIdx.x * blockDim.x + threadIdx.x;
+  if (curve >= B) return;
+  GlsCurve& cv = curves[curve];
+  const GlsPart* p = part + (long long)curve * g;
+  double tmin, tneg, sw, swy;
+  gls_reduce_pass1(p, g, tmin, tneg, sw, swy);
+  const double tmax = -tneg;
+  const double ymean = (flags & PDC_GLS_FIT_MEAN) ? swy / sw : 0.0;
+  double syy = 0.0;
+  for (int k = 0; k < g; ++k) syy += p[k].syy;
+  {
     double yy = syy / sw;  // spectral.py:120  YY = dot(w, y**2)
     cv.tmin = tmin;
     cv.tmax = tmax;
@@ -623,10 +674,25 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   const double* yy = y + off0;
   const double* ww = w ? w + off0 : nullptr;
 
-  gls_stats_kernel<<<(unsigned)B, 1024, 0, st>>>(tt, yy, ww, dc, flags, (long long)j0, (long long)nf,
-                                                 ctx->gls_three_term ? 1 : 0);
-  PDC_CUDA(cudaGetLastError());
-  ctx->launches++;
+  {
+    long long g = 1;
+    if (B < 64) {
+      g = (nmax + 8 * GLS_STATS_THREADS - 1) / (8 * GLS_STATS_THREADS);
+      if (g > 32) g = 32;
+      if (g < 1) g = 1;
+    }
+    PDC_TRY(ctx->gls_part.reserve(sizeof(GlsPart) * (size_t)g * B));
+    GlsPart* part = ctx->gls_part.as<GlsPart>();
+    dim3 grid((unsigned)g, (unsigned)B);
+    gls_stats1_kernel<<<grid, GLS_STATS_THREADS, 0, st>>>(tt, yy, ww, dc, part);
+    PDC_CUDA(cudaGetLastError());
+    gls_stats2_kernel<<<grid, GLS_STATS_THREADS, 0, st>>>(yy, ww, dc, part, flags);
+    PDC_CUDA(cudaGetLastError());
+    gls_stats3_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(dc, part, (int)g, (int)B, flags, (long long)j0,
+                                                               (long long)nf, ctx->gls_three_term ? 1 : 0);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches += 3;
+  }
 
   {
     long long bx = (nmax + 255) / 256;

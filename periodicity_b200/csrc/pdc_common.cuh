@@ -83,6 +83,7 @@ struct pdc_ctx {
 
   // GLS scratch
   pdc::DevBuf gls_curves;      // GlsCurve[B]
+  pdc::DevBuf gls_part;        // GlsPart[B][G]: per-block partial statistics
   pdc::DevBuf gls_rec1;        // double2[n]  (t - tmin, frac(df (t - tmin)))
   pdc::DevBuf gls_rec2;        // float4[n]   (cos, sin of the per-index rotation, y or w*y, w)
   pdc::DevBuf glsm_y;          // float [groups][n][R]: scaled values of the shared-time series (glsm.cu)
