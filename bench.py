@@ -12,6 +12,7 @@ One "step" = one pass of the hot path over one batch of synthetic input:
                     period grid sharded the same way.
   gls_c5            GLS 1e6 points x (1e7/8 per GPU) frequencies (configs[4] per-GPU share).
   gls_c4            batched GLS, 256 TESS-like curves x 20,000 points x 1e4 frequencies per GPU.
+  gls_c4_full       the whole configs[3] survey (1e4 curves) on every GPU -- one-GPU record of the full size.
 
 Printed line (rank 0): metric/value/unit/... as the driver contract asks, plus
   roofline      dominant kernel vs the FP32 issue roofline (the path is FP32-pipe bound, not
@@ -363,7 +364,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c1", "gls_multi", "sl"])
+    ap.add_argument("--workload", default="gls_c2", choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c4_full", "gls_c1", "gls_multi", "sl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1, GLS / PDM grids: 'p2p' = all-gather fused into the epilogue kernel over NVLink peer "
@@ -376,7 +377,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     per_gpu = {"gls_c2": 100_000, "pdm_c3": 100_000, "gls_c5": 1_250_000, "gls_c5_full": 10_000_000,
-               "gls_c4": 256, "gls_c1": 10_000, "gls_multi": 256, "sl": 100_000}[args.workload]
+               "gls_c4": 256, "gls_c4_full": 10_000, "gls_c1": 10_000, "gls_multi": 256, "sl": 100_000}[args.workload]
     total_units = per_gpu * max(world, 1)
     if args.workload == "gls_c2":
         wl = make_gls_c2(total_units)

@@ -186,6 +186,7 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
   if (const char* g = getenv("PDC_GLS_GEOM")) { ctx->gls_geom = atoi(g); ctx->gls_geom_forced = true; }
   if (const char* g = getenv("PDC_GLS_THREE_TERM")) ctx->gls_three_term = atoi(g) != 0;
   if (const char* g = getenv("PDC_GLS_NSPLIT")) ctx->gls_nsplit_override = atoi(g);
+  if (const char* g = getenv("PDC_PDM_PPT")) ctx->pdm_ppt_override = atoi(g);
   cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   cudaError_t e4 = cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming);
   if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);

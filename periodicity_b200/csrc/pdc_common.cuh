@@ -61,6 +61,7 @@ struct pdc_ctx {
   int gls_nsplit_override = 0;
   bool gls_geom_forced = false;  // PDC_GLS_GEOM given: no automatic small-problem geometry
   bool gls_three_term = true;  // env PDC_GLS_THREE_TERM=0 forces the rotation form of the strip step (tuning aid)
+  int pdm_ppt_override = 0;  // env PDC_PDM_PPT=1|2 forces the trial periods per thread of pdm_hist_kernel (tuning aid)
   int gls_geom = 0;  // index into kGlsGeoms (gls.cu); env PDC_GLS_GEOM overrides at ctx creation (tuning aid)
 
   // CUDA-event timing of the dominant kernel (GLS strip / PDM histogram), recorded on the

@@ -19,17 +19,20 @@
 // The argsort of phase.py:132-134 does not influence the result and is dropped.
 //
 // Mapping (north_star: "per-trial-period phase-bin variance histograms in shared
-// memory with warp-aggregated atomics"): one thread owns one trial period and a PRIVATE
-// histogram column in shared memory, hist[bin][thread] -- bank = thread % 32 whatever the
-// bin, so updates are conflict free and nothing needs aggregating.  Two levels:
+// memory with warp-aggregated atomics"): every trial period has a PRIVATE histogram column in shared
+// memory, hist[bin][column] -- bank = column % 32 whatever the bin, so updates are conflict free and nothing
+// needs aggregating.  A thread owns PPT = 2 columns (long curves; 1 for short ones): each sample read from the
+// tile feeds both periods, and a trip of 16 samples keeps 32 independent phase -> bin -> update chains in flight.
+// Two levels:
 //   level 1  one 32-bit word per bin, (count << 23) + sum rint(x' 2^q): one sample is ONE native
 //            shared-memory integer atomic without return value (ATOMS.ADD, fire-and-forget; the
 //            column is private, the atomic is used for its single-instruction read-modify-write,
 //            measured 13.7 updates/clk/SM against 9.5 for LDS + IADD + STS, profiles/pipes_r01.json);
-//   level 2  float2 (count, sum x') per bin, fed from level 1 every 256 samples, merged into the
-//            FP64 partials in global memory every 8192 samples.
+//   level 2  integer planes count[bin][column], sum[bin][column] (fixed point, exact) over the memory of the
+//            float2 columns, fed from level 1 every 256 samples with three atomics per bin (fetch-and-clear of
+//            the packed word, two adds), merged into the FP64 partials in global memory every 8192 samples.
 // Level 1 needs 256 max|x'| 2^q < 2^22 with a fine enough step 2^-q (q >= 11) and is skipped for
-// short curves, non-finite samples or huge |t / P|: then samples go straight to level 2
+// short curves, non-finite samples or huge |t / P|: then samples go straight to float2 (count, sum x') columns
 // (one LDS.64 + 2 FADD + STS.64).  A shared-memory FLOAT atomicAdd is a CAS loop on sm_100a
 // (ATOMS.CAST.SPIN, 0.96 updates/clk/SM for warp-shared histograms) and so is a 64-bit integer
 // one, which is why the packed word is 32 bits wide.
@@ -61,7 +64,21 @@ constexpr int PDM_PACK_FLUSH = 256;   // samples between flushes of the packed 3
 constexpr int PDM_PACK_MIN_Q = 11;    // coarsest usable quantisation of x' (2^-11 sigma)
 constexpr int PDM_PACK_MIN_N = 4096;  // shorter curves keep the FP32 columns (they are accurate to 1e-7 there)
 constexpr int PDM_TILE = 1024;        // samples per shared-memory tile
+#ifndef PDM_TRIP_CHAINS
+#define PDM_TRIP_CHAINS 32            // independent (sample, period) chains per trip of the packed loop = PDM_TRIP_CHAINS / PPT samples
+#endif
+// Build-time switches of the packed loop; the defaults are the best of the sweep in profiles/tune_pdm_r01.txt.
+#ifndef PDM_EDGE_FIXUP
+#define PDM_EDGE_FIXUP 1             // 1: updates go out with the fast bins at once, the rare edge sample is moved afterwards
+#endif
+#ifndef PDM_PREFETCH
+#define PDM_PREFETCH 1               // 1: time stamps of the next trip are loaded before this trip's atomics
+#endif
+#ifndef PDM_L2_INT
+#define PDM_L2_INT 1                 // 1: second level of the packed path = integer planes fed with shared-memory atomics
+#endif
 constexpr int PDM_FLUSH_TILES = 8;    // FP32 histograms are merged into FP64 every 8192 samples
+constexpr int PDM_TILE_PAD = PDM_PREFETCH ? PDM_TRIP_CHAINS : 0;  // the prefetch of the packed loop reads one trip past the tile
 
 // Statistics in three small launches so that a long curve is read by many SMs (one block would take ~100 us
 // for 1e5 samples): per-block partials in a fixed layout, reduced by every consumer in the same order, so the
@@ -245,32 +262,54 @@ __device__ __forceinline__ unsigned pdm_bin_fast_g(double tv, double rP, unsigne
   return (unsigned)(w >> 32);
 }
 
-// Shared-memory layout: hist[bin][THREADS] float2 = (count, sum x'): a thread's column is
-// conflict free and one sample costs one 64-bit read-modify-write.
-template <int THREADS>
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (N > 0) {
+    static_for<N - 1>(f);
+    f(std::integral_constant<int, N - 1>{});
+  }
+}
+
+// Shared-memory layout: hist[bin][VT] float2 = (count, sum x') and hist32[bin][VT] packed words, VT = THREADS * PPT
+// period columns per block: a column is private to one thread and conflict free (bank = column % 32).
+// PPT = trial periods per thread.  With PPT = 2 a thread owns columns tid and tid + THREADS: every sample read
+// from the tile (warp-uniform LDS.128) feeds two independent phase -> bin -> ATOMS chains, which halves the
+// shared-memory load traffic and the loop overhead per histogram update (the update itself stays one ATOMS.ADD).
+template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS)
 pdm_hist_kernel(const PdmArgs a) {
+  constexpr int VT = THREADS * PPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m0 = a.m0;
-  double* s_t = reinterpret_cast<double*>(smem_raw);                 // [PDM_TILE]
-  double* s_thr = s_t + PDM_TILE;                                    // [m0 + 1]  (padded to even)
-  float2* hist = reinterpret_cast<float2*>(s_thr + ((m0 + 2) & ~1)); // [m0][THREADS]
-  float* s_x = reinterpret_cast<float*>(hist + (size_t)m0 * THREADS); // [PDM_TILE]  (x' as float, or packed increments)
-  unsigned* hist32 = reinterpret_cast<unsigned*>(s_x + PDM_TILE);     // [m0][THREADS] packed first-level columns
+  double* s_t = reinterpret_cast<double*>(smem_raw);                 // [PDM_TILE + PDM_TILE_PAD]
+  double* s_thr = s_t + PDM_TILE + PDM_TILE_PAD;                     // [m0 + 1]  (padded to even)
+  float2* hist = reinterpret_cast<float2*>(s_thr + ((m0 + 2) & ~1)); // [m0][VT]
+  float* s_x = reinterpret_cast<float*>(hist + (size_t)m0 * VT);     // [PDM_TILE]  (x' as float, or packed increments)
+  unsigned* hist32 = reinterpret_cast<unsigned*>(s_x + PDM_TILE);    // [m0][VT] packed first-level columns
 
   const int split = blockIdx.x % a.nsplit;
   const long long pb = blockIdx.x / a.nsplit;
-  const long long pi = pb * THREADS + threadIdx.x;
-  const bool valid = pi < a.np;
-  double P = valid ? a.periods[pi] : 1.0;
-  if (!isfinite(1.0 / P) || !isfinite(P)) P = 1.0;  // invalid trial period: theta is set to NaN by the epilogue
-  const double rP = 1.0 / P;
+  long long pis[PPT];
+  bool valids[PPT];
+  double Ps[PPT], rPs[PPT];
+  bool in_range = true;
+#pragma unroll
+  for (int s = 0; s < PPT; ++s) {
+    pis[s] = pb * VT + s * THREADS + threadIdx.x;
+    valids[s] = pis[s] < a.np;
+    double P = valids[s] ? a.periods[pis[s]] : 1.0;
+    if (!isfinite(1.0 / P) || !isfinite(P)) P = 1.0;  // invalid trial period: theta is set to NaN by the epilogue
+    Ps[s] = P;
+    rPs[s] = 1.0 / P;
+    in_range = in_range && fabs(rPs[s]) * a.meta->t_absmax < PDM_FAST_LIMIT;
+  }
   const bool clamp_bins = a.meta->bad != 0;        // block-uniform
   const double m0d = (double)m0;
   const unsigned kmax = (unsigned)(m0 - 1);
 
   for (int k = threadIdx.x; k <= m0; k += THREADS) s_thr[k] = (double)k / m0d;  // phase.py:138-140
-  for (int k = threadIdx.x; k < m0 * THREADS; k += THREADS) {
+  for (int k = threadIdx.x; k < PDM_TILE_PAD; k += THREADS) s_t[PDM_TILE + k] = 0.0;
+  for (int k = threadIdx.x; k < m0 * VT; k += THREADS) {
     hist[k] = make_float2(0.f, 0.f);
     hist32[k] = 0u;
   }
@@ -279,115 +318,206 @@ pdm_hist_kernel(const PdmArgs a) {
   const long long sb = (long long)split * per;
   const long long se = sb + per < a.n ? sb + per : a.n;
 
-  float2* col = hist + threadIdx.x;
-  double* pcol = a.partial + (long long)split * 2 * m0 * a.np + pi;
+  // block-uniform: every period of this block keeps |t / P| small enough for the fixed-point phase
+  const bool fast = __syncthreads_and(in_range) != 0;
+  const int pack_q = a.meta->pack_q;
+  const bool packed = fast && !clamp_bins && pack_q >= 0;   // block-uniform
+#if PDM_L2_INT
+  const double unpack_d = packed ? 1.0 / (double)(1u << pack_q) : 0.0;
+#else
+  const float unpack = packed ? 1.0f / (float)(1u << pack_q) : 0.f;
+#endif
+  const unsigned* s_xq = reinterpret_cast<const unsigned*>(s_x);
+  const unsigned m0u = (unsigned)m0, guard = PDM_FAST_GUARD * m0u;
 
   // With finite inputs the bin index is always in range (phi == 1.0 is caught by the ambiguity test and
   // fixed by pdm_fix_bin), so the guard is compiled in only for the SAFE variant used when some
   // sample is NaN / inf: a NaN phase is in no bin (every comparison of phase.py:138-140 is false).
-  auto update = [&](auto safe, unsigned k, double phi, float xv) {
+  auto update = [&](auto safe, float2* col, unsigned k, double phi, float xv) {
     if (decltype(safe)::value) {
       if (!(phi == phi)) return;
       k = min(k, kmax);
     }
-    float2 h = col[k * THREADS];
+    float2 h = col[k * VT];
     h.x += 1.0f;
     h.y += xv;
-    col[k * THREADS] = h;
+    col[k * VT] = h;
   };
-  // block-uniform: every period of this block keeps |t / P| small enough for the fixed-point phase
-  const bool fast = __syncthreads_and(fabs(rP) * a.meta->t_absmax < PDM_FAST_LIMIT) != 0;
-  const int pack_q = a.meta->pack_q;
-  const bool packed = fast && !clamp_bins && pack_q >= 0;   // block-uniform
-  const float unpack = packed ? 1.0f / (float)(1u << pack_q) : 0.f;
-  unsigned* col32 = hist32 + threadIdx.x;
-  const unsigned* s_xq = reinterpret_cast<const unsigned*>(s_x);
-  const unsigned m0u = (unsigned)m0, guard = PDM_FAST_GUARD * m0u;
-  auto exact_bin = [&](double tv, double& phi) {
+  auto exact_bin = [&](double P, double rP, double tv, double& phi) {
     unsigned e;
     int k = pdm_bin(tv, P, rP, m0d, phi, e);
     if (e < PDM_AMBIG) k = pdm_fix_bin(k, phi, s_thr, m0);
     return (unsigned)k;
   };
   // Packed path: the private column is a 32-bit word per bin, (count << 23) + sum of fixed-point x', so one
-  // sample costs one LDS.32 + IADD + STS.32 (2 shared-memory wavefronts per warp instead of 4); every
-  // PDM_PACK_FLUSH samples the words are unpacked into the float2 columns.
-  auto flush32 = [&]() {
+  // sample costs one shared-memory integer add; every PDM_PACK_FLUSH samples the words are unpacked into the
+  // float2 columns.
+#if PDM_L2_INT
+  // Second level of the packed path: two integer planes over the memory of the float2 columns, count[bin][VT] and
+  // sum[bin][VT] (fixed point, exact), fed with three shared-memory atomics per bin (fetch-and-clear of the packed
+  // word, two adds without return value) instead of LDS.32 + LDS.64 + STS.64 + STS.32.
+  unsigned* cnt2 = reinterpret_cast<unsigned*>(hist);
+  int* sum2 = reinterpret_cast<int*>(hist) + (size_t)m0 * VT;
+  auto flush32 = [&](int column, unsigned* col32) {
     for (int b = 0; b < m0; ++b) {
-      const unsigned w = col32[b * THREADS];
+      const unsigned w = atomicExch(col32 + b * VT, 0u);
       const int sfix = ((int)(w << 9)) >> 9;               // low 23 bits, sign extended
       const unsigned cnt = (w - (unsigned)sfix) >> 23;
-      float2 h = col[b * THREADS];
-      h.x += (float)cnt;
-      h.y = fmaf((float)sfix, unpack, h.y);
-      col[b * THREADS] = h;
-      col32[b * THREADS] = 0u;
+      atomicAdd(cnt2 + b * VT + column, cnt);
+      atomicAdd(sum2 + b * VT + column, sfix);
     }
   };
+#else
+  auto flush32 = [&](int column, unsigned* col32) {
+    float2* col = hist + column;
+    for (int b = 0; b < m0; ++b) {
+      const unsigned w = col32[b * VT];
+      const int sfix = ((int)(w << 9)) >> 9;               // low 23 bits, sign extended
+      const unsigned cnt = (w - (unsigned)sfix) >> 23;
+      float2 h = col[b * VT];
+      h.x += (float)cnt;
+      h.y = fmaf((float)sfix, unpack, h.y);
+      col[b * VT] = h;
+      col32[b * VT] = 0u;
+    }
+  };
+#endif
 #ifndef PDM_PACK_ATOMIC
 #define PDM_PACK_ATOMIC 1
 #endif
   // The column is private, so the integer add needs no atomicity -- but a native shared-memory integer
   // atomic without a return value (ATOMS.ADD) is ONE fire-and-forget instruction instead of the dependent
   // LDS -> IADD -> STS chain, and same-bin updates of consecutive samples stay ordered in the memory pipe.
-  auto add32 = [&](unsigned k, unsigned inc) {
+  auto add32 = [&](unsigned* col32, unsigned k, unsigned inc) {
 #if PDM_PACK_ATOMIC
-    atomicAdd(col32 + k * THREADS, inc);
+    // keep the bin index (high word of the 32 x 32 -> 64 bit product) opaque: otherwise the compiler folds the
+    // column scaling into the 64-bit product (SHF.R.U64 + LOP3 + IADD per sample) instead of one IMAD on the high word
+    asm volatile("" : "+r"(k));
+    atomicAdd(col32 + k * VT, inc);
 #else
-    col32[k * THREADS] += inc;
+    col32[k * VT] += inc;
 #endif
   };
   // One sample of the packed path with the edge test (tail of a chunk, and the rare slow trips).
-  auto packed_one = [&](int i, unsigned guard2) {
+  auto packed_one = [&](auto sc, int i, unsigned guard2) {
+    constexpr int s = decltype(sc)::value;
     unsigned p0;
     const double tv = s_t[i];
-    unsigned k0 = pdm_bin_fast_g(tv, rP, m0u, p0);
+    unsigned k0 = pdm_bin_fast_g(tv, rPs[s], m0u, p0);
     double ph;
-    if (p0 < guard2) k0 = exact_bin(tv, ph);
-    add32(k0, s_xq[i]);
+    if (p0 < guard2) k0 = exact_bin(Ps[s], rPs[s], tv, ph);
+    add32(hist32 + s * THREADS + threadIdx.x, k0, s_xq[i]);
+  };
+  auto packed_one_all = [&](int i, unsigned guard2) {
+    static_for<PPT>([&](auto sc) { packed_one(sc, i, guard2); });
+  };
+  // Rare fix-up of one sample whose fast-path update has already been issued: if the exact bin differs from the
+  // fast one, move the increment (the packed word is a sum modulo 2^32, so adding -inc undoes the update exactly).
+  auto fixup_one = [&](auto sc, int i, unsigned guard2) {
+    constexpr int s = decltype(sc)::value;
+    unsigned p0;
+    const double tv = s_t[i];
+    const unsigned kf = pdm_bin_fast_g(tv, rPs[s], m0u, p0);
+    if (p0 < guard2) {
+      double ph;
+      const unsigned ke = exact_bin(Ps[s], rPs[s], tv, ph);
+      if (ke != kf) {
+        const unsigned inc = s_xq[i];
+        add32(hist32 + s * THREADS + threadIdx.x, kf, 0u - inc);
+        add32(hist32 + s * THREADS + threadIdx.x, ke, inc);
+      }
+    }
+  };
+  auto fixup_one_all = [&](int i, unsigned guard2) {
+    static_for<PPT>([&](auto sc) { fixup_one(sc, i, guard2); });
   };
   auto tile_loop_packed = [&](int cnt) {
-    constexpr int U = 8;  // samples per trip: eight independent DFMA -> IMAD.WIDE chains, one edge test
+    constexpr int U = PPT == 1 ? 8 : PDM_TRIP_CHAINS / PPT;  // samples per trip: U * PPT independent DFMA -> IMAD.WIDE -> IMAD -> ATOMS chains, one edge test
     const unsigned guard2 = 2u * guard;
+    unsigned* c32 = hist32 + threadIdx.x;
     for (int c0 = 0; c0 < cnt; c0 += PDM_PACK_FLUSH) {
       const int c1 = c0 + PDM_PACK_FLUSH < cnt ? c0 + PDM_PACK_FLUSH : cnt;
       int i = c0;
+      double tv[U];
+#if PDM_PREFETCH
+      // the time stamps of the next trip are fetched before this trip's atomics (the compiler cannot move a
+      // shared-memory load across them); the read past the last trip lands in the tile's padding and is unused
+#pragma unroll
+      for (int u = 0; u < U; u += 2) {
+        const double2 tt = *reinterpret_cast<const double2*>(s_t + i + u);
+        tv[u] = tt.x;
+        tv[u + 1] = tt.y;
+      }
+#endif
       for (; i + U <= c1; i += U) {
-        double tv[U];
-        unsigned xv[U], k[U], pos[U];
+        unsigned xv[U], k[PPT][U], pos;
+#if !PDM_PREFETCH
 #pragma unroll
         for (int u = 0; u < U; u += 2) {
           const double2 tt = *reinterpret_cast<const double2*>(s_t + i + u);
           tv[u] = tt.x;
           tv[u + 1] = tt.y;
         }
+#endif
+        unsigned pmin = 0xffffffffu;
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            k[s][u] = pdm_bin_fast_g(tv[u], rPs[s], m0u, pos);
+            pmin = min(pmin, pos);
+          }
+        }
+#if PDM_PREFETCH
+#pragma unroll
+        for (int u = 0; u < U; u += 2) {
+          const double2 tt = *reinterpret_cast<const double2*>(s_t + i + U + u);
+          tv[u] = tt.x;
+          tv[u + 1] = tt.y;
+        }
+#endif
 #pragma unroll
         for (int u = 0; u < U; u += 4) {
           const uint4 xx = *reinterpret_cast<const uint4*>(s_xq + i + u);
           xv[u] = xx.x; xv[u + 1] = xx.y; xv[u + 2] = xx.z; xv[u + 3] = xx.w;
         }
-        unsigned pmin = 0xffffffffu;
+#if PDM_EDGE_FIXUP
+        // the updates go out at once with the fast bins (always in range); the rare trip with a sample on a bin
+        // edge (about m0 * U * PPT * 4e-9 of them) re-bins exactly afterwards and moves the increment if needed
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          k[u] = pdm_bin_fast_g(tv[u], rP, m0u, pos[u]);
-          pmin = min(pmin, pos[u]);
+#pragma unroll
+          for (int s = 0; s < PPT; ++s) add32(c32 + s * THREADS, k[s][u], xv[u]);
         }
-        if (pmin < guard2) {  // rare (about m0 * U * 4e-9 of the trips): some sample sits on a bin edge
-          for (int u = 0; u < U; ++u) packed_one(i + u, guard2);
+        if (pmin < guard2) {
+          for (int u = 0; u < U; ++u) fixup_one_all(i + u, guard2);
+        }
+#else
+        if (pmin < guard2) {  // rare (about m0 * U * PPT * 4e-9 of the trips): some sample sits on a bin edge
+          for (int u = 0; u < U; ++u) packed_one_all(i + u, guard2);
           continue;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) add32(k[u], xv[u]);
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int s = 0; s < PPT; ++s) add32(c32 + s * THREADS, k[s][u], xv[u]);
+        }
+#endif
       }
-      for (; i < c1; ++i) packed_one(i, guard2);
+      for (; i < c1; ++i) packed_one_all(i, guard2);
 #if PDM_PACK_ATOMIC
       __syncwarp();
 #endif
-      flush32();
+#pragma unroll
+      for (int s = 0; s < PPT; ++s) flush32(s * THREADS + threadIdx.x, c32 + s * THREADS);
     }
   };
-  auto tile_loop_fast = [&](auto safe, int cnt) {
+  // The unpacked paths serve one period column after the other (sc = which of the thread's PPT columns).
+  auto tile_loop_fast = [&](auto safe, auto sc, int cnt) {
     constexpr bool SAFE = decltype(safe)::value;
+    constexpr int s = decltype(sc)::value;
+    const double P = Ps[s], rP = rPs[s];
+    float2* col = hist + s * THREADS + threadIdx.x;
     int i = 0;
     for (; i + 4 <= cnt; i += 4) {
       const double2 ta = *reinterpret_cast<const double2*>(s_t + i);
@@ -404,26 +534,29 @@ pdm_hist_kernel(const PdmArgs a) {
       }
       if (e0 | e1 | e2 | e3) {  // rare: a sample sits on a bin edge
         double ph;
-        if (e0) k0 = exact_bin(ta.x, ph);
-        if (e1) k1 = exact_bin(ta.y, ph);
-        if (e2) k2 = exact_bin(tb.x, ph);
-        if (e3) k3 = exact_bin(tb.y, ph);
+        if (e0) k0 = exact_bin(P, rP, ta.x, ph);
+        if (e1) k1 = exact_bin(P, rP, ta.y, ph);
+        if (e2) k2 = exact_bin(P, rP, tb.x, ph);
+        if (e3) k3 = exact_bin(P, rP, tb.y, ph);
       }
-      update(safe, k0, f0, xv.x);
-      update(safe, k1, f1, xv.y);
-      update(safe, k2, f2, xv.z);
-      update(safe, k3, f3, xv.w);
+      update(safe, col, k0, f0, xv.x);
+      update(safe, col, k1, f1, xv.y);
+      update(safe, col, k2, f2, xv.z);
+      update(safe, col, k3, f3, xv.w);
     }
     for (; i < cnt; ++i) {
       unsigned e0;
       const double tv = s_t[i];
       unsigned k0 = pdm_bin_fast(tv, rP, m0u, guard, e0);
       double ph;
-      if (e0) k0 = exact_bin(tv, ph);
-      update(safe, k0, SAFE ? tv - tv : 0.0, s_x[i]);
+      if (e0) k0 = exact_bin(P, rP, tv, ph);
+      update(safe, col, k0, SAFE ? tv - tv : 0.0, s_x[i]);
     }
   };
-  auto tile_loop = [&](auto safe, int cnt) {
+  auto tile_loop = [&](auto safe, auto sc, int cnt) {
+    constexpr int s = decltype(sc)::value;
+    const double P = Ps[s], rP = rPs[s];
+    float2* col = hist + s * THREADS + threadIdx.x;
     int i = 0;
     for (; i + 4 <= cnt; i += 4) {
       // four independent phase computations (FP64 chains overlap), then four updates in order
@@ -442,17 +575,26 @@ pdm_hist_kernel(const PdmArgs a) {
         if (e2 < PDM_AMBIG) k2 = pdm_fix_bin(k2, f2, s_thr, m0);
         if (e3 < PDM_AMBIG) k3 = pdm_fix_bin(k3, f3, s_thr, m0);
       }
-      update(safe, (unsigned)k0, f0, xv.x);
-      update(safe, (unsigned)k1, f1, xv.y);
-      update(safe, (unsigned)k2, f2, xv.z);
-      update(safe, (unsigned)k3, f3, xv.w);
+      update(safe, col, (unsigned)k0, f0, xv.x);
+      update(safe, col, (unsigned)k1, f1, xv.y);
+      update(safe, col, (unsigned)k2, f2, xv.z);
+      update(safe, col, (unsigned)k3, f3, xv.w);
     }
     for (; i < cnt; ++i) {
       double f0;
       unsigned e0;
       int k0 = pdm_bin(s_t[i], P, rP, m0d, f0, e0);
       if (e0 < PDM_AMBIG) k0 = pdm_fix_bin(k0, f0, s_thr, m0);
-      update(safe, (unsigned)k0, f0, s_x[i]);
+      update(safe, col, (unsigned)k0, f0, s_x[i]);
+    }
+  };
+  auto tile_unpacked = [&](auto sc, int cnt) {
+    if (fast) {
+      if (clamp_bins) tile_loop_fast(std::true_type{}, sc, cnt);
+      else tile_loop_fast(std::false_type{}, sc, cnt);
+    } else {
+      if (clamp_bins) tile_loop(std::true_type{}, sc, cnt);
+      else tile_loop(std::false_type{}, sc, cnt);
     }
   };
 
@@ -472,31 +614,48 @@ pdm_hist_kernel(const PdmArgs a) {
 
     if (packed) {
       tile_loop_packed(cnt);
-    } else if (fast) {
-      if (clamp_bins) tile_loop_fast(std::true_type{}, cnt);
-      else tile_loop_fast(std::false_type{}, cnt);
     } else {
-      if (clamp_bins) tile_loop(std::true_type{}, cnt);
-      else tile_loop(std::false_type{}, cnt);
+      static_for<PPT>([&](auto sc) { tile_unpacked(sc, cnt); });
     }
 
     tile0 += PDM_TILE;
     ++tiles_since_flush;
     if (tiles_since_flush == PDM_FLUSH_TILES || tile0 >= se) {
-      // merge this thread's FP32 column into the FP64 partials it owns ([stat][bin][period] rows)
-      if (valid) {
-        const long long stat = (long long)m0 * a.np;
+      // merge this thread's columns into the FP64 partials it owns ([stat][bin][period] rows)
+#if PDM_L2_INT && PDM_PACK_ATOMIC
+      __syncwarp();   // the second level was fed with atomics without return value
+#endif
+      const long long stat = (long long)m0 * a.np;
+#pragma unroll
+      for (int s = 0; s < PPT; ++s) {
+        if (!valids[s]) continue;
+        const int column = s * THREADS + threadIdx.x;
+        float2* col = hist + column;
+        double* pcol = a.partial + (long long)split * 2 * m0 * a.np + pis[s];
         for (int b = 0; b < m0; ++b) {
-          const float2 h = col[b * THREADS];
+          double hn, hs;
+#if PDM_L2_INT
+          if (packed) {   // integer planes (exact): count, fixed-point sum
+            hn = (double)cnt2[b * VT + column];
+            hs = (double)sum2[b * VT + column] * unpack_d;
+            cnt2[b * VT + column] = 0u;
+            sum2[b * VT + column] = 0;
+          } else
+#endif
+          {
+            const float2 h = col[b * VT];
+            hn = (double)h.x;
+            hs = (double)h.y;
+            col[b * VT] = make_float2(0.f, 0.f);
+          }
           double* g = pcol + (long long)b * a.np;
           if (first) {
-            g[0] = (double)h.x;
-            g[stat] = (double)h.y;
+            g[0] = hn;
+            g[stat] = hs;
           } else {  // RED.ADD.F64: only this thread touches g; order is fixed
-            atomicAdd(g, (double)h.x);
-            atomicAdd(g + stat, (double)h.y);
+            atomicAdd(g, hn);
+            atomicAdd(g + stat, hs);
           }
-          col[b * THREADS] = make_float2(0.f, 0.f);
         }
       }
       first = false;
@@ -557,14 +716,14 @@ pdm_epilogue_kernel(double* __restrict__ partial, const double* __restrict__ per
 }
 
 static size_t pdm_smem_bytes(int m0, int threads) {
-  return sizeof(double) * (PDM_TILE + ((m0 + 2) & ~1)) + sizeof(float) * PDM_TILE +
+  return sizeof(double) * (PDM_TILE + PDM_TILE_PAD + ((m0 + 2) & ~1)) + sizeof(float) * PDM_TILE +
          (sizeof(float2) + sizeof(unsigned)) * (size_t)m0 * threads;
 }
 
-template <int THREADS>
+template <int THREADS, int PPT>
 static int pdm_launch(pdc_ctx* ctx, const PdmArgs& a, size_t smem, long long blocks, cudaStream_t st) {
-  PDC_CUDA(cudaFuncSetAttribute(pdm_hist_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pdm_hist_kernel<THREADS><<<(unsigned)blocks, THREADS, smem, st>>>(a);
+  PDC_CUDA(cudaFuncSetAttribute(pdm_hist_kernel<THREADS, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pdm_hist_kernel<THREADS, PPT><<<(unsigned)blocks, THREADS, smem, st>>>(a);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
   return PDC_OK;
@@ -590,8 +749,8 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   }
   const int m0 = (int)m0l;
 
-  // threads per block: the candidate that keeps the most period-threads resident per SM
-  int threads = 32, best_res = 0;
+  // period columns per block (VT): the candidate that keeps the most columns resident per SM
+  int vt = 32, best_res = 0;
   const int cands[4] = {256, 128, 64, 32};
   for (int c = 0; c < 4; ++c) {
     size_t sm = pdm_smem_bytes(m0, cands[c]);
@@ -599,11 +758,18 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     int blocks = (int)((228 * 1024) / (sm + 1024));
     if (blocks > 2048 / cands[c]) blocks = 2048 / cands[c];
     int res = blocks * cands[c];
-    if (res > best_res) { best_res = res; threads = cands[c]; }
+    if (res > best_res) { best_res = res; vt = cands[c]; }
   }
-  const size_t smem = pdm_smem_bytes(m0, threads);
-  const long long resident = (long long)ctx->sm_count * (best_res / threads);
-  const long long npb = (np + threads - 1) / threads;
+  // Trial periods per thread: long curves run the packed path (decided on the device, PDM_PACK_MIN_N), where two
+  // columns per thread share every tile read; short curves keep one column per thread (more threads per SM).
+  int ppt = (n >= PDM_PACK_MIN_N && vt >= 64) ? 2 : 1;
+  {
+    const int o = ctx->pdm_ppt_override;
+    if (o == 1 || (o == 2 && vt >= 64)) ppt = o;
+  }
+  const size_t smem = pdm_smem_bytes(m0, vt);
+  const long long resident = (long long)ctx->sm_count * (best_res / vt);
+  const long long npb = (np + vt - 1) / vt;
 
   // sample split: same cost model as GLS (per-item overhead ~ one histogram flush)
   int nsplit = 1;
@@ -667,11 +833,14 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   a.nsplit = nsplit;
 
   PDC_TRY(ctx->main_begin(st));
-  switch (threads) {
-    case 256: PDC_TRY(pdm_launch<256>(ctx, a, smem, blocks, st)); break;
-    case 128: PDC_TRY(pdm_launch<128>(ctx, a, smem, blocks, st)); break;
-    case 64: PDC_TRY(pdm_launch<64>(ctx, a, smem, blocks, st)); break;
-    default: PDC_TRY(pdm_launch<32>(ctx, a, smem, blocks, st)); break;
+  switch (vt * 8 + ppt) {
+    case 256 * 8 + 1: PDC_TRY((pdm_launch<256, 1>(ctx, a, smem, blocks, st))); break;
+    case 256 * 8 + 2: PDC_TRY((pdm_launch<128, 2>(ctx, a, smem, blocks, st))); break;
+    case 128 * 8 + 1: PDC_TRY((pdm_launch<128, 1>(ctx, a, smem, blocks, st))); break;
+    case 128 * 8 + 2: PDC_TRY((pdm_launch<64, 2>(ctx, a, smem, blocks, st))); break;
+    case 64 * 8 + 1: PDC_TRY((pdm_launch<64, 1>(ctx, a, smem, blocks, st))); break;
+    case 64 * 8 + 2: PDC_TRY((pdm_launch<32, 2>(ctx, a, smem, blocks, st))); break;
+    default: PDC_TRY((pdm_launch<32, 1>(ctx, a, smem, blocks, st))); break;
   }
   PDC_TRY(ctx->main_end(st));
 
