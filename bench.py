@@ -592,7 +592,7 @@ def main():
         ach = units_local / (main_kernel_ms * 1e-3) / 1e9
         roof = {"bound": "smem", "kernel": "pdm_hist_kernel", "achieved": ach, "peak": PDM_PEAK_GEVALS_MEASURED,
                 "unit": "Gevals/s", "frac": ach / PDM_PEAK_GEVALS_MEASURED,
-                "traffic": ncu_traffic("ncu_pdm_hist_r01c.json") if args.workload == "pdm_c3" and world == 1 else None,
+                "traffic": ncu_traffic("ncu_pdm_hist_r01e.json") if args.workload == "pdm_c3" and world == 1 else None,
                 "kernel_ms": main_kernel_ms,
                 "peak_source": "profiles/pipes_r01.json smem_private_u32_atoms (one shared-memory ATOMS.ADD on a private "
                                "32-bit column word per sample update, 13.7 per clk per SM: the floor of the "
@@ -641,7 +641,7 @@ def main():
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"pdm": "f64 phase, f32 histograms", "sl": "f64"}.get(kind, "f32 sums, f64 phase/epilogue"),
+            "vs_baseline": None, "dtype": {"pdm": "f64 phase, integer (fixed-point) histograms", "sl": "f64"}.get(kind, "f32 sums, f64 phase/epilogue"),
             "data": "synthetic",
             "config": {"workload": wl["name"], "units_per_gpu": per_gpu, "sharding": "frequency grid" if kind == "gls"
                        else ("period grid" if kind in ("pdm", "sl") else "light-curve batch"),

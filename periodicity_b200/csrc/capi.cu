@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 
 #include "pdc_common.cuh"
@@ -187,6 +188,7 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
   if (const char* g = getenv("PDC_GLS_THREE_TERM")) ctx->gls_three_term = atoi(g) != 0;
   if (const char* g = getenv("PDC_GLS_NSPLIT")) ctx->gls_nsplit_override = atoi(g);
   if (const char* g = getenv("PDC_PDM_PPT")) ctx->pdm_ppt_override = atoi(g);
+  if (const char* g = getenv("PDC_BATCH_PIPE_BYTES")) ctx->pipe_min_bytes = (size_t)atoll(g);
   cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   cudaError_t e4 = cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming);
   if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
@@ -205,6 +207,8 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   ctx->in_a.release(); ctx->in_b.release(); ctx->in_c.release(); ctx->in_d.release();
   ctx->out_a.release(); ctx->out_small.release(); ctx->pin_small.release(); ctx->pin_out.release();
   for (auto& e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_up) if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   ctx->gls_curves.release(); ctx->gls_part.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->glsm_y.release();
   ctx->partial.release(); ctx->blockred.release(); ctx->pin_meta.release();
   ctx->pdm_meta.release(); ctx->pdm_x.release(); ctx->peak_cand.release();
@@ -318,6 +322,50 @@ static int staged_d2h(pdc_ctx* ctx, void* dst, const void* src, size_t bytes, cu
   return PDC_OK;
 }
 
+// Upload + compute of a batch in `nrun` runs of whole curves (boundaries balanced by sample count).  The upload of run
+// c+1 is issued after the kernels of run c have been enqueued: with pinned host memory it is asynchronous anyway, with
+// pageable memory cudaMemcpyAsync keeps the host busy staging while the GPU computes.  `off` is rebased to 0.
+static int gls_upload_and_run_pipelined(pdc_ctx* ctx, const double* t, const double* y, const double* w,
+                                        double* d_t, double* d_y, double* d_w, const int64_t* off, int64_t B, int nrun,
+                                        const double* fmin, const double* df, int64_t nf, unsigned flags,
+                                        const double* psd_scale, double* d_power, long long* d_arg, double* d_val,
+                                        cudaStream_t st) {
+  if (!ctx->copy_stream) PDC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < nrun; ++c)
+    if (!ctx->ev_up[c]) PDC_CUDA(cudaEventCreateWithFlags(&ctx->ev_up[c], cudaEventDisableTiming));
+  // first curve of each run
+  int64_t first[9];
+  first[0] = 0;
+  const int64_t ntot = off[B];
+  for (int c = 1; c < nrun; ++c) {
+    const int64_t target = ntot / nrun * c;
+    int64_t b = first[c - 1] + 1;
+    while (b < B - (nrun - c) && off[b] < target) ++b;
+    first[c] = b;
+  }
+  first[nrun] = B;
+  auto upload = [&](int c) -> int {
+    const int64_t s0 = off[first[c]], s1 = off[first[c + 1]];
+    const size_t bytes = sizeof(double) * (size_t)(s1 - s0);
+    PDC_CUDA(cudaMemcpyAsync(d_t + s0, t + s0, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    PDC_CUDA(cudaMemcpyAsync(d_y + s0, y + s0, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (w) PDC_CUDA(cudaMemcpyAsync(d_w + s0, w + s0, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    PDC_CUDA(cudaEventRecord(ctx->ev_up[c], ctx->copy_stream));
+    return PDC_OK;
+  };
+  int rc = upload(0);
+  for (int c = 0; c < nrun && rc == PDC_OK; ++c) {
+    const int64_t b0 = first[c], nb = first[c + 1] - first[c];
+    cudaError_t e = cudaStreamWaitEvent(st, ctx->ev_up[c], 0);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaStreamWaitEvent", __FILE__, __LINE__); break; }
+    rc = gls_run(ctx, d_t, d_y, d_w, off + b0, nb, fmin + b0, df + b0, 0, nf, flags, psd_scale ? psd_scale + b0 : nullptr,
+                 d_power ? d_power + (size_t)b0 * nf : nullptr, (int64_t*)(d_arg + b0), d_val + b0, st);
+    if (rc == PDC_OK && c + 1 < nrun) rc = upload(c + 1);
+  }
+  if (rc != PDC_OK) cudaStreamSynchronize(ctx->copy_stream);  // never return with a copy from the caller's memory in flight
+  return rc;
+}
+
 static int gls_host_common(pdc_ctx* ctx, const double* t, const double* y, const double* w,
                            const int64_t* offsets, int64_t B, const double* fmin, const double* df,
                            int64_t j0, int64_t nf, unsigned flags, const double* psd_scale,
@@ -334,29 +382,47 @@ static int gls_host_common(pdc_ctx* ctx, const double* t, const double* y, const
   if (power_out) PDC_TRY(ctx->out_a.reserve(sizeof(double) * (size_t)nf * B));
   PDC_TRY(ctx->out_small.reserve((sizeof(long long) + sizeof(double)) * (size_t)B));
   PDC_TRY(ctx->pin_small.reserve((sizeof(long long) + sizeof(double)) * (size_t)B));
-  PDC_CUDA(cudaMemcpyAsync(ctx->in_a.p, t + off0, nbytes, cudaMemcpyHostToDevice, st));
-  PDC_CUDA(cudaMemcpyAsync(ctx->in_b.p, y + off0, nbytes, cudaMemcpyHostToDevice, st));
-  if (w) PDC_CUDA(cudaMemcpyAsync(ctx->in_c.p, w + off0, nbytes, cudaMemcpyHostToDevice, st));
-
   // offsets rebased to the device copies
   int64_t local_off[2];
   const int64_t* use_off = offsets;
-  int64_t* heap_off = nullptr;
+  std::unique_ptr<int64_t[]> heap_off;
   if (off0 != 0) {
     if (B == 1) { local_off[0] = 0; local_off[1] = ntot; use_off = local_off; }
     else {
-      heap_off = new (std::nothrow) int64_t[B + 1];
+      heap_off.reset(new (std::nothrow) int64_t[B + 1]);
       if (!heap_off) { set_error("out of host memory"); return PDC_ENOMEM; }
       for (int64_t b = 0; b <= B; ++b) heap_off[b] = offsets[b] - off0;
-      use_off = heap_off;
+      use_off = heap_off.get();
     }
   }
   long long* d_arg = ctx->out_small.as<long long>();
   double* d_val = reinterpret_cast<double*>(d_arg + B);
-  int rc = gls_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), w ? ctx->in_c.as<double>() : nullptr,
-                   use_off, B, fmin, df, j0, nf, flags, psd_scale,
-                   power_out ? ctx->out_a.as<double>() : nullptr, (int64_t*)d_arg, d_val, st);
-  delete[] heap_off;
+  double* d_t = ctx->in_a.as<double>();
+  double* d_y = ctx->in_b.as<double>();
+  double* d_w = w ? ctx->in_c.as<double>() : nullptr;
+
+  // Survey-sized batches: the curves are independent, so the batch is cut into up to 8 runs of whole curves;
+  // run c+1 is uploaded on a second stream while the kernels of run c execute.
+  int nrun = 1;
+  const size_t in_bytes = nbytes * (w ? 3 : 2);
+  if (B >= 16 && in_bytes >= ctx->pipe_min_bytes) {
+    nrun = (int)(in_bytes / ((size_t)16 << 20));
+    if (nrun > 8) nrun = 8;
+    if (nrun > B / 8) nrun = (int)(B / 8);
+    if (nrun < 2) nrun = 2;
+  }
+  int rc = PDC_OK;
+  if (nrun == 1) {
+    PDC_CUDA(cudaMemcpyAsync(d_t, t + off0, nbytes, cudaMemcpyHostToDevice, st));
+    PDC_CUDA(cudaMemcpyAsync(d_y, y + off0, nbytes, cudaMemcpyHostToDevice, st));
+    if (w) PDC_CUDA(cudaMemcpyAsync(d_w, w + off0, nbytes, cudaMemcpyHostToDevice, st));
+    rc = gls_run(ctx, d_t, d_y, d_w, use_off, B, fmin, df, j0, nf, flags, psd_scale,
+                 power_out ? ctx->out_a.as<double>() : nullptr, (int64_t*)d_arg, d_val, st);
+  } else {
+    rc = gls_upload_and_run_pipelined(ctx, t + off0, y + off0, w ? w + off0 : nullptr, d_t, d_y, d_w, use_off, B, nrun,
+                                      fmin, df, nf, flags, psd_scale, power_out ? ctx->out_a.as<double>() : nullptr,
+                                      d_arg, d_val, st);
+  }
   PDC_TRY(rc);
   PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, ctx->out_small.p, (sizeof(long long) + sizeof(double)) * (size_t)B,
                            cudaMemcpyDeviceToHost, st));

@@ -81,6 +81,10 @@ struct pdc_ctx {
   pdc::PinnedBuf pin_small;    // pinned landing zone for the small records
   pdc::PinnedBuf pin_out;      // pinned staging of large results on their way to the caller's (pageable) buffer
   cudaEvent_t ev_chunk[8] = {};
+  // large batches through the host entry point: uploads on a second stream, chunk c+1 travels while chunk c is computed
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_up[8] = {};
+  size_t pipe_min_bytes = (size_t)32 << 20;  // env PDC_BATCH_PIPE_BYTES: smallest input size that is uploaded in chunks
 
   // GLS scratch
   pdc::DevBuf gls_curves;      // GlsCurve[B]

@@ -496,3 +496,46 @@ def test_shared_time_multi_series_coarse_grid_uses_rotation(gpu_ctx):
                 ref = cport.gls_exact(t, Y[s], None if ww is None else ww ** -0.5, fmin, df, nf)
                 assert_power_close(P[s], ref)
                 assert A[s] == np.nanargmax(ref)
+
+
+@pytest.mark.gpu
+def test_large_batch_is_uploaded_in_pipelined_runs(monkeypatch):
+    """Host entry pdc_gls_batch cuts survey-sized batches into runs of whole curves whose uploads overlap the
+    kernels of the previous run (PDC_BATCH_PIPE_BYTES, read at ctx creation, sets the size where that starts):
+    same peaks and periodograms as the one-shot path, with weights, PSD scaling and a non-zero first offset."""
+    from periodicity_b200 import _ffi
+    rng = np.random.default_rng(77)
+    B, nf = 45, 640
+    sizes = rng.integers(30, 1500, B)
+    sizes[7] = 5000                                  # one curve much longer than the rest
+    ts, ys, ws, fm, dfs = [], [], [], [], []
+    for n in sizes:
+        t = np.sort(rng.uniform(0, rng.uniform(20, 60), n))
+        ts.append(t)
+        ys.append(np.sin(2 * np.pi * t / rng.uniform(0.5, 5)) + rng.standard_normal(n))
+        ws.append(rng.uniform(0.5, 2, n))
+        d = 1 / (t[-1] - t[0]) / 5
+        dfs.append(d); fm.append(0.5 * d)
+    lead = 123                                       # offsets[0] != 0: the batch starts inside the caller's arrays
+    T = np.concatenate([np.zeros(lead)] + ts)
+    Y = np.concatenate([np.zeros(lead)] + ys)
+    W = np.concatenate([np.ones(lead)] + ws)
+    offsets = lead + np.concatenate([[0], np.cumsum(sizes)])
+    one_shot = _ffi.Context(0)
+    monkeypatch.setenv("PDC_BATCH_PIPE_BYTES", "1")
+    piped = _ffi.Context(0)
+    for w_all, psd in ((None, False), (W, False), (W, True)):
+        scale = rng.uniform(0.5, 2.0, B) if psd else None
+        P1, A1, M1 = one_shot.gls_batch(T, Y, w_all, offsets, fm, dfs, nf, psd_scale=scale)
+        P2, A2, M2 = piped.gls_batch(T, Y, w_all, offsets, fm, dfs, nf, psd_scale=scale)
+        _, A3, M3 = piped.gls_batch(T, Y, w_all, offsets, fm, dfs, nf, psd_scale=scale, want_power=False)
+        np.testing.assert_array_equal(A1, A2)
+        np.testing.assert_array_equal(A2, A3)
+        np.testing.assert_array_equal(M2, M3)
+        for b in range(B):
+            assert np.max(np.abs(P1[b] - P2[b])) <= 2e-6 * np.max(np.abs(P1[b]))
+    for b in (0, 7, B - 1):                           # and against the oracle
+        ref = cport.gls_exact(ts[b], ys[b], None, fm[b], dfs[b], nf)
+        P, A, _ = piped.gls_batch(T, Y, None, offsets, fm, dfs, nf)
+        assert_power_close(P[b], ref)
+        assert A[b] == np.nanargmax(ref)

@@ -33,4 +33,7 @@ ctx.stringlength(tt, mm, P[:8])                                 # global-scratch
 pw, _, _ = ctx.gls(t, y, None, 0.5 * df, df, 5000)
 idx, val = ctx.peaks_topk(pw, 5)
 ctx.peaks_halfmax(pw, idx)
+os.environ["PDC_BATCH_PIPE_BYTES"] = "1"                         # read at ctx creation: upload batches in pipelined runs
+ctx2 = _ffi.Context(0)
+ctx2.gls_batch(t, y, w, np.arange(17) * 375, np.full(16, 0.5 * df), np.full(16, df), 700)
 print("sanitize smoke done")
