@@ -209,6 +209,25 @@ PDC_API int pdc_pdm_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t 
                 double* theta_out, int64_t* argmin_out, double* min_out, void* stream);
 
 /*
+ * Analysis of Variance periodogram (Schwarzenberg-Czerny 1989).  The reference only lists it as a
+ * TODO (phase.py:11); it is computed from the same per-period phase-bin histograms as PDM
+ * (phase.py:131,137-141 with nc = 1: phi = (t / P) % 1, bin k = [k/nb, (k+1)/nb)):
+ *     Theta(P) = [(N - r) / (r - 1)] * sum_b n_b (mean_b - mean)^2 / sum_b sum_{i in b} (x_i - mean_b)^2
+ * over the r populated bins -- the F statistic of a one-way ANOVA of the values grouped by phase bin.
+ *
+ *   theta_out   float64[np]  statistic in the order of `periods` (NaN for period 0 / inf / NaN or r < 2)
+ *   argmax_out  index of the LARGEST non-NaN value, first occurrence; -1 if all NaN.  May be NULL.
+ *   max_out     that value.  May be NULL.
+ */
+PDC_API int pdc_aov(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+            const double* periods, int64_t np, int nb,
+            double* theta_out, int64_t* argmax_out, double* max_out);
+
+PDC_API int pdc_aov_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+                const double* periods, int64_t np, int nb,
+                double* theta_out, int64_t* argmax_out, double* max_out, void* stream);
+
+/*
  * String Length (Dworetsky 1983): `StringLength._stringlength` (phase.py:45-51) for each trial
  * period, replacing `pool.map(self._stringlength, periods)` (phase.py:68-70).
  *

@@ -72,6 +72,12 @@ SIGNATURES = {
     "pdc_pdm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_aov": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                               ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_aov_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                   ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_stringlength": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p]),
@@ -257,6 +263,21 @@ class Context:
                                      int(nb), int(nc), _ptr(theta), ctypes.addressof(arg), ctypes.addressof(mn)))
         return theta, arg.value, mn.value
 
+    def aov(self, t, x, periods, nb):
+        """Analysis-of-variance statistic for each trial period (``pdc_aov``): (theta, argmax, max)."""
+        t = _f64(t)
+        x = _f64(x)
+        periods = _f64(periods)
+        if t.ndim != 1 or t.shape != x.shape:
+            raise ValueError("Input arrays have incompatible lengths.")
+        theta = np.empty(periods.size, dtype=np.float64)
+        arg = ctypes.c_int64(-1)
+        mx = ctypes.c_double(float("nan"))
+        with self._lock:
+            _check(self._lib.pdc_aov(self._h, _ptr(t), _ptr(x), t.size, _ptr(periods), periods.size,
+                                     int(nb), _ptr(theta), ctypes.addressof(arg), ctypes.addressof(mx)))
+        return theta, arg.value, mx.value
+
     def peaks_halfmax(self, values, peak_idx, height=None):
         """Indices (left, right) of the half-maximum crossings around each given peak of each row (host arrays);
         ``height`` defaults to the peak values (``use_prominence=False`` of ``periods_at_half_max``)."""
@@ -333,6 +354,10 @@ class Context:
         _check(self._lib.pdc_gls_batch_dev(self._h, t_ptr, y_ptr, w_ptr or None, _ptr(offsets), B, _ptr(fmin),
                                            _ptr(df), int(nf), int(flags), _ptr(psd_scale), power_ptr or None,
                                            argmax_ptr or None, max_ptr or None, stream or None))
+
+    def aov_dev(self, t_ptr, x_ptr, n, periods_ptr, np_, nb, theta_ptr, argmax_ptr, max_ptr, stream=0):
+        _check(self._lib.pdc_aov_dev(self._h, t_ptr, x_ptr, int(n), periods_ptr, int(np_), int(nb),
+                                     theta_ptr, argmax_ptr or None, max_ptr or None, stream or None))
 
     def pdm_dev(self, t_ptr, x_ptr, n, periods_ptr, np_, nb, nc, theta_ptr, argmin_ptr, min_ptr, stream=0):
         _check(self._lib.pdc_pdm_dev(self._h, t_ptr, x_ptr, int(n), periods_ptr, int(np_), int(nb), int(nc),

@@ -526,11 +526,10 @@ int pdc_pdm_dev_fanout(pdc_ctx* ctx, const double* t, const double* x, int64_t n
   return pdm_run(ctx, t, x, n, periods, np, nb, nc, nullptr, nullptr, nullptr, st, dst, offset);
 }
 
-int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
-            const double* periods, int64_t np, int nb, int nc,
-            double* theta_out, int64_t* argmin_out, double* min_out) {
-  if (!ctx || !t || !x || !periods || !theta_out) { set_error("pdc_pdm: NULL argument"); return PDC_EINVAL; }
-  if (n < 2 || np < 1) { set_error("pdc_pdm: need n >= 2 samples and np >= 1 periods"); return PDC_EINVAL; }
+// host-pointer body shared by pdc_pdm and pdc_aov: upload, histogram kernels + epilogue for `statistic`, download
+static int phase_hist_host(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods,
+                           int64_t np, int nb, int nc, int statistic, double* stat_out, int64_t* arg_out,
+                           double* best_out) {
   DeviceGuard guard(ctx->device);
   cudaStream_t st = ctx->stream;
   PDC_TRY(ctx->in_a.reserve(sizeof(double) * (size_t)n));
@@ -544,14 +543,42 @@ int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
   PDC_CUDA(cudaMemcpyAsync(ctx->in_d.p, periods, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, st));
   SmallRec* d_rec = ctx->out_small.as<SmallRec>();
   PDC_TRY(pdm_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), n, ctx->in_d.as<double>(), np, nb, nc,
-                  ctx->out_a.as<double>(), (int64_t*)&d_rec->arg, &d_rec->val, st));
+                  ctx->out_a.as<double>(), (int64_t*)&d_rec->arg, &d_rec->val, st, nullptr, 0, statistic));
   PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, d_rec, sizeof(SmallRec), cudaMemcpyDeviceToHost, st));
-  PDC_TRY(staged_d2h(ctx, theta_out, ctx->out_a.p, sizeof(double) * (size_t)np, st));
+  PDC_TRY(staged_d2h(ctx, stat_out, ctx->out_a.p, sizeof(double) * (size_t)np, st));
   PDC_CUDA(cudaStreamSynchronize(st));
   const SmallRec* h = ctx->pin_small.as<SmallRec>();
-  if (argmin_out) *argmin_out = h->arg;
-  if (min_out) *min_out = h->val;
+  if (arg_out) *arg_out = h->arg;
+  if (best_out) *best_out = h->val;
   return PDC_OK;
+}
+
+int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+            const double* periods, int64_t np, int nb, int nc,
+            double* theta_out, int64_t* argmin_out, double* min_out) {
+  if (!ctx || !t || !x || !periods || !theta_out) { set_error("pdc_pdm: NULL argument"); return PDC_EINVAL; }
+  if (n < 2 || np < 1) { set_error("pdc_pdm: need n >= 2 samples and np >= 1 periods"); return PDC_EINVAL; }
+  return phase_hist_host(ctx, t, x, n, periods, np, nb, nc, PDC_STAT_PDM, theta_out, argmin_out, min_out);
+}
+
+// ---------------------------------------------------------------------------
+// analysis of variance (same histograms as PDM, nc = 1)
+// ---------------------------------------------------------------------------
+int pdc_aov_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np,
+                int nb, double* theta_out, int64_t* argmax_out, double* max_out, void* stream) {
+  if (!ctx || !t || !x || !periods || !theta_out) { set_error("pdc_aov_dev: NULL argument"); return PDC_EINVAL; }
+  if (nb < 2) { set_error("pdc_aov: needs at least 2 phase bins"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  return pdm_run(ctx, t, x, n, periods, np, nb, 1, theta_out, argmax_out, max_out, st, nullptr, 0, PDC_STAT_AOV);
+}
+
+int pdc_aov(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np,
+            int nb, double* theta_out, int64_t* argmax_out, double* max_out) {
+  if (!ctx || !t || !x || !periods || !theta_out) { set_error("pdc_aov: NULL argument"); return PDC_EINVAL; }
+  if (n < 2 || np < 1) { set_error("pdc_aov: need n >= 2 samples and np >= 1 periods"); return PDC_EINVAL; }
+  if (nb < 2) { set_error("pdc_aov: needs at least 2 phase bins"); return PDC_EINVAL; }
+  return phase_hist_host(ctx, t, x, n, periods, np, nb, 1, PDC_STAT_AOV, theta_out, argmax_out, max_out);
 }
 
 // ---------------------------------------------------------------------------

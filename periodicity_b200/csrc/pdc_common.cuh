@@ -107,6 +107,9 @@ struct pdc_ctx {
 
 namespace pdc {
 
+// statistic computed from the phase-bin histograms of pdm.cu
+enum { PDC_STAT_PDM = 0, PDC_STAT_AOV = 1 };
+
 // launchers implemented in gls.cu / pdm.cu; all device pointers, stream ordered
 int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
             const int64_t* offsets_host, int64_t B, const double* fmin_host, const double* df_host,
@@ -120,7 +123,8 @@ int glsm_run(pdc_ctx* ctx, const double* t, const double* Y, const double* w, in
 
 int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods,
             int64_t np, int nb, int nc, double* theta_out, int64_t* argmin_out, double* min_out,
-            cudaStream_t stream, const pdc_fanout* fanout = nullptr, int64_t fan_offset = 0);
+            cudaStream_t stream, const pdc_fanout* fanout = nullptr, int64_t fan_offset = 0,
+            int statistic = PDC_STAT_PDM);   // PDC_STAT_AOV: theta_out = AoV statistic, argmin/min_out = its arg-MAX / max
 
 int strlen_run(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const double* periods, int64_t np,
                double* ell_out, int64_t* argmin_out, double* min_out, cudaStream_t stream);

@@ -664,6 +664,11 @@ pdm_hist_kernel(const PdmArgs a) {
   } while (tile0 < se);
 }
 
+// STAT = PDC_STAT_PDM: theta of phase.py:145-149 (smaller is better).  STAT = PDC_STAT_AOV: the analysis-of-variance
+// statistic of Schwarzenberg-Czerny (1989) -- a TODO of the reference (phase.py:11) -- from the same fine-bin
+// histograms with nc = 1: Theta = [(N - r) / (r - 1)] * s1 / s2 over the r populated bins, s1 = sum_b n_b (mean_b - mean)^2
+// (between bins), s2 = sum_b sum_i (x_i - mean_b)^2 (within bins); larger is better.
+template <int STAT>
 __global__ void __launch_bounds__(256)
 pdm_epilogue_kernel(double* __restrict__ partial, const double* __restrict__ periods,
                     const PdmMeta* __restrict__ meta, int nsplit, int m0, int nc, long long np,
@@ -686,29 +691,47 @@ pdm_epilogue_kernel(double* __restrict__ partial, const double* __restrict__ per
     }
     const double* pn = partial + pi;
     const double* p1 = pn + (long long)m0 * np;
-    double sq = 0.0, den = 0.0;
-    for (int k = 0; k < m0; ++k) {
-      double N = 0.0, S = 0.0;
-      for (int c = 0; c < nc; ++c) {
-        int q = k + c;
-        if (q >= m0) q -= m0;
-        N += pn[(long long)q * np];
-        S += p1[(long long)q * np];
-      }
-      if (N >= 1.0) sq += S * S / N;
-      if (N > 1.0) den += N - 1.0;  // phase.py:142,147: bins with <= 1 sample are dropped
-    }
-    // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
-    theta = ((double)nc * meta->q_binned - sq) / den;
     const double P = periods[pi];
-    if (isinf(P)) theta = 1.0;  // every phase is 0: one populated fine bin holding all samples
-    else if (!isfinite(1.0 / P) || P != P) theta = nan("");  // period 0, denormal or NaN: phases are inf / NaN
+    if (STAT == PDC_STAT_AOV) {
+      double sq = 0.0, ntot = 0.0, stot = 0.0;
+      int r = 0;
+      for (int k = 0; k < m0; ++k) {
+        const double N = pn[(long long)k * np], S = p1[(long long)k * np];
+        if (N >= 1.0) {
+          sq += S * S / N;
+          ntot += N;
+          stot += S;
+          ++r;
+        }
+      }
+      const double s1 = sq - stot * stot / ntot;   // between the bins, about the mean of the binned samples
+      const double s2 = meta->q_binned - sq;       // within the bins
+      theta = ((ntot - (double)r) / (double)(r - 1)) * (s1 / s2);
+      if (!isfinite(P) || !isfinite(1.0 / P)) theta = nan("");  // no phases: period 0, denormal, inf or NaN
+    } else {
+      double sq = 0.0, den = 0.0;
+      for (int k = 0; k < m0; ++k) {
+        double N = 0.0, S = 0.0;
+        for (int c = 0; c < nc; ++c) {
+          int q = k + c;
+          if (q >= m0) q -= m0;
+          N += pn[(long long)q * np];
+          S += p1[(long long)q * np];
+        }
+        if (N >= 1.0) sq += S * S / N;
+        if (N > 1.0) den += N - 1.0;  // phase.py:142,147: bins with <= 1 sample are dropped
+      }
+      // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
+      theta = ((double)nc * meta->q_binned - sq) / den;
+      if (isinf(P)) theta = 1.0;  // every phase is 0: one populated fine bin holding all samples
+      else if (!isfinite(1.0 / P) || P != P) theta = nan("");  // period 0, denormal or NaN: phases are inf / NaN
+    }
     if (theta_out) theta_out[pi] = theta;
     // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
     for (int r = 0; r < fan.world; ++r) fan.power[r][fan_offset + pi] = theta;
     idx = pi;
   }
-  block_argext<-1>(theta, idx, sv, si);
+  block_argext<(STAT == PDC_STAT_AOV ? 1 : -1)>(theta, idx, sv, si);
   if (threadIdx.x == 0) {
     red_val[blockIdx.x] = theta;
     red_idx[blockIdx.x] = idx;
@@ -731,7 +754,9 @@ static int pdm_launch(pdc_ctx* ctx, const PdmArgs& a, size_t smem, long long blo
 
 int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods,
             int64_t np, int nb, int nc, double* theta_out, int64_t* argmin_out, double* min_out,
-            cudaStream_t st, const pdc_fanout* fanout, int64_t fan_offset) {
+            cudaStream_t st, const pdc_fanout* fanout, int64_t fan_offset, int statistic) {
+  if (statistic != PDC_STAT_PDM && statistic != PDC_STAT_AOV) { set_error("pdc_pdm: unknown statistic %d", statistic); return PDC_EINVAL; }
+  if (statistic == PDC_STAT_AOV && (nc != 1 || fanout)) { set_error("pdc_aov: needs nc == 1 and no fan-out"); return PDC_EINVAL; }
   if (fanout && (fanout->world < 1 || fanout->world > PDC_MAX_PEERS || fanout->rank < 0 ||
                  fanout->rank >= fanout->world)) {
     set_error("pdc_pdm_dev_fanout: needs 1 <= world <= %d", PDC_MAX_PEERS);
@@ -849,8 +874,14 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   pdc_fanout fan;
   if (fanout) fan = *fanout;
   else fan.world = 0;
-  pdm_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(a.partial, periods, meta, nsplit, m0, nc, np, theta_out,
-                                                      red_val, red_idx, fan, (long long)fan_offset);
+  if (statistic == PDC_STAT_AOV)
+    pdm_epilogue_kernel<PDC_STAT_AOV><<<(unsigned)eblk, 256, 0, st>>>(a.partial, periods, meta, nsplit, m0, nc, np,
+                                                                     theta_out, red_val, red_idx, fan,
+                                                                     (long long)fan_offset);
+  else
+    pdm_epilogue_kernel<PDC_STAT_PDM><<<(unsigned)eblk, 256, 0, st>>>(a.partial, periods, meta, nsplit, m0, nc, np,
+                                                                     theta_out, red_val, red_idx, fan,
+                                                                     (long long)fan_offset);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
   if (fanout) {
@@ -858,7 +889,10 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   } else if (argmin_out || min_out) {
-    argext_final_kernel<-1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmin_out, min_out);
+    if (statistic == PDC_STAT_AOV)
+      argext_final_kernel<+1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmin_out, min_out);
+    else
+      argext_final_kernel<-1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmin_out, min_out);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }

