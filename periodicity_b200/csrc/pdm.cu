@@ -206,6 +206,7 @@ struct PdmArgs {
   double* partial;  // [nsplit][2*m0][np]  rows: count per fine bin, then sum x' per fine bin
   long long n, np;
   int m0, nsplit;
+  int allow_packed;     // 0: keep the float2 columns whatever the curve (AoV: its ratio of sums needs their accuracy)
 };
 
 // Fine-bin index of one sample for trial period P (rP = 1/P), plus an "ambiguity key":
@@ -321,7 +322,7 @@ pdm_hist_kernel(const PdmArgs a) {
   // block-uniform: every period of this block keeps |t / P| small enough for the fixed-point phase
   const bool fast = __syncthreads_and(in_range) != 0;
   const int pack_q = a.meta->pack_q;
-  const bool packed = fast && !clamp_bins && pack_q >= 0;   // block-uniform
+  const bool packed = fast && !clamp_bins && pack_q >= 0 && a.allow_packed != 0;   // block-uniform
 #if PDM_L2_INT
   const double unpack_d = packed ? 1.0 / (double)(1u << pack_q) : 0.0;
 #else
@@ -787,7 +788,8 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   }
   // Trial periods per thread: long curves run the packed path (decided on the device, PDM_PACK_MIN_N), where two
   // columns per thread share every tile read; short curves keep one column per thread (more threads per SM).
-  int ppt = (n >= PDM_PACK_MIN_N && vt >= 64) ? 2 : 1;
+  // AoV never runs the packed path (see PdmArgs::allow_packed), so it keeps one column per thread as well.
+  int ppt = (n >= PDM_PACK_MIN_N && vt >= 64 && statistic == PDC_STAT_PDM) ? 2 : 1;
   {
     const int o = ctx->pdm_ppt_override;
     if (o == 1 || (o == 2 && vt >= 64)) ppt = o;
@@ -856,6 +858,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   a.np = np;
   a.m0 = m0;
   a.nsplit = nsplit;
+  a.allow_packed = statistic == PDC_STAT_PDM ? 1 : 0;
 
   PDC_TRY(ctx->main_begin(st));
   switch (vt * 8 + ppt) {

@@ -1,34 +1,38 @@
 """pdc_aov on the GPU against the numpy oracle (oracle/aov_numpy.py, itself pinned to scipy.stats.f_oneway).
 
-Tolerance (no reference implementation and no north-star figure exist for this statistic, phase.py:11 is a TODO;
-same form as the GLS criterion): peak-normalised error <= 2e-5, elementwise relative error <= 5e-5 where the statistic
-is >= 1 % of its maximum, identical arg-max.  Theta = s1 / s2 is a ratio of two sums that move in opposite directions
-with the bin sums, so the 2^-q sigma quantisation of the packed histogram path (q >= 11) that costs PDM's theta ~1e-6
-shows here as a few 1e-6 at the peak and, at noise level (Theta ~ 1, where the between-bin sum of squares is itself a
-small number), as ~1e-4 relative (bounded at 5e-3 below).
+Tolerance (no reference implementation and no north-star figure exist for this statistic, phase.py:11 is a TODO; same
+form as the GLS criterion): peak-normalised error <= 1e-5, elementwise relative error <= 2e-5 where the statistic is
+>= 1 % of its maximum, <= 1e-3 everywhere, identical arg-max.  Theta = s1 / s2 is a ratio of two sums that move in
+opposite directions with the bin sums, which is why pdc_aov keeps the float2 (FP32) histogram columns for every curve:
+their rounding error scales with the bin sum itself (small exactly where Theta is small), whereas the fixed 2^-q sigma
+quantisation of the packed path PDM uses would show as ~3e-5 at the peak and ~2e-4 at noise level.  A numpy emulation
+of the FP32 accumulation order predicts <= 2e-6 / <= 5e-6 / <= 1e-5 for the three figures on these cases.
+
+Hardware status: round 1 ran out of GPU budget while this file was being brought up.  The AoV epilogue itself passed
+three parity cases on B200 (through the packed path, at the looser tolerance that path allows); the final
+configuration -- the same epilogue behind the float2 path with one period per thread, a kernel path the PDM tests
+cover -- has not been executed yet, so every test here carries a NON-STRICT xfail mark: an XPASS is the expected
+outcome, and a first-run surprise in a statistic the reference does not even implement cannot stop `pytest -x`
+before the GLS / PDM parity tests.  Remove the mark after the first green run.
 """
 import numpy as np
 import pytest
 
 from oracle import aov_numpy
 
-pytestmark = pytest.mark.gpu
-
-# Round 1 ended its GPU budget while this file was being run for the first time: the three parity cases below without
-# a mark passed on B200; the cases carrying NOT_RUN_YET had not been executed on hardware when they were committed.
-# They are expected to pass (an XPASS is the normal outcome) -- the mark only keeps a first-run surprise in a
-# statistic the reference does not even implement from stopping `pytest -x` before the GLS / PDM parity tests.
-NOT_RUN_YET = pytest.mark.xfail(strict=False, reason="first hardware run pending (round-1 GPU budget exhausted)")
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first hardware run of the final AoV configuration pending "
+                                                     "(round-1 GPU budget exhausted)")]
 
 
 def assert_stat_close(got, ref):
     ok = ~np.isnan(ref)
     np.testing.assert_array_equal(np.isnan(got), ~ok)
     peak = np.max(ref[ok])
-    assert np.max(np.abs(got[ok] - ref[ok])) <= 2e-5 * peak
+    assert np.max(np.abs(got[ok] - ref[ok])) <= 1e-5 * peak
     big = ok & (ref >= 1e-2 * peak)
-    assert np.max(np.abs(got[big] - ref[big]) / ref[big]) <= 5e-5
-    assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(ref[ok], 1e-3)) <= 5e-3
+    assert np.max(np.abs(got[big] - ref[big]) / ref[big]) <= 2e-5
+    assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(ref[ok], 1e-3)) <= 1e-3
     assert np.nanargmax(got) == np.nanargmax(ref)
 
 
@@ -39,9 +43,8 @@ def synth(n, seed, period=3.7, noise=0.5):
     return t, x
 
 
-@pytest.mark.parametrize("n,nb,npd", [(6000, 10, 400), (800, 7, 333), (20_000, 16, 257),
-                                      pytest.param(4500, 2, 100, marks=NOT_RUN_YET)])
-def test_against_oracle_packed_and_unpacked_paths(gpu_ctx, n, nb, npd):
+@pytest.mark.parametrize("n,nb,npd", [(6000, 10, 400), (800, 7, 333), (20_000, 16, 257), (4500, 4, 150)])
+def test_against_oracle(gpu_ctx, n, nb, npd):
     t, x = synth(n, n + nb)
     periods = np.linspace(1.0, 9.0, npd)
     th, am, mx = gpu_ctx.aov(t, x, periods, nb)
@@ -52,7 +55,6 @@ def test_against_oracle_packed_and_unpacked_paths(gpu_ctx, n, nb, npd):
     assert min(abs(periods[am] - 3.7), abs(periods[am] - 7.4)) < 0.1
 
 
-@NOT_RUN_YET
 def test_empty_bins_and_degenerate_periods(gpu_ctx):
     rng = np.random.default_rng(3)
     ti = np.arange(64.0)
@@ -65,7 +67,6 @@ def test_empty_bins_and_degenerate_periods(gpu_ctx):
     assert am == int(np.nanargmax(th)) and mx == th[am]
 
 
-@NOT_RUN_YET
 def test_dropin_class_and_invalid_arguments(gpu_ctx):
     from periodicity_b200 import AOV, TSeries
     t, x = synth(5000, 11, period=2.2)
@@ -74,14 +75,13 @@ def test_dropin_class_and_invalid_arguments(gpu_ctx):
     ref = aov_numpy.aov(t, x, aov.periods, 12)
     assert_stat_close(out.values[::-1], ref)
     assert abs(aov.periods[aov.argmax_index] - 2.2) < 0.02
-    assert aov._aov(2.2) == pytest.approx(aov_numpy.aov_theta(t, x, 2.2, 12), rel=5e-5)
+    assert aov._aov(2.2) == pytest.approx(aov_numpy.aov_theta(t, x, 2.2, 12), rel=2e-5)
     with pytest.raises(ValueError):
         gpu_ctx.aov(t, x, [1.0, 2.0], 1)
     with pytest.raises(ValueError):
         gpu_ctx.aov(t, x[:-1], [1.0], 5)
 
 
-@NOT_RUN_YET
 def test_device_pointer_entry_matches_host_entry(gpu_ctx):
     import torch
     t, x = synth(7000, 13)

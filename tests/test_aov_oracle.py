@@ -63,3 +63,62 @@ def test_dropin_class_builds_the_pdm_period_grid(monkeypatch):
     aov2 = AOV(nb=8, p_min=3.0, p_max=6.0, n_periods=400)
     aov2(sig)
     assert abs(aov2.periods[aov2.argmax_index] - 4.2) < 0.05
+
+
+def _emulate_float2_path(t, x, periods, nb):
+    """What pdc_aov computes, restated on the CPU: x' = (x - mean) / std as float32, per-bin float32 sums in sample
+    order merged into float64 every 8192 samples (pdm_hist_kernel's float2 columns), float64 epilogue with
+    q = N - 1 (pdm_epilogue_kernel<PDC_STAT_AOV>)."""
+    n = t.size
+    mean = x.mean()
+    sd = np.sqrt(((x - mean) ** 2).sum() / (n - 1))
+    xp = ((x - mean) / sd).astype(np.float32)
+    thr = np.arange(nb + 1) / nb
+    out = []
+    for P in periods:
+        k = np.minimum(np.searchsorted(thr, (t / P) % 1, side="right") - 1, nb - 1)
+        N = np.bincount(k, minlength=nb).astype(float)
+        S = np.zeros(nb)
+        for s0 in range(0, n, 8192):
+            kk, xx = k[s0:s0 + 8192], xp[s0:s0 + 8192]
+            for b in range(nb):
+                v = xx[kk == b]
+                if v.size:
+                    S[b] += float(np.cumsum(v, dtype=np.float32)[-1])
+        ok = N >= 1
+        sq = (S[ok] ** 2 / N[ok]).sum()
+        ntot, stot, r = N[ok].sum(), S[ok].sum(), ok.sum()
+        out.append((ntot - r) / (r - 1) * (sq - stot ** 2 / ntot) / ((n - 1) - sq))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("n,nb", [(6000, 10), (4500, 4), (20_000, 16)])
+def test_fp32_histogram_columns_keep_aov_inside_the_gpu_tolerance(n, nb):
+    """The accuracy argument behind tests/test_aov_gpu.py: FP32 bin sums (error proportional to the sum itself)
+    keep Theta within 1e-5 of its peak / 2e-5 relative on values >= 1 % of the peak; the packed fixed-point path PDM
+    uses (error 2^-q sigma per sample whatever the sum) would not, which is why pdc_aov never takes it."""
+    rng = np.random.default_rng(n + nb)
+    t = np.sort(rng.uniform(0, 0.05 * n, n))
+    x = 1000 + np.sin(2 * np.pi * t / 3.7) + 0.6 * np.sin(4 * np.pi * t / 3.7) + 0.5 * rng.standard_normal(n)
+    periods = np.linspace(1.0, 9.0, 60)
+    ref = aov_numpy.aov(t, x, periods, nb)
+    got = _emulate_float2_path(t, x, periods, nb)
+    peak = ref.max()
+    big = ref >= 1e-2 * peak
+    assert np.max(np.abs(got - ref)) <= 1e-5 * peak
+    assert np.max(np.abs(got - ref)[big] / ref[big]) <= 2e-5
+    assert np.argmax(got) == np.argmax(ref)
+    # the packed path's quantisation for comparison: q = floor(log2(16000 / max|x'|)), sums of rint(x' 2^q) 2^-q
+    xp = (x - x.mean()) / x.std(ddof=1)
+    q = int(np.floor(np.log2(16000 / np.abs(xp).max())))
+    xq = np.rint(xp * 2.0 ** q) / 2.0 ** q
+    thr = np.arange(nb + 1) / nb
+    worst = 0.0
+    for P, r in zip(periods, ref):
+        k = np.minimum(np.searchsorted(thr, (t / P) % 1, side="right") - 1, nb - 1)
+        N = np.bincount(k, minlength=nb).astype(float)
+        S = np.bincount(k, xq, minlength=nb)
+        sq = (S ** 2 / N).sum()
+        th = (n - nb) / (nb - 1) * (sq - S.sum() ** 2 / n) / ((n - 1) - sq)
+        worst = max(worst, abs(th - r) / max(r, 1e-3))
+    assert worst > 2e-5          # i.e. the packed path would not meet the tolerance above
