@@ -88,3 +88,29 @@ def test_second_level_integer_planes_hold_a_global_flush_interval():
     xs = np.random.default_rng(2).uniform(-3, 3, 10_000)
     _, fix = increments(xs, q)
     assert np.max(np.abs(fix / 2.0 ** q - xs)) <= 2.0 ** -(q + 1)
+
+
+def test_packed_quantisation_keeps_theta_inside_the_parity_tolerance():
+    """The accuracy argument of the packed path: histogramming rint(x' 2^q) 2^-q instead of x' moves
+    PDM's theta by ~1e-6 relative on a C3-like curve -- inside the 1e-5 the GPU parity tests assert."""
+    from oracle import pdm_numpy
+    rng = np.random.default_rng(3)
+    n, nb, nc = 100_000, 10, 2
+    m0 = nb * nc
+    t = np.sort(rng.uniform(0, 1000.0, n))
+    x = 1000 + np.sin(2 * np.pi * t / 3.7) + 0.8 * np.sin(4 * np.pi * t / 3.7) + rng.standard_normal(n)
+    xp = (x - x.mean()) / x.std(ddof=1)
+    q = pack_q(np.abs(xp).max())
+    assert q >= MIN_Q
+    xq = np.rint(xp * 2.0 ** q) / 2.0 ** q
+    idx = (np.arange(m0)[:, None] + np.arange(nc)[None, :]) % m0
+    worst = 0.0
+    for P in (3.7, 1.85, 7.4, 2.345, 10.1):
+        k = pdm_numpy.fine_bin((t / P) % 1, m0)
+        N = np.bincount(k, minlength=m0).astype(float)[idx].sum(1)
+        S = np.bincount(k, xq, minlength=m0)[idx].sum(1)
+        # epilogue of pdm.cu: theta = [nc (N - 1) - sum S_k^2 / n_k] / sum (n_k - 1)
+        theta = (nc * (n - 1) - (S ** 2 / N).sum()) / (N - 1).sum()
+        ref = pdm_numpy.pdm_theta_hist(t, x, P, nb, nc)
+        worst = max(worst, abs(theta - ref) / ref)
+    assert worst < 5e-6
