@@ -1,5 +1,5 @@
 """Multi-GPU check of the fused epilogue + all-gather (run under torchrun on >= 2 GPUs)."""
-import os, sys, time
+import os, sys
 import numpy as np
 import torch
 import torch.distributed as dist
