@@ -1,9 +1,11 @@
 """Load the UNMODIFIED reference hot-path files -- authoring container only.
 
-TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  ``/root/reference`` does not
-exist on the GPU box, so nothing that runs there may call this module; it is
-used by ``tests/golden/make_golden.py`` (which writes the committed fixtures)
-and by CPU tests that skip themselves when the reference tree is absent.
+TEST / BENCH INFRASTRUCTURE (see ``oracle/__init__.py``).  ``/root/reference`` does not
+exist on the GPU box; there the two files are found under ``oracle/_ref/periodicity/`` if
+``oracle/make_ref.py`` staged them (git-ignored, byte-for-byte copies that travel with the
+snapshot).  Used by ``tests/golden/make_golden.py`` (which writes the committed fixtures), by
+CPU tests that skip themselves when neither location exists, and by ``bench.py``'s reference
+arm / ``cpu_baseline`` leg (``kind: "reference"``).
 
 The reference package cannot be imported as a whole (``core.py:6`` needs
 xarray, which is not installed).  ``spectral.py`` and ``phase.py`` only need
@@ -23,6 +25,17 @@ import types
 import numpy as np
 
 REFERENCE_ROOT = os.environ.get("PERIODICITY_REFERENCE_ROOT", "/root/reference")
+# byte-for-byte staged copies of the two files (oracle/make_ref.py; git-ignored, travels to the GPU box)
+STAGED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "periodicity")
+
+
+def source_dir():
+    """Directory holding the reference's spectral.py / phase.py: the reference tree when it exists (authoring
+    container), else the staged copies under oracle/_ref (GPU box), else None."""
+    for d in (os.path.join(REFERENCE_ROOT, "src", "periodicity"), STAGED_DIR):
+        if os.path.isfile(os.path.join(d, "spectral.py")) and os.path.isfile(os.path.join(d, "phase.py")):
+            return d
+    return None
 
 
 class _StubTSeries:
@@ -105,13 +118,14 @@ class _StubFSeries:
 
 
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "periodicity", "spectral.py"))
+    return source_dir() is not None
 
 
 def load():
     """Return ``(spectral, phase)`` modules of the unmodified reference."""
-    if not available():
-        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+    src = source_dir()
+    if src is None:
+        raise RuntimeError(f"reference files found neither under {REFERENCE_ROOT} nor under {STAGED_DIR}")
     pkg_name = "_periodicity_reference"
     if pkg_name + ".spectral" in sys.modules:
         return sys.modules[pkg_name + ".spectral"], sys.modules[pkg_name + ".phase"]
@@ -124,7 +138,7 @@ def load():
     sys.modules[pkg_name + ".core"] = core
     mods = []
     for name in ("spectral", "phase"):
-        path = os.path.join(REFERENCE_ROOT, "src", "periodicity", name + ".py")
+        path = os.path.join(src, name + ".py")
         spec = importlib.util.spec_from_file_location(f"{pkg_name}.{name}", path)
         mod = importlib.util.module_from_spec(spec)
         sys.modules[f"{pkg_name}.{name}"] = mod

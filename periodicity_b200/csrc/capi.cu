@@ -304,10 +304,10 @@ static int staged_d2h(pdc_ctx* ctx, void* dst, const void* src, size_t bytes, cu
   int nchunk = (int)(bytes / ((size_t)256 << 10));
   if (nchunk < 2) nchunk = 2;
   if (nchunk > 8) nchunk = 8;
-  const size_t step = ((bytes / nchunk) + 4095) & ~(size_t)4095;
+  const size_t step = (((bytes + nchunk - 1) / nchunk) + 4095) & ~(size_t)4095;  // ceil: at most nchunk <= 8 chunks
   char* pin = ctx->pin_out.as<char>();
   int used = 0;
-  for (size_t off = 0; off < bytes; off += step, ++used) {
+  for (size_t off = 0; off < bytes && used < 8; off += step, ++used) {
     const size_t len = off + step < bytes ? step : bytes - off;
     if (!ctx->ev_chunk[used]) PDC_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[used], cudaEventDisableTiming));
     PDC_CUDA(cudaMemcpyAsync(pin + off, (const char*)src + off, len, cudaMemcpyDeviceToHost, st));

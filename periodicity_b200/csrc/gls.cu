@@ -637,7 +637,8 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   if (B > 65535) { set_error("pdc_gls_batch: at most 65535 curves per call"); return PDC_EINVAL; }
 
   // scratch is shared by all calls on this ctx: order this stream after the previous call
-  PDC_TRY(ctx->scratch_acquire(st));
+  ScratchScope scratch(ctx, st);
+  PDC_TRY(scratch.acquire());
   // the pinned staging buffer is reused by every call: wait for the previous upload
   PDC_CUDA(cudaEventSynchronize(ctx->ev_fence));
 
@@ -747,7 +748,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  PDC_TRY(ctx->scratch_release(st));
+  PDC_TRY(scratch.release());
   return PDC_OK;
 }
 

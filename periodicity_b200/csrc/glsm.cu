@@ -469,7 +469,8 @@ int glsm_run(pdc_ctx* ctx, const double* t, const double* Y, const double* w, in
   if (nlowchunk > GLS_LOW_MAXCHUNKS) nlowchunk = GLS_LOW_MAXCHUNKS;
   const int eblk = (int)((nf + 255) / 256);
 
-  PDC_TRY(ctx->scratch_acquire(st));
+  ScratchScope scratch(ctx, st);
+  PDC_TRY(scratch.acquire());
   PDC_CUDA(cudaEventSynchronize(ctx->ev_fence));
   PDC_TRY(ctx->gls_curves.reserve(sizeof(GlsmShared) + sizeof(GlsmSeries) * S));
   PDC_TRY(ctx->pin_meta.reserve(sizeof(GlsmShared)));
@@ -542,7 +543,7 @@ int glsm_run(pdc_ctx* ctx, const double* t, const double* Y, const double* w, in
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  PDC_TRY(ctx->scratch_release(st));
+  PDC_TRY(scratch.release());
   return PDC_OK;
 }
 

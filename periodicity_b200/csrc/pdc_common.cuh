@@ -107,6 +107,29 @@ struct pdc_ctx {
 
 namespace pdc {
 
+// Scope of one call's use of the ctx's shared scratch: orders `st` after the previous call on construction
+// (acquire) and records the end-of-call event when the scope ends -- on the success path through release(), on
+// ANY early error return through the destructor, so the ordering contract of the header (every call is ordered
+// after the previous call on the same ctx) also holds after a failed call.
+struct ScratchScope {
+  pdc_ctx* ctx;
+  cudaStream_t st;
+  bool open = false;
+  ScratchScope(pdc_ctx* c, cudaStream_t s) : ctx(c), st(s) {}
+  int acquire() {
+    int rc = ctx->scratch_acquire(st);
+    open = rc == PDC_OK;
+    return rc;
+  }
+  int release() {
+    open = false;
+    return ctx->scratch_release(st);
+  }
+  ~ScratchScope() {
+    if (open) cudaEventRecord(ctx->ev_done, st);
+  }
+};
+
 // statistic computed from the phase-bin histograms of pdm.cu
 enum { PDC_STAT_PDM = 0, PDC_STAT_AOV = 1 };
 

@@ -737,6 +737,9 @@ pdm_epilogue_kernel(double* __restrict__ partial, const double* __restrict__ per
       const double s1 = sq - stot * stot / ntot;   // between the bins, about the mean of the binned samples
       const double s2 = meta->q_binned - sq;       // within the bins
       theta = ((ntot - (double)r) / (double)(r - 1)) * (s1 / s2);
+      // fewer than two populated bins (r - 1 == 0) or no scatter inside the bins: 0/0-like, the same NaN class as
+      // PDM's "every bin dropped" below -- never +-inf from FP32 accumulation residue
+      if (r < 2 || !(s2 > 0.0)) theta = nan("");
       if (!isfinite(P) || !isfinite(1.0 / P)) theta = nan("");  // no phases: period 0, denormal, inf or NaN
     } else {
       double sq = 0.0, den = 0.0;
@@ -753,6 +756,9 @@ pdm_epilogue_kernel(double* __restrict__ partial, const double* __restrict__ per
       }
       // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
       theta = ((double)nc * meta->q_binned - sq) / den;
+      // every coarse bin holds <= 1 sample: the reference divides 0.0 by 0.0 (phase.py:145-147 with an empty `mj`)
+      // and gets NaN, which its nan-aware reductions skip; the FP32 residue of the numerator must not turn it into +-inf
+      if (!(den > 0.0)) theta = nan("");
       if (isinf(P)) theta = 1.0;  // every phase is 0: one populated fine bin holding all samples
       else if (!isfinite(1.0 / P) || P != P) theta = nan("");  // period 0, denormal or NaN: phases are inf / NaN
     }
@@ -847,7 +853,8 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   const long long blocks = npb * nsplit;
   if (blocks > 0x7fffffffLL) { set_error("pdc_pdm: problem too large for one call"); return PDC_EINVAL; }
 
-  PDC_TRY(ctx->scratch_acquire(st));
+  ScratchScope scratch(ctx, st);
+  PDC_TRY(scratch.acquire());
   PDC_TRY(ctx->pdm_meta.reserve(sizeof(PdmMeta) + 16 + sizeof(PdmPart) * PDM_STATS_MAXBLK));
   PDC_TRY(ctx->pdm_x.reserve((sizeof(float) + sizeof(unsigned)) * (size_t)n));
   PDC_TRY(ctx->partial.reserve(sizeof(double) * 2 * m0 * (size_t)np * nsplit));
@@ -928,7 +935,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  PDC_TRY(ctx->scratch_release(st));
+  PDC_TRY(scratch.release());
   return PDC_OK;
 }
 

@@ -155,7 +155,8 @@ int peaks_run(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k
   if (rows > 65535) { set_error("pdc_peaks_topk: at most 65535 rows per call"); return PDC_EINVAL; }
   const long long nblk = (n + PEAK_ITEMS - 1) / PEAK_ITEMS;
   const size_t ncand = (size_t)rows * nblk * k;
-  PDC_TRY(ctx->scratch_acquire(st));
+  ScratchScope scratch(ctx, st);
+  PDC_TRY(scratch.acquire());
   PDC_TRY(ctx->peak_cand.reserve(ncand * (sizeof(double) + sizeof(long long))));
   double* cand_v = ctx->peak_cand.as<double>();
   long long* cand_i = reinterpret_cast<long long*>(cand_v + ncand);
@@ -167,7 +168,7 @@ int peaks_run(pdc_ctx* ctx, const double* values, int64_t rows, int64_t n, int k
                                                               (long long*)idx_out);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
-  PDC_TRY(ctx->scratch_release(st));
+  PDC_TRY(scratch.release());
   return PDC_OK;
 }
 

@@ -110,7 +110,8 @@ int strlen_run(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const 
   const bool smem = npad <= SL_SMEM_MAX_PAD;
   const size_t per_block = (size_t)npad * (sizeof(unsigned long long) + sizeof(unsigned));
 
-  PDC_TRY(ctx->scratch_acquire(st));
+  ScratchScope scratch(ctx, st);
+  PDC_TRY(scratch.acquire());
   long long grid;
   unsigned long long* gkeys = nullptr;
   unsigned* gidx = nullptr;
@@ -150,7 +151,7 @@ int strlen_run(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const 
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  PDC_TRY(ctx->scratch_release(st));
+  PDC_TRY(scratch.release());
   return PDC_OK;
 }
 

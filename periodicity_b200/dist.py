@@ -385,29 +385,82 @@ def pdm_sharded_p2p_torch(t, x, periods, nb, nc, ctx=None, group=None):
     return buf[:npd], buf[npd:].view(world, 2)
 
 
-def pdm_sharded_p2p(t, x, periods, nb, nc, device=None, group=None):
-    """numpy in / numpy out wrapper of :func:`pdm_sharded_p2p_torch` (same return as ``pdm_sharded``)."""
+_dev_cache = {}
+_pin_cache = {}
+
+
+def _upload_cached(name, arr, dev):
+    """Host float64 array -> cached (grow-only) device buffer on the current stream.  Pinned sources travel
+    asynchronously at full PCIe rate; pageable ones are staged by the driver before the call returns."""
+    torch = _torch()
+    a = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64))
+    key = (name, str(dev))
+    buf = _dev_cache.get(key)
+    if buf is None or buf.numel() < a.numel():
+        buf = torch.empty(max(1, a.numel()), dtype=torch.float64, device=dev)
+        _dev_cache[key] = buf
+    view = buf[: a.numel()]
+    view.copy_(a, non_blocking=True)
+    return view
+
+
+def _download(values, best, dev, copy):
+    """Device result -> pinned staging -> numpy (one stream sync).  ``copy=False`` returns views of the staging
+    buffer, valid until the next sharded call in this process."""
+    torch = _torch()
+    n = values.numel() + best.numel()
+    key = str(dev)
+    pin = _pin_cache.get(key)
+    if pin is None or pin.numel() < n:
+        pin = torch.empty(n, dtype=torch.float64).pin_memory()
+        _pin_cache[key] = pin
+    pin[: values.numel()].copy_(values, non_blocking=True)
+    pin[values.numel(): n].copy_(best.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    out = pin[:n].numpy()
+    vals, b = out[: values.numel()], out[values.numel():].reshape(best.shape)
+    return (vals.copy(), b.copy()) if copy else (vals, b)
+
+
+def pdm_sharded_p2p(t, x, periods, nb, nc, device=None, group=None, root=None, copy=True):
+    """numpy in / numpy out wrapper of :func:`pdm_sharded_p2p_torch` (same return as ``pdm_sharded``).
+
+    Every rank uploads the inputs (cached device buffers), evaluates its slice of the period grid and the fused
+    gather leaves the whole theta array on every GPU.  ``root=None``: every rank downloads it; ``root=r``: only
+    rank r does (the others return ``(None, index, value)``)."""
     torch = _torch()
     ctx = _ffi.default_context(device)
     dev = torch.device("cuda", ctx.device)
-    tt = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).to(dev)
-    xx = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
-    pp = torch.as_tensor(np.ascontiguousarray(periods, dtype=np.float64)).to(dev)
+    _, rank, _ = _dist_info(group)
+    tt = _upload_cached("pdm_t", t, dev)
+    xx = _upload_cached("pdm_x", x, dev)
+    pp = _upload_cached("pdm_p", periods, dev)
     theta, best = pdm_sharded_p2p_torch(tt, xx, pp, nb, nc, ctx=ctx, group=group)
-    best = best.cpu().numpy()
-    idx, val = reduce_best(best[:, 0], best[:, 1].astype(np.int64), -1)
-    return theta.cpu().numpy(), idx, val
+    if root is not None and rank != root:
+        b = best.cpu().numpy()
+        idx, val = reduce_best(b[:, 0], b[:, 1].astype(np.int64), -1)
+        return None, idx, val
+    th, b = _download(theta, best, dev, copy)
+    idx, val = reduce_best(b[:, 0], b[:, 1].astype(np.int64), -1)
+    return th, idx, val
 
 
-def gls_sharded_p2p(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, device=None, group=None):
-    """numpy in / numpy out wrapper of :func:`gls_sharded_p2p_torch` (same return as ``gls_sharded``)."""
+def gls_sharded_p2p(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, device=None, group=None, root=None,
+                    copy=True):
+    """numpy in / numpy out wrapper of :func:`gls_sharded_p2p_torch` (same return as ``gls_sharded``); ``root`` and
+    ``copy`` as in :func:`pdm_sharded_p2p`."""
     torch = _torch()
     ctx = _ffi.default_context(device)
     dev = torch.device("cuda", ctx.device)
-    tt = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).to(dev)
-    yy = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64)).to(dev)
-    ww = None if w is None else torch.as_tensor(np.ascontiguousarray(w, dtype=np.float64)).to(dev)
+    _, rank, _ = _dist_info(group)
+    tt = _upload_cached("gls_t", t, dev)
+    yy = _upload_cached("gls_y", y, dev)
+    ww = None if w is None else _upload_cached("gls_w", w, dev)
     power, best = gls_sharded_p2p_torch(tt, yy, ww, fmin, df, nf, fit_mean, psd_scale, ctx=ctx, group=group)
-    best = best.cpu().numpy()
-    idx, val = reduce_best(best[:, 0], best[:, 1].astype(np.int64), +1)
-    return power.cpu().numpy(), idx, val
+    if root is not None and rank != root:
+        b = best.cpu().numpy()
+        idx, val = reduce_best(b[:, 0], b[:, 1].astype(np.int64), +1)
+        return None, idx, val
+    p, b = _download(power, best, dev, copy)
+    idx, val = reduce_best(b[:, 0], b[:, 1].astype(np.int64), +1)
+    return p, idx, val

@@ -12,6 +12,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: takes tens of seconds (full-size BASELINE configs); still part of -m gpu")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices in one process / box (skips itself otherwise)")
 
 
 def load_golden(name):

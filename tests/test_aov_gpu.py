@@ -8,21 +8,14 @@ their rounding error scales with the bin sum itself (small exactly where Theta i
 quantisation of the packed path PDM uses would show as ~3e-5 at the peak and ~2e-4 at noise level.  A numpy emulation
 of the FP32 accumulation order predicts <= 2e-6 / <= 5e-6 / <= 1e-5 for the three figures on these cases.
 
-Hardware status: round 1 ran out of GPU budget while this file was being brought up.  The AoV epilogue itself passed
-three parity cases on B200 (through the packed path, at the looser tolerance that path allows); the final
-configuration -- the same epilogue behind the float2 path with one period per thread, a kernel path the PDM tests
-cover -- has not been executed yet, so every test here carries a NON-STRICT xfail mark: an XPASS is the expected
-outcome, and a first-run surprise in a statistic the reference does not even implement cannot stop `pytest -x`
-before the GLS / PDM parity tests.  Remove the mark after the first green run.
+Hardware status: first green run on B200 in round 1's driver test (7 XPASS); the xfail mark was removed in round 2.
 """
 import numpy as np
 import pytest
 
 from oracle import aov_numpy
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run of the final AoV configuration pending "
-                                                     "(round-1 GPU budget exhausted)")]
+pytestmark = pytest.mark.gpu
 
 
 def assert_stat_close(got, ref):

@@ -127,3 +127,17 @@ def test_stringlength_restatement_matches_reference_code(case):
     np.testing.assert_array_equal(stringlength_numpy.scale(x), g["m"])
     np.testing.assert_array_equal((1 / periods)[::-1], g["periodogram_frequency"])     # FSeries re-sorts (core.py:877-881)
     np.testing.assert_allclose(ell[::-1], g["periodogram_values"], rtol=1e-13)
+
+
+def test_c_oracle_indexed_and_free_frequency_entry_points_agree_with_the_grid_one():
+    """orc_gls_exact_at / orc_gls_exact_freqs (strided checks of huge grids, non-uniform grids) are the same
+    code as orc_gls_exact, which the golden vectors pin: same values at the same frequencies."""
+    g = load_golden("gls_err")
+    t, y, err = _gls_inputs(g)
+    fmin, df, f = gls_numpy.gls_grid(t, g["n"], opt(g["fmin"]), opt(g["fmax"]))
+    full = cport.gls_exact(t, y, err, fmin, df, f.size, bool(g["fit_mean"]), bool(g["psd"]))
+    sel = np.unique(np.concatenate([np.arange(0, f.size, 7), [f.size - 1]]))
+    at = cport.gls_exact_at(t, y, err, fmin, df, sel, bool(g["fit_mean"]), bool(g["psd"]))
+    np.testing.assert_array_equal(at, full[sel])
+    fr = cport.gls_exact_freqs(t, y, err, fmin + sel * df, bool(g["fit_mean"]), bool(g["psd"]))
+    np.testing.assert_array_equal(fr, full[sel])

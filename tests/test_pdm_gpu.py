@@ -77,6 +77,13 @@ def test_c3_full_size_properties(gpu_ctx):
     ref = cport.pdm(t, x, periods[lo:hi], 10, 2)
     np.testing.assert_allclose(th[lo:hi], ref, rtol=TOL)
     assert lo + np.argmin(ref) == am
+    # strided oracle pass over the WHOLE grid (every 50th period + the window above): a wrong global minimum
+    # anywhere else would show here, not only next to the GPU's own argmin
+    sel = np.arange(0, periods.size, 50)
+    ref_s = cport.pdm(t, x, periods[sel], 10, 2)
+    np.testing.assert_allclose(th[sel], ref_s, rtol=TOL)
+    assert ref_s.min() >= ref.min()                      # no strided period beats the window's minimum
+    assert np.nanmin(th) == th[am] and th[am] <= ref_s.min() * (1 + TOL)
     assert abs(periods[am] - 3.7) < 0.01 or abs(periods[am] - 7.4) < 0.02
 
 
@@ -186,3 +193,23 @@ def test_non_finite_samples_do_not_corrupt_memory(gpu_ctx):
     assert np.isnan(th).all()
     again, _, _ = gpu_ctx.pdm(t, x, periods, 10, 2)      # the ctx is still healthy and deterministic
     np.testing.assert_array_equal(again, base)
+
+
+def test_every_bin_dropped_gives_nan_like_the_reference(gpu_ctx):
+    """phase.py:142-147: when no coarse bin holds more than one sample the reference divides 0.0 by 0.0 -> NaN
+    (nan-aware reductions then skip the period).  The FP32 residue of the numerator must not become +-inf."""
+    t = np.array([0.0, 0.31, 0.77, 1.13, 1.52, 2.2, 2.9])
+    x = np.array([1.0, 2.5, -0.3, 0.9, 1.7, 0.2, 1.1])
+    periods = np.array([2.0, 3.0, 1.9, 0.5, 7.0])
+    for nb, nc in ((50, 1), (64, 1), (12, 1), (6, 1)):
+        th, am, mn = gpu_ctx.pdm(t, x, periods, nb, nc)
+        with np.errstate(all="ignore"):
+            ref = cport.pdm(t, x, periods, nb, nc)
+        np.testing.assert_array_equal(np.isnan(th), np.isnan(ref))
+        assert not np.isinf(th).any()
+        ok = ~np.isnan(ref)
+        if ok.any():
+            np.testing.assert_allclose(th[ok], ref[ok], rtol=TOL)
+            assert am == np.nanargmin(ref)
+        else:
+            assert am == -1 and np.isnan(mn)
