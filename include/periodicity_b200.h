@@ -23,8 +23,9 @@
  *     thread is returned by pdc_last_error().
  *   - The caller owns every buffer passed in; the library never retains a
  *     caller pointer past return.  A pdc_ctx owns one CUDA device, one stream
- *     and grow-only device scratch.  A ctx is not thread-safe; distinct ctxs
- *     may be used concurrently.
+ *     and grow-only device scratch (pdc_ctx_create), or several devices with one
+ *     worker thread each (pdc_ctx_create_multi).  A ctx is not thread-safe; distinct
+ *     ctxs may be used concurrently.
  *   - Host entry points (`pdc_gls`, `pdc_gls_batch`, `pdc_pdm`) take host
  *     pointers and are synchronous: inputs are copied to the device, results
  *     are back in the output buffers on return.
@@ -82,6 +83,24 @@ PDC_API const char* pdc_last_error(void);
  * reads the SM count used to size grids. */
 PDC_API int pdc_ctx_create(pdc_ctx** out, int device);
 PDC_API int pdc_ctx_destroy(pdc_ctx* ctx);
+
+/*
+ * Multi-device context (the single-process counterpart of the reference's transparent
+ * multiprocessing.Pool fan-out, phase.py:182-187).  `device_ids[0..ndev)` are distinct CUDA ordinals of this
+ * process, ndev <= PDC_MAX_PEERS.  HOST-pointer entry points called on such a ctx shard the work over the devices --
+ * pdc_gls: contiguous slices of the frequency grid; pdc_pdm / pdc_aov / pdc_ce / pdc_stringlength: slices of the
+ * period grid; pdc_gls_batch: contiguous groups of curves balanced by sample count; pdc_gls_multi: groups of series
+ * -- with one host worker thread per device: inputs are uploaded to every device concurrently, each device copies
+ * its slice of the result straight into the caller's host buffer, and the (best value, best index) candidates are
+ * reduced on the host (NaN ignored, first occurrence).  Values are identical to the single-device call's for the same
+ * slice.  Work too small to be worth cutting (below ~5e8 evaluations per device; env PDC_MULTI_MIN_EVALS) uses fewer
+ * devices.  Device-pointer (`*_dev`) entry points act on device_ids[0].  ndev == 1 gives an ordinary ctx.
+ * pdc_ctx_destroy releases everything.
+ */
+PDC_API int pdc_ctx_create_multi(pdc_ctx** out, const int* device_ids, int ndev);
+/* Number of devices of the ctx (1 for pdc_ctx_create) and the CUDA ordinal of its index-th device (-1 if out of range). */
+PDC_API int pdc_ctx_device_count(pdc_ctx* ctx);
+PDC_API int pdc_ctx_device_id(pdc_ctx* ctx, int index);
 /* Block until all work queued on the ctx's stream has finished. */
 PDC_API int pdc_ctx_synchronize(pdc_ctx* ctx);
 /* SM count of the ctx's device (148 on B200); negative on error. */

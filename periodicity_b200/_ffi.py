@@ -35,6 +35,9 @@ SIGNATURES = {
     "pdc_version": (ctypes.c_int, []),
     "pdc_last_error": (ctypes.c_char_p, []),
     "pdc_ctx_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "pdc_ctx_create_multi": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "pdc_ctx_device_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "pdc_ctx_device_id": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "pdc_ctx_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pdc_ctx_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "pdc_ctx_sm_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -144,14 +147,30 @@ def _ptr(a):
 
 
 class Context:
-    """One CUDA device + stream + grow-only scratch (``pdc_ctx``). Not thread-safe."""
+    """One CUDA device + stream + grow-only scratch (``pdc_ctx``), or -- ``device`` given as a list / tuple of
+    ordinals -- a multi-device ctx (``pdc_ctx_create_multi``) whose host entry points shard the grid or the batch over
+    the devices inside the library.  Not thread-safe."""
 
     def __init__(self, device=0):
         self._lib = load_library()
         self._h = ctypes.c_void_p()
-        self.device = int(device)
-        _check(self._lib.pdc_ctx_create(ctypes.byref(self._h), self.device))
+        if isinstance(device, (list, tuple)):
+            ids = [int(d) for d in device]
+            if not ids:
+                raise ValueError("empty device list")
+            arr = (ctypes.c_int * len(ids))(*ids)
+            self.device = ids[0]
+            self.devices = tuple(ids)
+            _check(self._lib.pdc_ctx_create_multi(ctypes.byref(self._h), arr, len(ids)))
+        else:
+            self.device = int(device)
+            self.devices = (self.device,)
+            _check(self._lib.pdc_ctx_create(ctypes.byref(self._h), self.device))
         self._lock = threading.Lock()
+
+    @property
+    def device_count(self):
+        return self._lib.pdc_ctx_device_count(self._h)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -369,9 +388,14 @@ _default_lock = threading.Lock()
 
 
 def default_context(device=None):
-    """Process-wide context for ``device`` (default: LOCAL_RANK or 0), created on first use."""
+    """Process-wide context for ``device`` (default: LOCAL_RANK or 0), created on first use.  ``device`` may be a
+    list / tuple of ordinals: a multi-device context (one entry: the ordinary context of that device)."""
     if device is None:
         device = int(os.environ.get("PERIODICITY_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if isinstance(device, (list, tuple)):
+        device = tuple(int(d) for d in device)
+        if len(device) == 1:
+            device = device[0]
     with _default_lock:
         ctx = _default_ctx.get(device)
         if ctx is None:

@@ -202,6 +202,7 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
 
 int pdc_ctx_destroy(pdc_ctx* ctx) {
   if (!ctx) return PDC_OK;
+  multi_destroy(ctx);   // stops the worker threads and destroys the child ctxs of a multi-device ctx
   DeviceGuard guard(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->in_a.release(); ctx->in_b.release(); ctx->in_c.release(); ctx->in_d.release();
@@ -230,7 +231,7 @@ int pdc_ctx_synchronize(pdc_ctx* ctx) {
 
 int pdc_ctx_sm_count(pdc_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
 
-int64_t pdc_ctx_launch_count(pdc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int64_t pdc_ctx_launch_count(pdc_ctx* ctx) { return ctx ? ctx->launches : -1; }  /* primary device; see pdc_ctx_device_count */
 
 double pdc_ctx_last_main_kernel_ms(pdc_ctx* ctx) {
   if (!ctx) return -1.0;
@@ -443,6 +444,8 @@ int pdc_gls(pdc_ctx* ctx, const double* t, const double* y, const double* w, int
   if (!ctx || !t || !y) { set_error("pdc_gls: NULL argument"); return PDC_EINVAL; }
   if (n < 1) { set_error("pdc_gls: n must be >= 1"); return PDC_EINVAL; }
   if (j0 < 0) { set_error("pdc_gls: j0 must be >= 0"); return PDC_EINVAL; }
+  if (nf < 1) { set_error("pdc_gls: need at least one curve and one frequency"); return PDC_EINVAL; }
+  if (ctx->multi) return multi_gls(ctx, t, y, w, n, fmin, df, j0, nf, flags, psd_scale, power_out, argmax_out, max_out);
   DeviceGuard guard(ctx->device);
   const int64_t offsets[2] = {0, n};
   return gls_host_common(ctx, t, y, w, offsets, 1, &fmin, &df, j0, nf, flags, &psd_scale, power_out, argmax_out, max_out);
@@ -453,6 +456,8 @@ int pdc_gls_batch(pdc_ctx* ctx, const double* t, const double* y, const double* 
                   int64_t nf, unsigned flags, const double* psd_scale,
                   double* power_out, int64_t* argmax_out, double* max_out) {
   if (!ctx || !t || !y || !offsets || !fmin || !df) { set_error("pdc_gls_batch: NULL argument"); return PDC_EINVAL; }
+  if (ctx->multi && B >= 1 && nf >= 1 && offsets[B] > offsets[0])
+    return multi_gls_batch(ctx, t, y, w, offsets, B, fmin, df, nf, flags, psd_scale, power_out, argmax_out, max_out);
   DeviceGuard guard(ctx->device);
   return gls_host_common(ctx, t, y, w, offsets, B, fmin, df, 0, nf, flags, psd_scale, power_out, argmax_out, max_out);
 }
@@ -473,6 +478,8 @@ int pdc_gls_multi(pdc_ctx* ctx, const double* t, const double* Y, const double* 
   if (!ctx || !t || !Y) { set_error("pdc_gls_multi: NULL argument"); return PDC_EINVAL; }
   if (n < 1 || S < 1 || nf < 1) { set_error("pdc_gls_multi: need n, S, nf >= 1"); return PDC_EINVAL; }
   if (j0 < 0) { set_error("pdc_gls_multi: j0 must be >= 0"); return PDC_EINVAL; }
+  if (ctx->multi)
+    return multi_gls_multi(ctx, t, Y, w, n, S, fmin, df, j0, nf, flags, psd_scale, power_out, argmax_out, max_out);
   DeviceGuard guard(ctx->device);
   cudaStream_t st = ctx->stream;
   const size_t tb = sizeof(double) * (size_t)n, yb = tb * (size_t)S;
@@ -558,6 +565,11 @@ int pdc_pdm(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
             double* theta_out, int64_t* argmin_out, double* min_out) {
   if (!ctx || !t || !x || !periods || !theta_out) { set_error("pdc_pdm: NULL argument"); return PDC_EINVAL; }
   if (n < 2 || np < 1) { set_error("pdc_pdm: need n >= 2 samples and np >= 1 periods"); return PDC_EINVAL; }
+  if (ctx->multi)
+    return multi_period_grid(ctx, n, periods, np, -1, theta_out, argmin_out, min_out,
+                             [=](pdc_ctx* c, const double* p, int64_t k, double* o, int64_t* a, double* b) {
+                               return pdc_pdm(c, t, x, n, p, k, nb, nc, o, a, b);
+                             });
   return phase_hist_host(ctx, t, x, n, periods, np, nb, nc, PDC_STAT_PDM, theta_out, argmin_out, min_out);
 }
 
@@ -578,6 +590,11 @@ int pdc_aov(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   if (!ctx || !t || !x || !periods || !theta_out) { set_error("pdc_aov: NULL argument"); return PDC_EINVAL; }
   if (n < 2 || np < 1) { set_error("pdc_aov: need n >= 2 samples and np >= 1 periods"); return PDC_EINVAL; }
   if (nb < 2) { set_error("pdc_aov: needs at least 2 phase bins"); return PDC_EINVAL; }
+  if (ctx->multi)
+    return multi_period_grid(ctx, n, periods, np, +1, theta_out, argmax_out, max_out,
+                             [=](pdc_ctx* c, const double* p, int64_t k, double* o, int64_t* a, double* b) {
+                               return pdc_aov(c, t, x, n, p, k, nb, o, a, b);
+                             });
   return phase_hist_host(ctx, t, x, n, periods, np, nb, 1, PDC_STAT_AOV, theta_out, argmax_out, max_out);
 }
 
@@ -596,6 +613,11 @@ int pdc_stringlength(pdc_ctx* ctx, const double* t, const double* m, int64_t n, 
                      int64_t np, double* ell_out, int64_t* argmin_out, double* min_out) {
   if (!ctx || !t || !m || !periods || !ell_out) { set_error("pdc_stringlength: NULL argument"); return PDC_EINVAL; }
   if (n < 1 || np < 1) { set_error("pdc_stringlength: need n >= 1 samples and np >= 1 periods"); return PDC_EINVAL; }
+  if (ctx->multi)   // the sort makes a sample*period ~ log2(n)^2 / 2 times dearer than a PDM update: weigh the split accordingly
+    return multi_period_grid(ctx, n * 64, periods, np, -1, ell_out, argmin_out, min_out,
+                             [=](pdc_ctx* c, const double* p, int64_t k, double* o, int64_t* a, double* b) {
+                               return pdc_stringlength(c, t, m, n, p, k, o, a, b);
+                             });
   DeviceGuard guard(ctx->device);
   cudaStream_t st = ctx->stream;
   PDC_TRY(ctx->in_a.reserve(sizeof(double) * (size_t)n));

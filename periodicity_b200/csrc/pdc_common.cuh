@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <functional>
 #include <utility>
 #include <vector>
 
@@ -46,8 +47,12 @@ struct PinnedBuf {
 
 }  // namespace pdc
 
-// The context: one device, one stream, scratch that only grows.
+namespace pdc { struct MultiState; }
+
+// The context: one device, one stream, scratch that only grows.  A multi-device ctx (pdc_ctx_create_multi) is the
+// ctx of its first device plus `multi`: one child ctx and one host worker thread per further device (multi.cu).
 struct pdc_ctx {
+  pdc::MultiState* multi = nullptr;
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
@@ -133,6 +138,19 @@ struct ScratchScope {
 // statistic computed from the phase-bin histograms of pdm.cu
 enum { PDC_STAT_PDM = 0, PDC_STAT_AOV = 1 };
 
+// multi-device dispatch of the host entry points (multi.cu)
+void multi_destroy(pdc_ctx* ctx);
+int multi_device_count(const pdc_ctx* ctx);
+int multi_gls(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n, double fmin, double df,
+              int64_t j0, int64_t nf, unsigned flags, double psd_scale, double* power_out, int64_t* argmax_out,
+              double* max_out);
+int multi_gls_batch(pdc_ctx* ctx, const double* t, const double* y, const double* w, const int64_t* offsets, int64_t B,
+                    const double* fmin, const double* df, int64_t nf, unsigned flags, const double* psd_scale,
+                    double* power_out, int64_t* argmax_out, double* max_out);
+int multi_gls_multi(pdc_ctx* ctx, const double* t, const double* Y, const double* w, int64_t n, int64_t S, double fmin,
+                    double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale, double* power_out,
+                    int64_t* argmax_out, double* max_out);
+
 // launchers implemented in gls.cu / pdm.cu; all device pointers, stream ordered
 int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
             const int64_t* offsets_host, int64_t B, const double* fmin_host, const double* df_host,
@@ -148,6 +166,11 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
             int64_t np, int nb, int nc, double* theta_out, int64_t* argmin_out, double* min_out,
             cudaStream_t stream, const pdc_fanout* fanout = nullptr, int64_t fan_offset = 0,
             int statistic = PDC_STAT_PDM);   // PDC_STAT_AOV: theta_out = AoV statistic, argmin/min_out = its arg-MAX / max
+
+// sign: -1 arg-min (PDM, String Length, conditional entropy), +1 arg-max (AoV)
+int multi_period_grid(pdc_ctx* ctx, int64_t n, const double* periods, int64_t np, int sign, double* out,
+                      int64_t* arg_out, double* best_out,
+                      const std::function<int(pdc_ctx*, const double*, int64_t, double*, int64_t*, double*)>& call);
 
 int strlen_run(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const double* periods, int64_t np,
                double* ell_out, int64_t* argmin_out, double* min_out, cudaStream_t stream);

@@ -60,7 +60,20 @@ struct PdmMeta {
   int bad;          // some t or x is NaN / inf: the histogram kernel then runs its guarded variant
 };
 
-constexpr int PDM_PACK_FLUSH = 256;   // samples between flushes of the packed 32-bit columns into the float2 columns
+// Packed level-1 word = (count << PDM_SUM_BITS) + sum of fixed-point x' (two's complement in the low PDM_SUM_BITS bits).
+// A window of PDM_PACK_FLUSH samples is fed into level 2 at once.  PDM_PACK_FLUSH = 256 (9 + 23 bits) holds ANY 256 samples
+// by the choice of the exponent q (256 max|x'| 2^q < 2^22).  PDM_PACK_FLUSH = 512 (10 + 22 bits) halves the number of feeds
+// (the feed is what separates the kernel from its ATOMS.ADD floor: 3 shared atomics per bin per window): a window is fed
+// whole only if the block has verified sum |increment| < 2^21 over it while staging the tile (true for anything but a
+// burst of outliers: Gaussian values reach 40 % of the bound); otherwise that window is fed in PDM_PACK_SUB = 128-sample
+// pieces, which the same rule for q guarantees (128 max|x'| 2^q < 2^21).  Both are exact.
+#ifndef PDM_PACK_FLUSH
+#define PDM_PACK_FLUSH 512
+#endif
+constexpr int PDM_CNT_BITS = PDM_PACK_FLUSH > 256 ? 10 : 9;
+constexpr int PDM_SUM_BITS = 32 - PDM_CNT_BITS;
+constexpr int PDM_PACK_SUB = 128;     // guaranteed sub-window of the 512-sample layout
+static_assert(PDM_PACK_FLUSH == 256 || PDM_PACK_FLUSH == 512, "PDM_PACK_FLUSH is 256 or 512");
 constexpr int PDM_PACK_MIN_Q = 11;    // coarsest usable quantisation of x' (2^-11 sigma)
 constexpr int PDM_PACK_MIN_N = 4096;  // shorter curves keep the FP32 columns (they are accurate to 1e-7 there)
 constexpr int PDM_TILE = 1024;        // samples per shared-memory tile
@@ -75,10 +88,15 @@ constexpr int PDM_TILE = 1024;        // samples per shared-memory tile
 #define PDM_PREFETCH 1               // 1: time stamps of the next trip are loaded before this trip's atomics
 #endif
 #ifndef PDM_FLUSH_BINS
-#define PDM_FLUSH_BINS 1               // > 1: the level-1 -> level-2 feed handles this many bins of all the thread's columns at once (untimed yet)
+#define PDM_FLUSH_BINS 10              // the level-1 -> level-2 feed handles this many bins of all the thread's columns at once: every
+                                       // fetch-and-clear is in flight before the first dependent add (C3, B200: 2.950 ms with 1, 2.912 with 4,
+                                       // 2.896 with 10, 2.903 with 20; profiles/tune_pdm_r02.txt)
 #endif
 #ifndef PDM_L2_INT
 #define PDM_L2_INT 1                 // 1: second level of the packed path = integer planes fed with shared-memory atomics
+#endif
+#ifndef PDM_FEED_PLAIN
+#define PDM_FEED_PLAIN 0             // 1: the feed uses plain LDS / STS on the (private) columns instead of atomics (needs PDM_L2_INT)
 #endif
 constexpr int PDM_FLUSH_TILES = 8;    // FP32 histograms are merged into FP64 every 8192 samples
 constexpr int PDM_TILE_PAD = PDM_PREFETCH ? PDM_TRIP_CHAINS : 0;  // the prefetch of the packed loop reads one trip past the tile
@@ -171,8 +189,9 @@ __global__ void pdm_stats3_kernel(const PdmPart* __restrict__ part, int nblk, lo
     meta->bad = bad;
     meta->t_absmax = tabs;
     // Packed first-level histogram (pdm_hist_kernel): one 32-bit word per (bin, period) holds the count in
-    // its top 9 bits and sum rint(x' 2^q) in the low 23 (two's complement) for at most PDM_PACK_FLUSH samples,
-    // so 256 * max|x'| * 2^q must stay below 2^22.  Worth it only if the quantisation step 2^-q is fine
+    // its top PDM_CNT_BITS bits and sum rint(x' 2^q) in the rest (two's complement) for one feed window,
+    // so 256 * max|x'| * 2^q must stay below 2^22 (9 + 23 bits; with 10 + 22 bits: 128 * max|x'| * 2^q < 2^21, the
+    // same condition, for the guaranteed sub-window).  Worth it only if the quantisation step 2^-q is fine
     // enough (q >= PDM_PACK_MIN_Q: relative theta error ~ 0.4 * 2^-q / sqrt(nc N) / theta) and the curve is long.
     int pq = -1;
     const double xmax = dmax / sqrt(var);
@@ -195,8 +214,8 @@ pdm_center_kernel(const double* __restrict__ x, long long n, const PdmMeta* __re
        i += (long long)gridDim.x * blockDim.x) {
     const double v = (x[i] - mean) * inv_sd;
     xs[i] = (float)v;
-    // one add per sample updates count and sum: 2^23 (count field) + signed fixed-point x'
-    if (pq >= 0) xq[i] = (1u << 23) + (unsigned)(int)rint(v * scale);
+    // one add per sample updates count and sum: one unit of the count field + signed fixed-point x'
+    if (pq >= 0) xq[i] = (1u << PDM_SUM_BITS) + (unsigned)(int)rint(v * scale);
   }
 }
 
@@ -290,6 +309,7 @@ pdm_hist_kernel(const PdmArgs a) {
   float2* hist = reinterpret_cast<float2*>(s_thr + ((m0 + 2) & ~1)); // [m0][VT]
   float* s_x = reinterpret_cast<float*>(hist + (size_t)m0 * VT);     // [PDM_TILE]  (x' as float, or packed increments)
   unsigned* hist32 = reinterpret_cast<unsigned*>(s_x + PDM_TILE);    // [m0][VT] packed first-level columns
+  __shared__ unsigned s_winabs[8][PDM_TILE / PDM_PACK_FLUSH];        // per warp: sum |increment| of each feed window of the tile
 
   const int split = blockIdx.x % a.nsplit;
   const long long pb = blockIdx.x / a.nsplit;
@@ -364,11 +384,20 @@ pdm_hist_kernel(const PdmArgs a) {
   int* sum2 = reinterpret_cast<int*>(hist) + (size_t)m0 * VT;
   auto flush32 = [&](int column, unsigned* col32) {
     for (int b = 0; b < m0; ++b) {
+#if PDM_FEED_PLAIN
+      const unsigned w = col32[b * VT];
+      col32[b * VT] = 0u;
+      const int sfix = ((int)(w << PDM_CNT_BITS)) >> PDM_CNT_BITS;
+      const unsigned cnt = (w - (unsigned)sfix) >> PDM_SUM_BITS;
+      cnt2[b * VT + column] += cnt;
+      sum2[b * VT + column] += sfix;
+#else
       const unsigned w = atomicExch(col32 + b * VT, 0u);
-      const int sfix = ((int)(w << 9)) >> 9;               // low 23 bits, sign extended
-      const unsigned cnt = (w - (unsigned)sfix) >> 23;
+      const int sfix = ((int)(w << PDM_CNT_BITS)) >> PDM_CNT_BITS;   // low PDM_SUM_BITS bits, sign extended
+      const unsigned cnt = (w - (unsigned)sfix) >> PDM_SUM_BITS;
       atomicAdd(cnt2 + b * VT + column, cnt);
       atomicAdd(sum2 + b * VT + column, sfix);
+#endif
     }
   };
 #else
@@ -376,8 +405,8 @@ pdm_hist_kernel(const PdmArgs a) {
     float2* col = hist + column;
     for (int b = 0; b < m0; ++b) {
       const unsigned w = col32[b * VT];
-      const int sfix = ((int)(w << 9)) >> 9;               // low 23 bits, sign extended
-      const unsigned cnt = (w - (unsigned)sfix) >> 23;
+      const int sfix = ((int)(w << PDM_CNT_BITS)) >> PDM_CNT_BITS;
+      const unsigned cnt = (w - (unsigned)sfix) >> PDM_SUM_BITS;
       float2 h = col[b * VT];
       h.x += (float)cnt;
       h.y = fmaf((float)sfix, unpack, h.y);
@@ -439,8 +468,18 @@ pdm_hist_kernel(const PdmArgs a) {
     constexpr int U = PPT == 1 ? 8 : PDM_TRIP_CHAINS / PPT;  // samples per trip: U * PPT independent DFMA -> IMAD.WIDE -> IMAD -> ATOMS chains, one edge test
     const unsigned guard2 = 2u * guard;
     unsigned* c32 = hist32 + threadIdx.x;
-    for (int c0 = 0; c0 < cnt; c0 += PDM_PACK_FLUSH) {
-      const int c1 = c0 + PDM_PACK_FLUSH < cnt ? c0 + PDM_PACK_FLUSH : cnt;
+    for (int w0 = 0; w0 < cnt; w0 += PDM_PACK_FLUSH) {
+     // block-uniform: may this window be fed whole?  (always, in the 256-sample layout)
+     int piece = PDM_PACK_FLUSH;
+     if (PDM_PACK_FLUSH > 256) {
+       unsigned wabs = 0;
+#pragma unroll
+       for (int wp = 0; wp < THREADS / 32; ++wp) wabs += s_winabs[wp][w0 / PDM_PACK_FLUSH];
+       if (wabs >= (1u << (PDM_SUM_BITS - 1))) piece = PDM_PACK_SUB;
+     }
+     const int w1 = w0 + PDM_PACK_FLUSH < cnt ? w0 + PDM_PACK_FLUSH : cnt;
+     for (int c0 = w0; c0 < w1; c0 += piece) {
+      const int c1 = c0 + piece < w1 ? c0 + piece : w1;
       int i = c0;
       double tv[U];
 #if PDM_PREFETCH
@@ -517,21 +556,39 @@ pdm_hist_kernel(const PdmArgs a) {
       // that depends on one (the plain loop waits for each ATOMS.EXCH: 23 % of the kernel's stall samples, r01e capture)
       for (int b0 = 0; b0 < m0; b0 += PDM_FLUSH_BINS) {
         unsigned w[PPT][PDM_FLUSH_BINS];
+#if PDM_FEED_PLAIN
+        unsigned oc[PPT][PDM_FLUSH_BINS];
+        int os[PPT][PDM_FLUSH_BINS];
+#endif
 #pragma unroll
         for (int j = 0; j < PDM_FLUSH_BINS; ++j) {
 #pragma unroll
-          for (int s = 0; s < PPT; ++s)
+          for (int s = 0; s < PPT; ++s) {
+#if PDM_FEED_PLAIN
+            const bool in = b0 + j < m0;
+            w[s][j] = in ? c32[s * THREADS + (b0 + j) * VT] : 0u;
+            oc[s][j] = in ? cnt2[(b0 + j) * VT + s * THREADS + threadIdx.x] : 0u;
+            os[s][j] = in ? sum2[(b0 + j) * VT + s * THREADS + threadIdx.x] : 0;
+#else
             w[s][j] = b0 + j < m0 ? atomicExch(c32 + s * THREADS + (b0 + j) * VT, 0u) : 0u;
+#endif
+          }
         }
 #pragma unroll
         for (int j = 0; j < PDM_FLUSH_BINS; ++j) {
 #pragma unroll
           for (int s = 0; s < PPT; ++s) {
             if (b0 + j < m0) {
-              const int sfix = ((int)(w[s][j] << 9)) >> 9;
-              const unsigned cnt = (w[s][j] - (unsigned)sfix) >> 23;
+              const int sfix = ((int)(w[s][j] << PDM_CNT_BITS)) >> PDM_CNT_BITS;
+              const unsigned cnt = (w[s][j] - (unsigned)sfix) >> PDM_SUM_BITS;
+#if PDM_FEED_PLAIN
+              c32[s * THREADS + (b0 + j) * VT] = 0u;
+              cnt2[(b0 + j) * VT + s * THREADS + threadIdx.x] = oc[s][j] + cnt;
+              sum2[(b0 + j) * VT + s * THREADS + threadIdx.x] = os[s][j] + sfix;
+#else
               atomicAdd(cnt2 + (b0 + j) * VT + s * THREADS + threadIdx.x, cnt);
               atomicAdd(sum2 + (b0 + j) * VT + s * THREADS + threadIdx.x, sfix);
+#endif
             }
           }
         }
@@ -540,6 +597,7 @@ pdm_hist_kernel(const PdmArgs a) {
 #pragma unroll
       for (int s = 0; s < PPT; ++s) flush32(s * THREADS + threadIdx.x, c32 + s * THREADS);
 #endif
+     }
     }
   };
   // The unpacked paths serve one period column after the other (sc = which of the thread's PPT columns).
@@ -635,10 +693,35 @@ pdm_hist_kernel(const PdmArgs a) {
     long long left = se - tile0;
     const int cnt = left <= 0 ? 0 : (left < PDM_TILE ? (int)left : PDM_TILE);
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt; i += THREADS) {
-      s_t[i] = a.t[tile0 + i];
-      if (packed) reinterpret_cast<unsigned*>(s_x)[i] = a.xq[tile0 + i];
-      else s_x[i] = a.xs[tile0 + i];
+    if (packed && PDM_PACK_FLUSH > 256) {
+      // staging + sum |increment| per feed window (decides, block-uniformly, whether the window may be fed whole)
+      unsigned wabs[PDM_TILE / PDM_PACK_FLUSH];
+#pragma unroll
+      for (int k = 0; k < PDM_TILE / PDM_PACK_FLUSH; ++k) wabs[k] = 0u;
+      static_assert(PDM_PACK_FLUSH % THREADS == 0 || THREADS > PDM_PACK_FLUSH, "a thread's staging stride stays inside windows");
+#pragma unroll
+      for (int k = 0; k < PDM_TILE / PDM_PACK_FLUSH; ++k) {
+        for (int i = k * PDM_PACK_FLUSH + threadIdx.x; i < (k + 1) * PDM_PACK_FLUSH && i < cnt; i += THREADS) {
+          s_t[i] = a.t[tile0 + i];
+          const unsigned inc = a.xq[tile0 + i];
+          reinterpret_cast<unsigned*>(s_x)[i] = inc;
+          const int sfix = ((int)(inc << PDM_CNT_BITS)) >> PDM_CNT_BITS;
+          wabs[k] += (unsigned)(sfix < 0 ? -sfix : sfix);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PDM_TILE / PDM_PACK_FLUSH; ++k) {
+        unsigned v = wabs[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s_winabs[threadIdx.x >> 5][k] = v;
+      }
+    } else {
+      for (int i = threadIdx.x; i < cnt; i += THREADS) {
+        s_t[i] = a.t[tile0 + i];
+        if (packed) reinterpret_cast<unsigned*>(s_x)[i] = a.xq[tile0 + i];
+        else s_x[i] = a.xs[tile0 + i];
+      }
     }
     __syncthreads();
 

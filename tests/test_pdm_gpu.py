@@ -213,3 +213,16 @@ def test_every_bin_dropped_gives_nan_like_the_reference(gpu_ctx):
             assert am == np.nanargmin(ref)
         else:
             assert am == -1 and np.isnan(mn)
+
+
+def test_outlier_burst_is_fed_in_guaranteed_pieces(gpu_ctx):
+    """The packed path feeds 512-sample windows whole only after checking sum |increment| < 2^21; a flare (hundreds of
+    consecutive samples several sigma high) fails that check and must be fed in 128-sample pieces -- still exact."""
+    t, x = synth(50_000, 600.0, 21)
+    x[20_000:21_500] += 6.0              # 1,500 consecutive samples ~4 sigma (of the flared curve) above the rest
+    x[40_000:40_700] -= 5.0
+    periods = np.linspace(1.0, 11.0, 900)
+    th, am, _ = gpu_ctx.pdm(t, x, periods, 10, 2)
+    ref = cport.pdm(t, x, periods, 10, 2)
+    np.testing.assert_allclose(th, ref, rtol=TOL)
+    assert am == np.nanargmin(ref)

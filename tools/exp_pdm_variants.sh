@@ -4,7 +4,7 @@ OUT=gpurun_out; mkdir -p $OUT
 python bench.py --workload pdm_c3 --steps 20 --warmup 3 --no-cpu-baseline > $OUT/y_bench_c3_main.json 2> $OUT/y_bench_c3_main.err
 for lib in gpurun_variants/*.so; do
   tag=$(basename $lib .so)
-  PERIODICITY_B200_LIB=$PWD/$lib python -m pytest tests/test_pdm_gpu.py -x -q > $OUT/y_pdm_tests_$tag.log 2>&1; echo "tests $tag rc=$?"
+  [ -n "$VARIANT_TESTS" ] && { PERIODICITY_B200_LIB=$PWD/$lib python -m pytest tests/test_pdm_gpu.py -x -q > $OUT/y_pdm_tests_$tag.log 2>&1; echo "tests $tag rc=$?"; }
   PERIODICITY_B200_LIB=$PWD/$lib python bench.py --workload pdm_c3 --steps 20 --warmup 3 --no-cpu-baseline > $OUT/y_bench_c3_$tag.json 2> $OUT/y_bench_c3_$tag.err
 done
 python - <<'PY'
