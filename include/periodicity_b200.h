@@ -86,8 +86,8 @@ PDC_API int pdc_ctx_destroy(pdc_ctx* ctx);
 
 /*
  * Multi-device context (the single-process counterpart of the reference's transparent
- * multiprocessing.Pool fan-out, phase.py:182-187).  `device_ids[0..ndev)` are distinct CUDA ordinals of this
- * process, ndev <= PDC_MAX_PEERS.  HOST-pointer entry points called on such a ctx shard the work over the devices --
+ * multiprocessing.Pool fan-out, phase.py:182-187).  `device_ids[0..ndev)` are CUDA ordinals of this
+ * process, ndev <= PDC_MAX_PEERS (an ordinal may repeat: each entry gets its own stream, scratch and worker).  HOST-pointer entry points called on such a ctx shard the work over the devices --
  * pdc_gls: contiguous slices of the frequency grid; pdc_pdm / pdc_aov / pdc_ce / pdc_stringlength: slices of the
  * period grid; pdc_gls_batch: contiguous groups of curves balanced by sample count; pdc_gls_multi: groups of series
  * -- with one host worker thread per device: inputs are uploaded to every device concurrently, each device copies

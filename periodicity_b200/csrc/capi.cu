@@ -210,9 +210,9 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   for (auto& e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev_up) if (e) cudaEventDestroy(e);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-  ctx->gls_curves.release(); ctx->gls_part.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->glsm_y.release();
+  ctx->gls_curves.release(); ctx->gls_part.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->gls_cnt.release(); ctx->glsm_y.release();
   ctx->partial.release(); ctx->blockred.release(); ctx->pin_meta.release();
-  ctx->pdm_meta.release(); ctx->pdm_x.release(); ctx->peak_cand.release();
+  ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->peak_cand.release();
   ctx->main_resolve();
   for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);

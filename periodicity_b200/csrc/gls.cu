@@ -17,19 +17,23 @@
 // first frequency of its strip EXACTLY (phase reduced mod 1 in FP64, then
 // MUFU sin/cos) and rotates K-1 times in FP32.  "K" = strip length = reseed period.
 //
-// Kernels (launch order):
-//   gls_stats{1,2,3}_kernel  per curve: t_min, sum w, weighted mean, YY  (FP64, multi-block partials)
-//   gls_records_kernel  per sample: (t - t_min, frac(df (t - t_min))) as double2 and
-//                       (cos, sin of 2 pi df (t - t_min), y', w') as float4
-//   gls_lowfreq_kernel  FP64 direct sums for the few frequencies with < 1 cycle over the baseline
-//   gls_strip_kernel    the hot kernel: six FP32 sums per frequency
-//                       {C, S, YC, YS, CC, CS}, flushed to FP64 partials per tile
-//   gls_epilogue_kernel FP64: merge partials, tau-offset algebra
-//                       (spectral.py:113-132), per-block NaN-aware argmax
-//   gls_argmax_kernel   per curve: final (max, argmax)
+// Kernels (launch order; three launches per call since round 2, eight in round 1):
+//   gls_stats_kernel    per curve: t_min, t_max, sum w, weighted mean, YY in ONE pass (FP64, moments about the
+//                       curve's first value), multi-block partials; the last block to finish a curve reduces
+//                       them in a fixed order and writes the curve's derived parameters
+//   gls_prep_kernel     two block roles in one launch: per sample (t - t_min, frac(df (t - t_min))) as double2 and
+//                       (cos, sin of 2 pi df (t - t_min), y', w') as float4; FP64 direct sums for the
+//                       frequencies with < 1 cycle over the baseline
+//   gls_strip_kernel    the hot kernel: six FP32 sums per frequency {C, S, YC, YS, CC, CS}, flushed to FP64
+//                       partials per tile.  Its TAIL is the epilogue: the last sample split to finish a block of
+//                       2048 frequencies merges the splits' partial planes in a fixed order (they are still in
+//                       L2), evaluates the tau-offset algebra (spectral.py:113-132) in FP64, stores the power
+//                       (to every rank's buffer in the fan-out variant) and the block's NaN-aware arg-max; the
+//                       last frequency block of a curve reduces those to the curve's (max, argmax).
 //
 // Algorithmic work of the hot kernel: per sample*frequency evaluation
 // 4 FP32 instructions for the rotation + 6 for the sums (7 with weights).
+#include <cstring>
 #include <type_traits>
 
 #include "gls_common.cuh"
@@ -57,87 +61,75 @@ namespace pdc {
 // reduces them in the same order, so the result does not depend on scheduling.
 // ---------------------------------------------------------------------------
 struct GlsPart {
-  double tmin, tneg, sw, swy, syy;
+  double tmin, tneg, sw, swd, swdd;   // moments of d = y - y[first sample of the curve]
 };
 constexpr int GLS_STATS_THREADS = 256;
 
+// `single`: a one-curve call passes its host-known fields by value (no metadata upload); batches read curves[].
 __global__ void __launch_bounds__(GLS_STATS_THREADS)
-gls_stats1_kernel(const double* __restrict__ t, const double* __restrict__ y,
-                  const double* __restrict__ w, const GlsCurve* __restrict__ curves, GlsPart* __restrict__ part) {
+gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ w,
+                 GlsCurve* curves, GlsPart* part, unsigned* done, const GlsCurve single, int use_single,
+                 unsigned flags, long long j0, long long nf, int allow_three_term, int low_cap) {
   __shared__ double scratch[33];
-  const GlsCurve& cv = curves[blockIdx.y];
-  const long long b = cv.begin, n = cv.n;
-  double tmin = INFINITY, tneg = INFINITY, sw = 0.0, swy = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    double ti = t[b + i], yi = y[b + i], wi = w ? w[b + i] : 1.0;
+  __shared__ int s_last;
+  const int curve = blockIdx.y, G = gridDim.x;
+  const GlsCurve cin = use_single ? single : curves[curve];
+  const long long b = cin.begin, n = cin.n;
+  const double y0 = y[b];
+  double tmin = INFINITY, tneg = INFINITY, sw = 0.0, swd = 0.0, swdd = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)G * blockDim.x) {
+    const double ti = t[b + i], d = y[b + i] - y0, wi = w ? w[b + i] : 1.0;
     tmin = fmin(tmin, ti);
     tneg = fmin(tneg, -ti);
     sw += wi;
-    swy = fma(wi, yi, swy);
+    const double wd = wi * d;
+    swd += wd;
+    swdd = fma(wd, d, swdd);
   }
   tmin = block_min(tmin, scratch);
   tneg = block_min(tneg, scratch);
   sw = block_sum(sw, scratch);
-  swy = block_sum(swy, scratch);
+  swd = block_sum(swd, scratch);
+  swdd = block_sum(swdd, scratch);
   if (threadIdx.x == 0) {
-    GlsPart& p = part[(long long)blockIdx.y * gridDim.x + blockIdx.x];
-    p.tmin = tmin;
-    p.tneg = tneg;
-    p.sw = sw;
-    p.swy = swy;
+    GlsPart& p = part[(long long)curve * G + blockIdx.x];
+    p.tmin = tmin; p.tneg = tneg; p.sw = sw; p.swd = swd; p.swdd = swdd;
+    __threadfence();
+    s_last = atomicAdd(done + curve, 1u) == (unsigned)(G - 1);
   }
-}
-
-__device__ __forceinline__ void gls_reduce_pass1(const GlsPart* p, int g, double& tmin, double& tneg, double& sw,
-                                                 double& swy) {
-  tmin = INFINITY; tneg = INFINITY; sw = 0.0; swy = 0.0;
-  for (int k = 0; k < g; ++k) {  // same order everywhere
-    tmin = fmin(tmin, p[k].tmin);
-    tneg = fmin(tneg, p[k].tneg);
-    sw += p[k].sw;
-    swy += p[k].swy;
+  __syncthreads();
+  if (!s_last || threadIdx.x >= 32) return;
+  // the last block of this curve: fixed-order (tree over the block index) reduction of the G <= 32 partials
+  __threadfence();
+  const int lane = threadIdx.x;
+  const GlsPart* p = part + (long long)curve * G;
+  tmin = lane < G ? __ldcg(&p[lane].tmin) : INFINITY;
+  tneg = lane < G ? __ldcg(&p[lane].tneg) : INFINITY;
+  sw = lane < G ? __ldcg(&p[lane].sw) : 0.0;
+  swd = lane < G ? __ldcg(&p[lane].swd) : 0.0;
+  swdd = lane < G ? __ldcg(&p[lane].swdd) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    tneg = fmin(tneg, __shfl_xor_sync(0xffffffffu, tneg, o));
+    sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    swd += __shfl_xor_sync(0xffffffffu, swd, o);
+    swdd += __shfl_xor_sync(0xffffffffu, swdd, o);
   }
-}
-
-__global__ void __launch_bounds__(GLS_STATS_THREADS)
-gls_stats2_kernel(const double* __restrict__ y, const double* __restrict__ w, const GlsCurve* __restrict__ curves,
-                  GlsPart* __restrict__ part, unsigned flags) {
-  __shared__ double scratch[33];
-  const GlsCurve& cv = curves[blockIdx.y];
-  const long long b = cv.begin, n = cv.n;
-  GlsPart* p = part + (long long)blockIdx.y * gridDim.x;
-  double tmin, tneg, sw, swy;
-  gls_reduce_pass1(p, gridDim.x, tmin, tneg, sw, swy);
-  // spectral.py:102-108: w /= w.sum(); y = values - dot(w, values) if fit_mean
-  const double ymean = (flags & PDC_GLS_FIT_MEAN) ? swy / sw : 0.0;
-  double syy = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    double d = y[b + i] - ymean, wi = w ? w[b + i] : 1.0;
-    syy = fma(wi * d, d, syy);
-  }
-  syy = block_sum(syy, scratch);
-  if (threadIdx.x == 0) p[blockIdx.x].syy = syy;
-}
-
-__global__ void __launch_bounds__(64)
-gls_stats3_kernel(GlsCurve* curves, const GlsPart* __restrict__ part, int g, int B, unsigned flags,
-                  long long j0, long long nf, int allow_three_term) {
-  const int curve = blockIdx.x * blockDim.x + threadIdx.x;
-  if (curve >= B) return;
-  GlsCurve& cv = curves[curve];
-  const GlsPart* p = part + (long long)curve * g;
-  double tmin, tneg, sw, swy;
-  gls_reduce_pass1(p, g, tmin, tneg, sw, swy);
-  const double tmax = -tneg;
-  const double ymean = (flags & PDC_GLS_FIT_MEAN) ? swy / sw : 0.0;
-  double syy = 0.0;
-  for (int k = 0; k < g; ++k) syy += p[k].syy;
-  {
-    double yy = syy / sw;  // spectral.py:120  YY = dot(w, y**2)
+  if (lane == 0) {
+    GlsCurve cv = cin;
+    const double tmax = -tneg;
+    // spectral.py:102-108: w /= w.sum(); y = values - dot(w, values) if fit_mean.  In terms of d = y - y0:
+    // mean = y0 + swd / sw;  sum w (y - mean)^2 = swdd - swd^2 / sw;  sum w y^2 = swdd + 2 y0 swd + y0^2 sw.
+    const bool fit_mean = flags & PDC_GLS_FIT_MEAN;
+    const double ymean = fit_mean ? y0 + swd / sw : 0.0;
+    double syy = fit_mean ? swdd - swd * (swd / sw) : fma(y0, fma(y0, sw, 2.0 * swd), swdd);
+    if (syy < 0.0) syy = 0.0;
+    const double yy = syy / sw;  // spectral.py:120  YY = dot(w, y**2)
     cv.tmin = tmin;
     cv.tmax = tmax;
     int lb, lc;
-    gls_low_range(cv.fmin, cv.df, j0, nf, tmax - tmin, lb, lc);
+    gls_low_range(cv.fmin, cv.df, j0, nf, tmax - tmin, lb, lc, low_cap);
     cv.low_begin = lb;
     cv.low_count = lc;
     cv.wsum = sw;
@@ -148,90 +140,104 @@ gls_stats3_kernel(GlsCurve* curves, const GlsPart* __restrict__ part, int g, int
     const bool tt = allow_three_term && cv.df > 0.0 && span <= GLS_TT_MAX_SPAN;
     cv.three_term = tt;
     cv.gamma = tt ? 0.25 - 0.5 * span : 0.0;
+    curves[curve] = cv;
+    done[curve] = 0u;  // self-resetting: the next call finds the counter at zero
   }
 }
 
 // ---------------------------------------------------------------------------
-// per-sample records
+// per-sample records + FP64 evaluation of the sub-cycle frequencies: one launch, two block roles
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-gls_records_kernel(const double* __restrict__ t, const double* __restrict__ y,
-                   const double* __restrict__ w, const GlsCurve* __restrict__ curves,
-                   double2* __restrict__ rec1, float4* __restrict__ rec2) {
-  const GlsCurve cv = curves[blockIdx.y];
-  const double wscale = (double)cv.n / cv.wsum;  // weights rescaled to mean 1 (O(1) in FP32)
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cv.n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long g = cv.begin + i;
-    const double tt = t[g] - cv.tmin;  // power is shift invariant; the reference shifts too (spectral.py:19-21)
-    // step of the phase per frequency index, in turns.  gamma is the same for every sample of the
-    // curve, i.e. a per-frequency phase origin, which the power does not depend on (the tau offset
-    // of spectral.py:113-119 absorbs it).
-    const double b = frac_of_product(cv.df, tt) + cv.gamma;
-    double sb, cb;
-    sincospi(2.0 * b, &sb, &cb);
-    const double yv = (y[g] - cv.ymean) * cv.inv_rms;  // unit weighted RMS before the FP32 cast
-    float4 r;
-    rec_set(r, rec_slot(REC_CR), (float)cb);
-    rec_set(r, rec_slot(REC_SR), (float)sb);
-    if (w && cv.three_term) {
-      // the three-term strip carries (sqrt(w') cos, sqrt(w') sin): every sum is then one FFMA
-      const double sw = sqrt(w[g] * wscale);
-      rec_set(r, rec_slot(REC_Y), (float)(sw * yv));
-      rec_set(r, rec_slot(REC_W), (float)sw);
-    } else if (w) {
-      const double wn = w[g] * wscale;
-      rec_set(r, rec_slot(REC_Y), (float)(wn * yv));
-      rec_set(r, rec_slot(REC_W), (float)wn);
-    } else {
-      rec_set(r, rec_slot(REC_Y), (float)yv);
-      rec_set(r, rec_slot(REC_W), 1.0f);
-    }
-    rec1[g] = make_double2(tt, b);
-    rec2[g] = r;
-  }
-}
+// grid = (rec_blocks + GLS_LOW_LANES * nlowchunk, curves).
+//  * blocks x < rec_blocks write the sample records (grid-stride over the curve's samples);
+//  * block x = rec_blocks + lane * nlowchunk + chunk sums chunk `chunk` of the samples for the sub-cycle frequencies
+//    slot = lane, lane + GLS_LOW_LANES, ... < low_count and writes NORMALISED sums (weights sum to 1) to
+//    lowsum[chunk][6][curve * low_cap + slot].
+constexpr int GLS_LOW_LANES = 16;
 
-// ---------------------------------------------------------------------------
-// FP64 evaluation of the (few) sub-cycle frequencies
-// ---------------------------------------------------------------------------
-// grid = (sample chunks, GLS_NLOW_MAX, curves); writes NORMALISED sums (weights sum to 1)
-// to lowsum[chunk][6][curve * GLS_NLOW_MAX + slot].
 __global__ void __launch_bounds__(256)
-gls_lowfreq_kernel(const double* __restrict__ t, const double* __restrict__ y,
-                   const double* __restrict__ w, const GlsCurve* __restrict__ curves,
-                   double* __restrict__ lowsum, long long j0, int B) {
-  __shared__ double scratch[33];
-  const int curve = blockIdx.z, slot = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+gls_prep_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ w,
+                const GlsCurve* __restrict__ curves, double2* __restrict__ rec1, float4* __restrict__ rec2,
+                double* __restrict__ lowsum, long long j0, int B, int rec_blocks, int nlowchunk, int low_cap) {
+  __shared__ double s_red[6][8];
+  const int curve = blockIdx.y;
   const GlsCurve cv = curves[curve];
-  if (slot >= cv.low_count) return;  // block-uniform
-  const double f = cv.fmin + (double)(j0 + cv.low_begin + slot) * cv.df;
-  const long long per = (cv.n + nchunk - 1) / nchunk;
+  if ((int)blockIdx.x < rec_blocks) {
+    const double wscale = (double)cv.n / cv.wsum;  // weights rescaled to mean 1 (O(1) in FP32)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cv.n;
+         i += (long long)rec_blocks * blockDim.x) {
+      const long long g = cv.begin + i;
+      const double tt = t[g] - cv.tmin;  // power is shift invariant; the reference shifts too (spectral.py:19-21)
+      // step of the phase per frequency index, in turns.  gamma is the same for every sample of the
+      // curve, i.e. a per-frequency phase origin, which the power does not depend on (the tau offset
+      // of spectral.py:113-119 absorbs it).
+      const double b = frac_of_product(cv.df, tt) + cv.gamma;
+      double sb, cb;
+      sincospi(2.0 * b, &sb, &cb);
+      const double yv = (y[g] - cv.ymean) * cv.inv_rms;  // unit weighted RMS before the FP32 cast
+      float4 r;
+      rec_set(r, rec_slot(REC_CR), (float)cb);
+      rec_set(r, rec_slot(REC_SR), (float)sb);
+      if (w && cv.three_term) {
+        // the three-term strip carries (sqrt(w') cos, sqrt(w') sin): every sum is then one FFMA
+        const double sw = sqrt(w[g] * wscale);
+        rec_set(r, rec_slot(REC_Y), (float)(sw * yv));
+        rec_set(r, rec_slot(REC_W), (float)sw);
+      } else if (w) {
+        const double wn = w[g] * wscale;
+        rec_set(r, rec_slot(REC_Y), (float)(wn * yv));
+        rec_set(r, rec_slot(REC_W), (float)wn);
+      } else {
+        rec_set(r, rec_slot(REC_Y), (float)yv);
+        rec_set(r, rec_slot(REC_W), 1.0f);
+      }
+      rec1[g] = make_double2(tt, b);
+      rec2[g] = r;
+    }
+    return;
+  }
+  // ---- sub-cycle frequencies, FP64 ----
+  const int q = (int)blockIdx.x - rec_blocks;
+  const int chunk = q % nlowchunk, lane0 = q / nlowchunk;
+  if (lane0 >= cv.low_count) return;  // block-uniform
+  const long long per = (cv.n + nlowchunk - 1) / nlowchunk;
   const long long sb = (long long)chunk * per;
   const long long se = sb + per < cv.n ? sb + per : cv.n;
   const double winv = 1.0 / cv.wsum;
-  double a[6] = {0, 0, 0, 0, 0, 0};
-  for (long long i = sb + threadIdx.x; i < se; i += blockDim.x) {
-    const long long g = cv.begin + i;
-    const double ph = frac_of_product(f, t[g] - cv.tmin);
-    double sn, cs;
-    sincospi(2.0 * ph, &sn, &cs);
-    const double wi = (w ? w[g] : 1.0) * winv;
-    const double wy = wi * ((y[g] - cv.ymean) * cv.inv_rms);
-    const double wc = wi * cs;
-    a[0] += wc;
-    a[1] = fma(wi, sn, a[1]);
-    a[2] = fma(wy, cs, a[2]);
-    a[3] = fma(wy, sn, a[3]);
-    a[4] = fma(wc, cs, a[4]);
-    a[5] = fma(wc, sn, a[5]);
-  }
-  const long long cols = (long long)B * GLS_NLOW_MAX;
+  const long long cols = (long long)B * low_cap;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int slot = lane0; slot < cv.low_count; slot += GLS_LOW_LANES) {
+    const double f = cv.fmin + (double)(j0 + cv.low_begin + slot) * cv.df;
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (long long i = sb + threadIdx.x; i < se; i += blockDim.x) {
+      const long long g = cv.begin + i;
+      const double ph = frac_of_product(f, t[g] - cv.tmin);
+      double sn, cs;
+      sincospi(2.0 * ph, &sn, &cs);
+      const double wi = (w ? w[g] : 1.0) * winv;
+      const double wy = wi * ((y[g] - cv.ymean) * cv.inv_rms);
+      const double wc = wi * cs;
+      a[0] += wc;
+      a[1] = fma(wi, sn, a[1]);
+      a[2] = fma(wy, cs, a[2]);
+      a[3] = fma(wy, sn, a[3]);
+      a[4] = fma(wc, cs, a[4]);
+      a[5] = fma(wc, sn, a[5]);
+    }
+    // six block sums with one pair of barriers (fixed tree: deterministic)
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    const double tot = block_sum(a[q], scratch);
-    if (threadIdx.x == 0)
-      lowsum[((long long)chunk * 6 + q) * cols + (long long)curve * GLS_NLOW_MAX + slot] = tot;
+    for (int k = 0; k < 6; ++k) a[k] = warp_sum(a[k]);
+    __syncthreads();  // previous slot's s_red fully consumed
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s_red[k][wid] = a[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      double tot = 0.0;
+      for (int k = 0; k < 8; ++k) tot += s_red[threadIdx.x][k];
+      lowsum[((long long)chunk * 6 + threadIdx.x) * cols + (long long)curve * low_cap + slot] = tot;
+    }
   }
 }
 
@@ -248,7 +254,101 @@ struct GlsMainArgs {
   long long j0;       // absolute index of this call's first frequency
   int nfb;            // frequency blocks per curve
   int nsplit;         // sample splits per curve
+  // ---- tail (epilogue) ----
+  const double* lowsum;   // FP64 sums of the sub-cycle bins [chunk][6][B * low_cap]
+  int nlowchunk, low_cap, B;
+  unsigned flags;
+  unsigned* blk_done;     // [B * nfb]  sample splits that have finished this frequency block (self-resetting)
+  unsigned* curve_done;   // [B]        frequency blocks of this curve whose epilogue has run (self-resetting)
+  double* power_out;      // [B * nf] or NULL
+  double* red_val;        // [B * nfb] per-block arg-max candidates
+  long long* red_idx;
+  long long* arg_out;     // [B] or NULL
+  double* max_out;        // [B] or NULL
+  pdc_fanout fan;         // fan.world == 0: no fan-out
 };
+
+// Tail of gls_strip_kernel, run by the LAST sample split to finish frequency block `fb` of `curve`: merges the splits'
+// FP64 partial planes in split order (fixed, whatever block happens to be last: bit-reproducible), evaluates
+// spectral.py:113-132 per frequency, stores the power and reduces the arg-max.  FPB = frequencies per block.
+template <int K, int THREADS>
+__device__ __forceinline__ void gls_tail(const GlsMainArgs& a, int curve, int fb, long long jB) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ int s_flag;
+  __threadfence();   // this block's partial stores / RED.ADDs are visible device-wide before it is counted
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = atomicAdd(a.blk_done + (long long)curve * a.nfb + fb, 1u) == (unsigned)(a.nsplit - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  if (threadIdx.x == 0) a.blk_done[(long long)curve * a.nfb + fb] = 0u;
+  __threadfence();
+  const GlsCurve cv = a.curves[curve];
+  double best = 0.0;
+  long long bidx = -1;
+#pragma unroll 1
+  for (int r = 0; r < K; ++r) {
+    const long long j = jB + (long long)r * THREADS + threadIdx.x;   // consecutive threads, consecutive frequencies
+    if (j >= a.nf) break;
+    double sums[6];
+    double inv_n;
+    if (j >= cv.low_begin && j < cv.low_begin + cv.low_count) {
+      // sub-cycle frequency: FP64 sums from gls_prep_kernel (already normalised)
+      const long long cols = (long long)a.B * a.low_cap;
+      const double* p = a.lowsum + (long long)curve * a.low_cap + (j - cv.low_begin);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double acc = 0.0;
+        for (int c = 0; c < a.nlowchunk; ++c) acc += p[((long long)c * 6 + q) * cols];
+        sums[q] = acc;
+      }
+      inv_n = 1.0;
+    } else {
+      const double* p = a.partial + (long long)curve * a.nf + j;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) sums[q] = 0.0;
+      for (int sp = 0; sp < a.nsplit; ++sp) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sums[q] += __ldcg(p + ((long long)sp * 6 + q) * a.nf_tot);   // L2: written by other SMs
+      }
+      inv_n = 1.0 / (double)cv.n;
+    }
+    const double power = gls_power_from_sums(sums, inv_n, a.flags, cv.yy, cv.psd_scale);
+    if (a.power_out) a.power_out[(long long)curve * a.nf + j] = power;
+    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
+    for (int rk = 0; rk < a.fan.world; ++rk) a.fan.power[rk][a.j0 + j] = power;
+    if (better<+1>(power, j, best, bidx)) { best = power; bidx = j; }
+  }
+  block_argext<+1>(best, bidx, sv, si);
+  if (threadIdx.x == 0) {
+    a.red_val[(long long)curve * a.nfb + fb] = best;
+    a.red_idx[(long long)curve * a.nfb + fb] = bidx;
+    __threadfence();
+    s_flag = atomicAdd(a.curve_done + curve, 1u) == (unsigned)(a.nfb - 1);
+  }
+  __syncthreads();
+  if (!s_flag) return;
+  // the last frequency block of this curve: final (max, argmax); NaN ignored, first occurrence (np.nanargmax)
+  if (threadIdx.x == 0) a.curve_done[curve] = 0u;
+  __threadfence();
+  best = 0.0;
+  bidx = -1;
+  for (int k = threadIdx.x; k < a.nfb; k += THREADS) {
+    const double v = __ldcg(a.red_val + (long long)curve * a.nfb + k);
+    const long long i = __ldcg(a.red_idx + (long long)curve * a.nfb + k);
+    if (better<+1>(v, i, best, bidx)) { best = v; bidx = i; }
+  }
+  block_argext<+1>(best, bidx, sv, si);
+  if (threadIdx.x == 0) {
+    const double val = bidx >= 0 ? best : nan("");
+    if (a.arg_out) a.arg_out[curve] = bidx;
+    if (a.max_out) a.max_out[curve] = val;
+    for (int rk = 0; rk < a.fan.world; ++rk) {   // slot `rank` of every rank's candidate table: (max, GLOBAL argmax)
+      a.fan.best[rk][2 * a.fan.rank] = val;
+      a.fan.best[rk][2 * a.fan.rank + 1] = bidx >= 0 ? (double)(bidx + a.j0) : -1.0;
+    }
+  }
+}
 
 template <int K, int THREADS, int MINB, bool WEIGHTED>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -442,59 +542,8 @@ gls_strip_kernel(const GlsMainArgs a) {
     first = false;
     tile0 += GLS_TILE;
   } while (tile0 < se);
-}
 
-// ---------------------------------------------------------------------------
-// FP64 epilogue: spectral.py:113-132 per frequency + block argmax
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-gls_epilogue_kernel(const GlsCurve* __restrict__ curves, const double* __restrict__ partial,
-                    const double* __restrict__ lowsum, int nlowchunk, int B,
-                    int nsplit, long long nf, long long nf_tot, unsigned flags,
-                    double* __restrict__ power_out, double* __restrict__ red_val,
-                    long long* __restrict__ red_idx, const pdc_fanout fan, long long fan_offset) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  const int curve = blockIdx.y;
-  const GlsCurve cv = curves[curve];
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  double power = 0.0;
-  long long idx = -1;
-  if (j < nf) {
-    double sums[6];
-    double inv_n;
-    if (j >= cv.low_begin && j < cv.low_begin + cv.low_count) {
-      // sub-cycle frequency: FP64 sums from gls_lowfreq_kernel (already normalised)
-      const long long cols = (long long)B * GLS_NLOW_MAX;
-      const double* p = lowsum + (long long)curve * GLS_NLOW_MAX + (j - cv.low_begin);
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        double acc = 0.0;
-        for (int c = 0; c < nlowchunk; ++c) acc += p[((long long)c * 6 + q) * cols];
-        sums[q] = acc;
-      }
-      inv_n = 1.0;
-    } else {
-      const double* p = partial + (long long)curve * nf + j;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        double acc = 0.0;
-        for (int s = 0; s < nsplit; ++s) acc += p[((long long)s * 6 + q) * nf_tot];
-        sums[q] = acc;
-      }
-      inv_n = 1.0 / (double)cv.n;
-    }
-    power = gls_power_from_sums(sums, inv_n, flags, cv.yy, cv.psd_scale);
-    if (power_out) power_out[(long long)curve * nf + j] = power;
-    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
-    for (int r = 0; r < fan.world; ++r) fan.power[r][fan_offset + j] = power;
-    idx = j;
-  }
-  block_argext<+1>(power, idx, sv, si);
-  if (threadIdx.x == 0) {
-    red_val[(long long)curve * gridDim.x + blockIdx.x] = power;
-    red_idx[(long long)curve * gridDim.x + blockIdx.x] = idx;
-  }
+  gls_tail<K, THREADS>(a, curve, fb, jB);
 }
 
 // ---------------------------------------------------------------------------
@@ -639,37 +688,63 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   // scratch is shared by all calls on this ctx: order this stream after the previous call
   ScratchScope scratch(ctx, st);
   PDC_TRY(scratch.acquire());
-  // the pinned staging buffer is reused by every call: wait for the previous upload
-  PDC_CUDA(cudaEventSynchronize(ctx->ev_fence));
+
+  // sub-cycle (FP64) bins: up to low_cap per curve -- the whole sub-cycle range of any reasonable grid for a single
+  // curve (GLS(n=1000) still fits), fewer for large batches so that the scratch stays small
+  long long nlowchunk = (nmax + GLS_LOW_CHUNK - 1) / GLS_LOW_CHUNK;
+  if (nlowchunk > GLS_LOW_MAXCHUNKS) nlowchunk = GLS_LOW_MAXCHUNKS;
+  long long low_cap = ((long long)1 << 21) / ((long long)B * nlowchunk);
+  if (low_cap > GLS_NLOW_CAP) low_cap = GLS_NLOW_CAP;
+  if (low_cap < GLS_NLOW_MAX) low_cap = GLS_NLOW_MAX;
 
   // scratch
   PDC_TRY(ctx->gls_curves.reserve(sizeof(GlsCurve) * B));
-  PDC_TRY(ctx->pin_meta.reserve(sizeof(GlsCurve) * B));
   PDC_TRY(ctx->gls_rec1.reserve(sizeof(double2) * ntot));
   PDC_TRY(ctx->gls_rec2.reserve(sizeof(float4) * ntot));
   PDC_TRY(ctx->partial.reserve(sizeof(double) * 6 * nf_tot * nsplit));
-  const int eblk = (int)((nf + 255) / 256);
-  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk * B));
-  long long nlowchunk = (nmax + GLS_LOW_CHUNK - 1) / GLS_LOW_CHUNK;
-  if (nlowchunk > GLS_LOW_MAXCHUNKS) nlowchunk = GLS_LOW_MAXCHUNKS;
-  PDC_TRY(ctx->gls_low.reserve(sizeof(double) * 6 * (size_t)nlowchunk * B * GLS_NLOW_MAX));
-
-  GlsCurve* hc = ctx->pin_meta.as<GlsCurve>();
-  const long long off0 = offsets_host[0];
-  for (int64_t b = 0; b < B; ++b) {
-    hc[b].begin = offsets_host[b] - off0;
-    hc[b].n = offsets_host[b + 1] - offsets_host[b];
-    hc[b].fmin = fmin_host[b];
-    hc[b].df = df_host[b];
-    hc[b].psd_scale = psd_scale_host ? psd_scale_host[b] : 1.0;
-    hc[b].tmin = hc[b].tmax = hc[b].wsum = hc[b].ymean = hc[b].yy = hc[b].inv_rms = 0.0;
-    hc[b].low_begin = hc[b].low_count = 0;
-    hc[b].gamma = 0.0;
-    hc[b].three_term = hc[b].pad_ = 0;
+  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)nfb * B));
+  PDC_TRY(ctx->gls_low.reserve(sizeof(double) * 6 * (size_t)nlowchunk * B * low_cap));
+  // completion counters (stats blocks per curve, sample splits per frequency block, frequency blocks per curve):
+  // zeroed when the buffer is (re)allocated, every kernel leaves them at zero again
+  {
+    const size_t need = sizeof(unsigned) * ((size_t)2 * B + (size_t)B * nfb);
+    const void* before = ctx->gls_cnt.p;
+    const size_t cap_before = ctx->gls_cnt.cap;
+    PDC_TRY(ctx->gls_cnt.reserve(need));
+    if (ctx->gls_cnt.p != before || ctx->gls_cnt.cap != cap_before)
+      PDC_CUDA(cudaMemsetAsync(ctx->gls_cnt.p, 0, ctx->gls_cnt.cap, st));
   }
+  unsigned* cnt_stats = ctx->gls_cnt.as<unsigned>();
+  unsigned* cnt_curve = cnt_stats + B;
+  unsigned* cnt_blk = cnt_curve + B;
+
   GlsCurve* dc = ctx->gls_curves.as<GlsCurve>();
-  PDC_CUDA(cudaMemcpyAsync(dc, hc, sizeof(GlsCurve) * B, cudaMemcpyHostToDevice, st));
-  PDC_CUDA(cudaEventRecord(ctx->ev_fence, st));
+  const long long off0 = offsets_host[0];
+  GlsCurve single;
+  memset(&single, 0, sizeof(single));
+  if (B == 1) {
+    // one curve: its host-known fields travel as a kernel argument (no metadata upload, no host-side fence)
+    single.begin = 0;
+    single.n = offsets_host[1] - offsets_host[0];
+    single.fmin = fmin_host[0];
+    single.df = df_host[0];
+    single.psd_scale = psd_scale_host ? psd_scale_host[0] : 1.0;
+  } else {
+    // the pinned staging buffer is reused by every call: wait for the previous upload
+    PDC_CUDA(cudaEventSynchronize(ctx->ev_fence));
+    PDC_TRY(ctx->pin_meta.reserve(sizeof(GlsCurve) * B));
+    GlsCurve* hc = ctx->pin_meta.as<GlsCurve>();
+    for (int64_t b = 0; b < B; ++b) {
+      memset(&hc[b], 0, sizeof(GlsCurve));
+      hc[b].begin = offsets_host[b] - off0;
+      hc[b].n = offsets_host[b + 1] - offsets_host[b];
+      hc[b].fmin = fmin_host[b];
+      hc[b].df = df_host[b];
+      hc[b].psd_scale = psd_scale_host ? psd_scale_host[b] : 1.0;
+    }
+    PDC_CUDA(cudaMemcpyAsync(dc, hc, sizeof(GlsCurve) * B, cudaMemcpyHostToDevice, st));
+    PDC_CUDA(cudaEventRecord(ctx->ev_fence, st));
+  }
 
   const double* tt = t + off0;
   const double* yy = y + off0;
@@ -683,30 +758,21 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
       if (g < 1) g = 1;
     }
     PDC_TRY(ctx->gls_part.reserve(sizeof(GlsPart) * (size_t)g * B));
-    GlsPart* part = ctx->gls_part.as<GlsPart>();
     dim3 grid((unsigned)g, (unsigned)B);
-    gls_stats1_kernel<<<grid, GLS_STATS_THREADS, 0, st>>>(tt, yy, ww, dc, part);
-    PDC_CUDA(cudaGetLastError());
-    gls_stats2_kernel<<<grid, GLS_STATS_THREADS, 0, st>>>(yy, ww, dc, part, flags);
-    PDC_CUDA(cudaGetLastError());
-    gls_stats3_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(dc, part, (int)g, (int)B, flags, (long long)j0,
-                                                               (long long)nf, ctx->gls_three_term ? 1 : 0);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches += 3;
-  }
-
-  {
-    long long bx = (nmax + 255) / 256;
-    if (bx > 1024) bx = 1024;
-    dim3 grid((unsigned)bx, (unsigned)B);
-    gls_records_kernel<<<grid, 256, 0, st>>>(tt, yy, ww, dc, ctx->gls_rec1.as<double2>(), ctx->gls_rec2.as<float4>());
+    gls_stats_kernel<<<grid, GLS_STATS_THREADS, 0, st>>>(tt, yy, ww, dc, ctx->gls_part.as<GlsPart>(), cnt_stats, single,
+                                                        B == 1 ? 1 : 0, flags, (long long)j0, (long long)nf,
+                                                        ctx->gls_three_term ? 1 : 0, (int)low_cap);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
 
   {
-    dim3 grid((unsigned)nlowchunk, GLS_NLOW_MAX, (unsigned)B);
-    gls_lowfreq_kernel<<<grid, 256, 0, st>>>(tt, yy, ww, dc, ctx->gls_low.as<double>(), (long long)j0, (int)B);
+    long long bx = (nmax + 255) / 256;
+    if (bx > 1024) bx = 1024;
+    dim3 grid((unsigned)(bx + GLS_LOW_LANES * nlowchunk), (unsigned)B);
+    gls_prep_kernel<<<grid, 256, 0, st>>>(tt, yy, ww, dc, ctx->gls_rec1.as<double2>(), ctx->gls_rec2.as<float4>(),
+                                          ctx->gls_low.as<double>(), (long long)j0, (int)B, (int)bx, (int)nlowchunk,
+                                          (int)low_cap);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -721,33 +787,24 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   a.j0 = j0;
   a.nfb = (int)nfb;
   a.nsplit = nsplit;
+  a.lowsum = ctx->gls_low.as<double>();
+  a.nlowchunk = (int)nlowchunk;
+  a.low_cap = (int)low_cap;
+  a.B = (int)B;
+  a.flags = flags;
+  a.blk_done = cnt_blk;
+  a.curve_done = cnt_curve;
+  a.power_out = power_out;
+  a.red_val = ctx->blockred.as<double>();
+  a.red_idx = reinterpret_cast<long long*>(a.red_val + (size_t)nfb * B);
+  a.arg_out = (long long*)argmax_out;
+  a.max_out = max_out;
+  if (fanout) a.fan = *fanout;
+  else memset(&a.fan, 0, sizeof(a.fan));
 
   PDC_TRY(ctx->main_begin(st));
   PDC_TRY(launch_strip(geom, ctx, a, w != nullptr, items, st));
   PDC_TRY(ctx->main_end(st));
-
-  double* red_val = ctx->blockred.as<double>();
-  long long* red_idx = reinterpret_cast<long long*>(red_val + (size_t)eblk * B);
-  {
-    dim3 grid((unsigned)eblk, (unsigned)B);
-    pdc_fanout fan;
-    if (fanout) fan = *fanout;
-    else fan.world = 0;
-    gls_epilogue_kernel<<<grid, 256, 0, st>>>(dc, a.partial, ctx->gls_low.as<double>(), (int)nlowchunk, (int)B,
-                                              nsplit, nf, nf_tot, flags, power_out, red_val, red_idx, fan,
-                                              (long long)j0);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches++;
-  }
-  if (fanout) {
-    best_fanout_kernel<+1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, *fanout, (long long)j0);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches++;
-  } else if (argmax_out || max_out) {
-    argext_final_kernel<+1><<<(unsigned)B, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmax_out, max_out);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches++;
-  }
   PDC_TRY(scratch.release());
   return PDC_OK;
 }

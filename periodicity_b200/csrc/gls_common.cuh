@@ -55,9 +55,13 @@ constexpr double GLS_TT_MAX_SPAN = 0.34;
 // baseline: there CC - C^2 and SS - S^2 (spectral.py:125-127) cancel almost completely
 // (a slow cosine is nearly degenerate with the floating mean) and amplify FP32 rounding
 // by 1/var(cos) ~ 300x at f*T = 0.1.  Those few bins (at most GLS_NLOW_MAX per curve) are
-// evaluated by gls_lowfreq_kernel entirely in FP64.
+// evaluated entirely in FP64 (gls.cu: the second block role of gls_prep_kernel; glsm.cu: glsm_lowfreq_kernel).
+// Their number is ~ the grid's samples per peak `n` (spectral.py:88) when fmin is at its default: 5 by default, 100
+// for GLS(n=100).  gls.cu sizes the range from the actual count up to a cap chosen per call (1024 for a single
+// curve, less for large batches: gls_run), glsm.cu keeps GLS_NLOW_MAX.
 constexpr double GLS_LOW_CYCLES = 1.0;
 constexpr int GLS_NLOW_MAX = 16;
+constexpr int GLS_NLOW_CAP = 1024;
 constexpr int GLS_LOW_CHUNK = 4096;   // samples per block of gls_lowfreq_kernel
 constexpr int GLS_LOW_MAXCHUNKS = 256;
 
@@ -81,7 +85,7 @@ __device__ __forceinline__ double np_sign(double x) {
 
 // Low-frequency range of a call: indices j in [0, nf) with |fmin + (j0 + j) df| * T < GLS_LOW_CYCLES.
 __device__ __forceinline__ void gls_low_range(double fmin, double df, long long j0, long long nf, double T,
-                                              int& low_begin, int& low_count) {
+                                              int& low_begin, int& low_count, int cap = GLS_NLOW_MAX) {
   low_begin = 0;
   low_count = 0;
   if (T > 0.0 && df > 0.0) {
@@ -93,7 +97,7 @@ __device__ __forceinline__ void gls_low_range(double fmin, double df, long long 
     if (jb >= ja) {
       const double cnt = jb - ja + 1.0;
       low_begin = (int)ja;
-      low_count = cnt > (double)GLS_NLOW_MAX ? GLS_NLOW_MAX : (int)cnt;
+      low_count = cnt > (double)cap ? cap : (int)cnt;
     }
   }
 }

@@ -260,12 +260,9 @@ int pdc_ctx_create_multi(pdc_ctx** out, const int* device_ids, int ndev) {
     set_error("pdc_ctx_create_multi: need 1 <= ndev <= %d device ordinals", PDC_MAX_PEERS);
     return PDC_EINVAL;
   }
-  for (int a = 0; a < ndev; ++a)
-    for (int b = a + 1; b < ndev; ++b)
-      if (device_ids[a] == device_ids[b]) {
-        set_error("pdc_ctx_create_multi: device %d listed twice", device_ids[a]);
-        return PDC_EINVAL;
-      }
+  // An ordinal may repeat: every entry gets its own child ctx (stream, scratch, worker thread).  That buys no speed,
+  // but it runs the whole sharded path -- slicing, concurrent workers, host reduction -- on a single-GPU box
+  // (tests/test_multi_device.py does exactly that).
   pdc_ctx* primary = nullptr;
   PDC_TRY(pdc_ctx_create(&primary, device_ids[0]));
   if (ndev == 1) { *out = primary; return PDC_OK; }

@@ -98,7 +98,8 @@ struct pdc_ctx {
   pdc::DevBuf gls_rec2;        // float4[n]   (cos, sin of the per-index rotation, y or w*y, w)
   pdc::DevBuf glsm_y;          // float [groups][n][R]: scaled values of the shared-time series (glsm.cu)
   int glsm_occ[2] = {0, 0};    // cached blocks/SM of glsm_strip_kernel [weighted]
-  pdc::DevBuf gls_low;         // float64 sums of the sub-cycle frequencies [chunk][6][B*16]
+  pdc::DevBuf gls_low;         // float64 sums of the sub-cycle frequencies [chunk][6][B*low_cap]
+  pdc::DevBuf gls_cnt;         // completion counters of the last-block-done reductions (gls.cu), self-resetting
   pdc::DevBuf partial;         // float64 partial sums [nsplit][rows][units]
   pdc::DevBuf blockred;        // per-block (value, index) candidates
   pdc::PinnedBuf pin_meta;     // host staging for per-curve metadata
@@ -107,7 +108,7 @@ struct pdc_ctx {
 
   // PDM scratch
   pdc::DevBuf pdm_meta;        // PdmMeta
-  pdc::DevBuf pdm_x;           // float[n] centred, unit-variance values
+  pdc::DevBuf pdm_cnt;         // completion counters of the last-block-done reductions (pdm.cu), self-resetting
 };
 
 namespace pdc {

@@ -43,9 +43,14 @@
 // 2^-30 of an integer, so ties on bin edges (integer times, rational periods)
 // fall exactly where the reference puts them.
 //
-// Kernels: pdm_stats{1,2,3}_kernel (mean, 1/std, packing exponent; multi-block), pdm_center_kernel (x' as float and as packed increment),
-// pdm_hist_kernel (hot), pdm_epilogue_kernel (FP64 theta + block argmin),
-// argext_final_kernel<-1>.
+// Kernels (two launches per call since round 2, seven in round 1):
+//   pdm_stats_kernel  mean, 1/std, packing exponent in one pass; multi-block partials, the last block finalises
+//   pdm_hist_kernel   the hot kernel; x' is formed while a tile is staged (no centring pass), and its TAIL is the
+//                     epilogue: the last sample split to finish a block of 256 trial periods merges the splits'
+//                     FP64 planes in a fixed order, evaluates theta (phase.py:145-149) in FP64, stores it (to every
+//                     rank's buffer in the fan-out variant) and the block's arg-min; the last period block of the
+//                     call reduces those to the (min, argmin) of the call.
+#include <cstring>
 #include <type_traits>
 
 #include "pdc_common.cuh"
@@ -101,91 +106,89 @@ constexpr int PDM_TILE = 1024;        // samples per shared-memory tile
 constexpr int PDM_FLUSH_TILES = 8;    // FP32 histograms are merged into FP64 every 8192 samples
 constexpr int PDM_TILE_PAD = PDM_PREFETCH ? PDM_TRIP_CHAINS : 0;  // the prefetch of the packed loop reads one trip past the tile
 
-// Statistics in three small launches so that a long curve is read by many SMs (one block would take ~100 us
-// for 1e5 samples): per-block partials in a fixed layout, reduced by every consumer in the same order, so the
-// result is deterministic.
+// Statistics in ONE launch: a long curve is read by many SMs (one block would take ~100 us for 1e5 samples); every
+// block writes its partial moments (about the first value x[0], one pass) in a fixed layout and the last block to
+// finish reduces them with a fixed tree, so the result is deterministic.
 struct PdmPart {
-  double s, tabs, q, qb, dmax;
+  double s1, s2;          // sum d, sum d^2 with d = x - x[0]
+  double s1b, s2b, nb;    // the same over the samples with a finite time stamp (used only if some stamp is not finite)
+  double xneg, xmax;      // -min x, max x
+  double tabs;            // max |t| over the finite stamps
   int bad, pad_;
 };
 constexpr int PDM_STATS_THREADS = 256;
 constexpr int PDM_STATS_MAXBLK = 128;
 
-// pass 1: sum x, max |t| over finite stamps, any non-finite sample
+__device__ __forceinline__ double block_max(double v, double* scratch) { return -block_min(-v, scratch); }
+
 __global__ void __launch_bounds__(PDM_STATS_THREADS)
-pdm_stats1_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmPart* part) {
+pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmPart* part,
+                 unsigned* done, PdmMeta* meta) {
   __shared__ double scratch[33];
-  double s = 0.0, tneg = 0.0;
+  __shared__ int s_last;
+  const int G = gridDim.x;
+  const double x0 = x[0];
+  double s1 = 0.0, s2 = 0.0, s1b = 0.0, s2b = 0.0, nb = 0.0, xneg = -INFINITY, xmax = -INFINITY, tabs = 0.0;
   int bad = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double xi = x[i], ti = t[i];
-    s += xi;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)G * blockDim.x) {
+    const double xi = x[i], ti = t[i], d = xi - x0;
+    s1 += d;
+    s2 = fma(d, d, s2);
+    xneg = fmax(xneg, -xi);
+    xmax = fmax(xmax, xi);
     bad |= !isfinite(xi) || !isfinite(ti);
-    if (isfinite(ti)) tneg = fmin(tneg, -fabs(ti));
+    if (isfinite(ti)) {
+      tabs = fmax(tabs, fabs(ti));
+      s1b += d;
+      s2b = fma(d, d, s2b);
+      nb += 1.0;
+    }
   }
   bad = __syncthreads_or(bad);
-  s = block_sum(s, scratch);
-  const double tabs = -block_min(tneg, scratch);
+  s1 = block_sum(s1, scratch);
+  s2 = block_sum(s2, scratch);
+  s1b = block_sum(s1b, scratch);
+  s2b = block_sum(s2b, scratch);
+  nb = block_sum(nb, scratch);
+  xneg = block_max(xneg, scratch);
+  xmax = block_max(xmax, scratch);
+  tabs = block_max(tabs, scratch);
   if (threadIdx.x == 0) {
-    part[blockIdx.x].s = s;
-    part[blockIdx.x].tabs = tabs;
-    part[blockIdx.x].bad = bad;
+    PdmPart& p = part[blockIdx.x];
+    p.s1 = s1; p.s2 = s2; p.s1b = s1b; p.s2b = s2b; p.nb = nb; p.xneg = xneg; p.xmax = xmax; p.tabs = tabs; p.bad = bad;
+    __threadfence();
+    s_last = atomicAdd(done, 1u) == (unsigned)(G - 1);
   }
-}
-
-__device__ __forceinline__ void pdm_reduce_pass1(const PdmPart* part, int nblk, double& s, double& tabs, int& bad) {
-  s = 0.0; tabs = 0.0; bad = 0;
-  for (int b = 0; b < nblk; ++b) {  // same order in every block
-    s += part[b].s;
-    tabs = fmax(tabs, part[b].tabs);
-    bad |= part[b].bad;
-  }
-}
-
-// pass 2: sum (x - mean)^2 (all samples, and those with a finite stamp), max |x - mean|
-__global__ void __launch_bounds__(PDM_STATS_THREADS)
-pdm_stats2_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmPart* part) {
-  __shared__ double scratch[33];
-  double s, tabs;
-  int bad;
-  pdm_reduce_pass1(part, gridDim.x, s, tabs, bad);
-  const double mean = s / (double)n;
-  double q = 0.0, qb = 0.0, dneg = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double d = x[i] - mean;
-    q = fma(d, d, q);
-    dneg = fmin(dneg, -fabs(d));
-    if (bad && isfinite(t[i])) qb = fma(d, d, qb);
-  }
-  q = block_sum(q, scratch);
-  qb = block_sum(qb, scratch);
-  const double dmax = -block_min(dneg, scratch);
+  __syncthreads();
+  if (!s_last) return;
+  // last block: thread k holds partial k (G <= PDM_STATS_MAXBLK <= blockDim), fixed-tree block reductions
+  __threadfence();
+  const bool has = (int)threadIdx.x < G;
+  const PdmPart* p = part + threadIdx.x;
+  s1 = block_sum(has ? __ldcg(&p->s1) : 0.0, scratch);
+  s2 = block_sum(has ? __ldcg(&p->s2) : 0.0, scratch);
+  s1b = block_sum(has ? __ldcg(&p->s1b) : 0.0, scratch);
+  s2b = block_sum(has ? __ldcg(&p->s2b) : 0.0, scratch);
+  nb = block_sum(has ? __ldcg(&p->nb) : 0.0, scratch);
+  xneg = block_max(has ? __ldcg(&p->xneg) : -INFINITY, scratch);
+  xmax = block_max(has ? __ldcg(&p->xmax) : -INFINITY, scratch);
+  tabs = block_max(has ? __ldcg(&p->tabs) : 0.0, scratch);
+  bad = __syncthreads_or(has ? __ldcg(&p->bad) : 0);
   if (threadIdx.x == 0) {
-    part[blockIdx.x].q = q;
-    part[blockIdx.x].qb = qb;
-    part[blockIdx.x].dmax = dmax;
-  }
-}
-
-__global__ void pdm_stats3_kernel(const PdmPart* __restrict__ part, int nblk, long long n, PdmMeta* meta) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double s, tabs;
-  int bad;
-  pdm_reduce_pass1(part, nblk, s, tabs, bad);
-  double q = 0.0, qb = 0.0, dmax = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    q += part[b].q;
-    qb += part[b].qb;
-    dmax = fmax(dmax, part[b].dmax);
-  }
-  const double mean = s / (double)n;
-  {
-    const double var = q / (double)(n - 1);  // phase.py:165  np.var(values, ddof=1)
+    const double dn = (double)n;
+    const double dm = s1 / dn;                       // mean - x0
+    const double mean = x0 + dm;
+    double q = s2 - s1 * dm;                         // sum (x - mean)^2
+    if (q < 0.0) q = 0.0;
+    const double var = q / (dn - 1.0);               // phase.py:165  np.var(values, ddof=1)
+    const double dmax = fmax(xmax - mean, mean + xneg);
     meta->mean = mean;
     meta->inv_sd = 1.0 / sqrt(var);
     // a sample whose phase is NaN fails every mask of phase.py:138-140 and is in no bin, but still
     // counts in sigma^2: the epilogue then needs sum x'^2 over the binned samples only
-    meta->q_binned = bad ? qb / var : (double)(n - 1);
+    double qb = s2b - 2.0 * dm * s1b + nb * dm * dm;   // sum (x - mean)^2 over the finite stamps
+    if (qb < 0.0) qb = 0.0;
+    meta->q_binned = bad ? qb / var : dn - 1.0;
     meta->bad = bad;
     meta->t_absmax = tabs;
     // Packed first-level histogram (pdm_hist_kernel): one 32-bit word per (bin, period) holds the count in
@@ -194,41 +197,37 @@ __global__ void pdm_stats3_kernel(const PdmPart* __restrict__ part, int nblk, lo
     // same condition, for the guaranteed sub-window).  Worth it only if the quantisation step 2^-q is fine
     // enough (q >= PDM_PACK_MIN_Q: relative theta error ~ 0.4 * 2^-q / sqrt(nc N) / theta) and the curve is long.
     int pq = -1;
-    const double xmax = dmax / sqrt(var);
-    if (!bad && xmax > 0.0 && isfinite(xmax) && n >= PDM_PACK_MIN_N) {
-      pq = (int)floor(log2(16000.0 / xmax));
+    const double xm = dmax / sqrt(var);
+    if (!bad && xm > 0.0 && isfinite(xm) && n >= PDM_PACK_MIN_N) {
+      pq = (int)floor(log2(16000.0 / xm));
       if (pq > 20) pq = 20;
       if (pq < PDM_PACK_MIN_Q) pq = -1;
     }
     meta->pack_q = pq;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-pdm_center_kernel(const double* __restrict__ x, long long n, const PdmMeta* __restrict__ meta,
-                  float* __restrict__ xs, unsigned* __restrict__ xq) {
-  const double mean = meta->mean, inv_sd = meta->inv_sd;
-  const int pq = meta->pack_q;
-  const double scale = pq >= 0 ? (double)(1u << pq) : 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const double v = (x[i] - mean) * inv_sd;
-    xs[i] = (float)v;
-    // one add per sample updates count and sum: one unit of the count field + signed fixed-point x'
-    if (pq >= 0) xq[i] = (1u << PDM_SUM_BITS) + (unsigned)(int)rint(v * scale);
+    *done = 0u;   // self-resetting
   }
 }
 
 struct PdmArgs {
   const double* t;
-  const float* xs;
-  const unsigned* xq;   // packed increments (valid if meta->pack_q >= 0)
+  const double* x;      // raw values: x' = (x - mean) / std is formed while a tile is staged (no separate pass, no copy)
   const double* periods;
   const PdmMeta* meta;
   double* partial;  // [nsplit][2*m0][np]  rows: count per fine bin, then sum x' per fine bin
   long long n, np;
   int m0, nsplit;
   int allow_packed;     // 0: keep the float2 columns whatever the curve (AoV: its ratio of sums needs their accuracy)
+  // ---- tail (epilogue) ----
+  int nc, statistic, npb;   // covers, PDC_STAT_*, period blocks
+  unsigned* blk_done;       // [npb] sample splits that have finished this period block (self-resetting)
+  unsigned* call_done;      // [1]   period blocks whose epilogue has run (self-resetting)
+  double* theta_out;        // [np] or NULL
+  double* red_val;          // [npb] per-block arg-extremum candidates
+  long long* red_idx;
+  long long* arg_out;       // or NULL
+  double* best_out;         // or NULL
+  pdc_fanout fan;           // fan.world == 0: no fan-out
+  long long fan_offset;
 };
 
 // Fine-bin index of one sample for trial period P (rP = 1/P), plus an "ambiguity key":
@@ -293,6 +292,126 @@ __device__ __forceinline__ void static_for(F&& f) {
   }
 }
 
+// Tail of pdm_hist_kernel, run by the LAST sample split to finish period block `pb`: folds the splits' FP64 planes
+// into plane 0 in split order (fixed, whatever block happens to be last: bit-reproducible), evaluates the statistic
+// per trial period in FP64, stores it and reduces the arg-extremum.
+//   PDC_STAT_PDM  theta of phase.py:145-149 (smaller is better)
+//   PDC_STAT_AOV  the analysis-of-variance statistic of Schwarzenberg-Czerny (1989) -- a TODO of the reference
+//                 (phase.py:11) -- from the same fine-bin histograms with nc = 1: Theta = [(N - r) / (r - 1)] * s1 / s2
+//                 over the r populated bins, s1 = sum_b n_b (mean_b - mean)^2 (between bins), s2 = sum_b sum_i
+//                 (x_i - mean_b)^2 (within bins); larger is better.
+template <int THREADS, int PPT>
+__device__ __forceinline__ void pdm_tail(const PdmArgs& a, long long pb, const long long* pis, const bool* valids) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ int s_flag;
+  __threadfence();   // this block's partial stores / RED.ADDs are visible device-wide before it is counted
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = atomicAdd(a.blk_done + pb, 1u) == (unsigned)(a.nsplit - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  if (threadIdx.x == 0) a.blk_done[pb] = 0u;
+  __threadfence();
+  const int m0 = a.m0, nc = a.nc;
+  const long long np = a.np, rows = 2LL * m0;
+  const bool aov = a.statistic == PDC_STAT_AOV;
+  const double q_binned = a.meta->q_binned;
+  double best = 0.0;
+  long long bidx = -1;
+#pragma unroll 1
+  for (int s = 0; s < PPT; ++s) {
+    if (!valids[s]) continue;
+    const long long pi = pis[s];
+    double* base = a.partial + pi;
+    if (a.nsplit > 1) {   // fold the sample splits into split 0 (this thread's own column only)
+      for (long long b = 0; b < rows; ++b) {
+        double acc = 0.0;
+        for (int sp = 0; sp < a.nsplit; ++sp) acc += __ldcg(base + ((long long)sp * rows + b) * np);
+        base[b * np] = acc;
+      }
+    }
+    const double* pn = base;
+    const double* p1 = base + (long long)m0 * np;
+    const double P = a.periods[pi];
+    double theta;
+    if (aov) {
+      double sq = 0.0, ntot = 0.0, stot = 0.0;
+      int r = 0;
+      for (int k = 0; k < m0; ++k) {
+        const double N = __ldcg(pn + (long long)k * np), S = __ldcg(p1 + (long long)k * np);
+        if (N >= 1.0) {
+          sq += S * S / N;
+          ntot += N;
+          stot += S;
+          ++r;
+        }
+      }
+      const double s1 = sq - stot * stot / ntot;   // between the bins, about the mean of the binned samples
+      const double s2 = q_binned - sq;             // within the bins
+      theta = ((ntot - (double)r) / (double)(r - 1)) * (s1 / s2);
+      // fewer than two populated bins (r - 1 == 0) or no scatter inside the bins: 0/0-like, the same NaN class as
+      // PDM's "every bin dropped" below -- never +-inf from FP32 accumulation residue
+      if (r < 2 || !(s2 > 0.0)) theta = nan("");
+      if (!isfinite(P) || !isfinite(1.0 / P)) theta = nan("");  // no phases: period 0, denormal, inf or NaN
+    } else {
+      double sq = 0.0, den = 0.0;
+      for (int k = 0; k < m0; ++k) {
+        double N = 0.0, S = 0.0;
+        for (int c = 0; c < nc; ++c) {
+          int q = k + c;
+          if (q >= m0) q -= m0;
+          N += __ldcg(pn + (long long)q * np);
+          S += __ldcg(p1 + (long long)q * np);
+        }
+        if (N >= 1.0) sq += S * S / N;
+        if (N > 1.0) den += N - 1.0;  // phase.py:142,147: bins with <= 1 sample are dropped
+      }
+      // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
+      theta = ((double)nc * q_binned - sq) / den;
+      // every coarse bin holds <= 1 sample: the reference divides 0.0 by 0.0 (phase.py:145-147 with an empty `mj`)
+      // and gets NaN, which its nan-aware reductions skip; the FP32 residue of the numerator must not turn it into +-inf
+      if (!(den > 0.0)) theta = nan("");
+      if (isinf(P)) theta = 1.0;  // every phase is 0: one populated fine bin holding all samples
+      else if (!isfinite(1.0 / P) || P != P) theta = nan("");  // period 0, denormal or NaN: phases are inf / NaN
+    }
+    if (a.theta_out) a.theta_out[pi] = theta;
+    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
+    for (int rk = 0; rk < a.fan.world; ++rk) a.fan.power[rk][a.fan_offset + pi] = theta;
+    if (aov ? better<+1>(theta, pi, best, bidx) : better<-1>(theta, pi, best, bidx)) { best = theta; bidx = pi; }
+  }
+  if (aov) block_argext<+1>(best, bidx, sv, si);
+  else block_argext<-1>(best, bidx, sv, si);
+  if (threadIdx.x == 0) {
+    a.red_val[pb] = best;
+    a.red_idx[pb] = bidx;
+    __threadfence();
+    s_flag = atomicAdd(a.call_done, 1u) == (unsigned)(a.npb - 1);
+  }
+  __syncthreads();
+  if (!s_flag) return;
+  // the last period block of the call: final arg-extremum; NaN ignored, first occurrence (np.nanargmin / nanargmax)
+  if (threadIdx.x == 0) *a.call_done = 0u;
+  __threadfence();
+  best = 0.0;
+  bidx = -1;
+  for (int k = threadIdx.x; k < a.npb; k += THREADS) {
+    const double v = __ldcg(a.red_val + k);
+    const long long i = __ldcg(a.red_idx + k);
+    if (aov ? better<+1>(v, i, best, bidx) : better<-1>(v, i, best, bidx)) { best = v; bidx = i; }
+  }
+  if (aov) block_argext<+1>(best, bidx, sv, si);
+  else block_argext<-1>(best, bidx, sv, si);
+  if (threadIdx.x == 0) {
+    const double val = bidx >= 0 ? best : nan("");
+    if (a.arg_out) *a.arg_out = bidx;
+    if (a.best_out) *a.best_out = val;
+    for (int rk = 0; rk < a.fan.world; ++rk) {   // slot `rank` of every rank's candidate table: (best, GLOBAL index)
+      a.fan.best[rk][2 * a.fan.rank] = val;
+      a.fan.best[rk][2 * a.fan.rank + 1] = bidx >= 0 ? (double)(bidx + a.fan_offset) : -1.0;
+    }
+  }
+}
+
 // Shared-memory layout: hist[bin][VT] float2 = (count, sum x') and hist32[bin][VT] packed words, VT = THREADS * PPT
 // period columns per block: a column is private to one thread and conflict free (bank = column % 32).
 // PPT = trial periods per thread.  With PPT = 2 a thread owns columns tid and tid + THREADS: every sample read
@@ -353,6 +472,10 @@ pdm_hist_kernel(const PdmArgs a) {
 #endif
   const unsigned* s_xq = reinterpret_cast<const unsigned*>(s_x);
   const unsigned m0u = (unsigned)m0, guard = PDM_FAST_GUARD * m0u;
+  // x' = (x - mean) / std(ddof=1) is formed while the tile is staged: as a float for the FP32 columns, as the packed
+  // increment (one unit of the count field + signed fixed-point x') for the packed ones
+  const double x_mean = a.meta->mean, x_inv_sd = a.meta->inv_sd;
+  const double x_scale = packed ? (double)(1u << pack_q) : 0.0;
 
   // With finite inputs the bin index is always in range (phi == 1.0 is caught by the ambiguity test and
   // fixed by pdm_fix_bin), so the guard is compiled in only for the SAFE variant used when some
@@ -703,9 +826,8 @@ pdm_hist_kernel(const PdmArgs a) {
       for (int k = 0; k < PDM_TILE / PDM_PACK_FLUSH; ++k) {
         for (int i = k * PDM_PACK_FLUSH + threadIdx.x; i < (k + 1) * PDM_PACK_FLUSH && i < cnt; i += THREADS) {
           s_t[i] = a.t[tile0 + i];
-          const unsigned inc = a.xq[tile0 + i];
-          reinterpret_cast<unsigned*>(s_x)[i] = inc;
-          const int sfix = ((int)(inc << PDM_CNT_BITS)) >> PDM_CNT_BITS;
+          const int sfix = (int)rint((a.x[tile0 + i] - x_mean) * x_inv_sd * x_scale);
+          reinterpret_cast<unsigned*>(s_x)[i] = (1u << PDM_SUM_BITS) + (unsigned)sfix;
           wabs[k] += (unsigned)(sfix < 0 ? -sfix : sfix);
         }
       }
@@ -719,8 +841,9 @@ pdm_hist_kernel(const PdmArgs a) {
     } else {
       for (int i = threadIdx.x; i < cnt; i += THREADS) {
         s_t[i] = a.t[tile0 + i];
-        if (packed) reinterpret_cast<unsigned*>(s_x)[i] = a.xq[tile0 + i];
-        else s_x[i] = a.xs[tile0 + i];
+        const double v = (a.x[tile0 + i] - x_mean) * x_inv_sd;
+        if (packed) reinterpret_cast<unsigned*>(s_x)[i] = (1u << PDM_SUM_BITS) + (unsigned)(int)rint(v * x_scale);
+        else s_x[i] = (float)v;
       }
     }
     __syncthreads();
@@ -775,86 +898,8 @@ pdm_hist_kernel(const PdmArgs a) {
       tiles_since_flush = 0;
     }
   } while (tile0 < se);
-}
 
-// STAT = PDC_STAT_PDM: theta of phase.py:145-149 (smaller is better).  STAT = PDC_STAT_AOV: the analysis-of-variance
-// statistic of Schwarzenberg-Czerny (1989) -- a TODO of the reference (phase.py:11) -- from the same fine-bin
-// histograms with nc = 1: Theta = [(N - r) / (r - 1)] * s1 / s2 over the r populated bins, s1 = sum_b n_b (mean_b - mean)^2
-// (between bins), s2 = sum_b sum_i (x_i - mean_b)^2 (within bins); larger is better.
-template <int STAT>
-__global__ void __launch_bounds__(256)
-pdm_epilogue_kernel(double* __restrict__ partial, const double* __restrict__ periods,
-                    const PdmMeta* __restrict__ meta, int nsplit, int m0, int nc, long long np,
-                    double* __restrict__ theta_out, double* __restrict__ red_val,
-                    long long* __restrict__ red_idx, const pdc_fanout fan, long long fan_offset) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  const long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  double theta = 0.0;
-  long long idx = -1;
-  if (pi < np) {
-    // fold the sample splits into split 0 (this thread's own column only)
-    const long long rows = 2LL * m0;
-    if (nsplit > 1) {
-      for (long long b = 0; b < rows; ++b) {
-        double acc = 0.0;
-        for (int s = 0; s < nsplit; ++s) acc += partial[((long long)s * rows + b) * np + pi];
-        partial[b * np + pi] = acc;
-      }
-    }
-    const double* pn = partial + pi;
-    const double* p1 = pn + (long long)m0 * np;
-    const double P = periods[pi];
-    if (STAT == PDC_STAT_AOV) {
-      double sq = 0.0, ntot = 0.0, stot = 0.0;
-      int r = 0;
-      for (int k = 0; k < m0; ++k) {
-        const double N = pn[(long long)k * np], S = p1[(long long)k * np];
-        if (N >= 1.0) {
-          sq += S * S / N;
-          ntot += N;
-          stot += S;
-          ++r;
-        }
-      }
-      const double s1 = sq - stot * stot / ntot;   // between the bins, about the mean of the binned samples
-      const double s2 = meta->q_binned - sq;       // within the bins
-      theta = ((ntot - (double)r) / (double)(r - 1)) * (s1 / s2);
-      // fewer than two populated bins (r - 1 == 0) or no scatter inside the bins: 0/0-like, the same NaN class as
-      // PDM's "every bin dropped" below -- never +-inf from FP32 accumulation residue
-      if (r < 2 || !(s2 > 0.0)) theta = nan("");
-      if (!isfinite(P) || !isfinite(1.0 / P)) theta = nan("");  // no phases: period 0, denormal, inf or NaN
-    } else {
-      double sq = 0.0, den = 0.0;
-      for (int k = 0; k < m0; ++k) {
-        double N = 0.0, S = 0.0;
-        for (int c = 0; c < nc; ++c) {
-          int q = k + c;
-          if (q >= m0) q -= m0;
-          N += pn[(long long)q * np];
-          S += p1[(long long)q * np];
-        }
-        if (N >= 1.0) sq += S * S / N;
-        if (N > 1.0) den += N - 1.0;  // phase.py:142,147: bins with <= 1 sample are dropped
-      }
-      // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
-      theta = ((double)nc * meta->q_binned - sq) / den;
-      // every coarse bin holds <= 1 sample: the reference divides 0.0 by 0.0 (phase.py:145-147 with an empty `mj`)
-      // and gets NaN, which its nan-aware reductions skip; the FP32 residue of the numerator must not turn it into +-inf
-      if (!(den > 0.0)) theta = nan("");
-      if (isinf(P)) theta = 1.0;  // every phase is 0: one populated fine bin holding all samples
-      else if (!isfinite(1.0 / P) || P != P) theta = nan("");  // period 0, denormal or NaN: phases are inf / NaN
-    }
-    if (theta_out) theta_out[pi] = theta;
-    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
-    for (int r = 0; r < fan.world; ++r) fan.power[r][fan_offset + pi] = theta;
-    idx = pi;
-  }
-  block_argext<(STAT == PDC_STAT_AOV ? 1 : -1)>(theta, idx, sv, si);
-  if (threadIdx.x == 0) {
-    red_val[blockIdx.x] = theta;
-    red_idx[blockIdx.x] = idx;
-  }
+  pdm_tail<THREADS, PPT>(a, pb, pis, valids);
 }
 
 static size_t pdm_smem_bytes(int m0, int threads) {
@@ -934,42 +979,40 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     }
   }
   const long long blocks = npb * nsplit;
-  if (blocks > 0x7fffffffLL) { set_error("pdc_pdm: problem too large for one call"); return PDC_EINVAL; }
+  if (blocks > 0x7fffffffLL || npb > 0x3fffffffLL) { set_error("pdc_pdm: problem too large for one call"); return PDC_EINVAL; }
 
   ScratchScope scratch(ctx, st);
   PDC_TRY(scratch.acquire());
   PDC_TRY(ctx->pdm_meta.reserve(sizeof(PdmMeta) + 16 + sizeof(PdmPart) * PDM_STATS_MAXBLK));
-  PDC_TRY(ctx->pdm_x.reserve((sizeof(float) + sizeof(unsigned)) * (size_t)n));
   PDC_TRY(ctx->partial.reserve(sizeof(double) * 2 * m0 * (size_t)np * nsplit));
-  const int eblk = (int)((np + 255) / 256);
-  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk));
+  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)npb));
+  // completion counters (stats blocks, sample splits per period block, period blocks): zeroed when the buffer is
+  // (re)allocated, every kernel leaves them at zero again
+  {
+    const size_t need = sizeof(unsigned) * (2 + (size_t)npb);
+    const void* before = ctx->pdm_cnt.p;
+    const size_t cap_before = ctx->pdm_cnt.cap;
+    PDC_TRY(ctx->pdm_cnt.reserve(need));
+    if (ctx->pdm_cnt.p != before || ctx->pdm_cnt.cap != cap_before)
+      PDC_CUDA(cudaMemsetAsync(ctx->pdm_cnt.p, 0, ctx->pdm_cnt.cap, st));
+  }
+  unsigned* cnt_stats = ctx->pdm_cnt.as<unsigned>();
+  unsigned* cnt_call = cnt_stats + 1;
+  unsigned* cnt_blk = cnt_stats + 2;
 
   PdmMeta* meta = ctx->pdm_meta.as<PdmMeta>();
   {
     PdmPart* part = reinterpret_cast<PdmPart*>(reinterpret_cast<char*>(meta) + ((sizeof(PdmMeta) + 15) & ~(size_t)15));
     long long sblk = (n + 8 * PDM_STATS_THREADS - 1) / (8 * PDM_STATS_THREADS);
     if (sblk > PDM_STATS_MAXBLK) sblk = PDM_STATS_MAXBLK;
-    pdm_stats1_kernel<<<(unsigned)sblk, PDM_STATS_THREADS, 0, st>>>(t, x, n, part);
-    PDC_CUDA(cudaGetLastError());
-    pdm_stats2_kernel<<<(unsigned)sblk, PDM_STATS_THREADS, 0, st>>>(t, x, n, part);
-    PDC_CUDA(cudaGetLastError());
-    pdm_stats3_kernel<<<1, 32, 0, st>>>(part, (int)sblk, n, meta);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches += 3;
-  }
-  {
-    long long bx = (n + 255) / 256;
-    if (bx > 2048) bx = 2048;
-    pdm_center_kernel<<<(unsigned)bx, 256, 0, st>>>(x, n, meta, ctx->pdm_x.as<float>(),
-                                                    reinterpret_cast<unsigned*>(ctx->pdm_x.as<float>() + n));
+    pdm_stats_kernel<<<(unsigned)sblk, PDM_STATS_THREADS, 0, st>>>(t, x, n, part, cnt_stats, meta);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
 
   PdmArgs a;
   a.t = t;
-  a.xs = ctx->pdm_x.as<float>();
-  a.xq = reinterpret_cast<const unsigned*>(ctx->pdm_x.as<float>() + n);
+  a.x = x;
   a.periods = periods;
   a.meta = meta;
   a.partial = ctx->partial.as<double>();
@@ -978,6 +1021,19 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   a.m0 = m0;
   a.nsplit = nsplit;
   a.allow_packed = statistic == PDC_STAT_PDM ? 1 : 0;
+  a.nc = nc;
+  a.statistic = statistic;
+  a.npb = (int)npb;
+  a.blk_done = cnt_blk;
+  a.call_done = cnt_call;
+  a.theta_out = theta_out;
+  a.red_val = ctx->blockred.as<double>();
+  a.red_idx = reinterpret_cast<long long*>(a.red_val + npb);
+  a.arg_out = (long long*)argmin_out;
+  a.best_out = min_out;
+  if (fanout) a.fan = *fanout;
+  else memset(&a.fan, 0, sizeof(a.fan));
+  a.fan_offset = fan_offset;
 
   PDC_TRY(ctx->main_begin(st));
   switch (vt * 8 + ppt) {
@@ -990,34 +1046,6 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     default: PDC_TRY((pdm_launch<32, 1>(ctx, a, smem, blocks, st))); break;
   }
   PDC_TRY(ctx->main_end(st));
-
-  double* red_val = ctx->blockred.as<double>();
-  long long* red_idx = reinterpret_cast<long long*>(red_val + eblk);
-  pdc_fanout fan;
-  if (fanout) fan = *fanout;
-  else fan.world = 0;
-  if (statistic == PDC_STAT_AOV)
-    pdm_epilogue_kernel<PDC_STAT_AOV><<<(unsigned)eblk, 256, 0, st>>>(a.partial, periods, meta, nsplit, m0, nc, np,
-                                                                     theta_out, red_val, red_idx, fan,
-                                                                     (long long)fan_offset);
-  else
-    pdm_epilogue_kernel<PDC_STAT_PDM><<<(unsigned)eblk, 256, 0, st>>>(a.partial, periods, meta, nsplit, m0, nc, np,
-                                                                     theta_out, red_val, red_idx, fan,
-                                                                     (long long)fan_offset);
-  PDC_CUDA(cudaGetLastError());
-  ctx->launches++;
-  if (fanout) {
-    best_fanout_kernel<-1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, *fanout, (long long)fan_offset);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches++;
-  } else if (argmin_out || min_out) {
-    if (statistic == PDC_STAT_AOV)
-      argext_final_kernel<+1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmin_out, min_out);
-    else
-      argext_final_kernel<-1><<<1, 256, 0, st>>>(red_val, red_idx, eblk, (long long*)argmin_out, min_out);
-    PDC_CUDA(cudaGetLastError());
-    ctx->launches++;
-  }
   PDC_TRY(scratch.release());
   return PDC_OK;
 }

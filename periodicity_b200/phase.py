@@ -34,11 +34,13 @@ class StringLength(object):
     per period ``phi = (t / P) % 1``, stable sort by ``phi``, closed-polygon length with ``np.roll``.
     """
 
-    def __init__(self, dphi=0.1, n_periods=1000, cores=None, *, device=None, shard=False):
+    def __init__(self, dphi=0.1, n_periods=1000, cores=None, *, device=None, shard=False, devices=None):
         self.dphi = dphi
         self.n_periods = n_periods
         self.cores = cores
-        self.device = device
+        # `devices=[0, 1, ...]`: one multi-device context (pdc_ctx_create_multi) -- the library shards the grid over these
+        # GPUs of THIS process, no torchrun / torch.distributed needed; `device` = a single ordinal
+        self.device = list(devices) if devices is not None else device
         self.shard = shard      # split the period grid across torch.distributed ranks (dist.stringlength_sharded)
 
     def _ell(self, periods):
@@ -93,7 +95,7 @@ class PDM(object):
     """
 
     def __init__(self, nb=5, nc=2, p_min=None, p_max=None, n_periods=1000, oversample=1,
-                 do_subharmonic=False, cores=None, *, device=None, shard=False):
+                 do_subharmonic=False, cores=None, *, device=None, shard=False, devices=None):
         self.nb = nb
         self.nc = nc
         self.p_min = p_min
@@ -102,7 +104,9 @@ class PDM(object):
         self.oversample = oversample
         self.do_subharmonic = do_subharmonic
         self.cores = cores
-        self.device = device
+        # `devices=[0, 1, ...]`: one multi-device context (pdc_ctx_create_multi) -- the library shards the grid over these
+        # GPUs of THIS process, no torchrun / torch.distributed needed; `device` = a single ordinal
+        self.device = list(devices) if devices is not None else device
         self.shard = shard
 
     def _theta(self, periods):
@@ -164,14 +168,16 @@ class AOV(object):
     phase-bin histograms as PDM (``pdc_aov``).  ``cores`` is accepted and ignored.
     """
 
-    def __init__(self, nb=10, p_min=None, p_max=None, n_periods=1000, oversample=1, cores=None, *, device=None):
+    def __init__(self, nb=10, p_min=None, p_max=None, n_periods=1000, oversample=1, cores=None, *, device=None, devices=None):
         self.nb = nb
         self.p_min = p_min
         self.p_max = p_max
         self.n_periods = n_periods
         self.oversample = oversample
         self.cores = cores
-        self.device = device
+        # `devices=[0, 1, ...]`: one multi-device context (pdc_ctx_create_multi) -- the library shards the grid over these
+        # GPUs of THIS process, no torchrun / torch.distributed needed; `device` = a single ordinal
+        self.device = list(devices) if devices is not None else device
 
     def _theta(self, periods):
         ctx = _ffi.default_context(self.device)

@@ -44,12 +44,14 @@ class GLS(object):
         stores its results directly into every rank's buffer over NVLink (no NCCL call).
     """
 
-    def __init__(self, fmin=None, fmax=None, n=5, psd=False, *, device=None, shard=False):
+    def __init__(self, fmin=None, fmax=None, n=5, psd=False, *, device=None, shard=False, devices=None):
         self.fmin = fmin
         self.fmax = fmax
         self.n = n
         self.psd = psd
-        self.device = device
+        # `devices=[0, 1, ...]`: one multi-device context (pdc_ctx_create_multi) -- the library shards the grid over these
+        # GPUs of THIS process, no torchrun / torch.distributed needed; `device` = a single ordinal
+        self.device = list(devices) if devices is not None else device
         self.shard = shard
 
     # -- helpers ---------------------------------------------------------------

@@ -37,4 +37,10 @@ ctx.peaks_halfmax(pw, idx)
 os.environ["PDC_BATCH_PIPE_BYTES"] = "1"                         # read at ctx creation: upload batches in pipelined runs
 ctx2 = _ffi.Context(0)
 ctx2.gls_batch(t, y, w, np.arange(17) * 375, np.full(16, 0.5 * df), np.full(16, df), 700)
+os.environ["PDC_MULTI_MIN_EVALS"] = "1"                          # read at ctx creation: shard even these small problems
+mctx = _ffi.Context([0, 0, 0])                                   # multi-device ctx: three workers on one GPU
+mctx.gls(t, y, w, 0.5 * df, df, 5000)
+mctx.pdm(t, y, P, 10, 2)
+mctx.gls_batch(t, y, None, off, np.full(3, 0.5 * df), np.full(3, df), 700)
+mctx.close()
 print("sanitize smoke done")
