@@ -330,7 +330,7 @@ def _cpu_sl_chunk(t, m, periods):
 
 def _cpu_ce_chunk(t, x, periods, nb, nm):
     from oracle import ce_numpy
-    return ce_numpy.conditional_entropy(t, x, periods, nb, nm)
+    return ce_numpy.ce(t, x, periods, nb, nm)
 
 
 def cpu_reference_step(wl, kind):
@@ -841,7 +841,7 @@ def check_parity(env, wl, result, gather_mode, check_ref_peak):
             oracle_best = int(sel[np.nanargmin(ref)])
         elif kind == "ce":
             from oracle import ce_numpy
-            ref = ce_numpy.conditional_entropy(wl["t"], wl["y"], wl["periods"][sel], wl["nb"], wl["nm"])
+            ref = ce_numpy.ce(wl["t"], wl["y"], wl["periods"][sel], wl["nb"], wl["nm"])
             max_rel = float(np.nanmax(np.abs(full[sel] - ref) / np.maximum(np.abs(ref), 1e-300)))
             oracle_best = int(sel[np.nanargmin(ref)])
             out["oracle"] = "oracle/ce_numpy.py (np.histogram2d statement; parity unpinned by the reference, phase.py:13 is a TODO)"

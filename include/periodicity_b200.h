@@ -247,6 +247,25 @@ PDC_API int pdc_aov_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t 
                 double* theta_out, int64_t* argmax_out, double* max_out, void* stream);
 
 /*
+ * Conditional-entropy periodogram (Graham et al. 2013).  The reference only lists it as a TODO (phase.py:13); it is
+ * computed from per-period COUNT histograms over nphi phase bins x nm magnitude bins, with the reference's phase and
+ * bin-edge conventions (phase.py:131,138-140 with nc = 1: phi = (t / P) % 1, phase bin k = [k/nphi, (k+1)/nphi)) and
+ * magnitude bin min(int(nm (x - min x) / (max x - min x)), nm - 1):
+ *     H_c(P) = sum_jk p(phi_j, m_k) ln( p(phi_j) / p(phi_j, m_k) ),   p = cell occupation / N, over occupied cells.
+ *
+ *   h_out       float64[np]  conditional entropy in the order of `periods` (NaN for period 0 / inf / NaN)
+ *   argmin_out  index of the SMALLEST non-NaN value, first occurrence; -1 if all NaN.  May be NULL.
+ *   min_out     that value.  May be NULL.
+ */
+PDC_API int pdc_ce(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+           const double* periods, int64_t np, int nphi, int nm,
+           double* h_out, int64_t* argmin_out, double* min_out);
+
+PDC_API int pdc_ce_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n,
+               const double* periods, int64_t np, int nphi, int nm,
+               double* h_out, int64_t* argmin_out, double* min_out, void* stream);
+
+/*
  * String Length (Dworetsky 1983): `StringLength._stringlength` (phase.py:45-51) for each trial
  * period, replacing `pool.map(self._stringlength, periods)` (phase.py:68-70).
  *

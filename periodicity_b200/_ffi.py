@@ -81,6 +81,12 @@ SIGNATURES = {
     "pdc_aov_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_ce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                              ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_ce_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_stringlength": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p]),
@@ -296,6 +302,25 @@ class Context:
             _check(self._lib.pdc_aov(self._h, _ptr(t), _ptr(x), t.size, _ptr(periods), periods.size,
                                      int(nb), _ptr(theta), ctypes.addressof(arg), ctypes.addressof(mx)))
         return theta, arg.value, mx.value
+
+    def ce(self, t, x, periods, nphi, nm):
+        """Conditional entropy for each trial period (``pdc_ce``): (h, argmin, min)."""
+        t = _f64(t)
+        x = _f64(x)
+        periods = _f64(periods)
+        if t.ndim != 1 or t.shape != x.shape:
+            raise ValueError("Input arrays have incompatible lengths.")
+        h = np.empty(periods.size, dtype=np.float64)
+        arg = ctypes.c_int64(-1)
+        mn = ctypes.c_double(float("nan"))
+        with self._lock:
+            _check(self._lib.pdc_ce(self._h, _ptr(t), _ptr(x), t.size, _ptr(periods), periods.size,
+                                    int(nphi), int(nm), _ptr(h), ctypes.addressof(arg), ctypes.addressof(mn)))
+        return h, arg.value, mn.value
+
+    def ce_dev(self, t_ptr, x_ptr, n, periods_ptr, np_, nphi, nm, h_ptr, argmin_ptr, min_ptr, stream=0):
+        _check(self._lib.pdc_ce_dev(self._h, t_ptr, x_ptr, int(n), periods_ptr, int(np_), int(nphi), int(nm),
+                                    h_ptr, argmin_ptr or None, min_ptr or None, stream or None))
 
     def peaks_halfmax(self, values, peak_idx, height=None):
         """Indices (left, right) of the half-maximum crossings around each given peak of each row (host arrays);

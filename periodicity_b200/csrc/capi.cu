@@ -211,7 +211,7 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   for (auto& e : ctx->ev_up) if (e) cudaEventDestroy(e);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   ctx->gls_curves.release(); ctx->gls_part.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->gls_cnt.release(); ctx->glsm_y.release();
-  ctx->partial.release(); ctx->blockred.release(); ctx->pin_meta.release();
+  ctx->partial.release(); ctx->gls_plane.release(); ctx->hist_plane.release(); ctx->blockred.release(); ctx->pin_meta.release();
   ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->peak_cand.release();
   ctx->main_resolve();
   for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -596,6 +596,50 @@ int pdc_aov(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
                                return pdc_aov(c, t, x, n, p, k, nb, o, a, b);
                              });
   return phase_hist_host(ctx, t, x, n, periods, np, nb, 1, PDC_STAT_AOV, theta_out, argmax_out, max_out);
+}
+
+// ---------------------------------------------------------------------------
+// conditional entropy (count histograms over phase x magnitude cells)
+// ---------------------------------------------------------------------------
+int pdc_ce_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np,
+               int nphi, int nm, double* h_out, int64_t* argmin_out, double* min_out, void* stream) {
+  if (!ctx || !t || !x || !periods || !h_out) { set_error("pdc_ce_dev: NULL argument"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  return ce_run(ctx, t, x, n, periods, np, nphi, nm, h_out, argmin_out, min_out, st);
+}
+
+int pdc_ce(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np,
+           int nphi, int nm, double* h_out, int64_t* argmin_out, double* min_out) {
+  if (!ctx || !t || !x || !periods || !h_out) { set_error("pdc_ce: NULL argument"); return PDC_EINVAL; }
+  if (n < 1 || np < 1) { set_error("pdc_ce: need n >= 1 samples and np >= 1 periods"); return PDC_EINVAL; }
+  if (nphi < 1 || nm < 1) { set_error("pdc_ce: nphi and nm must be >= 1"); return PDC_EINVAL; }
+  if (ctx->multi)
+    return multi_period_grid(ctx, n, periods, np, -1, h_out, argmin_out, min_out,
+                             [=](pdc_ctx* c, const double* p, int64_t k, double* o, int64_t* a, double* b) {
+                               return pdc_ce(c, t, x, n, p, k, nphi, nm, o, a, b);
+                             });
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  PDC_TRY(ctx->in_a.reserve(sizeof(double) * (size_t)n));
+  PDC_TRY(ctx->in_b.reserve(sizeof(double) * (size_t)n));
+  PDC_TRY(ctx->in_d.reserve(sizeof(double) * (size_t)np));
+  PDC_TRY(ctx->out_a.reserve(sizeof(double) * (size_t)np));
+  PDC_TRY(ctx->out_small.reserve(sizeof(SmallRec)));
+  PDC_TRY(ctx->pin_small.reserve(sizeof(SmallRec)));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_a.p, t, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_b.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_d.p, periods, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, st));
+  SmallRec* d_rec = ctx->out_small.as<SmallRec>();
+  PDC_TRY(ce_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), n, ctx->in_d.as<double>(), np, nphi, nm,
+                 ctx->out_a.as<double>(), (int64_t*)&d_rec->arg, &d_rec->val, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, d_rec, sizeof(SmallRec), cudaMemcpyDeviceToHost, st));
+  PDC_TRY(staged_d2h(ctx, h_out, ctx->out_a.p, sizeof(double) * (size_t)np, st));
+  PDC_CUDA(cudaStreamSynchronize(st));
+  const SmallRec* h = ctx->pin_small.as<SmallRec>();
+  if (argmin_out) *argmin_out = h->arg;
+  if (min_out) *min_out = h->val;
+  return PDC_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -1,0 +1,483 @@
+// Conditional-entropy periodogram (Graham et al. 2013) for a grid of trial periods.
+//
+// The reference only lists the method as a TODO (src/periodicity/phase.py:13, "conditional entropy"); there is no
+// reference code, so PARITY IS UNPINNED BY THE REFERENCE (oracle: oracle/ce_numpy.py, pinned to np.histogram2d).
+// Conventions follow the reference's PDM where they overlap: phase phi = (t / P) % 1 (phase.py:131), phase bin k
+// selected by the float64 thresholds k / nphi (phase.py:138-140 with nc = 1).  Magnitudes are scaled to [0, 1] with
+// the sample minimum and maximum and cut into nm equal bins (the maximum goes to the last bin):
+//     mbin_i = min(int(nm * (x_i - min) / (max - min)), nm - 1)           -- period independent
+//     H_c(P) = sum_jk p(phi_j, m_k) ln( p(phi_j) / p(phi_j, m_k) ),  p = cell occupation / N, over the occupied cells;
+// the best period MINIMISES it.
+//
+// It needs COUNTS only, in nphi * nm cells: `cell = phase_bin * nm + mbin`.  Mapping = the packed loop of
+// pdm_hist_kernel (pdm.cu) without its second level: every trial period owns a private column of 32-bit count words in
+// shared memory (consecutive columns -> consecutive words, conflict free), a sample is ONE native shared-memory
+// integer atomic without return value (ATOMS.ADD, fire-and-forget) and a 32-bit count cannot overflow, so there is no
+// feed, no flush window: the columns go to global memory once, when the block has seen its share of the samples.
+// Phase -> bin: the fixed-point fast path of phase_common.cuh (one DFMA + one 32 x 32 -> 64 bit multiply), samples
+// within 4 * 2^-32 of a bin edge re-binned exactly and the increment moved; huge |t / P| or non-finite samples take
+// the exact FP64 path for every sample.
+//
+// Kernels: ce_stats_kernel (min / max of x, max |t|, non-finite flag; multi-block, last block finalises),
+// ce_hist_kernel (hot; at the end a thread adds its columns to ONE plane of 32-bit counts shared by all sample splits,
+// RED.ADD.32 -- integer, hence order independent), ce_epilogue_kernel (FP64 entropy per trial period, clears the plane
+// for the next call, arg-min; the last block finalises).
+#include <cstring>
+
+#include "pdc_common.cuh"
+#include "phase_common.cuh"
+
+namespace pdc {
+
+struct CeMeta {
+  double xmin, xmax;
+  double t_absmax;
+  int bad, pad_;
+};
+
+struct CePart {
+  double xneg, xmax, tabs;
+  int bad, pad_;
+};
+constexpr int CE_STATS_THREADS = 256;
+constexpr int CE_STATS_MAXBLK = 128;
+constexpr int CE_TILE = 1024;
+constexpr int CE_U = 16;            // samples per trip: CE_U x PPT independent DFMA -> IMAD.WIDE -> IMAD -> ATOMS chains
+constexpr int CE_TILE_PAD = CE_U;   // the prefetch reads one trip past the tile
+
+__global__ void __launch_bounds__(CE_STATS_THREADS)
+ce_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, CePart* part, unsigned* done,
+                CeMeta* meta) {
+  __shared__ double scratch[33];
+  __shared__ int s_last;
+  const int G = gridDim.x;
+  double xneg = -INFINITY, xmax = -INFINITY, tabs = 0.0;
+  int bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)G * blockDim.x) {
+    const double xi = x[i], ti = t[i];
+    xneg = fmax(xneg, -xi);     // fmax / fmin ignore NaN, as np.nanmin / np.nanmax do (oracle: magnitude_bins)
+    xmax = fmax(xmax, xi);
+    bad |= !isfinite(xi) || !isfinite(ti);
+    if (isfinite(ti)) tabs = fmax(tabs, fabs(ti));
+  }
+  bad = __syncthreads_or(bad);
+  xneg = -block_min(-xneg, scratch);
+  xmax = -block_min(-xmax, scratch);
+  tabs = -block_min(-tabs, scratch);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x].xneg = xneg;
+    part[blockIdx.x].xmax = xmax;
+    part[blockIdx.x].tabs = tabs;
+    part[blockIdx.x].bad = bad;
+    __threadfence();
+    s_last = atomicAdd(done, 1u) == (unsigned)(G - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const bool has = (int)threadIdx.x < G;
+  const CePart* p = part + threadIdx.x;
+  xneg = -block_min(has ? -__ldcg(&p->xneg) : INFINITY, scratch);
+  xmax = -block_min(has ? -__ldcg(&p->xmax) : INFINITY, scratch);
+  tabs = -block_min(has ? -__ldcg(&p->tabs) : 0.0, scratch);
+  bad = __syncthreads_or(has ? __ldcg(&p->bad) : 0);
+  if (threadIdx.x == 0) {
+    meta->xmin = -xneg;
+    meta->xmax = xmax;
+    meta->t_absmax = tabs;
+    meta->bad = bad;
+    *done = 0u;
+  }
+}
+
+struct CeArgs {
+  const double* t;
+  const double* x;
+  const double* periods;
+  const CeMeta* meta;
+  unsigned* plane;      // [cells][np] counts, all sample splits add into it
+  long long n, np;
+  int nphi, nm, cells, nsplit;
+};
+
+// numpy's magnitude bin: scaled = (x - lo) / (hi - lo); min(int(scaled * nm), nm - 1)  (oracle/ce_numpy.py)
+__device__ __forceinline__ int ce_mbin(double xv, double lo, double range, int nm) {
+  const double scaled = __ddiv_rn(__dadd_rn(xv, -lo), range);
+  const double v = __dmul_rn(scaled, (double)nm);
+  if (!(v == v)) return -1;                 // NaN value (or a constant signal: 0 / 0): in no cell
+  int k = (int)v;                           // truncation towards zero, as astype(int64)
+  return k < 0 ? 0 : (k > nm - 1 ? nm - 1 : k);
+}
+
+struct CeEpiArgs {
+  unsigned* plane;      // [cells][np]; read and cleared
+  const double* periods;
+  long long np;
+  int nphi, nm;
+  double* h_out;        // [np]
+  double* red_val;      // [gridDim.x]
+  long long* red_idx;
+  unsigned* call_done;  // [1] self-resetting
+  long long* arg_out;
+  double* best_out;
+};
+
+__global__ void __launch_bounds__(256)
+ce_epilogue_kernel(const CeEpiArgs a) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ int s_last;
+  const long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long np = a.np;
+  double h = 0.0;
+  long long idx = -1;
+  if (pi < np) {
+    unsigned* base = a.plane + pi;
+    // H = (1 / N) sum_j [ r_j ln r_j - sum_k c_jk ln c_jk ],  r_j = sum_k c_jk,  N = sum_j r_j
+    double acc = 0.0, ntot = 0.0;
+    for (int j = 0; j < a.nphi; ++j) {
+      double r = 0.0, cl = 0.0;
+      for (int k = 0; k < a.nm; ++k) {
+        unsigned* cell = base + (long long)(j * a.nm + k) * np;
+        const double c = (double)__ldcg(cell);
+        *cell = 0u;                                          // the plane is clean for the next call
+        r += c;
+        if (c > 0.0) cl += c * log(c);
+      }
+      if (r > 0.0) acc += r * log(r) - cl;
+      ntot += r;
+    }
+    const double P = a.periods[pi];
+    h = acc / ntot;                                          // no binned sample: 0 / 0 = NaN
+    if (!isfinite(P) || !isfinite(1.0 / P)) h = nan("");     // period 0, denormal, inf or NaN: no phases
+    if (a.h_out) a.h_out[pi] = h;
+    idx = pi;
+  }
+  block_argext<-1>(h, idx, sv, si);
+  const int nblk = gridDim.x;
+  if (threadIdx.x == 0) {
+    a.red_val[blockIdx.x] = h;
+    a.red_idx[blockIdx.x] = idx;
+    __threadfence();
+    s_last = atomicAdd(a.call_done, 1u) == (unsigned)(nblk - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *a.call_done = 0u;
+  __threadfence();
+  double best = 0.0;
+  long long bidx = -1;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+    const double v = __ldcg(a.red_val + k);
+    const long long i = __ldcg(a.red_idx + k);
+    if (better<-1>(v, i, best, bidx)) { best = v; bidx = i; }
+  }
+  block_argext<-1>(best, bidx, sv, si);
+  if (threadIdx.x == 0) {
+    if (a.arg_out) *a.arg_out = bidx;
+    if (a.best_out) *a.best_out = bidx >= 0 ? best : nan("");
+  }
+}
+
+// Shared memory: s_t[CE_TILE + pad] time stamps, s_thr[nphi + 1] thresholds, s_m[CE_TILE] magnitude-bin word offsets
+// (mbin * VT, or 0xffffffff for a value in no cell), cnt[cells][VT] private count columns (VT = THREADS * PPT).
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS)
+ce_hist_kernel(const CeArgs a) {
+  constexpr int VT = THREADS * PPT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nphi = a.nphi, nm = a.nm, cells = a.cells;
+  double* s_t = reinterpret_cast<double*>(smem_raw);
+  double* s_thr = s_t + CE_TILE + CE_TILE_PAD;
+  unsigned* s_m = reinterpret_cast<unsigned*>(s_thr + ((nphi + 2) & ~1));
+  unsigned* cnt = s_m + CE_TILE;
+
+  const int split = blockIdx.x % a.nsplit;
+  const long long pb = blockIdx.x / a.nsplit;
+  long long pis[PPT];
+  bool valids[PPT];
+  double Ps[PPT], rPs[PPT];
+  bool in_range = true;
+#pragma unroll
+  for (int s = 0; s < PPT; ++s) {
+    pis[s] = pb * VT + s * THREADS + threadIdx.x;
+    valids[s] = pis[s] < a.np;
+    double P = valids[s] ? a.periods[pis[s]] : 1.0;
+    if (!isfinite(1.0 / P) || !isfinite(P)) P = 1.0;  // invalid trial period: the tail writes NaN
+    Ps[s] = P;
+    rPs[s] = 1.0 / P;
+    // padding columns (P = 1) must not veto the block's fast path
+    in_range = in_range && (!valids[s] || fabs(rPs[s]) * a.meta->t_absmax < PDM_FAST_LIMIT);
+  }
+  const bool bad = a.meta->bad != 0;   // block-uniform
+  const double nphid = (double)nphi;
+  const unsigned nphiu = (unsigned)nphi, guard2 = 2u * PDM_FAST_GUARD * nphiu;
+  const double xlo = a.meta->xmin, xrange = a.meta->xmax - a.meta->xmin;
+  const unsigned mstride = (unsigned)nm * VT;   // words between consecutive phase bins of one column
+
+  for (int k = threadIdx.x; k <= nphi; k += THREADS) s_thr[k] = (double)k / nphid;  // phase.py:138-140
+  for (int k = threadIdx.x; k < CE_TILE_PAD; k += THREADS) s_t[CE_TILE + k] = 0.0;
+  for (int k = threadIdx.x; k < cells * VT; k += THREADS) cnt[k] = 0u;
+
+  const long long per = (a.n + a.nsplit - 1) / a.nsplit;
+  const long long sb = (long long)split * per;
+  const long long se = sb + per < a.n ? sb + per : a.n;
+  // block-uniform; a constant signal (max == min) has no magnitude bins at all (0 / 0): every sample is in no cell
+  const bool fast = __syncthreads_and(in_range) != 0 && !bad && xrange > 0.0;
+
+  auto exact_bin = [&](double P, double rP, double tv, double& phi) {
+    unsigned e;
+    int k = pdm_bin(tv, P, rP, nphid, phi, e);
+    if (e < PDM_AMBIG) k = pdm_fix_bin(k, phi, s_thr, nphi);
+    return (unsigned)k;
+  };
+  auto add = [&](unsigned* col, unsigned k, unsigned moff, unsigned inc) {
+    asm volatile("" : "+r"(k));   // keep the bin index opaque: one IMAD on the high word of the 64-bit product (see pdm.cu)
+    atomicAdd(col + k * mstride + moff, inc);
+  };
+
+  long long tile0 = sb;
+  do {
+    long long left = se - tile0;
+    const int cntv = left <= 0 ? 0 : (left < CE_TILE ? (int)left : CE_TILE);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cntv; i += THREADS) {
+      s_t[i] = a.t[tile0 + i];
+      const int mb = ce_mbin(a.x[tile0 + i], xlo, xrange, nm);
+      s_m[i] = mb < 0 ? 0xffffffffu : (unsigned)mb * VT;
+    }
+    __syncthreads();
+
+    if (fast) {
+      // every sample is finite and in range: CE_U samples x PPT periods per trip, atomics issued at once with the fast
+      // bins, the rare trip with a sample on a bin edge re-bins those exactly afterwards and moves the increment
+      unsigned* c0 = cnt + threadIdx.x;
+      int i = 0;
+      double tv[CE_U];
+#pragma unroll
+      for (int u = 0; u < CE_U; u += 2) {
+        const double2 tt = *reinterpret_cast<const double2*>(s_t + u);
+        tv[u] = tt.x;
+        tv[u + 1] = tt.y;
+      }
+      for (; i + CE_U <= cntv; i += CE_U) {
+        unsigned k[PPT][CE_U], mo[CE_U], pos, pmin = 0xffffffffu;
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+#pragma unroll
+          for (int u = 0; u < CE_U; ++u) {
+            k[s][u] = pdm_bin_fast_g(tv[u], rPs[s], nphiu, pos);
+            pmin = min(pmin, pos);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < CE_U; u += 2) {   // next trip's time stamps before this trip's atomics
+          const double2 tt = *reinterpret_cast<const double2*>(s_t + i + CE_U + u);
+          tv[u] = tt.x;
+          tv[u + 1] = tt.y;
+        }
+#pragma unroll
+        for (int u = 0; u < CE_U; u += 4) {
+          const uint4 mm = *reinterpret_cast<const uint4*>(s_m + i + u);
+          mo[u] = mm.x; mo[u + 1] = mm.y; mo[u + 2] = mm.z; mo[u + 3] = mm.w;
+        }
+#pragma unroll
+        for (int u = 0; u < CE_U; ++u) {
+#pragma unroll
+          for (int s = 0; s < PPT; ++s) add(c0 + s * THREADS, k[s][u], mo[u], 1u);
+        }
+        if (pmin < guard2) {
+          for (int u = 0; u < CE_U; ++u) {
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) {
+              unsigned p0;
+              const double tvu = s_t[i + u];
+              const unsigned kf = pdm_bin_fast_g(tvu, rPs[s], nphiu, p0);
+              if (p0 < guard2) {
+                double ph;
+                const unsigned ke = exact_bin(Ps[s], rPs[s], tvu, ph);
+                if (ke != kf) {
+                  add(c0 + s * THREADS, kf, s_m[i + u], 0u - 1u);   // counts are sums modulo 2^32: -1 undoes the update
+                  add(c0 + s * THREADS, ke, s_m[i + u], 1u);
+                }
+              }
+            }
+          }
+        }
+      }
+      for (; i < cntv; ++i) {
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+          unsigned p0;
+          const double tvu = s_t[i];
+          unsigned kf = pdm_bin_fast_g(tvu, rPs[s], nphiu, p0);
+          if (p0 < guard2) {
+            double ph;
+            kf = exact_bin(Ps[s], rPs[s], tvu, ph);
+          }
+          add(c0 + s * THREADS, kf, s_m[i], 1u);
+        }
+      }
+    } else {
+      // exact FP64 phase for every sample; samples whose phase is NaN (non-finite stamp) or whose value is NaN are in no cell
+      for (int i = 0; i < cntv; ++i) {
+        const double tvu = s_t[i];
+        const unsigned mo = s_m[i];
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+          double ph;
+          unsigned k = exact_bin(Ps[s], rPs[s], tvu, ph);
+          if (!(ph == ph) || mo == 0xffffffffu) continue;
+          k = min(k, nphiu - 1u);
+          add(cnt + s * THREADS + threadIdx.x, k, mo, 1u);
+        }
+      }
+    }
+    tile0 += CE_TILE;
+  } while (tile0 < se);
+
+  // the thread's columns -> the count plane shared by all sample splits (RED.ADD.32; integer, hence order independent)
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < PPT; ++s) {
+    if (!valids[s]) continue;
+    unsigned* pcol = a.plane + pis[s];
+    const unsigned* col = cnt + s * THREADS + threadIdx.x;
+    for (int c = 0; c < cells; ++c) {
+      const unsigned v = col[c * VT];
+      if (v) atomicAdd(pcol + (long long)c * a.np, v);
+    }
+  }
+}
+
+static size_t ce_smem_bytes(int nphi, int cells, int vt) {
+  return sizeof(double) * (CE_TILE + CE_TILE_PAD + ((nphi + 2) & ~1)) + sizeof(unsigned) * CE_TILE +
+         sizeof(unsigned) * (size_t)cells * vt;
+}
+
+template <int THREADS, int PPT>
+static int ce_launch(pdc_ctx* ctx, const CeArgs& a, size_t smem, long long blocks, cudaStream_t st) {
+  PDC_CUDA(cudaFuncSetAttribute(ce_hist_kernel<THREADS, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ce_hist_kernel<THREADS, PPT><<<(unsigned)blocks, THREADS, smem, st>>>(a);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return PDC_OK;
+}
+
+int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np, int nphi,
+           int nm, double* h_out, int64_t* argmin_out, double* min_out, cudaStream_t st) {
+  if (n < 1) { set_error("pdc_ce: need at least 1 sample"); return PDC_EINVAL; }
+  if (np < 1) { set_error("pdc_ce: need at least one trial period"); return PDC_EINVAL; }
+  if (nphi < 1 || nm < 1) { set_error("pdc_ce: nphi and nm must be >= 1"); return PDC_EINVAL; }
+  const long long cells_l = (long long)nphi * nm;
+  const size_t smem_max = 227 * 1024;
+  if (cells_l > 100000 || ce_smem_bytes(nphi, (int)cells_l, 32) > smem_max) {
+    set_error("pdc_ce: nphi*nm = %lld cells do not fit a shared-memory histogram", cells_l);
+    return PDC_EINVAL;
+  }
+  const int cells = (int)cells_l;
+  // period columns per block: the candidate that keeps the most columns resident per SM
+  int vt = 32, best_res = 0;
+  const int cands[4] = {256, 128, 64, 32};
+  for (int c = 0; c < 4; ++c) {
+    size_t sm = ce_smem_bytes(nphi, cells, cands[c]);
+    if (sm > smem_max) continue;
+    int blocks = (int)((228 * 1024) / (sm + 1024));
+    if (blocks > 2048 / cands[c]) blocks = 2048 / cands[c];
+    int res = blocks * cands[c];
+    if (res > best_res) { best_res = res; vt = cands[c]; }
+  }
+  const int ppt = vt >= 64 ? 2 : 1;
+  const size_t smem = ce_smem_bytes(nphi, cells, vt);
+  const long long resident = (long long)ctx->sm_count * (best_res / vt);
+  const long long npb = (np + vt - 1) / vt;
+  int nsplit = 1;
+  if (npb < 24 * resident) {
+    long long cap = n / 512;
+    if (cap < 1) cap = 1;
+    if (cap > 1024) cap = 1024;
+    double best = 1e300;
+    for (long long s = 1; s <= cap; ++s) {
+      long long items = npb * s;
+      long long waves = (items + resident - 1) / resident;
+      double cost = (double)waves * ((double)((n + s - 1) / s) + 2.0 * cells + 64.0);
+      if (cost < best * 0.999) { best = cost; nsplit = (int)s; }
+      if (items > 64 * resident) break;
+    }
+  }
+  const long long blocks = npb * nsplit;
+  if (blocks > 0x7fffffffLL || npb > 0x3fffffffLL) { set_error("pdc_ce: problem too large for one call"); return PDC_EINVAL; }
+
+  ScratchScope scratch(ctx, st);
+  PDC_TRY(scratch.acquire());
+  PDC_TRY(ctx->pdm_meta.reserve(sizeof(CeMeta) + 16 + sizeof(CePart) * CE_STATS_MAXBLK));
+  {
+    const void* before = ctx->hist_plane.p;
+    const size_t cap_before = ctx->hist_plane.cap;
+    PDC_TRY(ctx->hist_plane.reserve(sizeof(unsigned) * (size_t)cells * np));
+    if (ctx->hist_plane.p != before || ctx->hist_plane.cap != cap_before || ctx->hist_plane_dirty) {
+      PDC_CUDA(cudaMemsetAsync(ctx->hist_plane.p, 0, ctx->hist_plane.cap, st));
+      ctx->hist_plane_dirty = false;
+    }
+  }
+  const int eblk = (int)((np + 255) / 256);
+  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk));
+  {
+    const void* before = ctx->pdm_cnt.p;
+    PDC_TRY(ctx->pdm_cnt.reserve(sizeof(unsigned) * 4));
+    if (ctx->pdm_cnt.p != before) PDC_CUDA(cudaMemsetAsync(ctx->pdm_cnt.p, 0, ctx->pdm_cnt.cap, st));
+  }
+  unsigned* cnt_stats = ctx->pdm_cnt.as<unsigned>();
+  CeMeta* meta = ctx->pdm_meta.as<CeMeta>();
+  {
+    CePart* part = reinterpret_cast<CePart*>(reinterpret_cast<char*>(meta) + ((sizeof(CeMeta) + 15) & ~(size_t)15));
+    long long sblk = (n + 8 * CE_STATS_THREADS - 1) / (8 * CE_STATS_THREADS);
+    if (sblk > CE_STATS_MAXBLK) sblk = CE_STATS_MAXBLK;
+    ce_stats_kernel<<<(unsigned)sblk, CE_STATS_THREADS, 0, st>>>(t, x, n, part, cnt_stats, meta);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  CeArgs a;
+  a.t = t;
+  a.x = x;
+  a.periods = periods;
+  a.meta = meta;
+  a.plane = ctx->hist_plane.as<unsigned>();
+  a.n = n;
+  a.np = np;
+  a.nphi = nphi;
+  a.nm = nm;
+  a.cells = cells;
+  a.nsplit = nsplit;
+
+  ctx->hist_plane_dirty = true;
+  PDC_TRY(ctx->main_begin(st));
+  switch (vt * 8 + ppt) {
+    case 256 * 8 + 2: PDC_TRY((ce_launch<128, 2>(ctx, a, smem, blocks, st))); break;
+    case 128 * 8 + 2: PDC_TRY((ce_launch<64, 2>(ctx, a, smem, blocks, st))); break;
+    case 64 * 8 + 2: PDC_TRY((ce_launch<32, 2>(ctx, a, smem, blocks, st))); break;
+    default: PDC_TRY((ce_launch<32, 1>(ctx, a, smem, blocks, st))); break;
+  }
+  PDC_TRY(ctx->main_end(st));
+
+  CeEpiArgs e;
+  e.plane = a.plane;
+  e.periods = periods;
+  e.np = np;
+  e.nphi = nphi;
+  e.nm = nm;
+  e.h_out = h_out;
+  e.red_val = ctx->blockred.as<double>();
+  e.red_idx = reinterpret_cast<long long*>(e.red_val + eblk);
+  e.call_done = cnt_stats + 1;
+  e.arg_out = (long long*)argmin_out;
+  e.best_out = min_out;
+  ce_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(e);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  ctx->hist_plane_dirty = false;
+  PDC_TRY(scratch.release());
+  return PDC_OK;
+}
+
+}  // namespace pdc

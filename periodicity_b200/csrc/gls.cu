@@ -24,12 +24,14 @@
 //   gls_prep_kernel     two block roles in one launch: per sample (t - t_min, frac(df (t - t_min))) as double2 and
 //                       (cos, sin of 2 pi df (t - t_min), y', w') as float4; FP64 direct sums for the
 //                       frequencies with < 1 cycle over the baseline
-//   gls_strip_kernel    the hot kernel: six FP32 sums per frequency {C, S, YC, YS, CC, CS}, flushed to FP64
-//                       partials per tile.  Its TAIL is the epilogue: the last sample split to finish a block of
-//                       2048 frequencies merges the splits' partial planes in a fixed order (they are still in
-//                       L2), evaluates the tau-offset algebra (spectral.py:113-132) in FP64, stores the power
-//                       (to every rank's buffer in the fan-out variant) and the block's NaN-aware arg-max; the
-//                       last frequency block of a curve reduces those to the curve's (max, argmax).
+//   gls_strip_kernel    the hot kernel: six FP32 sums per frequency {C, S, YC, YS, CC, CS}; every 1024-sample tile
+//                       the sums are converted to 64-bit fixed point (2^-30) and added to ONE plane of partial sums
+//                       with RED.ADD.64 -- integer addition is associative, so the result does not depend on
+//                       the order in which sample splits and tiles arrive (bit-reproducible), and the partial
+//                       planes of round 1 (one FP64 plane per sample split, 86 MB on C2) shrink to 4.8 MB
+//   gls_epilogue_kernel FP64: tau-offset algebra (spectral.py:113-132) per frequency, power store (to every
+//                       rank's buffer in the fan-out variant), clears the plane for the next call, per-block
+//                       NaN-aware arg-max; the last block of a curve reduces those to the curve's (max, argmax)
 //
 // Algorithmic work of the hot kernel: per sample*frequency evaluation
 // 4 FP32 instructions for the rotation + 6 for the sums (7 with weights).
@@ -62,6 +64,7 @@ namespace pdc {
 // ---------------------------------------------------------------------------
 struct GlsPart {
   double tmin, tneg, sw, swd, swdd;   // moments of d = y - y[first sample of the curve]
+  int bad, pad_;                      // some t, y or w of the curve is NaN / inf
 };
 constexpr int GLS_STATS_THREADS = 256;
 
@@ -77,8 +80,10 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y, con
   const long long b = cin.begin, n = cin.n;
   const double y0 = y[b];
   double tmin = INFINITY, tneg = INFINITY, sw = 0.0, swd = 0.0, swdd = 0.0;
+  int bad = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)G * blockDim.x) {
     const double ti = t[b + i], d = y[b + i] - y0, wi = w ? w[b + i] : 1.0;
+    bad |= !isfinite(ti) || !isfinite(d) || !isfinite(wi);
     tmin = fmin(tmin, ti);
     tneg = fmin(tneg, -ti);
     sw += wi;
@@ -91,9 +96,10 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y, con
   sw = block_sum(sw, scratch);
   swd = block_sum(swd, scratch);
   swdd = block_sum(swdd, scratch);
+  bad = __syncthreads_or(bad);
   if (threadIdx.x == 0) {
     GlsPart& p = part[(long long)curve * G + blockIdx.x];
-    p.tmin = tmin; p.tneg = tneg; p.sw = sw; p.swd = swd; p.swdd = swdd;
+    p.tmin = tmin; p.tneg = tneg; p.sw = sw; p.swd = swd; p.swdd = swdd; p.bad = bad;
     __threadfence();
     s_last = atomicAdd(done + curve, 1u) == (unsigned)(G - 1);
   }
@@ -108,6 +114,7 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y, con
   sw = lane < G ? __ldcg(&p[lane].sw) : 0.0;
   swd = lane < G ? __ldcg(&p[lane].swd) : 0.0;
   swdd = lane < G ? __ldcg(&p[lane].swdd) : 0.0;
+  bad = __any_sync(0xffffffffu, lane < G ? __ldcg(&p[lane].bad) : 0);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
@@ -140,6 +147,9 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y, con
     const bool tt = allow_three_term && cv.df > 0.0 && span <= GLS_TT_MAX_SPAN;
     cv.three_term = tt;
     cv.gamma = tt ? 0.25 - 0.5 * span : 0.0;
+    // non-finite input: the sums leave the strip kernel as fixed point, which cannot carry a NaN, so the epilogue
+    // writes the NaN the reference's float arithmetic would have produced for every frequency of this curve
+    cv.bad = bad;
     curves[curve] = cv;
     done[curve] = 0u;  // self-resetting: the next call finds the counter at zero
   }
@@ -248,106 +258,21 @@ struct GlsMainArgs {
   const GlsCurve* curves;
   const double2* rec1;
   const float4* rec2;
-  double* partial;    // [nsplit][6][nf_tot]
+  unsigned long long* partial;   // [6][nf_tot] fixed-point (2^-GLS_FIX_BITS) sums, all sample splits add into it
   long long nf;       // frequencies per curve in this call
   long long nf_tot;   // B * nf
   long long j0;       // absolute index of this call's first frequency
   int nfb;            // frequency blocks per curve
   int nsplit;         // sample splits per curve
-  // ---- tail (epilogue) ----
-  const double* lowsum;   // FP64 sums of the sub-cycle bins [chunk][6][B * low_cap]
-  int nlowchunk, low_cap, B;
-  unsigned flags;
-  unsigned* blk_done;     // [B * nfb]  sample splits that have finished this frequency block (self-resetting)
-  unsigned* curve_done;   // [B]        frequency blocks of this curve whose epilogue has run (self-resetting)
-  double* power_out;      // [B * nf] or NULL
-  double* red_val;        // [B * nfb] per-block arg-max candidates
-  long long* red_idx;
-  long long* arg_out;     // [B] or NULL
-  double* max_out;        // [B] or NULL
-  pdc_fanout fan;         // fan.world == 0: no fan-out
 };
 
-// Tail of gls_strip_kernel, run by the LAST sample split to finish frequency block `fb` of `curve`: merges the splits'
-// FP64 partial planes in split order (fixed, whatever block happens to be last: bit-reproducible), evaluates
-// spectral.py:113-132 per frequency, stores the power and reduces the arg-max.  FPB = frequencies per block.
-template <int K, int THREADS>
-__device__ __forceinline__ void gls_tail(const GlsMainArgs& a, int curve, int fb, long long jB) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  __shared__ int s_flag;
-  __threadfence();   // this block's partial stores / RED.ADDs are visible device-wide before it is counted
-  __syncthreads();
-  if (threadIdx.x == 0) s_flag = atomicAdd(a.blk_done + (long long)curve * a.nfb + fb, 1u) == (unsigned)(a.nsplit - 1);
-  __syncthreads();
-  if (!s_flag) return;
-  if (threadIdx.x == 0) a.blk_done[(long long)curve * a.nfb + fb] = 0u;
-  __threadfence();
-  const GlsCurve cv = a.curves[curve];
-  double best = 0.0;
-  long long bidx = -1;
-#pragma unroll 1
-  for (int r = 0; r < K; ++r) {
-    const long long j = jB + (long long)r * THREADS + threadIdx.x;   // consecutive threads, consecutive frequencies
-    if (j >= a.nf) break;
-    double sums[6];
-    double inv_n;
-    if (j >= cv.low_begin && j < cv.low_begin + cv.low_count) {
-      // sub-cycle frequency: FP64 sums from gls_prep_kernel (already normalised)
-      const long long cols = (long long)a.B * a.low_cap;
-      const double* p = a.lowsum + (long long)curve * a.low_cap + (j - cv.low_begin);
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        double acc = 0.0;
-        for (int c = 0; c < a.nlowchunk; ++c) acc += p[((long long)c * 6 + q) * cols];
-        sums[q] = acc;
-      }
-      inv_n = 1.0;
-    } else {
-      const double* p = a.partial + (long long)curve * a.nf + j;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) sums[q] = 0.0;
-      for (int sp = 0; sp < a.nsplit; ++sp) {
-#pragma unroll
-        for (int q = 0; q < 6; ++q) sums[q] += __ldcg(p + ((long long)sp * 6 + q) * a.nf_tot);   // L2: written by other SMs
-      }
-      inv_n = 1.0 / (double)cv.n;
-    }
-    const double power = gls_power_from_sums(sums, inv_n, a.flags, cv.yy, cv.psd_scale);
-    if (a.power_out) a.power_out[(long long)curve * a.nf + j] = power;
-    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
-    for (int rk = 0; rk < a.fan.world; ++rk) a.fan.power[rk][a.j0 + j] = power;
-    if (better<+1>(power, j, best, bidx)) { best = power; bidx = j; }
-  }
-  block_argext<+1>(best, bidx, sv, si);
-  if (threadIdx.x == 0) {
-    a.red_val[(long long)curve * a.nfb + fb] = best;
-    a.red_idx[(long long)curve * a.nfb + fb] = bidx;
-    __threadfence();
-    s_flag = atomicAdd(a.curve_done + curve, 1u) == (unsigned)(a.nfb - 1);
-  }
-  __syncthreads();
-  if (!s_flag) return;
-  // the last frequency block of this curve: final (max, argmax); NaN ignored, first occurrence (np.nanargmax)
-  if (threadIdx.x == 0) a.curve_done[curve] = 0u;
-  __threadfence();
-  best = 0.0;
-  bidx = -1;
-  for (int k = threadIdx.x; k < a.nfb; k += THREADS) {
-    const double v = __ldcg(a.red_val + (long long)curve * a.nfb + k);
-    const long long i = __ldcg(a.red_idx + (long long)curve * a.nfb + k);
-    if (better<+1>(v, i, best, bidx)) { best = v; bidx = i; }
-  }
-  block_argext<+1>(best, bidx, sv, si);
-  if (threadIdx.x == 0) {
-    const double val = bidx >= 0 ? best : nan("");
-    if (a.arg_out) a.arg_out[curve] = bidx;
-    if (a.max_out) a.max_out[curve] = val;
-    for (int rk = 0; rk < a.fan.world; ++rk) {   // slot `rank` of every rank's candidate table: (max, GLOBAL argmax)
-      a.fan.best[rk][2 * a.fan.rank] = val;
-      a.fan.best[rk][2 * a.fan.rank + 1] = bidx >= 0 ? (double)(bidx + a.j0) : -1.0;
-    }
-  }
+// Tile sums leave the strip kernel as 64-bit fixed point with GLS_FIX_BITS fraction bits.  With the weights rescaled to
+// mean 1 and y' to unit weighted RMS every one of the six sums is bounded by n in magnitude (Cauchy-Schwarz:
+// sum w'|y'| <= sqrt(sum w') sqrt(sum w' y'^2) = n), so 2^30 leaves room for n up to 8e9 samples; the quantisation,
+// 2^-31 per tile flush, is nine orders of magnitude below the rounding of the FP32 tile sum it converts.
+constexpr int GLS_FIX_BITS = 30;
+__device__ __forceinline__ void gls_flush(unsigned long long* p, float v) {
+  atomicAdd(p, (unsigned long long)__float2ll_rn(v * (float)(1 << GLS_FIX_BITS)));   // RED.ADD.64, no return value
 }
 
 template <int K, int THREADS, int MINB, bool WEIGHTED>
@@ -378,14 +303,13 @@ gls_strip_kernel(const GlsMainArgs a) {
   double gB = (double)(a.j0 + jB) * cvp->gamma;  // phase origin of the block's first frequency (turns)
   gB -= floor(gB);
 
-  double* pbase = a.partial + (long long)split * 6 * a.nf_tot + (long long)curve * a.nf + jB + lK;
+  unsigned long long* pbase = a.partial + (long long)curve * a.nf + jB + lK;
   const long long jrem = a.nf - (jB + lK);  // strip entries with k < jrem are real frequencies
 
   if (threadIdx.x < 2) {
     s_ab[GLS_TILE + threadIdx.x] = make_double2(0.0, 0.0);
     s_r2[GLS_TILE + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  bool first = true;
   long long tile0 = sb;
   do {
     long long left = se - tile0;
@@ -515,35 +439,115 @@ gls_strip_kernel(const GlsMainArgs a) {
       else run_tile(std::false_type{});
     }
 
-    // flush this tile's FP32 sums into the FP64 partials this item owns
+    // flush this tile's FP32 sums into the fixed-point plane (RED.ADD.64: no load latency to wait for, and integer
+    // addition makes the total independent of the order in which splits and tiles arrive)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (k < jrem) {
-        double* p = pbase + k;
-        if (first) {
-          p[0] = (double)aC[k];
-          p[a.nf_tot] = (double)aS[k];
-          p[2 * a.nf_tot] = (double)aYC[k];
-          p[3 * a.nf_tot] = (double)aYS[k];
-          p[4 * a.nf_tot] = (double)aCC[k];
-          p[5 * a.nf_tot] = (double)aCS[k];
-        } else {
-          // RED.ADD.F64: no load latency to wait for.  Only this thread ever touches these
-          // addresses and its updates are issued in tile order, so the sum stays deterministic.
-          atomicAdd(p, (double)aC[k]);
-          atomicAdd(p + a.nf_tot, (double)aS[k]);
-          atomicAdd(p + 2 * a.nf_tot, (double)aYC[k]);
-          atomicAdd(p + 3 * a.nf_tot, (double)aYS[k]);
-          atomicAdd(p + 4 * a.nf_tot, (double)aCC[k]);
-          atomicAdd(p + 5 * a.nf_tot, (double)aCS[k]);
-        }
+        unsigned long long* p = pbase + k;
+        gls_flush(p, aC[k]);
+        gls_flush(p + a.nf_tot, aS[k]);
+        gls_flush(p + 2 * a.nf_tot, aYC[k]);
+        gls_flush(p + 3 * a.nf_tot, aYS[k]);
+        gls_flush(p + 4 * a.nf_tot, aCC[k]);
+        gls_flush(p + 5 * a.nf_tot, aCS[k]);
       }
     }
-    first = false;
     tile0 += GLS_TILE;
   } while (tile0 < se);
+}
 
-  gls_tail<K, THREADS>(a, curve, fb, jB);
+// ---------------------------------------------------------------------------
+// FP64 epilogue: spectral.py:113-132 per frequency + arg-max
+// ---------------------------------------------------------------------------
+struct GlsEpiArgs {
+  const GlsCurve* curves;
+  unsigned long long* partial;  // [6][nf_tot]; read and cleared
+  const double* lowsum;         // FP64 sums of the sub-cycle bins [chunk][6][B * low_cap]
+  int nlowchunk, low_cap, B;
+  unsigned flags;
+  long long nf, nf_tot, j0;
+  double* power_out;            // [B * nf] or NULL
+  double* red_val;              // [B * gridDim.x] per-block arg-max candidates
+  long long* red_idx;
+  unsigned* curve_done;         // [B] epilogue blocks of this curve that have finished (self-resetting)
+  long long* arg_out;           // [B] or NULL
+  double* max_out;              // [B] or NULL
+  pdc_fanout fan;               // fan.world == 0: no fan-out
+};
+
+__global__ void __launch_bounds__(256)
+gls_epilogue_kernel(const GlsEpiArgs a) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ int s_last;
+  const int curve = blockIdx.y;
+  const GlsCurve cv = a.curves[curve];
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double power = 0.0;
+  long long idx = -1;
+  if (j < a.nf) {
+    double sums[6];
+    double inv_n;
+    unsigned long long* p = a.partial + (long long)curve * a.nf + j;
+    unsigned long long raw[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) raw[q] = __ldcg(p + (long long)q * a.nf_tot);   // written with RED at L2
+#pragma unroll
+    for (int q = 0; q < 6; ++q) p[(long long)q * a.nf_tot] = 0ull;              // the plane is clean for the next call
+    if (j >= cv.low_begin && j < cv.low_begin + cv.low_count) {
+      // sub-cycle frequency: FP64 sums from gls_prep_kernel (already normalised)
+      const long long cols = (long long)a.B * a.low_cap;
+      const double* lp = a.lowsum + (long long)curve * a.low_cap + (j - cv.low_begin);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double acc = 0.0;
+        for (int c = 0; c < a.nlowchunk; ++c) acc += lp[((long long)c * 6 + q) * cols];
+        sums[q] = acc;
+      }
+      inv_n = 1.0;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) sums[q] = (double)(long long)raw[q] * (1.0 / (double)(1 << GLS_FIX_BITS));
+      inv_n = 1.0 / (double)cv.n;
+    }
+    power = gls_power_from_sums(sums, inv_n, a.flags, cv.yy, cv.psd_scale);
+    if (cv.bad) power = nan("");
+    if (a.power_out) a.power_out[(long long)curve * a.nf + j] = power;
+    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
+    for (int r = 0; r < a.fan.world; ++r) a.fan.power[r][a.j0 + j] = power;
+    idx = j;
+  }
+  block_argext<+1>(power, idx, sv, si);
+  const int nblk = gridDim.x;
+  if (threadIdx.x == 0) {
+    a.red_val[(long long)curve * nblk + blockIdx.x] = power;
+    a.red_idx[(long long)curve * nblk + blockIdx.x] = idx;
+    __threadfence();
+    s_last = atomicAdd(a.curve_done + curve, 1u) == (unsigned)(nblk - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // the last block of this curve: final (max, argmax); NaN ignored, first occurrence (np.nanargmax, core.py:202-205)
+  if (threadIdx.x == 0) a.curve_done[curve] = 0u;
+  __threadfence();
+  double best = 0.0;
+  long long bidx = -1;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+    const double v = __ldcg(a.red_val + (long long)curve * nblk + k);
+    const long long i = __ldcg(a.red_idx + (long long)curve * nblk + k);
+    if (better<+1>(v, i, best, bidx)) { best = v; bidx = i; }
+  }
+  block_argext<+1>(best, bidx, sv, si);
+  if (threadIdx.x == 0) {
+    const double val = bidx >= 0 ? best : nan("");
+    if (a.arg_out) a.arg_out[curve] = bidx;
+    if (a.max_out) a.max_out[curve] = val;
+    for (int r = 0; r < a.fan.world; ++r) {   // slot `rank` of every rank's candidate table: (max, GLOBAL argmax)
+      a.fan.best[r][2 * a.fan.rank] = val;
+      a.fan.best[r][2 * a.fan.rank + 1] = bidx >= 0 ? (double)(bidx + a.j0) : -1.0;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -620,9 +624,10 @@ static int choose_nsplit(long long base_items, long long nmax, long long residen
   long long cap = nmax / min_samples;
   if (cap < 1) cap = 1;
   if (cap > 4096) cap = 4096;
-  // every split owns one FP64 plane of partial sums: keep the scratch below 2 GiB
-  const long long mem_cap = ((long long)2 << 30) / (plane_bytes > 0 ? plane_bytes : 1);
-  if (cap > mem_cap) cap = mem_cap < 1 ? 1 : mem_cap;
+  if (plane_bytes > 0) {   // a caller whose splits own one plane of partial sums each: keep the scratch below 2 GiB
+    const long long mem_cap = ((long long)2 << 30) / plane_bytes;
+    if (cap > mem_cap) cap = mem_cap < 1 ? 1 : mem_cap;
+  }
   double best = 1e300;
   int best_s = 1;
   for (long long s = 1; s <= cap; ++s) {
@@ -677,7 +682,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   (void)MINB;
   if (ctx->gls_occ[geom][w != nullptr] == 0) ctx->gls_occ[geom][w != nullptr] = strip_occupancy(geom, w != nullptr);
   const long long resident = (long long)ctx->sm_count * ctx->gls_occ[geom][w != nullptr];
-  int nsplit = choose_nsplit((long long)B * nfb, nmax, resident, (long long)sizeof(double) * 6 * nf_tot,
+  int nsplit = choose_nsplit((long long)B * nfb, nmax, resident, 0 /* splits share one plane: no memory cost */,
                              geom == 1 ? 96 : 256);
   if (ctx->gls_nsplit_override > 0) nsplit = ctx->gls_nsplit_override;  // tuning aid (env PDC_GLS_NSPLIT)
   const long long items = (long long)B * nfb * nsplit;
@@ -701,13 +706,24 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   PDC_TRY(ctx->gls_curves.reserve(sizeof(GlsCurve) * B));
   PDC_TRY(ctx->gls_rec1.reserve(sizeof(double2) * ntot));
   PDC_TRY(ctx->gls_rec2.reserve(sizeof(float4) * ntot));
-  PDC_TRY(ctx->partial.reserve(sizeof(double) * 6 * nf_tot * nsplit));
-  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)nfb * B));
+  // ONE fixed-point plane of partial sums for all sample splits; the epilogue leaves it cleared, so it is zeroed only
+  // when it is (re)allocated or when a previous call failed between the strip kernel and the epilogue
+  {
+    const void* before = ctx->gls_plane.p;
+    const size_t cap_before = ctx->gls_plane.cap;
+    PDC_TRY(ctx->gls_plane.reserve(sizeof(unsigned long long) * 6 * (size_t)nf_tot));
+    if (ctx->gls_plane.p != before || ctx->gls_plane.cap != cap_before || ctx->gls_plane_dirty) {
+      PDC_CUDA(cudaMemsetAsync(ctx->gls_plane.p, 0, ctx->gls_plane.cap, st));
+      ctx->gls_plane_dirty = false;
+    }
+  }
+  const int eblk = (int)((nf + 255) / 256);
+  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk * B));
   PDC_TRY(ctx->gls_low.reserve(sizeof(double) * 6 * (size_t)nlowchunk * B * low_cap));
   // completion counters (stats blocks per curve, sample splits per frequency block, frequency blocks per curve):
   // zeroed when the buffer is (re)allocated, every kernel leaves them at zero again
   {
-    const size_t need = sizeof(unsigned) * ((size_t)2 * B + (size_t)B * nfb);
+    const size_t need = sizeof(unsigned) * ((size_t)2 * B);
     const void* before = ctx->gls_cnt.p;
     const size_t cap_before = ctx->gls_cnt.cap;
     PDC_TRY(ctx->gls_cnt.reserve(need));
@@ -716,7 +732,6 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   }
   unsigned* cnt_stats = ctx->gls_cnt.as<unsigned>();
   unsigned* cnt_curve = cnt_stats + B;
-  unsigned* cnt_blk = cnt_curve + B;
 
   GlsCurve* dc = ctx->gls_curves.as<GlsCurve>();
   const long long off0 = offsets_host[0];
@@ -781,30 +796,44 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   a.curves = dc;
   a.rec1 = ctx->gls_rec1.as<double2>();
   a.rec2 = ctx->gls_rec2.as<float4>();
-  a.partial = ctx->partial.as<double>();
+  a.partial = ctx->gls_plane.as<unsigned long long>();
   a.nf = nf;
   a.nf_tot = nf_tot;
   a.j0 = j0;
   a.nfb = (int)nfb;
   a.nsplit = nsplit;
-  a.lowsum = ctx->gls_low.as<double>();
-  a.nlowchunk = (int)nlowchunk;
-  a.low_cap = (int)low_cap;
-  a.B = (int)B;
-  a.flags = flags;
-  a.blk_done = cnt_blk;
-  a.curve_done = cnt_curve;
-  a.power_out = power_out;
-  a.red_val = ctx->blockred.as<double>();
-  a.red_idx = reinterpret_cast<long long*>(a.red_val + (size_t)nfb * B);
-  a.arg_out = (long long*)argmax_out;
-  a.max_out = max_out;
-  if (fanout) a.fan = *fanout;
-  else memset(&a.fan, 0, sizeof(a.fan));
 
+  ctx->gls_plane_dirty = true;   // until the epilogue that clears the plane has been enqueued
   PDC_TRY(ctx->main_begin(st));
   PDC_TRY(launch_strip(geom, ctx, a, w != nullptr, items, st));
   PDC_TRY(ctx->main_end(st));
+
+  {
+    GlsEpiArgs e;
+    e.curves = dc;
+    e.partial = a.partial;
+    e.lowsum = ctx->gls_low.as<double>();
+    e.nlowchunk = (int)nlowchunk;
+    e.low_cap = (int)low_cap;
+    e.B = (int)B;
+    e.flags = flags;
+    e.nf = nf;
+    e.nf_tot = nf_tot;
+    e.j0 = j0;
+    e.power_out = power_out;
+    e.red_val = ctx->blockred.as<double>();
+    e.red_idx = reinterpret_cast<long long*>(e.red_val + (size_t)eblk * B);
+    e.curve_done = cnt_curve;
+    e.arg_out = (long long*)argmax_out;
+    e.max_out = max_out;
+    if (fanout) e.fan = *fanout;
+    else memset(&e.fan, 0, sizeof(e.fan));
+    dim3 grid((unsigned)eblk, (unsigned)B);
+    gls_epilogue_kernel<<<grid, 256, 0, st>>>(e);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    ctx->gls_plane_dirty = false;
+  }
   PDC_TRY(scratch.release());
   return PDC_OK;
 }

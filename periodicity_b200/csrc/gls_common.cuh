@@ -17,7 +17,8 @@ struct GlsCurve {
   // per-sample step angles 2 pi (df (t - tmin) + gamma) on a quarter turn; three_term == 0 when the step
   // angles span too much of the circle and the strip kernel has to use the plain rotation.
   double gamma;
-  int three_term, pad_;
+  int three_term;
+  int bad;       // some t, y or w of the curve is NaN / inf: every power of the curve is NaN (gls.cu)
 };
 
 // Order of (cos, sin, y', w') inside the float4 sample record.  The record is loaded with one

@@ -77,8 +77,11 @@ struct Worker {
 };
 
 struct MultiState {
-  std::vector<pdc_ctx*> devs;      // devs[0] is the owning (primary) ctx itself; devs[1..] are children
-  std::vector<Worker*> workers;    // workers[d - 1] serves devs[d]
+  // One ordinary single-device ctx per entry of device_ids.  devs[0] is a child too (NOT the owning ctx: the owner's
+  // `multi` pointer is what routes a host call here, a child must take the single-device path); its piece of the work
+  // runs on the calling thread.
+  std::vector<pdc_ctx*> devs;
+  std::vector<Worker*> workers;    // workers[d - 1] serves devs[d], d >= 1
   long long min_evals_per_device = 500000000LL;  // env PDC_MULTI_MIN_EVALS: below this much work per device, use fewer devices
 };
 
@@ -94,7 +97,7 @@ void multi_destroy(pdc_ctx* ctx) {
     if (w->th.joinable()) w->th.join();
     delete w;
   }
-  for (size_t d = 1; d < m->devs.size(); ++d) pdc_ctx_destroy(m->devs[d]);
+  for (size_t d = 0; d < m->devs.size(); ++d) pdc_ctx_destroy(m->devs[d]);
   delete m;
   ctx->multi = nullptr;
 }
@@ -269,13 +272,13 @@ int pdc_ctx_create_multi(pdc_ctx** out, const int* device_ids, int ndev) {
   MultiState* m = new (std::nothrow) MultiState();
   if (!m) { pdc_ctx_destroy(primary); set_error("pdc_ctx_create_multi: out of host memory"); return PDC_ENOMEM; }
   if (const char* g = getenv("PDC_MULTI_MIN_EVALS")) m->min_evals_per_device = atoll(g) > 0 ? atoll(g) : 1;
-  m->devs.push_back(primary);
   primary->multi = m;
-  for (int d = 1; d < ndev; ++d) {
+  for (int d = 0; d < ndev; ++d) {
     pdc_ctx* child = nullptr;
     int rc = pdc_ctx_create(&child, device_ids[d]);
     if (rc != PDC_OK) { pdc_ctx_destroy(primary); return rc; }   // destroys the children created so far too
     m->devs.push_back(child);
+    if (d == 0) continue;   // the first device's piece runs on the calling thread
     Worker* w = new (std::nothrow) Worker();
     if (!w) { pdc_ctx_destroy(primary); set_error("pdc_ctx_create_multi: out of host memory"); return PDC_ENOMEM; }
     w->ctx = child;

@@ -100,7 +100,12 @@ struct pdc_ctx {
   int glsm_occ[2] = {0, 0};    // cached blocks/SM of glsm_strip_kernel [weighted]
   pdc::DevBuf gls_low;         // float64 sums of the sub-cycle frequencies [chunk][6][B*low_cap]
   pdc::DevBuf gls_cnt;         // completion counters of the last-block-done reductions (gls.cu), self-resetting
-  pdc::DevBuf partial;         // float64 partial sums [nsplit][rows][units]
+  pdc::DevBuf partial;         // glsm.cu: float64 partial sums [nsplit][rows][units]; strlen.cu: sort scratch
+  // Planes of partial sums shared by ALL sample splits of a call: gls.cu 64-bit fixed point [6][B*nf]; pdm.cu counts +
+  // 64-bit fixed-point sums [m0][np]; ce.cu counts [cells][np].  The epilogue that reads a plane clears it, so a plane
+  // is all zeros between calls; it is memset only when (re)allocated or when a call failed before its epilogue.
+  pdc::DevBuf gls_plane, hist_plane;
+  bool gls_plane_dirty = false, hist_plane_dirty = false;
   pdc::DevBuf blockred;        // per-block (value, index) candidates
   pdc::PinnedBuf pin_meta;     // host staging for per-curve metadata
 
@@ -172,6 +177,9 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
 int multi_period_grid(pdc_ctx* ctx, int64_t n, const double* periods, int64_t np, int sign, double* out,
                       int64_t* arg_out, double* best_out,
                       const std::function<int(pdc_ctx*, const double*, int64_t, double*, int64_t*, double*)>& call);
+
+int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np, int nphi,
+           int nm, double* h_out, int64_t* argmin_out, double* min_out, cudaStream_t stream);
 
 int strlen_run(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const double* periods, int64_t np,
                double* ell_out, int64_t* argmin_out, double* min_out, cudaStream_t stream);

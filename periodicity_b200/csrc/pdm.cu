@@ -45,15 +45,17 @@
 //
 // Kernels (two launches per call since round 2, seven in round 1):
 //   pdm_stats_kernel  mean, 1/std, packing exponent in one pass; multi-block partials, the last block finalises
-//   pdm_hist_kernel   the hot kernel; x' is formed while a tile is staged (no centring pass), and its TAIL is the
-//                     epilogue: the last sample split to finish a block of 256 trial periods merges the splits'
-//                     FP64 planes in a fixed order, evaluates theta (phase.py:145-149) in FP64, stores it (to every
-//                     rank's buffer in the fan-out variant) and the block's arg-min; the last period block of the
-//                     call reduces those to the (min, argmin) of the call.
+//   pdm_hist_kernel   the hot kernel; x' is formed while a tile is staged (no centring pass); every 8192 samples a
+//                     thread adds its columns to ONE count plane (RED.ADD.32) and ONE 64-bit fixed-point sum plane
+//                     (RED.ADD.64) shared by all sample splits -- integer addition is associative, so the totals do
+//                     not depend on arrival order, and round 1's nine FP64 planes (288 MB on C3) shrink to 24 MB
+//   pdm_epilogue_kernel  FP64 theta (phase.py:145-149) per trial period, clears the planes for the next call, stores
+//                     theta (to every rank's buffer in the fan-out variant), arg-min; the last block finalises.
 #include <cstring>
 #include <type_traits>
 
 #include "pdc_common.cuh"
+#include "phase_common.cuh"
 
 namespace pdc {
 
@@ -213,204 +215,12 @@ struct PdmArgs {
   const double* x;      // raw values: x' = (x - mean) / std is formed while a tile is staged (no separate pass, no copy)
   const double* periods;
   const PdmMeta* meta;
-  double* partial;  // [nsplit][2*m0][np]  rows: count per fine bin, then sum x' per fine bin
+  unsigned* cnt_plane;           // [m0][np]  samples per fine bin, all sample splits add into it (RED.ADD.32)
+  unsigned long long* sum_plane; // [m0][np]  sum x' per fine bin as 64-bit fixed point, 32 fraction bits (RED.ADD.64)
   long long n, np;
   int m0, nsplit;
   int allow_packed;     // 0: keep the float2 columns whatever the curve (AoV: its ratio of sums needs their accuracy)
-  // ---- tail (epilogue) ----
-  int nc, statistic, npb;   // covers, PDC_STAT_*, period blocks
-  unsigned* blk_done;       // [npb] sample splits that have finished this period block (self-resetting)
-  unsigned* call_done;      // [1]   period blocks whose epilogue has run (self-resetting)
-  double* theta_out;        // [np] or NULL
-  double* red_val;          // [npb] per-block arg-extremum candidates
-  long long* red_idx;
-  long long* arg_out;       // or NULL
-  double* best_out;         // or NULL
-  pdc_fanout fan;           // fan.world == 0: no fan-out
-  long long fan_offset;
 };
-
-// Fine-bin index of one sample for trial period P (rP = 1/P), plus an "ambiguity key":
-// key < PDM_AMBIG means phi*m0 is within 2^-20 of an integer and the bin has to be decided
-// against the reference's own thresholds (pdm_fix_bin).
-constexpr unsigned PDM_AMBIG = 2u << 12;
-
-__device__ __forceinline__ int pdm_bin(double tv, double P, double rP, double m0d, double& phi, unsigned& key) {
-  // correctly rounded t / P: q0 = t * (1/P), exact FMA residual, one correction (phase.py:131)
-  const double q0 = __dmul_rn(tv, rP);
-  const double r = __fma_rn(-q0, P, tv);
-  const double q1 = __fma_rn(r, rP, q0);
-  phi = __dadd_rn(q1, -floor(q1));                 // exact; == np.remainder(q1, 1)
-  // phi * m0 + 1.5 * 2^32 in ONE rounding: ulp = 2^-20, low word = rint(phi * m0 * 2^20)
-  const double v = __fma_rn(phi, m0d, 6442450944.0);
-  const int lo = __double2loint(v);
-  key = (unsigned)(lo + 1) << 12;                  // fraction bits of u (+1 ulp), top-aligned
-  return lo >> 20;                                 // floor(u) unless ambiguous
-}
-
-__device__ __forceinline__ int pdm_fix_bin(int k, double phi, const double* s_thr, int m0) {
-  k = k < 0 ? 0 : (k > m0 - 1 ? m0 - 1 : k);
-  if (phi < s_thr[k]) --k;
-  else if (k < m0 - 1 && phi >= s_thr[k + 1]) ++k;
-  return k;
-}
-
-// Fast path: |t / P| < 2^19 for every sample.  fma(t, 1/P, 1.5 * 2^20) leaves frac(t / P) in units of 2^-32
-// turn in the low mantissa word (one DFMA, as in the GLS seed), a 32 x 32 -> 64 bit multiply by m0
-// then gives the fine bin (high word) and the position inside the bin (low word).  The fixed-point
-// phase is within 2^-32 + |t/P| 2^-52 of the reference's (t / P) % 1, so the bin can differ only
-// if the phase lies within PDM_FAST_GUARD * 2^-32 of a bin edge: those samples (about m0 * 4e-9 of
-// them) are re-binned by the exact path below.
-constexpr double PDM_FAST_MAGIC = 1572864.0;   // 1.5 * 2^20
-constexpr double PDM_FAST_LIMIT = 262144.0;    // |t / P| < 2^18 keeps the sum inside [2^20, 2^21)
-constexpr unsigned PDM_FAST_GUARD = 4u;
-
-__device__ __forceinline__ unsigned pdm_bin_fast(double tv, double rP, unsigned m0u, unsigned guard, unsigned& edge) {
-  const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, PDM_FAST_MAGIC));
-  const unsigned long long w = (unsigned long long)u * m0u;
-  edge = ((unsigned)w + guard) < 2u * guard ? 1u : 0u;   // within guard of either edge of the bin
-  return (unsigned)(w >> 32);
-}
-
-// Same with the guard folded into the magic constant: the phase is shifted up by PDM_FAST_GUARD units of
-// 2^-32 turn (exact: ulp of the sum is 2^-32), so `pos` = position inside the bin + guard, and
-// pos < 2 guard  <=>  the unshifted phase is within guard of a bin edge (then the bin index may be off by
-// one and the caller re-bins exactly); otherwise the shift cannot have carried into the bin index.
-constexpr double PDM_FAST_MAGIC_G = PDM_FAST_MAGIC + PDM_FAST_GUARD * (1.0 / 4294967296.0);
-__device__ __forceinline__ unsigned pdm_bin_fast_g(double tv, double rP, unsigned m0u, unsigned& pos) {
-  const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, PDM_FAST_MAGIC_G));
-  const unsigned long long w = (unsigned long long)u * m0u;
-  pos = (unsigned)w;
-  return (unsigned)(w >> 32);
-}
-
-template <int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (N > 0) {
-    static_for<N - 1>(f);
-    f(std::integral_constant<int, N - 1>{});
-  }
-}
-
-// Tail of pdm_hist_kernel, run by the LAST sample split to finish period block `pb`: folds the splits' FP64 planes
-// into plane 0 in split order (fixed, whatever block happens to be last: bit-reproducible), evaluates the statistic
-// per trial period in FP64, stores it and reduces the arg-extremum.
-//   PDC_STAT_PDM  theta of phase.py:145-149 (smaller is better)
-//   PDC_STAT_AOV  the analysis-of-variance statistic of Schwarzenberg-Czerny (1989) -- a TODO of the reference
-//                 (phase.py:11) -- from the same fine-bin histograms with nc = 1: Theta = [(N - r) / (r - 1)] * s1 / s2
-//                 over the r populated bins, s1 = sum_b n_b (mean_b - mean)^2 (between bins), s2 = sum_b sum_i
-//                 (x_i - mean_b)^2 (within bins); larger is better.
-template <int THREADS, int PPT>
-__device__ __forceinline__ void pdm_tail(const PdmArgs& a, long long pb, const long long* pis, const bool* valids) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  __shared__ int s_flag;
-  __threadfence();   // this block's partial stores / RED.ADDs are visible device-wide before it is counted
-  __syncthreads();
-  if (threadIdx.x == 0) s_flag = atomicAdd(a.blk_done + pb, 1u) == (unsigned)(a.nsplit - 1);
-  __syncthreads();
-  if (!s_flag) return;
-  if (threadIdx.x == 0) a.blk_done[pb] = 0u;
-  __threadfence();
-  const int m0 = a.m0, nc = a.nc;
-  const long long np = a.np, rows = 2LL * m0;
-  const bool aov = a.statistic == PDC_STAT_AOV;
-  const double q_binned = a.meta->q_binned;
-  double best = 0.0;
-  long long bidx = -1;
-#pragma unroll 1
-  for (int s = 0; s < PPT; ++s) {
-    if (!valids[s]) continue;
-    const long long pi = pis[s];
-    double* base = a.partial + pi;
-    if (a.nsplit > 1) {   // fold the sample splits into split 0 (this thread's own column only)
-      for (long long b = 0; b < rows; ++b) {
-        double acc = 0.0;
-        for (int sp = 0; sp < a.nsplit; ++sp) acc += __ldcg(base + ((long long)sp * rows + b) * np);
-        base[b * np] = acc;
-      }
-    }
-    const double* pn = base;
-    const double* p1 = base + (long long)m0 * np;
-    const double P = a.periods[pi];
-    double theta;
-    if (aov) {
-      double sq = 0.0, ntot = 0.0, stot = 0.0;
-      int r = 0;
-      for (int k = 0; k < m0; ++k) {
-        const double N = __ldcg(pn + (long long)k * np), S = __ldcg(p1 + (long long)k * np);
-        if (N >= 1.0) {
-          sq += S * S / N;
-          ntot += N;
-          stot += S;
-          ++r;
-        }
-      }
-      const double s1 = sq - stot * stot / ntot;   // between the bins, about the mean of the binned samples
-      const double s2 = q_binned - sq;             // within the bins
-      theta = ((ntot - (double)r) / (double)(r - 1)) * (s1 / s2);
-      // fewer than two populated bins (r - 1 == 0) or no scatter inside the bins: 0/0-like, the same NaN class as
-      // PDM's "every bin dropped" below -- never +-inf from FP32 accumulation residue
-      if (r < 2 || !(s2 > 0.0)) theta = nan("");
-      if (!isfinite(P) || !isfinite(1.0 / P)) theta = nan("");  // no phases: period 0, denormal, inf or NaN
-    } else {
-      double sq = 0.0, den = 0.0;
-      for (int k = 0; k < m0; ++k) {
-        double N = 0.0, S = 0.0;
-        for (int c = 0; c < nc; ++c) {
-          int q = k + c;
-          if (q >= m0) q -= m0;
-          N += __ldcg(pn + (long long)q * np);
-          S += __ldcg(p1 + (long long)q * np);
-        }
-        if (N >= 1.0) sq += S * S / N;
-        if (N > 1.0) den += N - 1.0;  // phase.py:142,147: bins with <= 1 sample are dropped
-      }
-      // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
-      theta = ((double)nc * q_binned - sq) / den;
-      // every coarse bin holds <= 1 sample: the reference divides 0.0 by 0.0 (phase.py:145-147 with an empty `mj`)
-      // and gets NaN, which its nan-aware reductions skip; the FP32 residue of the numerator must not turn it into +-inf
-      if (!(den > 0.0)) theta = nan("");
-      if (isinf(P)) theta = 1.0;  // every phase is 0: one populated fine bin holding all samples
-      else if (!isfinite(1.0 / P) || P != P) theta = nan("");  // period 0, denormal or NaN: phases are inf / NaN
-    }
-    if (a.theta_out) a.theta_out[pi] = theta;
-    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
-    for (int rk = 0; rk < a.fan.world; ++rk) a.fan.power[rk][a.fan_offset + pi] = theta;
-    if (aov ? better<+1>(theta, pi, best, bidx) : better<-1>(theta, pi, best, bidx)) { best = theta; bidx = pi; }
-  }
-  if (aov) block_argext<+1>(best, bidx, sv, si);
-  else block_argext<-1>(best, bidx, sv, si);
-  if (threadIdx.x == 0) {
-    a.red_val[pb] = best;
-    a.red_idx[pb] = bidx;
-    __threadfence();
-    s_flag = atomicAdd(a.call_done, 1u) == (unsigned)(a.npb - 1);
-  }
-  __syncthreads();
-  if (!s_flag) return;
-  // the last period block of the call: final arg-extremum; NaN ignored, first occurrence (np.nanargmin / nanargmax)
-  if (threadIdx.x == 0) *a.call_done = 0u;
-  __threadfence();
-  best = 0.0;
-  bidx = -1;
-  for (int k = threadIdx.x; k < a.npb; k += THREADS) {
-    const double v = __ldcg(a.red_val + k);
-    const long long i = __ldcg(a.red_idx + k);
-    if (aov ? better<+1>(v, i, best, bidx) : better<-1>(v, i, best, bidx)) { best = v; bidx = i; }
-  }
-  if (aov) block_argext<+1>(best, bidx, sv, si);
-  else block_argext<-1>(best, bidx, sv, si);
-  if (threadIdx.x == 0) {
-    const double val = bidx >= 0 ? best : nan("");
-    if (a.arg_out) *a.arg_out = bidx;
-    if (a.best_out) *a.best_out = val;
-    for (int rk = 0; rk < a.fan.world; ++rk) {   // slot `rank` of every rank's candidate table: (best, GLOBAL index)
-      a.fan.best[rk][2 * a.fan.rank] = val;
-      a.fan.best[rk][2 * a.fan.rank + 1] = bidx >= 0 ? (double)(bidx + a.fan_offset) : -1.0;
-    }
-  }
-}
 
 // Shared-memory layout: hist[bin][VT] float2 = (count, sum x') and hist32[bin][VT] packed words, VT = THREADS * PPT
 // period columns per block: a column is private to one thread and conflict free (bank = column % 32).
@@ -444,7 +254,8 @@ pdm_hist_kernel(const PdmArgs a) {
     if (!isfinite(1.0 / P) || !isfinite(P)) P = 1.0;  // invalid trial period: theta is set to NaN by the epilogue
     Ps[s] = P;
     rPs[s] = 1.0 / P;
-    in_range = in_range && fabs(rPs[s]) * a.meta->t_absmax < PDM_FAST_LIMIT;
+    // (padding columns, P = 1, must not veto the block's fast path)
+    in_range = in_range && (!valids[s] || fabs(rPs[s]) * a.meta->t_absmax < PDM_FAST_LIMIT);
   }
   const bool clamp_bins = a.meta->bad != 0;        // block-uniform
   const double m0d = (double)m0;
@@ -465,9 +276,7 @@ pdm_hist_kernel(const PdmArgs a) {
   const bool fast = __syncthreads_and(in_range) != 0;
   const int pack_q = a.meta->pack_q;
   const bool packed = fast && !clamp_bins && pack_q >= 0 && a.allow_packed != 0;   // block-uniform
-#if PDM_L2_INT
-  const double unpack_d = packed ? 1.0 / (double)(1u << pack_q) : 0.0;
-#else
+#if !PDM_L2_INT
   const float unpack = packed ? 1.0f / (float)(1u << pack_q) : 0.f;
 #endif
   const unsigned* s_xq = reinterpret_cast<const unsigned*>(s_x);
@@ -809,7 +618,6 @@ pdm_hist_kernel(const PdmArgs a) {
     }
   };
 
-  bool first = true;
   int tiles_since_flush = 0;
   long long tile0 = sb;
   do {
@@ -857,49 +665,170 @@ pdm_hist_kernel(const PdmArgs a) {
     tile0 += PDM_TILE;
     ++tiles_since_flush;
     if (tiles_since_flush == PDM_FLUSH_TILES || tile0 >= se) {
-      // merge this thread's columns into the FP64 partials it owns ([stat][bin][period] rows)
+      // merge this thread's columns into the planes shared by all sample splits: counts as 32-bit, sums as 64-bit fixed
+      // point with 32 fraction bits.  Integer addition is associative, so the totals do not depend on the order in which
+      // splits and flushes arrive (bit-reproducible) and one plane serves all splits (|sum x'| < n by Cauchy-Schwarz with
+      // sum x'^2 = n - 1, so 2^32 n < 2^63 for any n this library can be given).
 #if PDM_L2_INT && PDM_PACK_ATOMIC
       __syncwarp();   // the second level was fed with atomics without return value
 #endif
-      const long long stat = (long long)m0 * a.np;
 #pragma unroll
       for (int s = 0; s < PPT; ++s) {
         if (!valids[s]) continue;
         const int column = s * THREADS + threadIdx.x;
         float2* col = hist + column;
-        double* pcol = a.partial + (long long)split * 2 * m0 * a.np + pis[s];
+        unsigned* gc = a.cnt_plane + pis[s];
+        unsigned long long* gs = a.sum_plane + pis[s];
         for (int b = 0; b < m0; ++b) {
-          double hn, hs;
+          unsigned hn;
+          long long hs;
 #if PDM_L2_INT
-          if (packed) {   // integer planes (exact): count, fixed-point sum
-            hn = (double)cnt2[b * VT + column];
-            hs = (double)sum2[b * VT + column] * unpack_d;
+          if (packed) {   // integer planes (exact): count, fixed-point sum with pack_q fraction bits
+            hn = cnt2[b * VT + column];
+            hs = (long long)sum2[b * VT + column] << (32 - pack_q);
             cnt2[b * VT + column] = 0u;
             sum2[b * VT + column] = 0;
           } else
 #endif
           {
             const float2 h = col[b * VT];
-            hn = (double)h.x;
-            hs = (double)h.y;
+            hn = (unsigned)h.x;                                   // an integer <= 8192 held exactly by the float
+            hs = __double2ll_rn((double)h.y * 4294967296.0);      // NaN -> 0x8000...: only with NaN values, where the epilogue writes NaN anyway
             col[b * VT] = make_float2(0.f, 0.f);
           }
-          double* g = pcol + (long long)b * a.np;
-          if (first) {
-            g[0] = hn;
-            g[stat] = hs;
-          } else {  // RED.ADD.F64: only this thread touches g; order is fixed
-            atomicAdd(g, hn);
-            atomicAdd(g + stat, hs);
-          }
+          if (hn) atomicAdd(gc + (long long)b * a.np, hn);
+          if (hs) atomicAdd(gs + (long long)b * a.np, (unsigned long long)hs);
         }
       }
-      first = false;
       tiles_since_flush = 0;
     }
   } while (tile0 < se);
+}
 
-  pdm_tail<THREADS, PPT>(a, pb, pis, valids);
+// FP64 epilogue, one thread per trial period: reads (and clears) the period's column of the count / sum planes,
+// evaluates the statistic, stores it (to every rank's buffer in the fan-out variant), per-block arg-extremum; the last
+// block reduces those to the call's (best, index).
+//   PDC_STAT_PDM  theta of phase.py:145-149 (smaller is better)
+//   PDC_STAT_AOV  the analysis-of-variance statistic of Schwarzenberg-Czerny (1989) -- a TODO of the reference
+//                 (phase.py:11) -- from the same fine-bin histograms with nc = 1: Theta = [(N - r) / (r - 1)] * s1 / s2
+//                 over the r populated bins, s1 = sum_b n_b (mean_b - mean)^2 (between bins), s2 = sum_b sum_i
+//                 (x_i - mean_b)^2 (within bins); larger is better.
+struct PdmEpiArgs {
+  unsigned* cnt_plane;
+  unsigned long long* sum_plane;
+  const double* periods;
+  const PdmMeta* meta;
+  int m0, nc;
+  long long np;
+  double* theta_out;        // [np] or NULL
+  double* red_val;          // [gridDim.x] per-block candidates
+  long long* red_idx;
+  unsigned* call_done;      // [1] epilogue blocks that have finished (self-resetting)
+  long long* arg_out;       // or NULL
+  double* best_out;         // or NULL
+  pdc_fanout fan;           // fan.world == 0: no fan-out
+  long long fan_offset;
+};
+
+template <int STAT>
+__global__ void __launch_bounds__(256)
+pdm_epilogue_kernel(const PdmEpiArgs a) {
+  constexpr int SIGN = STAT == PDC_STAT_AOV ? +1 : -1;
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ int s_last;
+  const long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m0 = a.m0, nc = a.nc;
+  const long long np = a.np;
+  double theta = 0.0;
+  long long idx = -1;
+  if (pi < np) {
+    unsigned* pn = a.cnt_plane + pi;
+    unsigned long long* p1 = a.sum_plane + pi;
+    const double P = a.periods[pi];
+    const double q_binned = a.meta->q_binned;
+    auto cnt_of = [&](int k) { return (double)__ldcg(pn + (long long)k * np); };
+    auto sum_of = [&](int k) { return (double)(long long)__ldcg(p1 + (long long)k * np) * (1.0 / 4294967296.0); };
+    if (STAT == PDC_STAT_AOV) {
+      double sq = 0.0, ntot = 0.0, stot = 0.0;
+      int r = 0;
+      for (int k = 0; k < m0; ++k) {
+        const double N = cnt_of(k), S = sum_of(k);
+        if (N >= 1.0) {
+          sq += S * S / N;
+          ntot += N;
+          stot += S;
+          ++r;
+        }
+      }
+      const double s1 = sq - stot * stot / ntot;   // between the bins, about the mean of the binned samples
+      const double s2 = q_binned - sq;             // within the bins
+      theta = ((ntot - (double)r) / (double)(r - 1)) * (s1 / s2);
+      // fewer than two populated bins (r - 1 == 0) or no scatter inside the bins: 0/0-like, the same NaN class as
+      // PDM's "every bin dropped" below -- never +-inf from accumulation residue
+      if (r < 2 || !(s2 > 0.0)) theta = nan("");
+      if (!isfinite(P) || !isfinite(1.0 / P)) theta = nan("");  // no phases: period 0, denormal, inf or NaN
+    } else {
+      double sq = 0.0, den = 0.0;
+      for (int k = 0; k < m0; ++k) {
+        double N = 0.0, S = 0.0;
+        for (int c = 0; c < nc; ++c) {
+          int q = k + c;
+          if (q >= m0) q -= m0;
+          N += cnt_of(q);
+          S += sum_of(q);
+        }
+        if (N >= 1.0) sq += S * S / N;
+        if (N > 1.0) den += N - 1.0;  // phase.py:142,147: bins with <= 1 sample are dropped
+      }
+      // sum_k (n_k - 1) s_k^2 = nc (N - 1) - sum S_k^2 / n_k in units of sigma^2 (see file header)
+      theta = ((double)nc * q_binned - sq) / den;
+      // every coarse bin holds <= 1 sample: the reference divides 0.0 by 0.0 (phase.py:145-147 with an empty `mj`)
+      // and gets NaN, which its nan-aware reductions skip; accumulation residue in the numerator must not turn it into +-inf
+      if (!(den > 0.0)) theta = nan("");
+      if (isinf(P)) theta = 1.0;  // every phase is 0: one populated fine bin holding all samples
+      else if (!isfinite(1.0 / P) || P != P) theta = nan("");  // period 0, denormal or NaN: phases are inf / NaN
+    }
+    if (!(a.meta->inv_sd == a.meta->inv_sd)) theta = nan("");   // NaN values poison sigma^2 and hence every theta (phase.py:165)
+    for (int k = 0; k < m0; ++k) {                              // the planes are clean for the next call
+      pn[(long long)k * np] = 0u;
+      p1[(long long)k * np] = 0ull;
+    }
+    if (a.theta_out) a.theta_out[pi] = theta;
+    // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
+    for (int r = 0; r < a.fan.world; ++r) a.fan.power[r][a.fan_offset + pi] = theta;
+    idx = pi;
+  }
+  block_argext<SIGN>(theta, idx, sv, si);
+  const int nblk = gridDim.x;
+  if (threadIdx.x == 0) {
+    a.red_val[blockIdx.x] = theta;
+    a.red_idx[blockIdx.x] = idx;
+    __threadfence();
+    s_last = atomicAdd(a.call_done, 1u) == (unsigned)(nblk - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // the last block: final arg-extremum; NaN ignored, first occurrence (np.nanargmin / np.nanargmax, core.py:202-210)
+  if (threadIdx.x == 0) *a.call_done = 0u;
+  __threadfence();
+  double best = 0.0;
+  long long bidx = -1;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+    const double v = __ldcg(a.red_val + k);
+    const long long i = __ldcg(a.red_idx + k);
+    if (better<SIGN>(v, i, best, bidx)) { best = v; bidx = i; }
+  }
+  block_argext<SIGN>(best, bidx, sv, si);
+  if (threadIdx.x == 0) {
+    const double val = bidx >= 0 ? best : nan("");
+    if (a.arg_out) *a.arg_out = bidx;
+    if (a.best_out) *a.best_out = val;
+    for (int r = 0; r < a.fan.world; ++r) {   // slot `rank` of every rank's candidate table: (best, GLOBAL index)
+      a.fan.best[r][2 * a.fan.rank] = val;
+      a.fan.best[r][2 * a.fan.rank + 1] = bidx >= 0 ? (double)(bidx + a.fan_offset) : -1.0;
+    }
+  }
 }
 
 static size_t pdm_smem_bytes(int m0, int threads) {
@@ -967,9 +896,7 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     long long cap = n / 512;
     if (cap < 1) cap = 1;
     if (cap > 1024) cap = 1024;
-    const long long mem_cap = ((long long)2 << 30) / ((long long)sizeof(double) * 2 * m0 * np);
-    if (cap > mem_cap) cap = mem_cap < 1 ? 1 : mem_cap;
-    double best = 1e300;
+    double best = 1e300;   // (all splits share one pair of planes: no memory cost per split)
     for (long long s = 1; s <= cap; ++s) {
       long long items = npb * s;
       long long waves = (items + resident - 1) / resident;
@@ -984,21 +911,28 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   ScratchScope scratch(ctx, st);
   PDC_TRY(scratch.acquire());
   PDC_TRY(ctx->pdm_meta.reserve(sizeof(PdmMeta) + 16 + sizeof(PdmPart) * PDM_STATS_MAXBLK));
-  PDC_TRY(ctx->partial.reserve(sizeof(double) * 2 * m0 * (size_t)np * nsplit));
-  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)npb));
-  // completion counters (stats blocks, sample splits per period block, period blocks): zeroed when the buffer is
-  // (re)allocated, every kernel leaves them at zero again
+  // count plane (32-bit) + sum plane (64-bit fixed point) shared by all sample splits; the epilogue leaves them
+  // cleared, so they are zeroed only when (re)allocated or after a call that failed before its epilogue
+  const size_t plane_elems = (size_t)m0 * np;
   {
-    const size_t need = sizeof(unsigned) * (2 + (size_t)npb);
+    const void* before = ctx->hist_plane.p;
+    const size_t cap_before = ctx->hist_plane.cap;
+    PDC_TRY(ctx->hist_plane.reserve((sizeof(unsigned long long) + sizeof(unsigned)) * plane_elems));
+    if (ctx->hist_plane.p != before || ctx->hist_plane.cap != cap_before || ctx->hist_plane_dirty) {
+      PDC_CUDA(cudaMemsetAsync(ctx->hist_plane.p, 0, ctx->hist_plane.cap, st));
+      ctx->hist_plane_dirty = false;
+    }
+  }
+  const int eblk = (int)((np + 255) / 256);
+  PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk));
+  // completion counters (stats blocks, epilogue blocks): zeroed when allocated, every kernel leaves them at zero again
+  {
     const void* before = ctx->pdm_cnt.p;
-    const size_t cap_before = ctx->pdm_cnt.cap;
-    PDC_TRY(ctx->pdm_cnt.reserve(need));
-    if (ctx->pdm_cnt.p != before || ctx->pdm_cnt.cap != cap_before)
-      PDC_CUDA(cudaMemsetAsync(ctx->pdm_cnt.p, 0, ctx->pdm_cnt.cap, st));
+    PDC_TRY(ctx->pdm_cnt.reserve(sizeof(unsigned) * 4));
+    if (ctx->pdm_cnt.p != before) PDC_CUDA(cudaMemsetAsync(ctx->pdm_cnt.p, 0, ctx->pdm_cnt.cap, st));
   }
   unsigned* cnt_stats = ctx->pdm_cnt.as<unsigned>();
   unsigned* cnt_call = cnt_stats + 1;
-  unsigned* cnt_blk = cnt_stats + 2;
 
   PdmMeta* meta = ctx->pdm_meta.as<PdmMeta>();
   {
@@ -1015,26 +949,15 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
   a.x = x;
   a.periods = periods;
   a.meta = meta;
-  a.partial = ctx->partial.as<double>();
+  a.sum_plane = ctx->hist_plane.as<unsigned long long>();
+  a.cnt_plane = reinterpret_cast<unsigned*>(a.sum_plane + plane_elems);
   a.n = n;
   a.np = np;
   a.m0 = m0;
   a.nsplit = nsplit;
   a.allow_packed = statistic == PDC_STAT_PDM ? 1 : 0;
-  a.nc = nc;
-  a.statistic = statistic;
-  a.npb = (int)npb;
-  a.blk_done = cnt_blk;
-  a.call_done = cnt_call;
-  a.theta_out = theta_out;
-  a.red_val = ctx->blockred.as<double>();
-  a.red_idx = reinterpret_cast<long long*>(a.red_val + npb);
-  a.arg_out = (long long*)argmin_out;
-  a.best_out = min_out;
-  if (fanout) a.fan = *fanout;
-  else memset(&a.fan, 0, sizeof(a.fan));
-  a.fan_offset = fan_offset;
 
+  ctx->hist_plane_dirty = true;   // until the epilogue that clears the planes has been enqueued
   PDC_TRY(ctx->main_begin(st));
   switch (vt * 8 + ppt) {
     case 256 * 8 + 1: PDC_TRY((pdm_launch<256, 1>(ctx, a, smem, blocks, st))); break;
@@ -1046,6 +969,29 @@ int pdm_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const dou
     default: PDC_TRY((pdm_launch<32, 1>(ctx, a, smem, blocks, st))); break;
   }
   PDC_TRY(ctx->main_end(st));
+
+  PdmEpiArgs e;
+  e.cnt_plane = a.cnt_plane;
+  e.sum_plane = a.sum_plane;
+  e.periods = periods;
+  e.meta = meta;
+  e.m0 = m0;
+  e.nc = nc;
+  e.np = np;
+  e.theta_out = theta_out;
+  e.red_val = ctx->blockred.as<double>();
+  e.red_idx = reinterpret_cast<long long*>(e.red_val + eblk);
+  e.call_done = cnt_call;
+  e.arg_out = (long long*)argmin_out;
+  e.best_out = min_out;
+  if (fanout) e.fan = *fanout;
+  else memset(&e.fan, 0, sizeof(e.fan));
+  e.fan_offset = fan_offset;
+  if (statistic == PDC_STAT_AOV) pdm_epilogue_kernel<PDC_STAT_AOV><<<(unsigned)eblk, 256, 0, st>>>(e);
+  else pdm_epilogue_kernel<PDC_STAT_PDM><<<(unsigned)eblk, 256, 0, st>>>(e);
+  PDC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  ctx->hist_plane_dirty = false;
   PDC_TRY(scratch.release());
   return PDC_OK;
 }

@@ -1,0 +1,74 @@
+// Phase -> fine-bin helpers shared by the phase-histogram kernels (pdm.cu: PDM / AoV; ce.cu: conditional entropy).
+// Conventions of the reference: phi = (t / P) % 1 (phase.py:131), bin k = [k/m0, (k+1)/m0) against the very float64
+// thresholds k/m0 the reference compares with (phase.py:138-140).
+#pragma once
+
+#include <type_traits>
+
+#include "pdc_common.cuh"
+
+namespace pdc {
+
+// Fine-bin index of one sample for trial period P (rP = 1/P), plus an "ambiguity key":
+// key < PDM_AMBIG means phi*m0 is within 2^-20 of an integer and the bin has to be decided
+// against the reference's own thresholds (pdm_fix_bin).
+constexpr unsigned PDM_AMBIG = 2u << 12;
+
+__device__ __forceinline__ int pdm_bin(double tv, double P, double rP, double m0d, double& phi, unsigned& key) {
+  // correctly rounded t / P: q0 = t * (1/P), exact FMA residual, one correction (phase.py:131)
+  const double q0 = __dmul_rn(tv, rP);
+  const double r = __fma_rn(-q0, P, tv);
+  const double q1 = __fma_rn(r, rP, q0);
+  phi = __dadd_rn(q1, -floor(q1));                 // exact; == np.remainder(q1, 1)
+  // phi * m0 + 1.5 * 2^32 in ONE rounding: ulp = 2^-20, low word = rint(phi * m0 * 2^20)
+  const double v = __fma_rn(phi, m0d, 6442450944.0);
+  const int lo = __double2loint(v);
+  key = (unsigned)(lo + 1) << 12;                  // fraction bits of u (+1 ulp), top-aligned
+  return lo >> 20;                                 // floor(u) unless ambiguous
+}
+
+__device__ __forceinline__ int pdm_fix_bin(int k, double phi, const double* s_thr, int m0) {
+  k = k < 0 ? 0 : (k > m0 - 1 ? m0 - 1 : k);
+  if (phi < s_thr[k]) --k;
+  else if (k < m0 - 1 && phi >= s_thr[k + 1]) ++k;
+  return k;
+}
+
+// Fast path: |t / P| < 2^19 for every sample.  fma(t, 1/P, 1.5 * 2^20) leaves frac(t / P) in units of 2^-32
+// turn in the low mantissa word (one DFMA, as in the GLS seed), a 32 x 32 -> 64 bit multiply by m0
+// then gives the fine bin (high word) and the position inside the bin (low word).  The fixed-point
+// phase is within 2^-32 + |t/P| 2^-52 of the reference's (t / P) % 1, so the bin can differ only
+// if the phase lies within PDM_FAST_GUARD * 2^-32 of a bin edge: those samples (about m0 * 4e-9 of
+// them) are re-binned by the exact path below.
+constexpr double PDM_FAST_MAGIC = 1572864.0;   // 1.5 * 2^20
+constexpr double PDM_FAST_LIMIT = 262144.0;    // |t / P| < 2^18 keeps the sum inside [2^20, 2^21)
+constexpr unsigned PDM_FAST_GUARD = 4u;
+
+__device__ __forceinline__ unsigned pdm_bin_fast(double tv, double rP, unsigned m0u, unsigned guard, unsigned& edge) {
+  const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, PDM_FAST_MAGIC));
+  const unsigned long long w = (unsigned long long)u * m0u;
+  edge = ((unsigned)w + guard) < 2u * guard ? 1u : 0u;   // within guard of either edge of the bin
+  return (unsigned)(w >> 32);
+}
+
+// Same with the guard folded into the magic constant: the phase is shifted up by PDM_FAST_GUARD units of
+// 2^-32 turn (exact: ulp of the sum is 2^-32), so `pos` = position inside the bin + guard, and
+// pos < 2 guard  <=>  the unshifted phase is within guard of a bin edge (then the bin index may be off by
+// one and the caller re-bins exactly); otherwise the shift cannot have carried into the bin index.
+constexpr double PDM_FAST_MAGIC_G = PDM_FAST_MAGIC + PDM_FAST_GUARD * (1.0 / 4294967296.0);
+__device__ __forceinline__ unsigned pdm_bin_fast_g(double tv, double rP, unsigned m0u, unsigned& pos) {
+  const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, PDM_FAST_MAGIC_G));
+  const unsigned long long w = (unsigned long long)u * m0u;
+  pos = (unsigned)w;
+  return (unsigned)(w >> 32);
+}
+
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (N > 0) {
+    static_for<N - 1>(f);
+    f(std::integral_constant<int, N - 1>{});
+  }
+}
+
+}  // namespace pdc

@@ -115,6 +115,23 @@ def pdm_torch(t, x, periods, nb, nc, ctx=None):
     return theta, arg, mn
 
 
+def ce_torch(t, x, periods, nphi, nm, ctx=None):
+    """Conditional entropy for CUDA float64 tensors; returns (h[np], argmin[1] int64, min[1]) tensors."""
+    torch = _torch()
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise ValueError("t must be a contiguous CUDA float64 tensor")
+    ctx = ctx or _ffi.default_context(t.device.index)
+    x = x.contiguous()
+    periods = periods.contiguous()
+    h = torch.empty(periods.numel(), dtype=torch.float64, device=t.device)
+    arg = torch.empty(1, dtype=torch.int64, device=t.device)
+    mn = torch.empty(1, dtype=torch.float64, device=t.device)
+    stream = torch.cuda.current_stream(t.device).cuda_stream
+    ctx.ce_dev(t.data_ptr(), x.data_ptr(), t.numel(), periods.data_ptr(), periods.numel(), nphi, nm,
+               h.data_ptr(), arg.data_ptr(), mn.data_ptr(), stream)
+    return h, arg, mn
+
+
 def stringlength_torch(t, m, periods, ctx=None):
     """String length for CUDA float64 tensors; returns (ell[np], argmin[1] int64, min[1]) tensors."""
     torch = _torch()

@@ -13,7 +13,7 @@ import numpy as np
 from . import _ffi
 from .core import FSeries, TSeries
 
-__all__ = ["StringLength", "PDM", "AOV"]
+__all__ = ["StringLength", "PDM", "AOV", "CE", "ConditionalEntropy"]
 
 
 class StringLength(object):
@@ -206,3 +206,60 @@ class AOV(object):
         self.periods = np.linspace(p_min, p_max, n_periods)
         self.periodogram = FSeries(1 / self.periods, self._theta(self.periods))
         return self.periodogram
+
+
+class CE(object):
+    """Conditional-entropy periodogram (Graham et al. 2013).
+
+    The reference lists this method as a TODO (``phase.py:13``) and has no implementation; the class follows the
+    conventions of its ``PDM`` (``phase.py:75-195``): the same period-grid options with the same defaults
+    (``p_min = 2*median_dt``, ``p_max = oversample*baseline``, ``linspace`` in period), the same phase definition
+    ``(t / P) % 1`` (``phase.py:131``) and bin edges ``k / nb`` (``phase.py:138-140`` with ``nc = 1``), an ``FSeries``
+    over ``1/P`` as result.  Values are scaled to [0, 1] with their minimum and maximum and cut into ``nm`` equal
+    magnitude bins; the statistic is ``H(m | phi) = sum p(phi, m) ln(p(phi) / p(phi, m))`` over the occupied cells of
+    the ``nb x nm`` phase-magnitude histogram and the best period MINIMISES it.  It is evaluated on a B200 from
+    per-period count histograms in shared memory (``pdc_ce``).  ``cores`` is accepted and ignored.
+    """
+
+    def __init__(self, nb=10, nm=5, p_min=None, p_max=None, n_periods=1000, oversample=1, cores=None, *,
+                 device=None, devices=None):
+        self.nb = nb
+        self.nm = nm
+        self.p_min = p_min
+        self.p_max = p_max
+        self.n_periods = n_periods
+        self.oversample = oversample
+        self.cores = cores
+        # `devices=[0, 1, ...]`: one multi-device context (pdc_ctx_create_multi); `device` = a single ordinal
+        self.device = list(devices) if devices is not None else device
+
+    def _entropy(self, periods):
+        ctx = _ffi.default_context(self.device)
+        h, self.argmin_index, self.min_entropy = ctx.ce(self.t, self.x, periods, self.nb, self.nm)
+        return h
+
+    def _ce(self, period):
+        """The statistic for a single trial period."""
+        return float(self._entropy(np.array([period], dtype=np.float64))[0])
+
+    def __call__(self, signal):
+        """H_c(P) on ``linspace(p_min, p_max, n_periods)`` as an ``FSeries`` over ``1/P``;
+        sets ``signal, t, x, periods, periodogram``."""
+        if not isinstance(signal, TSeries):
+            signal = TSeries(values=signal)
+        self.signal = signal
+        self.t = signal.time
+        self.x = signal.values
+        t0 = signal.baseline
+        p_min = 2 * signal.median_dt if self.p_min is None else self.p_min
+        p_max = self.oversample * t0 if self.p_max is None else self.p_max
+        if self.n_periods is None:
+            n_periods = int((1 / p_min - 1 / p_max) * self.oversample * t0 + 1)
+        else:
+            n_periods = self.n_periods
+        self.periods = np.linspace(p_min, p_max, n_periods)
+        self.periodogram = FSeries(1 / self.periods, self._entropy(self.periods))
+        return self.periodogram
+
+
+ConditionalEntropy = CE

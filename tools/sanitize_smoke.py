@@ -27,6 +27,8 @@ tb = t.copy(); tb[5] = np.nan
 ctx.pdm(tb, y, P, 10, 2)                                        # guarded path
 ctx.pdm(t * 1e9, y, P, 10, 2)                                   # exact (large |t/P|) path
 ctx.aov(t, y, P, 10)                                            # AoV epilogue on the same histograms
+ctx.ce(t, y, P, 10, 5)                                          # conditional entropy: count histograms
+ctx.ce(tb, y, P, 10, 5)                                         # ... exact / guarded path
 m = (y - y.max()) / (2 * (y.max() - y.min())) + 0.25
 ctx.stringlength(t, m, P)                                       # shared-memory sort
 tt = np.sort(rng.uniform(0, 100, 20000)); mm = rng.uniform(-0.25, 0.25, 20000)
@@ -41,6 +43,7 @@ os.environ["PDC_MULTI_MIN_EVALS"] = "1"                          # read at ctx c
 mctx = _ffi.Context([0, 0, 0])                                   # multi-device ctx: three workers on one GPU
 mctx.gls(t, y, w, 0.5 * df, df, 5000)
 mctx.pdm(t, y, P, 10, 2)
+mctx.ce(t, y, P, 10, 5)
 mctx.gls_batch(t, y, None, off, np.full(3, 0.5 * df), np.full(3, df), 700)
 mctx.close()
 print("sanitize smoke done")
