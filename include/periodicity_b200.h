@@ -140,6 +140,23 @@ PDC_API int pdc_gls_dev(pdc_ctx* ctx, const double* t, const double* y, const do
                 double* power_out, int64_t* argmax_out, double* max_out, void* stream);
 
 /*
+ * GLS power at an ARBITRARY list of frequencies (non-uniform or user-supplied grids; the reference lists flexible
+ * grids among its TODOs, phase.py:11-15, and its GLS cannot offer them because `_trig_sum` is an FFT on a uniform
+ * grid, spectral.py:11-40).  Same formula and outputs as pdc_gls (spectral.py:113-132 with exact sums); every
+ * (sample, frequency) pair is seeded exactly, there is no recurrence along the frequency axis.
+ *
+ *   freqs       float64[nfreq]  frequencies in any order (host pointer in pdc_gls_freqs, device pointer in the _dev twin)
+ *   power_out   float64[nfreq]  in the order of `freqs`
+ *   argmax_out / max_out        index into `freqs` of the largest non-NaN power (first occurrence) and that power
+ */
+PDC_API int pdc_gls_freqs(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+                          const double* freqs, int64_t nfreq, unsigned flags, double psd_scale,
+                          double* power_out, int64_t* argmax_out, double* max_out);
+PDC_API int pdc_gls_freqs_dev(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+                              const double* freqs, int64_t nfreq, unsigned flags, double psd_scale,
+                              double* power_out, int64_t* argmax_out, double* max_out, void* stream);
+
+/*
  * Frequency-grid-sharded GLS with the all-gather FUSED into the epilogue: rank `rank` of `world`
  * evaluates frequencies [j0, j0 + nf) like pdc_gls_dev, and its epilogue kernel stores every power
  * value straight into ALL ranks' result buffers through NVLink peer mappings (one coalesced 8-byte

@@ -52,6 +52,12 @@ SIGNATURES = {
                                    ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                    ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gls_freqs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gls_freqs_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pdc_gls_dev_fanout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
@@ -228,6 +234,27 @@ class Context:
             _check(self._lib.pdc_gls(self._h, _ptr(t), _ptr(y), _ptr(w), t.size, float(fmin), float(df),
                                      int(j0), nf, flags, float(psd_scale if psd_scale is not None else 1.0),
                                      _ptr(power), ctypes.addressof(arg), ctypes.addressof(mx)))
+        return power, arg.value, mx.value
+
+    def gls_freqs(self, t, y, w, freqs, fit_mean=True, psd_scale=None):
+        """GLS power at an arbitrary list of frequencies (``pdc_gls_freqs``): (power, argmax, max)."""
+        t = _f64(t)
+        y = _f64(y)
+        freqs = _f64(freqs)
+        if t.ndim != 1 or t.shape != y.shape:
+            raise ValueError("Input arrays have incompatible lengths.")
+        if w is not None:
+            w = _f64(w)
+            if w.shape != t.shape:
+                raise ValueError("Input arrays have incompatible lengths.")
+        flags = (GLS_FIT_MEAN if fit_mean else 0) | (GLS_PSD if psd_scale is not None else 0)
+        power = np.empty(freqs.size, dtype=np.float64)
+        arg = ctypes.c_int64(-1)
+        mx = ctypes.c_double(float("nan"))
+        with self._lock:
+            _check(self._lib.pdc_gls_freqs(self._h, _ptr(t), _ptr(y), _ptr(w), t.size, _ptr(freqs), freqs.size, flags,
+                                           float(psd_scale if psd_scale is not None else 1.0), _ptr(power),
+                                           ctypes.addressof(arg), ctypes.addressof(mx)))
         return power, arg.value, mx.value
 
     def gls_batch(self, t, y, w, offsets, fmin, df, nf, fit_mean=True, psd_scale=None, want_power=True):

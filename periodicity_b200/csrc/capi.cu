@@ -248,6 +248,11 @@ double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out) {
   return ctx->main_ms_total;
 }
 
+struct SmallRec {
+  long long arg;
+  double val;
+};
+
 // ---------------------------------------------------------------------------
 // GLS
 // ---------------------------------------------------------------------------
@@ -286,11 +291,6 @@ int pdc_gls_dev_fanout(pdc_ctx* ctx, const double* t, const double* y, const dou
   const int64_t offsets[2] = {0, n};
   return gls_run(ctx, t, y, w, offsets, 1, &fmin, &df, j0, nf, flags, &psd_scale, nullptr, nullptr, nullptr, st, dst);
 }
-
-struct SmallRec {
-  long long arg;
-  double val;
-};
 
 // Device -> caller's host buffer.  A cudaMemcpyAsync into pageable memory is staged by the driver at ~10 GB/s
 // (0.8 MB periodogram: 86 us); going through our own pinned buffer in a few chunks, each copied out by the CPU
@@ -460,6 +460,59 @@ int pdc_gls_batch(pdc_ctx* ctx, const double* t, const double* y, const double* 
     return multi_gls_batch(ctx, t, y, w, offsets, B, fmin, df, nf, flags, psd_scale, power_out, argmax_out, max_out);
   DeviceGuard guard(ctx->device);
   return gls_host_common(ctx, t, y, w, offsets, B, fmin, df, 0, nf, flags, psd_scale, power_out, argmax_out, max_out);
+}
+
+// GLS at an arbitrary list of frequencies (non-uniform / user-supplied grids)
+int pdc_gls_freqs_dev(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+                      const double* freqs, int64_t nfreq, unsigned flags, double psd_scale,
+                      double* power_out, int64_t* argmax_out, double* max_out, void* stream) {
+  if (!ctx || !t || !y || !freqs) { set_error("pdc_gls_freqs_dev: NULL argument"); return PDC_EINVAL; }
+  if (n < 1 || nfreq < 1) { set_error("pdc_gls_freqs: need n >= 1 samples and nfreq >= 1 frequencies"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  const int64_t offsets[2] = {0, n};
+  const double zero = 0.0;
+  return gls_run(ctx, t, y, w, offsets, 1, &zero, &zero, 0, nfreq, flags, &psd_scale, power_out, argmax_out, max_out, st,
+                 nullptr, freqs);
+}
+
+int pdc_gls_freqs(pdc_ctx* ctx, const double* t, const double* y, const double* w, int64_t n,
+                  const double* freqs, int64_t nfreq, unsigned flags, double psd_scale,
+                  double* power_out, int64_t* argmax_out, double* max_out) {
+  if (!ctx || !t || !y || !freqs || !power_out) { set_error("pdc_gls_freqs: NULL argument"); return PDC_EINVAL; }
+  if (n < 1 || nfreq < 1) { set_error("pdc_gls_freqs: need n >= 1 samples and nfreq >= 1 frequencies"); return PDC_EINVAL; }
+  if (ctx->multi)
+    return multi_period_grid(ctx, n, freqs, nfreq, +1, power_out, argmax_out, max_out,
+                             [=](pdc_ctx* c, const double* f, int64_t k, double* o, int64_t* a, double* b) {
+                               return pdc_gls_freqs(c, t, y, w, n, f, k, flags, psd_scale, o, a, b);
+                             });
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t nbytes = sizeof(double) * (size_t)n;
+  PDC_TRY(ctx->in_a.reserve(nbytes));
+  PDC_TRY(ctx->in_b.reserve(nbytes));
+  if (w) PDC_TRY(ctx->in_c.reserve(nbytes));
+  PDC_TRY(ctx->in_d.reserve(sizeof(double) * (size_t)nfreq));
+  PDC_TRY(ctx->out_a.reserve(sizeof(double) * (size_t)nfreq));
+  PDC_TRY(ctx->out_small.reserve(sizeof(SmallRec)));
+  PDC_TRY(ctx->pin_small.reserve(sizeof(SmallRec)));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_a.p, t, nbytes, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_b.p, y, nbytes, cudaMemcpyHostToDevice, st));
+  if (w) PDC_CUDA(cudaMemcpyAsync(ctx->in_c.p, w, nbytes, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_d.p, freqs, sizeof(double) * (size_t)nfreq, cudaMemcpyHostToDevice, st));
+  SmallRec* d_rec = ctx->out_small.as<SmallRec>();
+  const int64_t offsets[2] = {0, n};
+  const double zero = 0.0;
+  PDC_TRY(gls_run(ctx, ctx->in_a.as<double>(), ctx->in_b.as<double>(), w ? ctx->in_c.as<double>() : nullptr, offsets, 1,
+                  &zero, &zero, 0, nfreq, flags, &psd_scale, ctx->out_a.as<double>(), (int64_t*)&d_rec->arg, &d_rec->val,
+                  st, nullptr, ctx->in_d.as<double>()));
+  PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, d_rec, sizeof(SmallRec), cudaMemcpyDeviceToHost, st));
+  PDC_TRY(staged_d2h(ctx, power_out, ctx->out_a.p, sizeof(double) * (size_t)nfreq, st));
+  PDC_CUDA(cudaStreamSynchronize(st));
+  const SmallRec* h = ctx->pin_small.as<SmallRec>();
+  if (argmax_out) *argmax_out = h->arg;
+  if (max_out) *max_out = h->val;
+  return PDC_OK;
 }
 
 int pdc_gls_multi_dev(pdc_ctx* ctx, const double* t, const double* Y, const double* w, int64_t n, int64_t S,

@@ -458,6 +458,130 @@ gls_strip_kernel(const GlsMainArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// arbitrary (non-uniform, user-supplied) frequency lists: pdc_gls_freqs
+// ---------------------------------------------------------------------------
+// The formula of spectral.py:113-132 does not need a uniform grid -- only the reference's FFT in `_trig_sum` does
+// (spectral.py:11-40), which is why its GLS has no such option.  Without a uniform grid there is no recurrence along
+// the frequency axis: a thread owns ONE frequency and seeds (cos, sin) exactly for every sample -- phase f (t - t_min)
+// reduced mod 1 by ONE DFMA against a magic number (the product is exact inside the FMA, the sum's ulp is 2^-32 turn),
+// I2F, FMUL, MUFU.SIN / MUFU.COS -- and accumulates the same six FP32 sums per 1024-sample tile, flushed to the same
+// fixed-point plane and read by the same epilogue.  Bound: the MUFU pipe (2 per evaluation, 16 lanes per clk per SM).
+// Frequencies with |f| T >= 2^19 turns reduce the phase with the FMA-residual product instead; frequencies with less
+// than one cycle over the baseline (|f| T < 1) keep FP64 sums (the cancellation described in gls_common.cuh).
+struct GlsFreeArgs {
+  const GlsCurve* curves;    // one curve
+  const double2* rec1;       // (t - t_min, unused)
+  const float4* rec2;        // (unused, unused, y' or w'y', w')  -- rotation-form records (df == 0)
+  const double* freqs;       // [nf]
+  unsigned long long* partial;
+  long long nf;
+  int nsplit;
+};
+
+constexpr int GLS_FREE_THREADS = 128;
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(GLS_FREE_THREADS)
+gls_free_kernel(const GlsFreeArgs a) {
+  __shared__ double s_t[GLS_TILE];
+  __shared__ __align__(16) float2 s_yw[GLS_TILE];
+  const int split = blockIdx.x % a.nsplit;
+  const long long fb = blockIdx.x / a.nsplit;
+  const GlsCurve* cvp = a.curves;
+  const long long cn = cvp->n;
+  const double T = cvp->tmax - cvp->tmin;
+  const long long j = fb * GLS_FREE_THREADS + threadIdx.x;
+  const bool active = j < a.nf;
+  const double f = active ? a.freqs[j] : 0.0;
+  const double fT = fabs(f) * T;
+  const bool lowf = fT < GLS_LOW_CYCLES;          // FP64 sums
+  const bool wide = !(fT < 262144.0);             // 2^18: beyond the magic-number reduction (also NaN / inf)
+  const long long per = (cn + a.nsplit - 1) / a.nsplit;
+  const long long sb = (long long)split * per;
+  const long long se = sb + per < cn ? sb + per : cn;
+  const int yslot = rec_slot(REC_Y), wslot = rec_slot(REC_W);
+  const float TWO_PI_32 = 1.4629180792671596e-9f;  // 2 pi / 2^32
+
+  long long tile0 = sb;
+  do {
+    long long left = se - tile0;
+    const int cnt = left <= 0 ? 0 : (left < GLS_TILE ? (int)left : GLS_TILE);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += GLS_FREE_THREADS) {
+      s_t[i] = a.rec1[tile0 + i].x;
+      const float4 r = a.rec2[tile0 + i];
+      s_yw[i] = make_float2(rec_get(r, yslot), rec_get(r, wslot));
+    }
+    __syncthreads();
+    float aC = 0.f, aS = 0.f, aYC = 0.f, aYS = 0.f, aCC = 0.f, aCS = 0.f;
+    double dC = 0.0, dS = 0.0, dYC = 0.0, dYS = 0.0, dCC = 0.0, dCS = 0.0;
+    if (lowf || wide) {
+      for (int i = 0; i < cnt; ++i) {
+        const double ph = frac_of_product(f, s_t[i]);
+        const float2 yw = s_yw[i];
+        if (lowf) {
+          double sn, cs;
+          sincospi(2.0 * ph, &sn, &cs);
+          const double wv = WEIGHTED ? (double)yw.y : 1.0, wc = wv * cs;
+          dC += wc;
+          dS = fma(wv, sn, dS);
+          dYC = fma((double)yw.x, cs, dYC);
+          dYS = fma((double)yw.x, sn, dYS);
+          dCC = fma(wc, cs, dCC);
+          dCS = fma(wc, sn, dCS);
+        } else {
+          float sn, cs;
+          __sincosf((float)ph * 6.2831853071795864f, &sn, &cs);
+          const float wc = WEIGHTED ? yw.y * cs : cs;
+          aC += wc;
+          aS = WEIGHTED ? fmaf(yw.y, sn, aS) : aS + sn;
+          aYC = fmaf(yw.x, cs, aYC);
+          aYS = fmaf(yw.x, sn, aYS);
+          aCC = fmaf(wc, cs, aCC);
+          aCS = fmaf(wc, sn, aCS);
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int i = 0; i < cnt; ++i) {
+        const double v = __fma_rn(f, s_t[i], 1572864.0);      // 1.5 * 2^20: ulp(v) = 2^-32 turn
+        const float x = (float)__double2loint(v) * TWO_PI_32;   // two's-complement fraction -> radians in [-pi, pi)
+        float sn, cs;
+        __sincosf(x, &sn, &cs);
+        const float2 yw = s_yw[i];
+        const float wc = WEIGHTED ? yw.y * cs : cs;
+        aC += wc;
+        aS = WEIGHTED ? fmaf(yw.y, sn, aS) : aS + sn;
+        aYC = fmaf(yw.x, cs, aYC);
+        aYS = fmaf(yw.x, sn, aYS);
+        aCC = fmaf(wc, cs, aCC);
+        aCS = fmaf(wc, sn, aCS);
+      }
+    }
+    if (active && cnt > 0) {
+      unsigned long long* p = a.partial + j;
+      if (lowf) {
+        const double sc = (double)(1 << GLS_FIX_BITS);
+        atomicAdd(p, (unsigned long long)__double2ll_rn(dC * sc));
+        atomicAdd(p + a.nf, (unsigned long long)__double2ll_rn(dS * sc));
+        atomicAdd(p + 2 * a.nf, (unsigned long long)__double2ll_rn(dYC * sc));
+        atomicAdd(p + 3 * a.nf, (unsigned long long)__double2ll_rn(dYS * sc));
+        atomicAdd(p + 4 * a.nf, (unsigned long long)__double2ll_rn(dCC * sc));
+        atomicAdd(p + 5 * a.nf, (unsigned long long)__double2ll_rn(dCS * sc));
+      } else {
+        gls_flush(p, aC);
+        gls_flush(p + a.nf, aS);
+        gls_flush(p + 2 * a.nf, aYC);
+        gls_flush(p + 3 * a.nf, aYS);
+        gls_flush(p + 4 * a.nf, aCC);
+        gls_flush(p + 5 * a.nf, aCS);
+      }
+    }
+    tile0 += GLS_TILE;
+  } while (tile0 < se);
+}
+
+// ---------------------------------------------------------------------------
 // FP64 epilogue: spectral.py:113-132 per frequency + arg-max
 // ---------------------------------------------------------------------------
 struct GlsEpiArgs {
@@ -646,7 +770,8 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
             const int64_t* offsets_host, int64_t B, const double* fmin_host, const double* df_host,
             int64_t j0, int64_t nf, unsigned flags, const double* psd_scale_host,
             double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t st,
-            const pdc_fanout* fanout) {
+            const pdc_fanout* fanout, const double* freqs_dev) {
+  if (freqs_dev && (B != 1 || fanout || j0 != 0)) { set_error("pdc_gls_freqs: one curve, no fan-out"); return PDC_EINVAL; }
   if (fanout && (B != 1 || fanout->world < 1 || fanout->world > PDC_MAX_PEERS || fanout->rank < 0 ||
                  fanout->rank >= fanout->world)) {
     set_error("pdc_gls_dev_fanout: needs one curve and 1 <= world <= %d", PDC_MAX_PEERS);
@@ -685,7 +810,12 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   int nsplit = choose_nsplit((long long)B * nfb, nmax, resident, 0 /* splits share one plane: no memory cost */,
                              geom == 1 ? 96 : 256);
   if (ctx->gls_nsplit_override > 0) nsplit = ctx->gls_nsplit_override;  // tuning aid (env PDC_GLS_NSPLIT)
-  const long long items = (long long)B * nfb * nsplit;
+  long long free_blocks = 0;
+  if (freqs_dev) {   // one frequency per thread, 128 per block, 8 blocks per SM
+    free_blocks = (nf + GLS_FREE_THREADS - 1) / GLS_FREE_THREADS;
+    nsplit = choose_nsplit(free_blocks, nmax, (long long)ctx->sm_count * 8, 0, 256);
+  }
+  const long long items = freqs_dev ? free_blocks * nsplit : (long long)B * nfb * nsplit;
   if (items > 0x7fffffffLL) { set_error("pdc_gls: problem too large for one call (%lld work items)", items); return PDC_EINVAL; }
 
   if (B > 65535) { set_error("pdc_gls_batch: at most 65535 curves per call"); return PDC_EINVAL; }
@@ -805,7 +935,22 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
 
   ctx->gls_plane_dirty = true;   // until the epilogue that clears the plane has been enqueued
   PDC_TRY(ctx->main_begin(st));
-  PDC_TRY(launch_strip(geom, ctx, a, w != nullptr, items, st));
+  if (freqs_dev) {
+    GlsFreeArgs fa;
+    fa.curves = dc;
+    fa.rec1 = a.rec1;
+    fa.rec2 = a.rec2;
+    fa.freqs = freqs_dev;
+    fa.partial = a.partial;
+    fa.nf = nf;
+    fa.nsplit = nsplit;
+    if (w) gls_free_kernel<true><<<(unsigned)items, GLS_FREE_THREADS, 0, st>>>(fa);
+    else gls_free_kernel<false><<<(unsigned)items, GLS_FREE_THREADS, 0, st>>>(fa);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+  } else {
+    PDC_TRY(launch_strip(geom, ctx, a, w != nullptr, items, st));
+  }
   PDC_TRY(ctx->main_end(st));
 
   {

@@ -162,7 +162,9 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
             const int64_t* offsets_host, int64_t B, const double* fmin_host, const double* df_host,
             int64_t j0, int64_t nf, unsigned flags, const double* psd_scale_host,
             double* power_out, int64_t* argmax_out, double* max_out, cudaStream_t stream,
-            const pdc_fanout* fanout = nullptr);
+            const pdc_fanout* fanout = nullptr,
+            const double* freqs_dev = nullptr);  // non-NULL: evaluate at this device list of nf frequencies (pdc_gls_freqs);
+                                                 // fmin_host / df_host must then be {0}, {0}
 
 int glsm_run(pdc_ctx* ctx, const double* t, const double* Y, const double* w, int64_t n, int64_t S,
              double fmin, double df, int64_t j0, int64_t nf, unsigned flags, double psd_scale,

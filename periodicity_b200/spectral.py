@@ -44,7 +44,11 @@ class GLS(object):
         stores its results directly into every rank's buffer over NVLink (no NCCL call).
     """
 
-    def __init__(self, fmin=None, fmax=None, n=5, psd=False, *, device=None, shard=False, devices=None):
+    def __init__(self, fmin=None, fmax=None, n=5, psd=False, *, device=None, shard=False, devices=None,
+                 frequency=None):
+        # `frequency`: evaluate on this user-supplied list of frequencies (any spacing) instead of the uniform grid
+        # derived from fmin / fmax / n (pdc_gls_freqs); not in the reference, whose FFT needs a uniform grid
+        self.user_frequency = None if frequency is None else np.sort(np.asarray(frequency, dtype=np.float64).ravel())
         self.fmin = fmin
         self.fmax = fmax
         self.n = n
@@ -71,6 +75,8 @@ class GLS(object):
         """
         if not isinstance(signal, TSeries):
             signal = TSeries(values=signal)
+        if self.user_frequency is not None:
+            return self._call_on_user_grid(signal, err, fit_mean)
         fmin, df, self.frequency = self._grid(signal)
         nf = self.frequency.size
         if err is None:
@@ -92,6 +98,24 @@ class GLS(object):
                 signal.time, signal.values, weights, fmin, df, nf, fit_mean=fit_mean, psd_scale=psd_scale)
         self.signal = signal
         self.periodogram = FSeries(self.frequency, power)
+        return self.periodogram
+
+    def _call_on_user_grid(self, signal, err, fit_mean):
+        """``__call__`` on ``frequency=`` (non-uniform grid): same weights, mean removal, formula and attributes."""
+        self.frequency = self.user_frequency
+        if err is None:
+            err = np.ones_like(signal.values)
+            weights = None
+        else:
+            err = np.asarray(err)
+            weights = np.asarray(err, dtype=np.float64) ** -2.0
+        self.err = err
+        psd_scale = 0.5 * (np.asarray(err, dtype=np.float64) ** -2.0).sum() if self.psd else None
+        ctx = _ffi.default_context(self.device)
+        power, self.argmax_index, self.max_power = ctx.gls_freqs(
+            signal.time, signal.values, weights, self.frequency, fit_mean=fit_mean, psd_scale=psd_scale)
+        self.signal = signal
+        self.periodogram = FSeries(self.frequency, power, assume_sorted=True)
         return self.periodogram
 
     def copy(self):
