@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(GLS_STATS_THREADS)
 gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ w,
                  GlsCurve* curves, GlsPart* part, unsigned* done, const GlsCurve single, int use_single,
                  unsigned flags, long long j0, long long nf, int allow_three_term, int low_cap) {
-  __shared__ double scratch[33];
+  __shared__ double scratch[32 * 5];
   __shared__ int s_last;
   const int curve = blockIdx.y, G = gridDim.x;
   const GlsCurve cin = use_single ? single : curves[curve];
@@ -91,11 +91,11 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y, con
     swd += wd;
     swdd = fma(wd, d, swdd);
   }
-  tmin = block_min(tmin, scratch);
-  tneg = block_min(tneg, scratch);
-  sw = block_sum(sw, scratch);
-  swd = block_sum(swd, scratch);
-  swdd = block_sum(swdd, scratch);
+  {
+    double sums[3] = {sw, swd, swdd}, maxs[2] = {-tmin, -tneg};
+    block_reduce_many<3, 2>(sums, maxs, scratch);
+    sw = sums[0]; swd = sums[1]; swdd = sums[2]; tmin = -maxs[0]; tneg = -maxs[1];
+  }
   bad = __syncthreads_or(bad);
   if (threadIdx.x == 0) {
     GlsPart& p = part[(long long)curve * G + blockIdx.x];
@@ -161,14 +161,15 @@ gls_stats_kernel(const double* __restrict__ t, const double* __restrict__ y, con
 // grid = (rec_blocks + GLS_LOW_LANES * nlowchunk, curves).
 //  * blocks x < rec_blocks write the sample records (grid-stride over the curve's samples);
 //  * block x = rec_blocks + lane * nlowchunk + chunk sums chunk `chunk` of the samples for the sub-cycle frequencies
-//    slot = lane, lane + GLS_LOW_LANES, ... < low_count and writes NORMALISED sums (weights sum to 1) to
-//    lowsum[chunk][6][curve * low_cap + slot].
+//    slot = lane, lane + GLS_LOW_LANES, ... < low_count in FP64 and adds them to a small fixed-point plane of their
+//    own, lowplane[6][curve * low_cap + slot], which the epilogue prefers over the strip kernel's sums for those bins.
 constexpr int GLS_LOW_LANES = 16;
 
 __global__ void __launch_bounds__(256)
 gls_prep_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ w,
                 const GlsCurve* __restrict__ curves, double2* __restrict__ rec1, float4* __restrict__ rec2,
-                double* __restrict__ lowsum, long long j0, int B, int rec_blocks, int nlowchunk, int low_cap) {
+                unsigned long long* __restrict__ lowplane, int B, int low_cap, double fix_scale,
+                long long j0, int rec_blocks, int nlowchunk) {
   __shared__ double s_red[6][8];
   const int curve = blockIdx.y;
   const GlsCurve cv = curves[curve];
@@ -213,8 +214,7 @@ gls_prep_kernel(const double* __restrict__ t, const double* __restrict__ y, cons
   const long long per = (cv.n + nlowchunk - 1) / nlowchunk;
   const long long sb = (long long)chunk * per;
   const long long se = sb + per < cv.n ? sb + per : cv.n;
-  const double winv = 1.0 / cv.wsum;
-  const long long cols = (long long)B * low_cap;
+  const double wscale = (double)cv.n / cv.wsum;   // weights of mean 1: the same convention as the strip kernel's sums
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int slot = lane0; slot < cv.low_count; slot += GLS_LOW_LANES) {
     const double f = cv.fmin + (double)(j0 + cv.low_begin + slot) * cv.df;
@@ -224,7 +224,7 @@ gls_prep_kernel(const double* __restrict__ t, const double* __restrict__ y, cons
       const double ph = frac_of_product(f, t[g] - cv.tmin);
       double sn, cs;
       sincospi(2.0 * ph, &sn, &cs);
-      const double wi = (w ? w[g] : 1.0) * winv;
+      const double wi = w ? w[g] * wscale : 1.0;
       const double wy = wi * ((y[g] - cv.ymean) * cv.inv_rms);
       const double wc = wi * cs;
       a[0] += wc;
@@ -246,7 +246,9 @@ gls_prep_kernel(const double* __restrict__ t, const double* __restrict__ y, cons
     if (threadIdx.x < 6) {
       double tot = 0.0;
       for (int k = 0; k < 8; ++k) tot += s_red[threadIdx.x][k];
-      lowsum[((long long)chunk * 6 + threadIdx.x) * cols + (long long)curve * low_cap + slot] = tot;
+      // 64-bit fixed point, order-independent integer adds over the sample chunks: lowplane[6][curve * low_cap + slot]
+      atomicAdd(lowplane + (long long)threadIdx.x * B * low_cap + (long long)curve * low_cap + slot,
+                (unsigned long long)__double2ll_rn(tot * fix_scale));
     }
   }
 }
@@ -264,15 +266,16 @@ struct GlsMainArgs {
   long long j0;       // absolute index of this call's first frequency
   int nfb;            // frequency blocks per curve
   int nsplit;         // sample splits per curve
+  float fix_scale;    // 2^fix_bits
 };
 
-// Tile sums leave the strip kernel as 64-bit fixed point with GLS_FIX_BITS fraction bits.  With the weights rescaled to
+// Tile sums leave the hot kernels as 64-bit fixed point with fix_bits fraction bits.  With the weights rescaled to
 // mean 1 and y' to unit weighted RMS every one of the six sums is bounded by n in magnitude (Cauchy-Schwarz:
-// sum w'|y'| <= sqrt(sum w') sqrt(sum w' y'^2) = n), so 2^30 leaves room for n up to 8e9 samples; the quantisation,
-// 2^-31 per tile flush, is nine orders of magnitude below the rounding of the FP32 tile sum it converts.
-constexpr int GLS_FIX_BITS = 30;
-__device__ __forceinline__ void gls_flush(unsigned long long* p, float v) {
-  atomicAdd(p, (unsigned long long)__float2ll_rn(v * (float)(1 << GLS_FIX_BITS)));   // RED.ADD.64, no return value
+// sum w'|y'| <= sqrt(sum w') sqrt(sum w' y'^2) = n), so fix_bits = 61 - ceil(log2 n) (gls_run) uses the whole word:
+// the resolution relative to the sums' scale n is 2^-61, finer than float64's -- the FP64 sums of the sub-cycle bins
+// travel through the same plane without loss, and for the FP32 tile sums the conversion is exact.
+__device__ __forceinline__ void gls_flush(unsigned long long* p, float v, float fix_scale) {
+  atomicAdd(p, (unsigned long long)__float2ll_rn(v * fix_scale));   // RED.ADD.64, no return value
 }
 
 template <int K, int THREADS, int MINB, bool WEIGHTED>
@@ -445,12 +448,12 @@ gls_strip_kernel(const GlsMainArgs a) {
     for (int k = 0; k < K; ++k) {
       if (k < jrem) {
         unsigned long long* p = pbase + k;
-        gls_flush(p, aC[k]);
-        gls_flush(p + a.nf_tot, aS[k]);
-        gls_flush(p + 2 * a.nf_tot, aYC[k]);
-        gls_flush(p + 3 * a.nf_tot, aYS[k]);
-        gls_flush(p + 4 * a.nf_tot, aCC[k]);
-        gls_flush(p + 5 * a.nf_tot, aCS[k]);
+        gls_flush(p, aC[k], a.fix_scale);
+        gls_flush(p + a.nf_tot, aS[k], a.fix_scale);
+        gls_flush(p + 2 * a.nf_tot, aYC[k], a.fix_scale);
+        gls_flush(p + 3 * a.nf_tot, aYS[k], a.fix_scale);
+        gls_flush(p + 4 * a.nf_tot, aCC[k], a.fix_scale);
+        gls_flush(p + 5 * a.nf_tot, aCS[k], a.fix_scale);
       }
     }
     tile0 += GLS_TILE;
@@ -476,6 +479,7 @@ struct GlsFreeArgs {
   unsigned long long* partial;
   long long nf;
   int nsplit;
+  float fix_scale;
 };
 
 constexpr int GLS_FREE_THREADS = 128;
@@ -561,7 +565,7 @@ gls_free_kernel(const GlsFreeArgs a) {
     if (active && cnt > 0) {
       unsigned long long* p = a.partial + j;
       if (lowf) {
-        const double sc = (double)(1 << GLS_FIX_BITS);
+        const double sc = (double)a.fix_scale;
         atomicAdd(p, (unsigned long long)__double2ll_rn(dC * sc));
         atomicAdd(p + a.nf, (unsigned long long)__double2ll_rn(dS * sc));
         atomicAdd(p + 2 * a.nf, (unsigned long long)__double2ll_rn(dYC * sc));
@@ -569,12 +573,12 @@ gls_free_kernel(const GlsFreeArgs a) {
         atomicAdd(p + 4 * a.nf, (unsigned long long)__double2ll_rn(dCC * sc));
         atomicAdd(p + 5 * a.nf, (unsigned long long)__double2ll_rn(dCS * sc));
       } else {
-        gls_flush(p, aC);
-        gls_flush(p + a.nf, aS);
-        gls_flush(p + 2 * a.nf, aYC);
-        gls_flush(p + 3 * a.nf, aYS);
-        gls_flush(p + 4 * a.nf, aCC);
-        gls_flush(p + 5 * a.nf, aCS);
+        gls_flush(p, aC, a.fix_scale);
+        gls_flush(p + a.nf, aS, a.fix_scale);
+        gls_flush(p + 2 * a.nf, aYC, a.fix_scale);
+        gls_flush(p + 3 * a.nf, aYS, a.fix_scale);
+        gls_flush(p + 4 * a.nf, aCC, a.fix_scale);
+        gls_flush(p + 5 * a.nf, aCS, a.fix_scale);
       }
     }
     tile0 += GLS_TILE;
@@ -587,8 +591,9 @@ gls_free_kernel(const GlsFreeArgs a) {
 struct GlsEpiArgs {
   const GlsCurve* curves;
   unsigned long long* partial;  // [6][nf_tot]; read and cleared
-  const double* lowsum;         // FP64 sums of the sub-cycle bins [chunk][6][B * low_cap]
-  int nlowchunk, low_cap, B;
+  unsigned long long* lowplane; // [6][B * low_cap] FP64-accurate sums of the sub-cycle bins; read and cleared
+  int low_cap, B;
+  double inv_fix;               // 2^-fix_bits
   unsigned flags;
   long long nf, nf_tot, j0;
   double* power_out;            // [B * nf] or NULL
@@ -620,21 +625,17 @@ gls_epilogue_kernel(const GlsEpiArgs a) {
 #pragma unroll
     for (int q = 0; q < 6; ++q) p[(long long)q * a.nf_tot] = 0ull;              // the plane is clean for the next call
     if (j >= cv.low_begin && j < cv.low_begin + cv.low_count) {
-      // sub-cycle frequency: FP64 sums from gls_prep_kernel (already normalised)
-      const long long cols = (long long)a.B * a.low_cap;
-      const double* lp = a.lowsum + (long long)curve * a.low_cap + (j - cv.low_begin);
+      // sub-cycle frequency: the FP64 sums of gls_prep_kernel replace the strip kernel's FP32 ones
+      unsigned long long* lp = a.lowplane + (long long)curve * a.low_cap + (j - cv.low_begin);
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
-        double acc = 0.0;
-        for (int c = 0; c < a.nlowchunk; ++c) acc += lp[((long long)c * 6 + q) * cols];
-        sums[q] = acc;
+        raw[q] = __ldcg(lp + (long long)q * a.B * a.low_cap);
+        lp[(long long)q * a.B * a.low_cap] = 0ull;
       }
-      inv_n = 1.0;
-    } else {
-#pragma unroll
-      for (int q = 0; q < 6; ++q) sums[q] = (double)(long long)raw[q] * (1.0 / (double)(1 << GLS_FIX_BITS));
-      inv_n = 1.0 / (double)cv.n;
     }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) sums[q] = (double)(long long)raw[q] * a.inv_fix;
+    inv_n = 1.0 / (double)cv.n;
     power = gls_power_from_sums(sums, inv_n, a.flags, cv.yy, cv.psd_scale);
     if (cv.bad) power = nan("");
     if (a.power_out) a.power_out[(long long)curve * a.nf + j] = power;
@@ -824,13 +825,16 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   ScratchScope scratch(ctx, st);
   PDC_TRY(scratch.acquire());
 
-  // sub-cycle (FP64) bins: up to low_cap per curve -- the whole sub-cycle range of any reasonable grid for a single
-  // curve (GLS(n=1000) still fits), fewer for large batches so that the scratch stays small
+  // sub-cycle (FP64) bins: sized from the actual count, up to GLS_NLOW_CAP per curve (beyond that the surplus is FP32)
   long long nlowchunk = (nmax + GLS_LOW_CHUNK - 1) / GLS_LOW_CHUNK;
   if (nlowchunk > GLS_LOW_MAXCHUNKS) nlowchunk = GLS_LOW_MAXCHUNKS;
-  long long low_cap = ((long long)1 << 21) / ((long long)B * nlowchunk);
+  long long low_cap = ((long long)1 << 22) / B;   // keeps the low plane below 200 MB for the largest batches
   if (low_cap > GLS_NLOW_CAP) low_cap = GLS_NLOW_CAP;
   if (low_cap < GLS_NLOW_MAX) low_cap = GLS_NLOW_MAX;
+  // fixed-point scale of the plane of partial sums: |sum| <= n, one bit of slack
+  int fix_bits = 61;
+  while (fix_bits > 8 && ((long long)1 << (61 - fix_bits)) < nmax) --fix_bits;
+  const double fix_scale = ldexp(1.0, fix_bits);
 
   // scratch
   PDC_TRY(ctx->gls_curves.reserve(sizeof(GlsCurve) * B));
@@ -847,9 +851,17 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
       ctx->gls_plane_dirty = false;
     }
   }
+  {   // the small plane of the sub-cycle bins: same clean-between-calls contract (and the same dirty flag)
+    const void* before = ctx->gls_low.p;
+    const size_t cap_before = ctx->gls_low.cap;
+    PDC_TRY(ctx->gls_low.reserve(sizeof(unsigned long long) * 6 * (size_t)B * low_cap));
+    if (ctx->gls_low.p != before || ctx->gls_low.cap != cap_before || ctx->gls_low_dirty) {
+      PDC_CUDA(cudaMemsetAsync(ctx->gls_low.p, 0, ctx->gls_low.cap, st));
+      ctx->gls_low_dirty = false;
+    }
+  }
   const int eblk = (int)((nf + 255) / 256);
   PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk * B));
-  PDC_TRY(ctx->gls_low.reserve(sizeof(double) * 6 * (size_t)nlowchunk * B * low_cap));
   // completion counters (stats blocks per curve, sample splits per frequency block, frequency blocks per curve):
   // zeroed when the buffer is (re)allocated, every kernel leaves them at zero again
   {
@@ -916,8 +928,8 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     if (bx > 1024) bx = 1024;
     dim3 grid((unsigned)(bx + GLS_LOW_LANES * nlowchunk), (unsigned)B);
     gls_prep_kernel<<<grid, 256, 0, st>>>(tt, yy, ww, dc, ctx->gls_rec1.as<double2>(), ctx->gls_rec2.as<float4>(),
-                                          ctx->gls_low.as<double>(), (long long)j0, (int)B, (int)bx, (int)nlowchunk,
-                                          (int)low_cap);
+                                          ctx->gls_low.as<unsigned long long>(), (int)B, (int)low_cap, fix_scale,
+                                          (long long)j0, (int)bx, (int)nlowchunk);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -932,8 +944,9 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   a.j0 = j0;
   a.nfb = (int)nfb;
   a.nsplit = nsplit;
+  a.fix_scale = (float)fix_scale;
 
-  ctx->gls_plane_dirty = true;   // until the epilogue that clears the plane has been enqueued
+  ctx->gls_plane_dirty = ctx->gls_low_dirty = true;   // until the epilogue that clears the planes has been enqueued
   PDC_TRY(ctx->main_begin(st));
   if (freqs_dev) {
     GlsFreeArgs fa;
@@ -944,6 +957,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     fa.partial = a.partial;
     fa.nf = nf;
     fa.nsplit = nsplit;
+    fa.fix_scale = (float)fix_scale;
     if (w) gls_free_kernel<true><<<(unsigned)items, GLS_FREE_THREADS, 0, st>>>(fa);
     else gls_free_kernel<false><<<(unsigned)items, GLS_FREE_THREADS, 0, st>>>(fa);
     PDC_CUDA(cudaGetLastError());
@@ -957,10 +971,10 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     GlsEpiArgs e;
     e.curves = dc;
     e.partial = a.partial;
-    e.lowsum = ctx->gls_low.as<double>();
-    e.nlowchunk = (int)nlowchunk;
+    e.lowplane = ctx->gls_low.as<unsigned long long>();
     e.low_cap = (int)low_cap;
     e.B = (int)B;
+    e.inv_fix = 1.0 / fix_scale;
     e.flags = flags;
     e.nf = nf;
     e.nf_tot = nf_tot;
@@ -977,7 +991,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     gls_epilogue_kernel<<<grid, 256, 0, st>>>(e);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
-    ctx->gls_plane_dirty = false;
+    ctx->gls_plane_dirty = ctx->gls_low_dirty = false;
   }
   PDC_TRY(scratch.release());
   return PDC_OK;

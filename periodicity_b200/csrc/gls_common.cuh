@@ -58,12 +58,11 @@ constexpr double GLS_TT_MAX_SPAN = 0.34;
 // by 1/var(cos) ~ 300x at f*T = 0.1.  Those few bins (at most GLS_NLOW_MAX per curve) are
 // evaluated entirely in FP64 (gls.cu: the second block role of gls_prep_kernel; glsm.cu: glsm_lowfreq_kernel).
 // Their number is ~ the grid's samples per peak `n` (spectral.py:88) when fmin is at its default: 5 by default, 100
-// for GLS(n=100).  gls.cu sizes the range from the actual count up to a cap chosen per call (1024 for a single
-// curve, less for large batches: gls_run), glsm.cu keeps GLS_NLOW_MAX.
+// for GLS(n=100).  gls.cu sizes the range from the actual count up to GLS_NLOW_CAP per curve, glsm.cu keeps GLS_NLOW_MAX.
 constexpr double GLS_LOW_CYCLES = 1.0;
 constexpr int GLS_NLOW_MAX = 16;
 constexpr int GLS_NLOW_CAP = 1024;
-constexpr int GLS_LOW_CHUNK = 4096;   // samples per block of gls_lowfreq_kernel
+constexpr int GLS_LOW_CHUNK = 2048;   // samples per FP64 block (gls_prep_kernel's second role / glsm_lowfreq_kernel)
 constexpr int GLS_LOW_MAXCHUNKS = 256;
 
 

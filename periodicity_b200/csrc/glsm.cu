@@ -479,6 +479,7 @@ int glsm_run(pdc_ctx* ctx, const double* t, const double* Y, const double* w, in
   PDC_TRY(ctx->glsm_y.reserve(sizeof(float) * (size_t)S_pad * n));
   PDC_TRY(ctx->partial.reserve(sizeof(double) * (size_t)nsplit * (4 + 2 * S_pad) * nf));
   PDC_TRY(ctx->gls_low.reserve(sizeof(double) * (size_t)nlowchunk * (4 + 2 * S_pad) * GLS_NLOW_MAX));
+  ctx->gls_low_dirty = true;   // gls.cu keeps this buffer as an all-zero fixed-point plane between its calls: it must re-clear it
   PDC_TRY(ctx->blockred.reserve((sizeof(double) + sizeof(long long)) * (size_t)eblk * S));
 
   GlsmShared* hs = ctx->pin_meta.as<GlsmShared>();

@@ -98,14 +98,15 @@ struct pdc_ctx {
   pdc::DevBuf gls_rec2;        // float4[n]   (cos, sin of the per-index rotation, y or w*y, w)
   pdc::DevBuf glsm_y;          // float [groups][n][R]: scaled values of the shared-time series (glsm.cu)
   int glsm_occ[2] = {0, 0};    // cached blocks/SM of glsm_strip_kernel [weighted]
-  pdc::DevBuf gls_low;         // float64 sums of the sub-cycle frequencies [chunk][6][B*low_cap]
+  pdc::DevBuf gls_low;         // gls.cu: fixed-point plane of the sub-cycle bins' FP64 sums [6][B*low_cap] (clean between calls,
+                               // gls_low_dirty); glsm.cu: float64 [chunk][...] scratch -- glsm_run marks it dirty
   pdc::DevBuf gls_cnt;         // completion counters of the last-block-done reductions (gls.cu), self-resetting
   pdc::DevBuf partial;         // glsm.cu: float64 partial sums [nsplit][rows][units]; strlen.cu: sort scratch
   // Planes of partial sums shared by ALL sample splits of a call: gls.cu 64-bit fixed point [6][B*nf]; pdm.cu counts +
   // 64-bit fixed-point sums [m0][np]; ce.cu counts [cells][np].  The epilogue that reads a plane clears it, so a plane
   // is all zeros between calls; it is memset only when (re)allocated or when a call failed before its epilogue.
   pdc::DevBuf gls_plane, hist_plane;
-  bool gls_plane_dirty = false, hist_plane_dirty = false;
+  bool gls_plane_dirty = false, gls_low_dirty = false, hist_plane_dirty = false;
   pdc::DevBuf blockred;        // per-block (value, index) candidates
   pdc::PinnedBuf pin_meta;     // host staging for per-curve metadata
 
@@ -231,6 +232,42 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   }
   __syncthreads();
   return scratch[32];
+}
+
+// NS sums and NM maxima at once with ONE pair of barriers (the statistics kernels reduce 5-8 quantities: one
+// reduction each costs three barriers apiece).  Fixed xor-tree order: deterministic.  Results valid in thread 0.
+// `scratch` holds 32 * (NS + NM) doubles.
+template <int NS, int NM>
+__device__ __forceinline__ void block_reduce_many(double (&s)[NS], double (&m)[NM], double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+#pragma unroll
+    for (int i = 0; i < NM; ++i) m[i] = fmax(m[i], __shfl_xor_sync(0xffffffffu, m[i], o));
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) scratch[i * 32 + wid] = s[i];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) scratch[(NS + i) * 32 + wid] = m[i];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s[i] = lane < nw ? scratch[i * 32 + lane] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NM; ++i) m[i] = lane < nw ? scratch[(NS + i) * 32 + lane] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+#pragma unroll
+      for (int i = 0; i < NM; ++i) m[i] = fmax(m[i], __shfl_xor_sync(0xffffffffu, m[i], o));
+    }
+  }
 }
 
 __device__ __forceinline__ double block_min(double v, double* scratch) {

@@ -126,7 +126,7 @@ __device__ __forceinline__ double block_max(double v, double* scratch) { return 
 __global__ void __launch_bounds__(PDM_STATS_THREADS)
 pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmPart* part,
                  unsigned* done, PdmMeta* meta) {
-  __shared__ double scratch[33];
+  __shared__ double scratch[32 * 8];
   __shared__ int s_last;
   const int G = gridDim.x;
   const double x0 = x[0];
@@ -147,14 +147,11 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
     }
   }
   bad = __syncthreads_or(bad);
-  s1 = block_sum(s1, scratch);
-  s2 = block_sum(s2, scratch);
-  s1b = block_sum(s1b, scratch);
-  s2b = block_sum(s2b, scratch);
-  nb = block_sum(nb, scratch);
-  xneg = block_max(xneg, scratch);
-  xmax = block_max(xmax, scratch);
-  tabs = block_max(tabs, scratch);
+  {
+    double sums[5] = {s1, s2, s1b, s2b, nb}, maxs[3] = {xneg, xmax, tabs};
+    block_reduce_many<5, 3>(sums, maxs, scratch);
+    s1 = sums[0]; s2 = sums[1]; s1b = sums[2]; s2b = sums[3]; nb = sums[4]; xneg = maxs[0]; xmax = maxs[1]; tabs = maxs[2];
+  }
   if (threadIdx.x == 0) {
     PdmPart& p = part[blockIdx.x];
     p.s1 = s1; p.s2 = s2; p.s1b = s1b; p.s2b = s2b; p.nb = nb; p.xneg = xneg; p.xmax = xmax; p.tabs = tabs; p.bad = bad;
@@ -167,14 +164,13 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
   __threadfence();
   const bool has = (int)threadIdx.x < G;
   const PdmPart* p = part + threadIdx.x;
-  s1 = block_sum(has ? __ldcg(&p->s1) : 0.0, scratch);
-  s2 = block_sum(has ? __ldcg(&p->s2) : 0.0, scratch);
-  s1b = block_sum(has ? __ldcg(&p->s1b) : 0.0, scratch);
-  s2b = block_sum(has ? __ldcg(&p->s2b) : 0.0, scratch);
-  nb = block_sum(has ? __ldcg(&p->nb) : 0.0, scratch);
-  xneg = block_max(has ? __ldcg(&p->xneg) : -INFINITY, scratch);
-  xmax = block_max(has ? __ldcg(&p->xmax) : -INFINITY, scratch);
-  tabs = block_max(has ? __ldcg(&p->tabs) : 0.0, scratch);
+  {
+    double sums[5] = {has ? __ldcg(&p->s1) : 0.0, has ? __ldcg(&p->s2) : 0.0, has ? __ldcg(&p->s1b) : 0.0,
+                      has ? __ldcg(&p->s2b) : 0.0, has ? __ldcg(&p->nb) : 0.0};
+    double maxs[3] = {has ? __ldcg(&p->xneg) : -INFINITY, has ? __ldcg(&p->xmax) : -INFINITY, has ? __ldcg(&p->tabs) : 0.0};
+    block_reduce_many<5, 3>(sums, maxs, scratch);
+    s1 = sums[0]; s2 = sums[1]; s1b = sums[2]; s2b = sums[3]; nb = sums[4]; xneg = maxs[0]; xmax = maxs[1]; tabs = maxs[2];
+  }
   bad = __syncthreads_or(has ? __ldcg(&p->bad) : 0);
   if (threadIdx.x == 0) {
     const double dn = (double)n;
