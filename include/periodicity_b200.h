@@ -283,6 +283,25 @@ PDC_API int pdc_ce_dev(pdc_ctx* ctx, const double* t, const double* x, int64_t n
                double* h_out, int64_t* argmin_out, double* min_out, void* stream);
 
 /*
+ * Gregory-Loredo (1992) periodogram for EVENT ARRIVAL TIMES (no values): a TODO of the reference (phase.py:14).  For
+ * every trial period the odds ratio of a stepwise periodic model with m phase bins against the constant model,
+ * marginalised over the bin rates and over the phase offset (nc offsets per bin: events are counted in m * nc fine
+ * phase bins with the reference's phase and edge conventions, phase.py:131,138-140, and the m bins at offset c are
+ * circular unions of nc consecutive fine bins),
+ *     O_m(P) = [(m - 1)! / (N + m - 1)!] m^N < prod_j n_j! >_offsets ,
+ * averaged over m = 2 .. m_max with equal weights.  One count-histogram pass per m.
+ *
+ *   t           float64[n]   event arrival times
+ *   lnodds_out  float64[np]  ln O(P) in the order of `periods` (NaN for period 0 / inf / NaN)
+ *   argmax_out / max_out     index and value of the LARGEST non-NaN ln O (first occurrence).  May be NULL.
+ *   m_max >= 2, nc >= 1, m_max * nc <= 4096 (and the fine bins must fit a shared-memory histogram).
+ */
+PDC_API int pdc_gl(pdc_ctx* ctx, const double* t, int64_t n, const double* periods, int64_t np, int m_max, int nc,
+                   double* lnodds_out, int64_t* argmax_out, double* max_out);
+PDC_API int pdc_gl_dev(pdc_ctx* ctx, const double* t, int64_t n, const double* periods, int64_t np, int m_max, int nc,
+                       double* lnodds_out, int64_t* argmax_out, double* max_out, void* stream);
+
+/*
  * String Length (Dworetsky 1983): `StringLength._stringlength` (phase.py:45-51) for each trial
  * period, replacing `pool.map(self._stringlength, periods)` (phase.py:68-70).
  *

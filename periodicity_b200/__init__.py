@@ -6,8 +6,8 @@ dispatching through a C ABI (``include/periodicity_b200.h``) into hand-written
 sm_100a CUDA kernels.  No CPU fallback.
 """
 from .core import FSeries, TSeries  # noqa: F401
-from .phase import AOV, CE, PDM, ConditionalEntropy, StringLength  # noqa: F401
+from .phase import AOV, CE, GL, PDM, ConditionalEntropy, GregoryLoredo, StringLength  # noqa: F401
 from .spectral import GLS  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["GLS", "PDM", "StringLength", "AOV", "CE", "ConditionalEntropy", "TSeries", "FSeries"]
+__all__ = ["GLS", "PDM", "StringLength", "AOV", "CE", "ConditionalEntropy", "GL", "GregoryLoredo", "TSeries", "FSeries"]

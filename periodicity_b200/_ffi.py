@@ -93,6 +93,11 @@ SIGNATURES = {
     "pdc_ce_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                   ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                              ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pdc_gl_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_void_p]),
     "pdc_stringlength": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p]),
@@ -348,6 +353,20 @@ class Context:
     def ce_dev(self, t_ptr, x_ptr, n, periods_ptr, np_, nphi, nm, h_ptr, argmin_ptr, min_ptr, stream=0):
         _check(self._lib.pdc_ce_dev(self._h, t_ptr, x_ptr, int(n), periods_ptr, int(np_), int(nphi), int(nm),
                                     h_ptr, argmin_ptr or None, min_ptr or None, stream or None))
+
+    def gl(self, t, periods, m_max=12, nc=10):
+        """Gregory-Loredo ln odds for each trial period from event arrival times (``pdc_gl``): (lnodds, argmax, max)."""
+        t = _f64(t)
+        periods = _f64(periods)
+        if t.ndim != 1:
+            raise ValueError("t must be one-dimensional")
+        out = np.empty(periods.size, dtype=np.float64)
+        arg = ctypes.c_int64(-1)
+        mx = ctypes.c_double(float("nan"))
+        with self._lock:
+            _check(self._lib.pdc_gl(self._h, _ptr(t), t.size, _ptr(periods), periods.size, int(m_max), int(nc),
+                                    _ptr(out), ctypes.addressof(arg), ctypes.addressof(mx)))
+        return out, arg.value, mx.value
 
     def peaks_halfmax(self, values, peak_idx, height=None):
         """Indices (left, right) of the half-maximum crossings around each given peak of each row (host arrays);

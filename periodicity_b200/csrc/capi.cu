@@ -212,7 +212,7 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   ctx->gls_curves.release(); ctx->gls_part.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->gls_cnt.release(); ctx->glsm_y.release();
   ctx->partial.release(); ctx->gls_plane.release(); ctx->hist_plane.release(); ctx->blockred.release(); ctx->pin_meta.release();
-  ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->peak_cand.release();
+  ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->gl_acc.release(); ctx->peak_cand.release();
   ctx->main_resolve();
   for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);
@@ -692,6 +692,51 @@ int pdc_ce(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const doub
   const SmallRec* h = ctx->pin_small.as<SmallRec>();
   if (argmin_out) *argmin_out = h->arg;
   if (min_out) *min_out = h->val;
+  return PDC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Gregory-Loredo (event arrival times; count histograms for m = 2 .. m_max phase bins)
+// ---------------------------------------------------------------------------
+int pdc_gl_dev(pdc_ctx* ctx, const double* t, int64_t n, const double* periods, int64_t np, int m_max, int nc,
+               double* lnodds_out, int64_t* argmax_out, double* max_out, void* stream) {
+  if (!ctx || !t || !periods || !lnodds_out) { set_error("pdc_gl_dev: NULL argument"); return PDC_EINVAL; }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = stream == PDC_STREAM_CTX ? ctx->stream : (cudaStream_t)stream;
+  return gl_run(ctx, t, n, periods, np, m_max, nc, lnodds_out, argmax_out, max_out, st);
+}
+
+int pdc_gl(pdc_ctx* ctx, const double* t, int64_t n, const double* periods, int64_t np, int m_max, int nc,
+           double* lnodds_out, int64_t* argmax_out, double* max_out) {
+  if (!ctx || !t || !periods || !lnodds_out) { set_error("pdc_gl: NULL argument"); return PDC_EINVAL; }
+  if (n < 1 || np < 1) { set_error("pdc_gl: need n >= 1 events and np >= 1 periods"); return PDC_EINVAL; }
+  if (m_max < 2 || nc < 1 || (long long)m_max * nc > 4096) {
+    set_error("pdc_gl: need m_max >= 2, nc >= 1 and m_max * nc <= 4096");
+    return PDC_EINVAL;
+  }
+  if (ctx->multi)
+    return multi_period_grid(ctx, n * (int64_t)(m_max - 1), periods, np, +1, lnodds_out, argmax_out, max_out,
+                             [=](pdc_ctx* c, const double* p, int64_t k, double* o, int64_t* a, double* b) {
+                               return pdc_gl(c, t, n, p, k, m_max, nc, o, a, b);
+                             });
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  PDC_TRY(ctx->in_a.reserve(sizeof(double) * (size_t)n));
+  PDC_TRY(ctx->in_d.reserve(sizeof(double) * (size_t)np));
+  PDC_TRY(ctx->out_a.reserve(sizeof(double) * (size_t)np));
+  PDC_TRY(ctx->out_small.reserve(sizeof(SmallRec)));
+  PDC_TRY(ctx->pin_small.reserve(sizeof(SmallRec)));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_a.p, t, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->in_d.p, periods, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, st));
+  SmallRec* d_rec = ctx->out_small.as<SmallRec>();
+  PDC_TRY(gl_run(ctx, ctx->in_a.as<double>(), n, ctx->in_d.as<double>(), np, m_max, nc, ctx->out_a.as<double>(),
+                 (int64_t*)&d_rec->arg, &d_rec->val, st));
+  PDC_CUDA(cudaMemcpyAsync(ctx->pin_small.p, d_rec, sizeof(SmallRec), cudaMemcpyDeviceToHost, st));
+  PDC_TRY(staged_d2h(ctx, lnodds_out, ctx->out_a.p, sizeof(double) * (size_t)np, st));
+  PDC_CUDA(cudaStreamSynchronize(st));
+  const SmallRec* h = ctx->pin_small.as<SmallRec>();
+  if (argmax_out) *argmax_out = h->arg;
+  if (max_out) *max_out = h->val;
   return PDC_OK;
 }
 

@@ -98,6 +98,7 @@ struct CeArgs {
   unsigned* plane;      // [cells][np] counts, all sample splits add into it
   long long n, np;
   int nphi, nm, cells, nsplit;
+  int counts_only;      // 1: phase bins only (nm == 1, x is not read): the Gregory-Loredo passes
 };
 
 // numpy's magnitude bin: scaled = (x - lo) / (hi - lo); min(int(scaled * nm), nm - 1)  (oracle/ce_numpy.py)
@@ -223,7 +224,7 @@ ce_hist_kernel(const CeArgs a) {
   const long long sb = (long long)split * per;
   const long long se = sb + per < a.n ? sb + per : a.n;
   // block-uniform; a constant signal (max == min) has no magnitude bins at all (0 / 0): every sample is in no cell
-  const bool fast = __syncthreads_and(in_range) != 0 && !bad && xrange > 0.0;
+  const bool fast = __syncthreads_and(in_range) != 0 && !bad && (xrange > 0.0 || a.counts_only);
 
   auto exact_bin = [&](double P, double rP, double tv, double& phi) {
     unsigned e;
@@ -243,7 +244,7 @@ ce_hist_kernel(const CeArgs a) {
     __syncthreads();
     for (int i = threadIdx.x; i < cntv; i += THREADS) {
       s_t[i] = a.t[tile0 + i];
-      const int mb = ce_mbin(a.x[tile0 + i], xlo, xrange, nm);
+      const int mb = a.counts_only ? 0 : ce_mbin(a.x[tile0 + i], xlo, xrange, nm);
       s_m[i] = mb < 0 ? 0xffffffffu : (unsigned)mb * VT;
     }
     __syncthreads();
@@ -364,8 +365,10 @@ static int ce_launch(pdc_ctx* ctx, const CeArgs& a, size_t smem, long long block
   return PDC_OK;
 }
 
-int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np, int nphi,
-           int nm, double* h_out, int64_t* argmin_out, double* min_out, cudaStream_t st) {
+// statistics + count histograms of one call (or one Gregory-Loredo pass): leaves the counts in ctx->hist_plane
+// ([nphi * nm][np], marked dirty until an epilogue has cleared it).  x == NULL: phase bins only.
+static int ce_hist_pass(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np,
+                        int nphi, int nm, cudaStream_t st) {
   if (n < 1) { set_error("pdc_ce: need at least 1 sample"); return PDC_EINVAL; }
   if (np < 1) { set_error("pdc_ce: need at least one trial period"); return PDC_EINVAL; }
   if (nphi < 1 || nm < 1) { set_error("pdc_ce: nphi and nm must be >= 1"); return PDC_EINVAL; }
@@ -408,8 +411,6 @@ int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const doub
   const long long blocks = npb * nsplit;
   if (blocks > 0x7fffffffLL || npb > 0x3fffffffLL) { set_error("pdc_ce: problem too large for one call"); return PDC_EINVAL; }
 
-  ScratchScope scratch(ctx, st);
-  PDC_TRY(scratch.acquire());
   PDC_TRY(ctx->pdm_meta.reserve(sizeof(CeMeta) + 16 + sizeof(CePart) * CE_STATS_MAXBLK));
   {
     const void* before = ctx->hist_plane.p;
@@ -433,7 +434,7 @@ int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const doub
     CePart* part = reinterpret_cast<CePart*>(reinterpret_cast<char*>(meta) + ((sizeof(CeMeta) + 15) & ~(size_t)15));
     long long sblk = (n + 8 * CE_STATS_THREADS - 1) / (8 * CE_STATS_THREADS);
     if (sblk > CE_STATS_MAXBLK) sblk = CE_STATS_MAXBLK;
-    ce_stats_kernel<<<(unsigned)sblk, CE_STATS_THREADS, 0, st>>>(t, x, n, part, cnt_stats, meta);
+    ce_stats_kernel<<<(unsigned)sblk, CE_STATS_THREADS, 0, st>>>(t, x ? x : t, n, part, cnt_stats, meta);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -449,6 +450,7 @@ int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const doub
   a.nm = nm;
   a.cells = cells;
   a.nsplit = nsplit;
+  a.counts_only = x == nullptr;
 
   ctx->hist_plane_dirty = true;
   PDC_TRY(ctx->main_begin(st));
@@ -459,9 +461,18 @@ int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const doub
     default: PDC_TRY((ce_launch<32, 1>(ctx, a, smem, blocks, st))); break;
   }
   PDC_TRY(ctx->main_end(st));
+  return PDC_OK;
+}
 
+int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np, int nphi,
+           int nm, double* h_out, int64_t* argmin_out, double* min_out, cudaStream_t st) {
+  if (!x) { set_error("pdc_ce: x is NULL"); return PDC_EINVAL; }
+  ScratchScope scratch(ctx, st);
+  PDC_TRY(scratch.acquire());
+  PDC_TRY(ce_hist_pass(ctx, t, x, n, periods, np, nphi, nm, st));
+  const int eblk = (int)((np + 255) / 256);
   CeEpiArgs e;
-  e.plane = a.plane;
+  e.plane = ctx->hist_plane.as<unsigned>();
   e.periods = periods;
   e.np = np;
   e.nphi = nphi;
@@ -469,13 +480,162 @@ int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const doub
   e.h_out = h_out;
   e.red_val = ctx->blockred.as<double>();
   e.red_idx = reinterpret_cast<long long*>(e.red_val + eblk);
-  e.call_done = cnt_stats + 1;
+  e.call_done = ctx->pdm_cnt.as<unsigned>() + 1;
   e.arg_out = (long long*)argmin_out;
   e.best_out = min_out;
   ce_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(e);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
   ctx->hist_plane_dirty = false;
+  PDC_TRY(scratch.release());
+  return PDC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Gregory-Loredo (1992) periodogram for event arrival times
+// ---------------------------------------------------------------------------
+// A TODO of the reference (phase.py:14); PARITY UNPINNED BY THE REFERENCE (oracle: oracle/gl_numpy.py).  For N events,
+// trial period P and a stepwise light-curve model with m phase bins, the likelihood marginalised over the bin rates is
+// inversely proportional to the multiplicity W_m(P, phi) = N! / prod_j n_j! of the binned events, and the odds ratio of
+// the m-bin periodic model against the constant model, marginalised over the phase offset phi, is
+//     O_m(P) = [ (m - 1)! / (N + m - 1)! ] m^N  < prod_j n_j(P, phi)! >_phi                       (GL 1992, eq. 5.25 ff.)
+// The phase offset is integrated on a grid of nc offsets per bin: events are counted in m * nc fine phase bins (the
+// reference's phase and edge conventions, phase.py:131,138-140) and the m coarse bins at offset c are circular unions
+// of nc consecutive fine bins starting at c -- the "covers" structure of PDM.  One count-histogram pass (the
+// conditional-entropy kernel with phase bins only) per m = 2 .. m_max; this kernel turns the counts of pass m into
+// ln O_m and folds it into the running ln sum_m O_m per trial period.  The periodogram is
+//     ln O(P) = ln [ (1 / (m_max - 1)) sum_{m=2}^{m_max} O_m(P) ]      (equal prior weight for every m),
+// to be MAXIMISED.
+struct GlEpiArgs {
+  unsigned* plane;        // [m * nc][np] counts of this pass; read and cleared
+  const double* periods;
+  long long np;
+  int m, nc, last;        // last: this is the m_max pass -> normalise, store, arg-max
+  double ln_prior;        // lgamma(m) - lgamma(N + m) + N ln m   (N = number of events)
+  double ln_norm;         // ln(m_max - 1)
+  double* acc;            // [np] running ln sum_m O_m (read-modify-write by the thread that owns the period)
+  double* out;            // [np]
+  double* red_val;
+  long long* red_idx;
+  unsigned* call_done;
+  long long* arg_out;
+  double* best_out;
+};
+
+__global__ void __launch_bounds__(256)
+gl_epilogue_kernel(const GlEpiArgs a) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ int s_last;
+  const long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long np = a.np;
+  const int m = a.m, nc = a.nc, F = m * nc;
+  double val = 0.0;
+  long long idx = -1;
+  if (pi < np) {
+    unsigned* base = a.plane + pi;
+    // ln < prod_j n_j! >_phi  =  logsumexp_c( sum_j lgamma(n_j(c) + 1) ) - ln nc
+    double mx = -INFINITY, se = 0.0;
+    for (int c = 0; c < nc; ++c) {
+      double L = 0.0;
+      for (int j = 0; j < m; ++j) {
+        unsigned nj = 0;
+        for (int k = 0; k < nc; ++k) {
+          int f = c + j * nc + k;
+          if (f >= F) f -= F;
+          nj += __ldcg(base + (long long)f * np);
+        }
+        L += lgamma((double)nj + 1.0);
+      }
+      if (L > mx) { se = se * exp(mx - L) + 1.0; mx = L; }
+      else se += exp(L - mx);
+    }
+    for (int f = 0; f < F; ++f) base[(long long)f * np] = 0u;    // the plane is clean for the next pass / call
+    const double ln_om = a.ln_prior + mx + log(se) - log((double)nc);
+    double acc = a.m == 2 ? ln_om : a.acc[pi];
+    if (a.m != 2) {   // logaddexp
+      const double hi = fmax(acc, ln_om), lo = fmin(acc, ln_om);
+      acc = hi + log1p(exp(lo - hi));
+    }
+    a.acc[pi] = acc;
+    if (a.last) {
+      const double P = a.periods[pi];
+      val = acc - a.ln_norm;
+      if (!isfinite(P) || !isfinite(1.0 / P)) val = nan("");
+      a.out[pi] = val;
+      idx = pi;
+    }
+  }
+  if (!a.last) return;
+  block_argext<+1>(val, idx, sv, si);
+  const int nblk = gridDim.x;
+  if (threadIdx.x == 0) {
+    a.red_val[blockIdx.x] = val;
+    a.red_idx[blockIdx.x] = idx;
+    __threadfence();
+    s_last = atomicAdd(a.call_done, 1u) == (unsigned)(nblk - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *a.call_done = 0u;
+  __threadfence();
+  double best = 0.0;
+  long long bidx = -1;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+    const double v = __ldcg(a.red_val + k);
+    const long long i = __ldcg(a.red_idx + k);
+    if (better<+1>(v, i, best, bidx)) { best = v; bidx = i; }
+  }
+  block_argext<+1>(best, bidx, sv, si);
+  if (threadIdx.x == 0) {
+    if (a.arg_out) *a.arg_out = bidx;
+    if (a.best_out) *a.best_out = bidx >= 0 ? best : nan("");
+  }
+}
+
+int gl_run(pdc_ctx* ctx, const double* t, int64_t n, const double* periods, int64_t np, int m_max, int nc,
+           double* lnodds_out, int64_t* argmax_out, double* max_out, cudaStream_t st) {
+  if (n < 1 || np < 1) { set_error("pdc_gl: need n >= 1 events and np >= 1 periods"); return PDC_EINVAL; }
+  if (m_max < 2 || nc < 1 || (long long)m_max * nc > 4096) {
+    set_error("pdc_gl: need m_max >= 2, nc >= 1 and m_max * nc <= 4096");
+    return PDC_EINVAL;
+  }
+  ScratchScope scratch(ctx, st);
+  PDC_TRY(scratch.acquire());
+  PDC_TRY(ctx->gl_acc.reserve(sizeof(double) * (size_t)np));
+  {   // size the count plane for the largest pass once (the passes must not reallocate it between them)
+    const void* before = ctx->hist_plane.p;
+    const size_t cap_before = ctx->hist_plane.cap;
+    PDC_TRY(ctx->hist_plane.reserve(sizeof(unsigned) * (size_t)m_max * nc * np));
+    if (ctx->hist_plane.p != before || ctx->hist_plane.cap != cap_before || ctx->hist_plane_dirty) {
+      PDC_CUDA(cudaMemsetAsync(ctx->hist_plane.p, 0, ctx->hist_plane.cap, st));
+      ctx->hist_plane_dirty = false;
+    }
+  }
+  const int eblk = (int)((np + 255) / 256);
+  for (int m = 2; m <= m_max; ++m) {
+    PDC_TRY(ce_hist_pass(ctx, t, nullptr, n, periods, np, m * nc, 1, st));
+    GlEpiArgs e;
+    e.plane = ctx->hist_plane.as<unsigned>();
+    e.periods = periods;
+    e.np = np;
+    e.m = m;
+    e.nc = nc;
+    e.last = m == m_max;
+    e.ln_prior = lgamma((double)m) - lgamma((double)n + (double)m) + (double)n * log((double)m);
+    e.ln_norm = log((double)(m_max - 1));
+    e.acc = ctx->gl_acc.as<double>();
+    e.out = lnodds_out;
+    e.red_val = ctx->blockred.as<double>();
+    e.red_idx = reinterpret_cast<long long*>(e.red_val + eblk);
+    e.call_done = ctx->pdm_cnt.as<unsigned>() + 1;
+    e.arg_out = (long long*)argmax_out;
+    e.best_out = max_out;
+    gl_epilogue_kernel<<<(unsigned)eblk, 256, 0, st>>>(e);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    ctx->hist_plane_dirty = false;
+  }
   PDC_TRY(scratch.release());
   return PDC_OK;
 }

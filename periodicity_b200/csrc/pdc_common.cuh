@@ -114,6 +114,7 @@ struct pdc_ctx {
 
   // PDM scratch
   pdc::DevBuf pdm_meta;        // PdmMeta
+  pdc::DevBuf gl_acc;          // Gregory-Loredo: running ln sum_m O_m per trial period (ce.cu)
   pdc::DevBuf pdm_cnt;         // completion counters of the last-block-done reductions (pdm.cu), self-resetting
 };
 
@@ -183,6 +184,9 @@ int multi_period_grid(pdc_ctx* ctx, int64_t n, const double* periods, int64_t np
 
 int ce_run(pdc_ctx* ctx, const double* t, const double* x, int64_t n, const double* periods, int64_t np, int nphi,
            int nm, double* h_out, int64_t* argmin_out, double* min_out, cudaStream_t stream);
+
+int gl_run(pdc_ctx* ctx, const double* t, int64_t n, const double* periods, int64_t np, int m_max, int nc,
+           double* lnodds_out, int64_t* argmax_out, double* max_out, cudaStream_t stream);
 
 int strlen_run(pdc_ctx* ctx, const double* t, const double* m, int64_t n, const double* periods, int64_t np,
                double* ell_out, int64_t* argmin_out, double* min_out, cudaStream_t stream);

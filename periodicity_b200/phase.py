@@ -13,7 +13,7 @@ import numpy as np
 from . import _ffi
 from .core import FSeries, TSeries
 
-__all__ = ["StringLength", "PDM", "AOV", "CE", "ConditionalEntropy"]
+__all__ = ["StringLength", "PDM", "AOV", "CE", "ConditionalEntropy", "GL", "GregoryLoredo"]
 
 
 class StringLength(object):
@@ -263,3 +263,50 @@ class CE(object):
 
 
 ConditionalEntropy = CE
+
+
+class GL(object):
+    """Gregory-Loredo (1992) periodogram for event arrival times.
+
+    The reference lists this method as a TODO (``phase.py:14``) and has no implementation; the class follows the
+    conventions of its ``PDM`` (``phase.py:75-195``): the same period-grid options with the same defaults, the phase
+    definition ``(t / P) % 1`` (``phase.py:131``), an ``FSeries`` over ``1/P`` as result.  The input is a series of
+    event times (a ``TSeries``' time axis, or a plain array of times; values are ignored).  For every trial period
+    the odds of stepwise periodic models with ``m = 2 .. m_max`` phase bins against a constant rate, marginalised over
+    the bin rates and the phase offset (``nc`` offsets per bin), are averaged; the best period MAXIMISES ``ln O``.
+    Evaluated on a B200 from count histograms in shared memory (``pdc_gl``).  ``cores`` is accepted and ignored.
+    """
+
+    def __init__(self, m_max=12, nc=10, p_min=None, p_max=None, n_periods=1000, oversample=1, cores=None, *,
+                 device=None, devices=None):
+        self.m_max = m_max
+        self.nc = nc
+        self.p_min = p_min
+        self.p_max = p_max
+        self.n_periods = n_periods
+        self.oversample = oversample
+        self.cores = cores
+        self.device = list(devices) if devices is not None else device
+
+    def _lnodds(self, periods):
+        ctx = _ffi.default_context(self.device)
+        out, self.argmax_index, self.max_lnodds = ctx.gl(self.t, periods, self.m_max, self.nc)
+        return out
+
+    def __call__(self, events):
+        """ln O(P) on ``linspace(p_min, p_max, n_periods)`` as an ``FSeries`` over ``1/P``; sets ``t, periods, periodogram``."""
+        t = np.sort(np.asarray(events.time if isinstance(events, TSeries) else events, dtype=np.float64).ravel())
+        self.t = t
+        t0 = t[-1] - t[0]
+        p_min = 2 * np.median(np.diff(t)) if self.p_min is None else self.p_min
+        p_max = self.oversample * t0 if self.p_max is None else self.p_max
+        if self.n_periods is None:
+            n_periods = int((1 / p_min - 1 / p_max) * self.oversample * t0 + 1)
+        else:
+            n_periods = self.n_periods
+        self.periods = np.linspace(p_min, p_max, n_periods)
+        self.periodogram = FSeries(1 / self.periods, self._lnodds(self.periods))
+        return self.periodogram
+
+
+GregoryLoredo = GL
