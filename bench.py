@@ -27,7 +27,7 @@ same.  A failed check makes the run exit non-zero AFTER printing the line.
 Printed line (rank 0): metric/value/unit/... as the driver contract asks, plus
   roofline      dominant kernel vs the FP32 issue roofline (the path is FP32-pipe bound, not HBM or tensor bound;
                 SURVEY.md 8d): achieved = evals x 20 FLOP / kernel time (CUDA events on the launching stream inside
-                the library), peak = measured FFMA rate (profiles/pipes_r01.json; MEASURED_PEAKS.json has no FP32
+                the library), peak = measured FFMA rate (profiles/r01/pipes_r01.json; MEASURED_PEAKS.json has no FP32
                 entry).  PDM: updates/s vs the measured shared-memory ATOMS.ADD rate.
   cpu_baseline  the reference's CPU path timed on this box's host cores: the UNMODIFIED reference files when
                 oracle/_ref holds them (kind "reference"; staged by oracle/make_ref.py), else the numpy port (kind "port").
@@ -53,13 +53,13 @@ if ROOT not in sys.path:
 
 KERNEL_TAG = "r02"            # profiles/ncu_{gls_strip,pdm_hist}_<tag>.json: `ncu --set full` capture of the CURRENT kernels
 FLOP_PER_EVAL_GLS = 20.0      # 12 FP32 instructions = 20 FLOP per sample*frequency
-FP32_PEAK_TFLOPS_MEASURED = 72.3   # profiles/pipes_r01.json: 36,172 GFFMA/s x 2
+FP32_PEAK_TFLOPS_MEASURED = 72.3   # profiles/r01/pipes_r01.json: 36,172 GFFMA/s x 2
 FP32_PEAK_GINSTR_MEASURED = 36172.0  # same measurement as thread-instructions/s (125 per clk per SM)
 # what gls_strip_kernel<16,128> executes in its three-term form (SASS hot loop: 282 instructions per
 # 2 samples x 16 frequencies; 6 FFMA + 2 FADD per evaluation): the 20 FLOP of the accounting figure are NOT all executed
 GLS_EXECUTED_INSTR_PER_EVAL = 282.0 / 32.0
 GLS_EXECUTED_FLOP_PER_EVAL = 14.0
-PDM_PEAK_GEVALS_MEASURED = 3841.3  # profiles/pipes_r01.json smem_private_u32_atoms: private-column ATOMS.ADD, updates/s
+PDM_PEAK_GEVALS_MEASURED = 3841.3  # profiles/r01/pipes_r01.json smem_private_u32_atoms: private-column ATOMS.ADD, updates/s
 
 METRICS = {"pdm": "PDM sample*period evaluations per second",
            "sl": "String Length sample*period evaluations per second",
@@ -756,7 +756,7 @@ def run_workload(env, wl, per_gpu, scaling, steps, warmup, cpu_budget_s=10.0, wa
                 "peak": PDM_PEAK_GEVALS_MEASURED, "unit": "Gevals/s", "frac": ach / PDM_PEAK_GEVALS_MEASURED,
                 "traffic": traffic if world == 1 and wl["nf"] == 100_000 else None, "traffic_source": f"profiles/{tfile}",
                 "kernel_ms": main_kernel_ms,
-                "peak_source": "profiles/pipes_r01.json smem_private_u32_atoms (one shared-memory ATOMS.ADD on a private "
+                "peak_source": "profiles/r01/pipes_r01.json smem_private_u32_atoms (one shared-memory ATOMS.ADD on a private "
                                "32-bit column word per sample update, 13.7 per clk per SM: the floor of the "
                                "kernel's histogram update); path is shared-memory/issue bound, not HBM or tensor bound"}
     else:
@@ -780,7 +780,7 @@ def run_workload(env, wl, per_gpu, scaling, steps, warmup, cpu_budget_s=10.0, wa
                     "note": "three-term recurrence along the frequency axis: 8 FP32 instructions per evaluation "
                             "instead of the 12 of SURVEY 8d's accounting figure; `frac` stays on the 20-FLOP figure "
                             "as SURVEY 8d prescribes, issue_frac = executed instructions / measured FP32 issue peak"},
-                "peak_source": "profiles/pipes_r01.json ffma_shared_operands x2 FLOP (measured on this pool's B200; "
+                "peak_source": "profiles/r01/pipes_r01.json ffma_shared_operands x2 FLOP (measured on this pool's B200; "
                                "MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5)",
                 "hbm": {"achieved_gbs": (32.0 * nsamp + 6 * 8 * 2 * (units_local / max(1, nsamp))) / (main_kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": measured_hbm_gbs()[0], "peak_source": measured_hbm_gbs()[1],

@@ -44,7 +44,7 @@
 // derives its register allocation and schedule from it, and on B200 the resulting register-file
 // operand conflicts ("dispatch" stalls) move the kernel time between 1.90 and 2.47 ms on the C2
 // shape.  The default is the best of ~250 orders timed on B200 for BOTH the plain and the weighted
-// kernel (tools/build_variants.sh + tools/tune_strip.py; profiles/tune_strip_r01.txt).
+// kernel (tools/build_variants.sh + tools/tune_strip.py; profiles/r01/tune_strip_r01.txt).
 #ifndef PDC_TT_ORDER
 #define PDC_TT_ORDER ST_CC ST_YC ST_RC ST_YS ST_RS ST_S ST_CS ST_C
 #endif

@@ -27,7 +27,7 @@
 //   level 1  one 32-bit word per bin, (count << 23) + sum rint(x' 2^q): one sample is ONE native
 //            shared-memory integer atomic without return value (ATOMS.ADD, fire-and-forget; the
 //            column is private, the atomic is used for its single-instruction read-modify-write,
-//            measured 13.7 updates/clk/SM against 9.5 for LDS + IADD + STS, profiles/pipes_r01.json);
+//            measured 13.7 updates/clk/SM against 9.5 for LDS + IADD + STS, profiles/r01/pipes_r01.json);
 //   level 2  integer planes count[bin][column], sum[bin][column] (fixed point, exact) over the memory of the
 //            float2 columns, fed from level 1 every 256 samples with three atomics per bin (fetch-and-clear of
 //            the packed word, two adds), merged into the FP64 partials in global memory every 8192 samples.
@@ -87,7 +87,7 @@ constexpr int PDM_TILE = 1024;        // samples per shared-memory tile
 #ifndef PDM_TRIP_CHAINS
 #define PDM_TRIP_CHAINS 32            // independent (sample, period) chains per trip of the packed loop = PDM_TRIP_CHAINS / PPT samples
 #endif
-// Build-time switches of the packed loop; the defaults are the best of the sweep in profiles/tune_pdm_r01.txt.
+// Build-time switches of the packed loop; the defaults are the best of the sweep in profiles/r01/tune_pdm_r01.txt.
 #ifndef PDM_EDGE_FIXUP
 #define PDM_EDGE_FIXUP 1             // 1: updates go out with the fast bins at once, the rare edge sample is moved afterwards
 #endif

@@ -3,7 +3,7 @@
 // MEASURED_PEAKS.json only records HBM and bf16 tensor
 // peaks; the GLS / PDM hot path is bound by the FP32, FP64, XU (MUFU + 64-bit
 // conversions) and shared-memory pipes, so their achievable rates are measured
-// here and used as roofline denominators (profiles/pipes_r01.json).
+// here and used as roofline denominators (profiles/r01/pipes_r01.json).
 //
 // Every test is one persistent wave (148 * BPS blocks of 256 threads) running
 // an unrolled body of independent dependency chains. Reported:
