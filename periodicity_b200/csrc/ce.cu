@@ -32,11 +32,12 @@ namespace pdc {
 struct CeMeta {
   double xmin, xmax;
   double t_absmax;
+  double t0, t_span;   // smallest finite stamp, span of the finite stamps (the fixed-point phase works on t - t0)
   int bad, pad_;
 };
 
 struct CePart {
-  double xneg, xmax, tabs;
+  double xneg, xmax, tabs, tneg, tmax;
   int bad, pad_;
 };
 constexpr int CE_STATS_THREADS = 256;
@@ -48,26 +49,34 @@ constexpr int CE_TILE_PAD = CE_U;   // the prefetch reads one trip past the tile
 __global__ void __launch_bounds__(CE_STATS_THREADS)
 ce_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, CePart* part, unsigned* done,
                 CeMeta* meta) {
-  __shared__ double scratch[33];
+  __shared__ double scratch[32 * 6];
   __shared__ int s_last;
   const int G = gridDim.x;
-  double xneg = -INFINITY, xmax = -INFINITY, tabs = 0.0;
+  double xneg = -INFINITY, xmax = -INFINITY, tabs = 0.0, tneg = -INFINITY, tmax = -INFINITY;
   int bad = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)G * blockDim.x) {
     const double xi = x[i], ti = t[i];
     xneg = fmax(xneg, -xi);     // fmax / fmin ignore NaN, as np.nanmin / np.nanmax do (oracle: magnitude_bins)
     xmax = fmax(xmax, xi);
     bad |= !isfinite(xi) || !isfinite(ti);
-    if (isfinite(ti)) tabs = fmax(tabs, fabs(ti));
+    if (isfinite(ti)) {
+      tabs = fmax(tabs, fabs(ti));
+      tneg = fmax(tneg, -ti);
+      tmax = fmax(tmax, ti);
+    }
   }
   bad = __syncthreads_or(bad);
-  xneg = -block_min(-xneg, scratch);
-  xmax = -block_min(-xmax, scratch);
-  tabs = -block_min(-tabs, scratch);
+  {
+    double none[1] = {0.0}, maxs[5] = {xneg, xmax, tabs, tneg, tmax};
+    block_reduce_many<1, 5>(none, maxs, scratch);
+    xneg = maxs[0]; xmax = maxs[1]; tabs = maxs[2]; tneg = maxs[3]; tmax = maxs[4];
+  }
   if (threadIdx.x == 0) {
     part[blockIdx.x].xneg = xneg;
     part[blockIdx.x].xmax = xmax;
     part[blockIdx.x].tabs = tabs;
+    part[blockIdx.x].tneg = tneg;
+    part[blockIdx.x].tmax = tmax;
     part[blockIdx.x].bad = bad;
     __threadfence();
     s_last = atomicAdd(done, 1u) == (unsigned)(G - 1);
@@ -77,14 +86,20 @@ ce_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, long
   __threadfence();
   const bool has = (int)threadIdx.x < G;
   const CePart* p = part + threadIdx.x;
-  xneg = -block_min(has ? -__ldcg(&p->xneg) : INFINITY, scratch);
-  xmax = -block_min(has ? -__ldcg(&p->xmax) : INFINITY, scratch);
-  tabs = -block_min(has ? -__ldcg(&p->tabs) : 0.0, scratch);
+  {
+    double none[1] = {0.0};
+    double maxs[5] = {has ? __ldcg(&p->xneg) : -INFINITY, has ? __ldcg(&p->xmax) : -INFINITY, has ? __ldcg(&p->tabs) : 0.0,
+                      has ? __ldcg(&p->tneg) : -INFINITY, has ? __ldcg(&p->tmax) : -INFINITY};
+    block_reduce_many<1, 5>(none, maxs, scratch);
+    xneg = maxs[0]; xmax = maxs[1]; tabs = maxs[2]; tneg = maxs[3]; tmax = maxs[4];
+  }
   bad = __syncthreads_or(has ? __ldcg(&p->bad) : 0);
   if (threadIdx.x == 0) {
     meta->xmin = -xneg;
     meta->xmax = xmax;
     meta->t_absmax = tabs;
+    meta->t0 = tmax >= -tneg ? -tneg : 0.0;
+    meta->t_span = tmax >= -tneg ? tmax + tneg : 0.0;
     meta->bad = bad;
     *done = 0u;
   }
@@ -208,11 +223,12 @@ ce_hist_kernel(const CeArgs a) {
     Ps[s] = P;
     rPs[s] = 1.0 / P;
     // padding columns (P = 1) must not veto the block's fast path
-    in_range = in_range && (!valids[s] || fabs(rPs[s]) * a.meta->t_absmax < PDM_FAST_LIMIT);
+    in_range = in_range && (!valids[s] || (fabs(rPs[s]) * a.meta->t_span < PDM_FAST_LIMIT &&
+                                           fabs(rPs[s]) * a.meta->t_absmax < PDM_SHIFT_LIMIT));
   }
   const bool bad = a.meta->bad != 0;   // block-uniform
   const double nphid = (double)nphi;
-  const unsigned nphiu = (unsigned)nphi, guard2 = 2u * PDM_FAST_GUARD * nphiu;
+  const unsigned nphiu = (unsigned)nphi;
   const double xlo = a.meta->xmin, xrange = a.meta->xmax - a.meta->xmin;
   const unsigned mstride = (unsigned)nm * VT;   // words between consecutive phase bins of one column
 
@@ -223,6 +239,23 @@ ce_hist_kernel(const CeArgs a) {
   const long long per = (a.n + a.nsplit - 1) / a.nsplit;
   const long long sb = (long long)split * per;
   const long long se = sb + per < a.n ? sb + per : a.n;
+  // guard band of the block (see phase_common.cuh: shifted fixed-point phase on t - t0)
+  __shared__ unsigned s_guard;
+  if (threadIdx.x == 0) s_guard = 0u;
+  __syncthreads();
+  {
+    unsigned g = 0u;
+#pragma unroll
+    for (int s = 0; s < PPT; ++s)
+      if (valids[s] && in_range) g = max(g, pdm_guard_units(fabs(rPs[s]), a.meta->t_absmax));
+    atomicMax(&s_guard, g);
+  }
+  __syncthreads();
+  const unsigned guard2 = 2u * s_guard * nphiu;
+  const double t0 = a.meta->t0;
+  double magic[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; ++s) magic[s] = pdm_fast_magic(t0, rPs[s], s_guard);
   // block-uniform; a constant signal (max == min) has no magnitude bins at all (0 / 0): every sample is in no cell
   const bool fast = __syncthreads_and(in_range) != 0 && !bad && (xrange > 0.0 || a.counts_only);
 
@@ -243,7 +276,7 @@ ce_hist_kernel(const CeArgs a) {
     const int cntv = left <= 0 ? 0 : (left < CE_TILE ? (int)left : CE_TILE);
     __syncthreads();
     for (int i = threadIdx.x; i < cntv; i += THREADS) {
-      s_t[i] = a.t[tile0 + i];
+      s_t[i] = fast ? a.t[tile0 + i] - t0 : a.t[tile0 + i];
       const int mb = a.counts_only ? 0 : ce_mbin(a.x[tile0 + i], xlo, xrange, nm);
       s_m[i] = mb < 0 ? 0xffffffffu : (unsigned)mb * VT;
     }
@@ -267,7 +300,7 @@ ce_hist_kernel(const CeArgs a) {
         for (int s = 0; s < PPT; ++s) {
 #pragma unroll
           for (int u = 0; u < CE_U; ++u) {
-            k[s][u] = pdm_bin_fast_g(tv[u], rPs[s], nphiu, pos);
+            k[s][u] = pdm_bin_fast_m(tv[u], rPs[s], magic[s], nphiu, pos);
             pmin = min(pmin, pos);
           }
         }
@@ -292,11 +325,10 @@ ce_hist_kernel(const CeArgs a) {
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
               unsigned p0;
-              const double tvu = s_t[i + u];
-              const unsigned kf = pdm_bin_fast_g(tvu, rPs[s], nphiu, p0);
+              const unsigned kf = pdm_bin_fast_m(s_t[i + u], rPs[s], magic[s], nphiu, p0);
               if (p0 < guard2) {
                 double ph;
-                const unsigned ke = exact_bin(Ps[s], rPs[s], tvu, ph);
+                const unsigned ke = exact_bin(Ps[s], rPs[s], a.t[tile0 + i + u], ph);   // the ORIGINAL stamp
                 if (ke != kf) {
                   add(c0 + s * THREADS, kf, s_m[i + u], 0u - 1u);   // counts are sums modulo 2^32: -1 undoes the update
                   add(c0 + s * THREADS, ke, s_m[i + u], 1u);
@@ -310,11 +342,10 @@ ce_hist_kernel(const CeArgs a) {
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
           unsigned p0;
-          const double tvu = s_t[i];
-          unsigned kf = pdm_bin_fast_g(tvu, rPs[s], nphiu, p0);
+          unsigned kf = pdm_bin_fast_m(s_t[i], rPs[s], magic[s], nphiu, p0);
           if (p0 < guard2) {
             double ph;
-            kf = exact_bin(Ps[s], rPs[s], tvu, ph);
+            kf = exact_bin(Ps[s], rPs[s], a.t[tile0 + i], ph);
           }
           add(c0 + s * THREADS, kf, s_m[i], 1u);
         }

@@ -62,7 +62,8 @@ namespace pdc {
 struct PdmMeta {
   double mean, inv_sd;
   double q_binned;  // sum of x'^2 over the samples with a finite time stamp (== N - 1 when all are)
-  double t_absmax;  // max |t| over the finite time stamps: decides whether the 32-bit fixed-point phase is usable
+  double t_absmax;  // max |t| over the finite time stamps: sizes the guard band of the fixed-point phase
+  double t0, t_span;  // smallest finite stamp and the span of the finite stamps: the fixed-point phase works on t - t0
   int pack_q;       // >= 0: x' is also provided as 2^23 + rint(x' 2^pack_q) for the packed 32-bit histogram; -1: not usable
   int bad;          // some t or x is NaN / inf: the histogram kernel then runs its guarded variant
 };
@@ -116,6 +117,7 @@ struct PdmPart {
   double s1b, s2b, nb;    // the same over the samples with a finite time stamp (used only if some stamp is not finite)
   double xneg, xmax;      // -min x, max x
   double tabs;            // max |t| over the finite stamps
+  double tneg, tmax;      // -min t, max t over the finite stamps
   int bad, pad_;
 };
 constexpr int PDM_STATS_THREADS = 256;
@@ -126,11 +128,12 @@ __device__ __forceinline__ double block_max(double v, double* scratch) { return 
 __global__ void __launch_bounds__(PDM_STATS_THREADS)
 pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, long long n, PdmPart* part,
                  unsigned* done, PdmMeta* meta) {
-  __shared__ double scratch[32 * 8];
+  __shared__ double scratch[32 * 10];
   __shared__ int s_last;
   const int G = gridDim.x;
   const double x0 = x[0];
   double s1 = 0.0, s2 = 0.0, s1b = 0.0, s2b = 0.0, nb = 0.0, xneg = -INFINITY, xmax = -INFINITY, tabs = 0.0;
+  double tneg = -INFINITY, tmax = -INFINITY;
   int bad = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)G * blockDim.x) {
     const double xi = x[i], ti = t[i], d = xi - x0;
@@ -141,6 +144,8 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
     bad |= !isfinite(xi) || !isfinite(ti);
     if (isfinite(ti)) {
       tabs = fmax(tabs, fabs(ti));
+      tneg = fmax(tneg, -ti);
+      tmax = fmax(tmax, ti);
       s1b += d;
       s2b = fma(d, d, s2b);
       nb += 1.0;
@@ -148,13 +153,14 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
   }
   bad = __syncthreads_or(bad);
   {
-    double sums[5] = {s1, s2, s1b, s2b, nb}, maxs[3] = {xneg, xmax, tabs};
-    block_reduce_many<5, 3>(sums, maxs, scratch);
+    double sums[5] = {s1, s2, s1b, s2b, nb}, maxs[5] = {xneg, xmax, tabs, tneg, tmax};
+    block_reduce_many<5, 5>(sums, maxs, scratch);
     s1 = sums[0]; s2 = sums[1]; s1b = sums[2]; s2b = sums[3]; nb = sums[4]; xneg = maxs[0]; xmax = maxs[1]; tabs = maxs[2];
+    tneg = maxs[3]; tmax = maxs[4];
   }
   if (threadIdx.x == 0) {
     PdmPart& p = part[blockIdx.x];
-    p.s1 = s1; p.s2 = s2; p.s1b = s1b; p.s2b = s2b; p.nb = nb; p.xneg = xneg; p.xmax = xmax; p.tabs = tabs; p.bad = bad;
+    p.s1 = s1; p.s2 = s2; p.s1b = s1b; p.s2b = s2b; p.nb = nb; p.xneg = xneg; p.xmax = xmax; p.tabs = tabs; p.tneg = tneg; p.tmax = tmax; p.bad = bad;
     __threadfence();
     s_last = atomicAdd(done, 1u) == (unsigned)(G - 1);
   }
@@ -167,9 +173,11 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
   {
     double sums[5] = {has ? __ldcg(&p->s1) : 0.0, has ? __ldcg(&p->s2) : 0.0, has ? __ldcg(&p->s1b) : 0.0,
                       has ? __ldcg(&p->s2b) : 0.0, has ? __ldcg(&p->nb) : 0.0};
-    double maxs[3] = {has ? __ldcg(&p->xneg) : -INFINITY, has ? __ldcg(&p->xmax) : -INFINITY, has ? __ldcg(&p->tabs) : 0.0};
-    block_reduce_many<5, 3>(sums, maxs, scratch);
+    double maxs[5] = {has ? __ldcg(&p->xneg) : -INFINITY, has ? __ldcg(&p->xmax) : -INFINITY, has ? __ldcg(&p->tabs) : 0.0,
+                      has ? __ldcg(&p->tneg) : -INFINITY, has ? __ldcg(&p->tmax) : -INFINITY};
+    block_reduce_many<5, 5>(sums, maxs, scratch);
     s1 = sums[0]; s2 = sums[1]; s1b = sums[2]; s2b = sums[3]; nb = sums[4]; xneg = maxs[0]; xmax = maxs[1]; tabs = maxs[2];
+    tneg = maxs[3]; tmax = maxs[4];
   }
   bad = __syncthreads_or(has ? __ldcg(&p->bad) : 0);
   if (threadIdx.x == 0) {
@@ -189,6 +197,8 @@ pdm_stats_kernel(const double* __restrict__ t, const double* __restrict__ x, lon
     meta->q_binned = bad ? qb / var : dn - 1.0;
     meta->bad = bad;
     meta->t_absmax = tabs;
+    meta->t0 = tmax >= -tneg ? -tneg : 0.0;            // no finite stamp at all: any origin will do
+    meta->t_span = tmax >= -tneg ? tmax + tneg : 0.0;
     // Packed first-level histogram (pdm_hist_kernel): one 32-bit word per (bin, period) holds the count in
     // its top PDM_CNT_BITS bits and sum rint(x' 2^q) in the rest (two's complement) for one feed window,
     // so 256 * max|x'| * 2^q must stay below 2^22 (9 + 23 bits; with 10 + 22 bits: 128 * max|x'| * 2^q < 2^21, the
@@ -250,8 +260,10 @@ pdm_hist_kernel(const PdmArgs a) {
     if (!isfinite(1.0 / P) || !isfinite(P)) P = 1.0;  // invalid trial period: theta is set to NaN by the epilogue
     Ps[s] = P;
     rPs[s] = 1.0 / P;
-    // (padding columns, P = 1, must not veto the block's fast path)
-    in_range = in_range && (!valids[s] || fabs(rPs[s]) * a.meta->t_absmax < PDM_FAST_LIMIT);
+    // the fixed-point phase works on t - t0: |(t - t0) / P| < 2^18 and |t / P| < 2^30 (guard band, see phase_common.cuh);
+    // padding columns (P = 1) must not veto the block's fast path
+    in_range = in_range && (!valids[s] || (fabs(rPs[s]) * a.meta->t_span < PDM_FAST_LIMIT &&
+                                           fabs(rPs[s]) * a.meta->t_absmax < PDM_SHIFT_LIMIT));
   }
   const bool clamp_bins = a.meta->bad != 0;        // block-uniform
   const double m0d = (double)m0;
@@ -268,15 +280,33 @@ pdm_hist_kernel(const PdmArgs a) {
   const long long sb = (long long)split * per;
   const long long se = sb + per < a.n ? sb + per : a.n;
 
-  // block-uniform: every period of this block keeps |t / P| small enough for the fixed-point phase
+  // block-uniform: every period of this block keeps |(t - t0) / P| small enough for the fixed-point phase
   const bool fast = __syncthreads_and(in_range) != 0;
+  // guard band of the block = the widest any of its periods needs (block-uniform so that one compare serves a trip)
+  __shared__ unsigned s_guard;
+  if (threadIdx.x == 0) s_guard = 0u;
+  __syncthreads();
+  {
+    unsigned g = 0u;
+#pragma unroll
+    for (int s = 0; s < PPT; ++s)
+      if (valids[s] && fast) g = max(g, pdm_guard_units(fabs(rPs[s]), a.meta->t_absmax));
+    atomicMax(&s_guard, g);
+  }
+  __syncthreads();
+  const unsigned guard_units = s_guard;
+  const double t0 = a.meta->t0;
+  double magic[PPT];
+#pragma unroll
+  for (int s = 0; s < PPT; ++s) magic[s] = pdm_fast_magic(t0, rPs[s], guard_units);
+  long long tile0 = 0;   // first sample of the tile being processed (the exact path re-reads the ORIGINAL stamps)
   const int pack_q = a.meta->pack_q;
   const bool packed = fast && !clamp_bins && pack_q >= 0 && a.allow_packed != 0;   // block-uniform
 #if !PDM_L2_INT
   const float unpack = packed ? 1.0f / (float)(1u << pack_q) : 0.f;
 #endif
   const unsigned* s_xq = reinterpret_cast<const unsigned*>(s_x);
-  const unsigned m0u = (unsigned)m0, guard = PDM_FAST_GUARD * m0u;
+  const unsigned m0u = (unsigned)m0, guard = guard_units * m0u;
   // x' = (x - mean) / std(ddof=1) is formed while the tile is staged: as a float for the FP32 columns, as the packed
   // increment (one unit of the count field + signed fixed-point x') for the packed ones
   const double x_mean = a.meta->mean, x_inv_sd = a.meta->inv_sd;
@@ -363,10 +393,9 @@ pdm_hist_kernel(const PdmArgs a) {
   auto packed_one = [&](auto sc, int i, unsigned guard2) {
     constexpr int s = decltype(sc)::value;
     unsigned p0;
-    const double tv = s_t[i];
-    unsigned k0 = pdm_bin_fast_g(tv, rPs[s], m0u, p0);
+    unsigned k0 = pdm_bin_fast_m(s_t[i], rPs[s], magic[s], m0u, p0);
     double ph;
-    if (p0 < guard2) k0 = exact_bin(Ps[s], rPs[s], tv, ph);
+    if (p0 < guard2) k0 = exact_bin(Ps[s], rPs[s], a.t[tile0 + i], ph);
     add32(hist32 + s * THREADS + threadIdx.x, k0, s_xq[i]);
   };
   auto packed_one_all = [&](int i, unsigned guard2) {
@@ -377,11 +406,10 @@ pdm_hist_kernel(const PdmArgs a) {
   auto fixup_one = [&](auto sc, int i, unsigned guard2) {
     constexpr int s = decltype(sc)::value;
     unsigned p0;
-    const double tv = s_t[i];
-    const unsigned kf = pdm_bin_fast_g(tv, rPs[s], m0u, p0);
+    const unsigned kf = pdm_bin_fast_m(s_t[i], rPs[s], magic[s], m0u, p0);
     if (p0 < guard2) {
       double ph;
-      const unsigned ke = exact_bin(Ps[s], rPs[s], tv, ph);
+      const unsigned ke = exact_bin(Ps[s], rPs[s], a.t[tile0 + i], ph);
       if (ke != kf) {
         const unsigned inc = s_xq[i];
         add32(hist32 + s * THREADS + threadIdx.x, kf, 0u - inc);
@@ -435,7 +463,7 @@ pdm_hist_kernel(const PdmArgs a) {
         for (int s = 0; s < PPT; ++s) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            k[s][u] = pdm_bin_fast_g(tv[u], rPs[s], m0u, pos);
+            k[s][u] = pdm_bin_fast_m(tv[u], rPs[s], magic[s], m0u, pos);
             pmin = min(pmin, pos);
           }
         }
@@ -532,28 +560,29 @@ pdm_hist_kernel(const PdmArgs a) {
   auto tile_loop_fast = [&](auto safe, auto sc, int cnt) {
     constexpr bool SAFE = decltype(safe)::value;
     constexpr int s = decltype(sc)::value;
-    const double P = Ps[s], rP = rPs[s];
+    const double P = Ps[s], rP = rPs[s], mg = magic[s];
+    const unsigned guard2 = 2u * guard;
     float2* col = hist + s * THREADS + threadIdx.x;
     int i = 0;
     for (; i + 4 <= cnt; i += 4) {
       const double2 ta = *reinterpret_cast<const double2*>(s_t + i);
       const double2 tb = *reinterpret_cast<const double2*>(s_t + i + 2);
       const float4 xv = *reinterpret_cast<const float4*>(s_x + i);
-      unsigned e0, e1, e2, e3;
-      unsigned k0 = pdm_bin_fast(ta.x, rP, m0u, guard, e0);
-      unsigned k1 = pdm_bin_fast(ta.y, rP, m0u, guard, e1);
-      unsigned k2 = pdm_bin_fast(tb.x, rP, m0u, guard, e2);
-      unsigned k3 = pdm_bin_fast(tb.y, rP, m0u, guard, e3);
+      unsigned p0, p1, p2, p3;   // position inside the bin + guard (stamps are t - t0 here)
+      unsigned k0 = pdm_bin_fast_m(ta.x, rP, mg, m0u, p0);
+      unsigned k1 = pdm_bin_fast_m(ta.y, rP, mg, m0u, p1);
+      unsigned k2 = pdm_bin_fast_m(tb.x, rP, mg, m0u, p2);
+      unsigned k3 = pdm_bin_fast_m(tb.y, rP, mg, m0u, p3);
       double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;   // only the guarded variant looks at them (NaN = skip)
       if (SAFE) {
         f0 = ta.x - ta.x; f1 = ta.y - ta.y; f2 = tb.x - tb.x; f3 = tb.y - tb.y;   // NaN for NaN / inf stamps
       }
-      if (e0 | e1 | e2 | e3) {  // rare: a sample sits on a bin edge
+      if (min(min(p0, p1), min(p2, p3)) < guard2) {  // rare: a sample sits on a bin edge -> exact path, original stamp
         double ph;
-        if (e0) k0 = exact_bin(P, rP, ta.x, ph);
-        if (e1) k1 = exact_bin(P, rP, ta.y, ph);
-        if (e2) k2 = exact_bin(P, rP, tb.x, ph);
-        if (e3) k3 = exact_bin(P, rP, tb.y, ph);
+        if (p0 < guard2) k0 = exact_bin(P, rP, a.t[tile0 + i], ph);
+        if (p1 < guard2) k1 = exact_bin(P, rP, a.t[tile0 + i + 1], ph);
+        if (p2 < guard2) k2 = exact_bin(P, rP, a.t[tile0 + i + 2], ph);
+        if (p3 < guard2) k3 = exact_bin(P, rP, a.t[tile0 + i + 3], ph);
       }
       update(safe, col, k0, f0, xv.x);
       update(safe, col, k1, f1, xv.y);
@@ -561,11 +590,11 @@ pdm_hist_kernel(const PdmArgs a) {
       update(safe, col, k3, f3, xv.w);
     }
     for (; i < cnt; ++i) {
-      unsigned e0;
+      unsigned p0;
       const double tv = s_t[i];
-      unsigned k0 = pdm_bin_fast(tv, rP, m0u, guard, e0);
+      unsigned k0 = pdm_bin_fast_m(tv, rP, mg, m0u, p0);
       double ph;
-      if (e0) k0 = exact_bin(P, rP, tv, ph);
+      if (p0 < guard2) k0 = exact_bin(P, rP, a.t[tile0 + i], ph);
       update(safe, col, k0, SAFE ? tv - tv : 0.0, s_x[i]);
     }
   };
@@ -615,7 +644,7 @@ pdm_hist_kernel(const PdmArgs a) {
   };
 
   int tiles_since_flush = 0;
-  long long tile0 = sb;
+  tile0 = sb;
   do {
     long long left = se - tile0;
     const int cnt = left <= 0 ? 0 : (left < PDM_TILE ? (int)left : PDM_TILE);
@@ -629,7 +658,7 @@ pdm_hist_kernel(const PdmArgs a) {
 #pragma unroll
       for (int k = 0; k < PDM_TILE / PDM_PACK_FLUSH; ++k) {
         for (int i = k * PDM_PACK_FLUSH + threadIdx.x; i < (k + 1) * PDM_PACK_FLUSH && i < cnt; i += THREADS) {
-          s_t[i] = a.t[tile0 + i];
+          s_t[i] = a.t[tile0 + i] - t0;   // packed implies fast: the fixed-point phase works on t - t0
           const int sfix = (int)rint((a.x[tile0 + i] - x_mean) * x_inv_sd * x_scale);
           reinterpret_cast<unsigned*>(s_x)[i] = (1u << PDM_SUM_BITS) + (unsigned)sfix;
           wabs[k] += (unsigned)(sfix < 0 ? -sfix : sfix);
@@ -644,7 +673,7 @@ pdm_hist_kernel(const PdmArgs a) {
       }
     } else {
       for (int i = threadIdx.x; i < cnt; i += THREADS) {
-        s_t[i] = a.t[tile0 + i];
+        s_t[i] = fast ? a.t[tile0 + i] - t0 : a.t[tile0 + i];   // the exact path keeps the original stamps
         const double v = (a.x[tile0 + i] - x_mean) * x_inv_sd;
         if (packed) reinterpret_cast<unsigned*>(s_x)[i] = (1u << PDM_SUM_BITS) + (unsigned)(int)rint(v * x_scale);
         else s_x[i] = (float)v;

@@ -56,6 +56,32 @@ __device__ __forceinline__ unsigned pdm_bin_fast(double tv, double rP, unsigned 
 // pos < 2 guard  <=>  the unshifted phase is within guard of a bin edge (then the bin index may be off by
 // one and the caller re-bins exactly); otherwise the shift cannot have carried into the bin index.
 constexpr double PDM_FAST_MAGIC_G = PDM_FAST_MAGIC + PDM_FAST_GUARD * (1.0 / 4294967296.0);
+
+// Shifted form, usable for time stamps far from zero (Julian dates: t ~ 2.45e6 d with periods of a day make
+// |t / P| ~ 2^21, beyond the magic-number reduction).  With t0 = the smallest finite stamp,
+//     (t / P) mod 1 = ((t - t0) / P + c) mod 1,   c = frac(t0 / P)  (one constant per trial period),
+// so the kernel stages t' = t - t0 (exact in float64 for stamps of one series) and evaluates
+//     fma(t', 1/P, magic),   magic = 1.5 * 2^20 + c + G * 2^-32 ,
+// which needs only |t' / P| < 2^18.  The guard G (units of 2^-32 turn, folded into the magic number as above) must
+// now cover the distance between this phase and the REFERENCE's own (t / P) % 1, whose quotient is rounded at the
+// magnitude of t / P: |difference| <= 2 |t / P| 2^-53 + 2 * 2^-32, i.e. G = 4 + ceil(|t / P|_max 2^-20) units.  Samples
+// inside the guard are re-binned by the exact path from the ORIGINAL stamp, so they land where the reference puts them.
+constexpr double PDM_SHIFT_LIMIT = 1073741824.0;   // |t / P| < 2^30: G stays <= 1028 units (2.4e-7 turn)
+__device__ __forceinline__ unsigned pdm_guard_units(double rP_abs, double t_absmax) {
+  return 4u + (unsigned)ceil(rP_abs * t_absmax * (1.0 / 1048576.0));
+}
+__device__ __forceinline__ double pdm_fast_magic(double t0, double rP, unsigned guard_units) {
+  const double p = __dmul_rn(t0, rP);
+  const double e = __fma_rn(t0, rP, -p);
+  const double c = __dadd_rn(__dadd_rn(p, -rint(p)), e);     // frac(t0 / P) in [-0.5, 0.5], exact product
+  return __dadd_rn(__dadd_rn(PDM_FAST_MAGIC, c), (double)guard_units * (1.0 / 4294967296.0));
+}
+__device__ __forceinline__ unsigned pdm_bin_fast_m(double tv, double rP, double magic, unsigned m0u, unsigned& pos) {
+  const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, magic));
+  const unsigned long long w = (unsigned long long)u * m0u;
+  pos = (unsigned)w;
+  return (unsigned)(w >> 32);
+}
 __device__ __forceinline__ unsigned pdm_bin_fast_g(double tv, double rP, unsigned m0u, unsigned& pos) {
   const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, PDM_FAST_MAGIC_G));
   const unsigned long long w = (unsigned long long)u * m0u;

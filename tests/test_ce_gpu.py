@@ -68,7 +68,7 @@ def test_integer_times_rational_periods_bin_edges_exact(gpu_ctx):
 def test_negative_and_julian_date_times(gpu_ctx):
     t, x = synth(6000, 300.0, 9)
     periods = np.linspace(1.0, 8.0, 400)
-    for shift in (-150.0, 2_450_000.0):        # the second puts |t / P| beyond the fixed-point phase: exact FP64 path
+    for shift in (-150.0, 2_450_000.0, 3.0e12):   # JD stamps: shifted fixed-point phase; 3e12: exact FP64 path for every sample
         h, am, _ = gpu_ctx.ce(t + shift, x, periods, 10, 5)
         assert_close(h, ce_numpy.ce(t + shift, x, periods, 10, 5))
 

@@ -226,3 +226,21 @@ def test_outlier_burst_is_fed_in_guaranteed_pieces(gpu_ctx):
     ref = cport.pdm(t, x, periods, 10, 2)
     np.testing.assert_allclose(th, ref, rtol=TOL)
     assert am == np.nanargmin(ref)
+
+
+@pytest.mark.parametrize("offset", [2_450_000.0, 2_457_000.5, -1.0e6])
+def test_julian_date_stamps_use_the_shifted_fast_path(gpu_ctx, offset):
+    """Absolute JD / BJD stamps (|t / P| ~ 2^21 .. 2^24) run the fixed-point phase on t - t0 with a guard band sized
+    by |t / P|: samples inside it are re-binned exactly from the ORIGINAL stamp, so the result must equal the
+    reference's (t / P) % 1 binning -- including its rounding of the quotient at that magnitude -- on irregular stamps
+    and on a regular quarter-day cadence whose phases sit exactly on bin edges."""
+    t, x = synth(30_000, 400.0, 23)
+    periods = np.concatenate([np.linspace(0.2, 11.0, 1500), [0.25, 0.5, 1.0, 2.0, 2.5, 4.0, 5.0]])
+    th, am, mn = gpu_ctx.pdm(t + offset, x, periods, 10, 2)
+    ref = cport.pdm(t + offset, x, periods, 10, 2)
+    np.testing.assert_allclose(th, ref, rtol=TOL)
+    assert am == np.nanargmin(ref)
+    tc = offset + 0.25 * np.arange(20_000.0)                            # regular cadence: t / P exactly on bin edges
+    xc = np.sin(2 * np.pi * tc / 2.5) + 0.3 * np.random.default_rng(5).standard_normal(tc.size)
+    thc, amc, _ = gpu_ctx.pdm(tc, xc, periods[-7:], 10, 2)
+    np.testing.assert_allclose(thc, cport.pdm(tc, xc, periods[-7:], 10, 2), rtol=2e-6)
