@@ -141,14 +141,15 @@ def make_gls_c5(nf_total):
                 name=f"GLS 1e6 points x {nf_total} frequencies (C5)")
 
 
-def make_pdm_c3(np_total):
+def make_pdm_c3(np_total, t_offset=0.0):
     rng = np.random.default_rng(3)
     n = 100_000
-    t = np.sort(rng.uniform(0, 1000.0, n))
+    t = np.sort(rng.uniform(0, 1000.0, n)) + t_offset
     x = 1000 + np.sin(2 * np.pi * t / 3.7) + 0.8 * np.sin(4 * np.pi * t / 3.7) + rng.standard_normal(n)
     periods = np.linspace(1.0, 11.0, np_total)
     return dict(kind="pdm", t=t, y=x, periods=periods, nb=10, nc=2, nf=np_total,
-                name=f"PDM 1e5 points x {np_total} trial periods, nb=10 nc=2 (C3)")
+                name=f"PDM 1e5 points x {np_total} trial periods, nb=10 nc=2 (C3)" +
+                     (f", time stamps offset by {t_offset:g} (Julian dates)" if t_offset else ""))
 
 
 def make_ce_c3(np_total):
@@ -909,7 +910,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gls_c2",
                     choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c4_full", "gls_c1", "gls_multi",
-                             "sl", "ce_c3"])
+                             "sl", "ce_c3", "pdm_c3_jd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true",
                     help="default workload only: skip the `configs` block (C3 / C5 / C4 / C1 at their BASELINE sizes)")
@@ -926,7 +927,7 @@ def main():
 
     per_gpu = {"gls_c2": 100_000, "pdm_c3": 100_000, "gls_c5": 1_250_000, "gls_c5_full": 10_000_000,
                "gls_c4": 256, "gls_c4_full": 10_000, "gls_c1": 10_000, "gls_multi": 256, "sl": 100_000,
-               "ce_c3": 100_000}[args.workload]
+               "ce_c3": 100_000, "pdm_c3_jd": 100_000}[args.workload]
     strong = args.strong or args.workload in ("gls_c5_full",)
     total_units = per_gpu if strong else per_gpu * max(world, 1)
     scaling = "strong" if (strong and world > 1) else "weak"
@@ -942,6 +943,8 @@ def main():
             return make_gls_multi(units)
         if workload == "pdm_c3":
             return make_pdm_c3(units)
+        if workload == "pdm_c3_jd":
+            return make_pdm_c3(units, t_offset=2_457_000.5)
         if workload == "ce_c3":
             return make_ce_c3(units)
         if workload == "sl":
