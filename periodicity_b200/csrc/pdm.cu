@@ -251,7 +251,7 @@ pdm_hist_kernel(const PdmArgs a) {
   long long pis[PPT];
   bool valids[PPT];
   double Ps[PPT], rPs[PPT];
-  bool in_range = true;
+  bool in_range = true, plain_ok = true;
 #pragma unroll
   for (int s = 0; s < PPT; ++s) {
     pis[s] = pb * VT + s * THREADS + threadIdx.x;
@@ -264,6 +264,7 @@ pdm_hist_kernel(const PdmArgs a) {
     // padding columns (P = 1) must not veto the block's fast path
     in_range = in_range && (!valids[s] || (fabs(rPs[s]) * a.meta->t_span < PDM_FAST_LIMIT &&
                                            fabs(rPs[s]) * a.meta->t_absmax < PDM_SHIFT_LIMIT));
+    plain_ok = plain_ok && (!valids[s] || fabs(rPs[s]) * a.meta->t_absmax < PDM_FAST_LIMIT);
   }
   const bool clamp_bins = a.meta->bad != 0;        // block-uniform
   const double m0d = (double)m0;
@@ -282,7 +283,10 @@ pdm_hist_kernel(const PdmArgs a) {
 
   // block-uniform: every period of this block keeps |(t - t0) / P| small enough for the fixed-point phase
   const bool fast = __syncthreads_and(in_range) != 0;
-  // guard band of the block = the widest any of its periods needs (block-uniform so that one compare serves a trip)
+  // block-uniform: even |t / P| is small for every period of the block (stamps near zero): no shift, the magic number is
+  // a compile-time constant and the packed loop is the round-1 / round-2 tuned code; otherwise (Julian dates) the shifted
+  // form with one magic number per period and a guard band sized by |t / P| (phase_common.cuh)
+  const bool plain = __syncthreads_and(plain_ok) != 0;
   __shared__ unsigned s_guard;
   if (threadIdx.x == 0) s_guard = 0u;
   __syncthreads();
@@ -294,11 +298,8 @@ pdm_hist_kernel(const PdmArgs a) {
     atomicMax(&s_guard, g);
   }
   __syncthreads();
-  const unsigned guard_units = s_guard;
-  const double t0 = a.meta->t0;
-  double magic[PPT];
-#pragma unroll
-  for (int s = 0; s < PPT; ++s) magic[s] = pdm_fast_magic(t0, rPs[s], guard_units);
+  const unsigned guard_units = plain ? PDM_FAST_GUARD : s_guard;   // the widest any period of the block needs
+  const double t0 = plain ? 0.0 : a.meta->t0;                      // pdm_fast_magic(0, rP, 4) == PDM_FAST_MAGIC_G exactly
   long long tile0 = 0;   // first sample of the tile being processed (the exact path re-reads the ORIGINAL stamps)
   const int pack_q = a.meta->pack_q;
   const bool packed = fast && !clamp_bins && pack_q >= 0 && a.allow_packed != 0;   // block-uniform
@@ -393,7 +394,7 @@ pdm_hist_kernel(const PdmArgs a) {
   auto packed_one = [&](auto sc, int i, unsigned guard2) {
     constexpr int s = decltype(sc)::value;
     unsigned p0;
-    unsigned k0 = pdm_bin_fast_m(s_t[i], rPs[s], magic[s], m0u, p0);
+    unsigned k0 = pdm_bin_fast_m(s_t[i], rPs[s], pdm_fast_magic(t0, rPs[s], guard_units), m0u, p0);   // (rare path: recomputed, not kept live)
     double ph;
     if (p0 < guard2) k0 = exact_bin(Ps[s], rPs[s], a.t[tile0 + i], ph);
     add32(hist32 + s * THREADS + threadIdx.x, k0, s_xq[i]);
@@ -406,7 +407,7 @@ pdm_hist_kernel(const PdmArgs a) {
   auto fixup_one = [&](auto sc, int i, unsigned guard2) {
     constexpr int s = decltype(sc)::value;
     unsigned p0;
-    const unsigned kf = pdm_bin_fast_m(s_t[i], rPs[s], magic[s], m0u, p0);
+    const unsigned kf = pdm_bin_fast_m(s_t[i], rPs[s], pdm_fast_magic(t0, rPs[s], guard_units), m0u, p0);
     if (p0 < guard2) {
       double ph;
       const unsigned ke = exact_bin(Ps[s], rPs[s], a.t[tile0 + i], ph);
@@ -420,8 +421,11 @@ pdm_hist_kernel(const PdmArgs a) {
   auto fixup_one_all = [&](int i, unsigned guard2) {
     static_for<PPT>([&](auto sc) { fixup_one(sc, i, guard2); });
   };
-  auto tile_loop_packed = [&](int cnt) {
+  auto tile_loop_packed = [&](auto shifted, int cnt) {
     constexpr int U = PPT == 1 ? 8 : PDM_TRIP_CHAINS / PPT;  // samples per trip: U * PPT independent DFMA -> IMAD.WIDE -> IMAD -> ATOMS chains, one edge test
+    double mg[PPT];   // magic number per column: a compile-time constant unless the stamps are shifted
+#pragma unroll
+    for (int s = 0; s < PPT; ++s) mg[s] = decltype(shifted)::value ? pdm_fast_magic(t0, rPs[s], guard_units) : PDM_FAST_MAGIC_G;
     const unsigned guard2 = 2u * guard;
     unsigned* c32 = hist32 + threadIdx.x;
     for (int w0 = 0; w0 < cnt; w0 += PDM_PACK_FLUSH) {
@@ -463,7 +467,7 @@ pdm_hist_kernel(const PdmArgs a) {
         for (int s = 0; s < PPT; ++s) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            k[s][u] = pdm_bin_fast_m(tv[u], rPs[s], magic[s], m0u, pos);
+            k[s][u] = pdm_bin_fast_m(tv[u], rPs[s], mg[s], m0u, pos);
             pmin = min(pmin, pos);
           }
         }
@@ -560,7 +564,7 @@ pdm_hist_kernel(const PdmArgs a) {
   auto tile_loop_fast = [&](auto safe, auto sc, int cnt) {
     constexpr bool SAFE = decltype(safe)::value;
     constexpr int s = decltype(sc)::value;
-    const double P = Ps[s], rP = rPs[s], mg = magic[s];
+    const double P = Ps[s], rP = rPs[s], mg = pdm_fast_magic(t0, rP, guard_units);
     const unsigned guard2 = 2u * guard;
     float2* col = hist + s * THREADS + threadIdx.x;
     int i = 0;
@@ -682,7 +686,8 @@ pdm_hist_kernel(const PdmArgs a) {
     __syncthreads();
 
     if (packed) {
-      tile_loop_packed(cnt);
+      if (plain) tile_loop_packed(std::false_type{}, cnt);
+      else tile_loop_packed(std::true_type{}, cnt);
     } else {
       static_for<PPT>([&](auto sc) { tile_unpacked(sc, cnt); });
     }

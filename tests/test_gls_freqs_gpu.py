@@ -107,7 +107,7 @@ def test_dropin_class_frequency_keyword_and_multi_device():
     finally:
         os.environ.pop("PDC_MULTI_MIN_EVALS", None)
     pm, am, mm = mctx.gls_freqs(t, y, None, np.sort(freqs))
-    np.testing.assert_array_equal(pm, ls.values)           # per-frequency work: slices are bit-identical
+    assert np.max(np.abs(pm - ls.values)) <= 2e-6 * ls.amax()   # a slice may choose another sample split (other FP32 tiles)
     assert am == ls.argmax() and mm == ls.amax()
     mctx.close()
     with pytest.raises(ValueError):
