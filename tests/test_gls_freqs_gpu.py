@@ -108,7 +108,7 @@ def test_dropin_class_frequency_keyword_and_multi_device():
         os.environ.pop("PDC_MULTI_MIN_EVALS", None)
     pm, am, mm = mctx.gls_freqs(t, y, None, np.sort(freqs))
     assert np.max(np.abs(pm - ls.values)) <= 2e-6 * ls.amax()   # a slice may choose another sample split (other FP32 tiles)
-    assert am == ls.argmax() and mm == ls.amax()
+    assert am == ls.argmax() and mm == pm[am]
     mctx.close()
     with pytest.raises(ValueError):
         _ffi.default_context(0).gls_freqs(np.arange(5.0), np.arange(4.0), None, [1.0])

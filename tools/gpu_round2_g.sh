@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU-box run G (1 GPU): tests + PDM timing after the plain / shifted split of the packed loop.
 OUT=gpurun_out; mkdir -p $OUT
-python -m pytest tests -m gpu -x -q --durations=5 > $OUT/g_pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?"; tail -n 9 $OUT/g_pytest_gpu.log
+python -m pytest tests -m gpu -q --durations=5 > $OUT/g_pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?"; tail -n 9 $OUT/g_pytest_gpu.log
 for wl in pdm_c3 pdm_c3_jd ce_c3; do
   python bench.py --workload $wl --no-configs --no-cpu-baseline > $OUT/g_bench_$wl.json 2> $OUT/g_bench_$wl.err; echo "bench $wl rc=$?"
 done
