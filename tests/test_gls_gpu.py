@@ -584,3 +584,22 @@ def test_c5_full_grid_peak_index_vs_reference_algorithm_and_strided_oracle(gpu_c
     assert sel[np.argmax(ref)] == am
     fast = gls_numpy.gls_power(t, y, None, fmin, df, nf, True, False)      # the reference's algorithm as shipped
     assert int(np.nanargmax(fast)) == am
+
+
+@pytest.mark.parametrize("n_per_peak,weighted", [(100.0, False), (100.0, True), (30.0, False)])
+def test_dense_grid_has_many_sub_cycle_bins(gpu_ctx, n_per_peak, weighted):
+    """GLS(n=100) puts ~100 bins below one cycle over the baseline, where CC - C^2 cancels ~300x and FP32
+    sums are not enough (gls_common.cuh).  The FP64 range is sized from the actual count (round 1 stopped at 16)."""
+    N, nf = 4000, 3000
+    rng = np.random.default_rng(33)
+    t = np.sort(rng.uniform(0, 80.0, N))
+    df = 1 / (t[-1] - t[0]) / n_per_peak
+    fmin = 0.5 * df
+    y = 3 + np.sin(2 * np.pi * (fmin + 0.61 * nf * df) * t) + 0.7 * rng.standard_normal(N)
+    err = rng.uniform(0.5, 1.5, N) if weighted else None
+    p, am, _ = gpu_ctx.gls(t, y, None if err is None else err ** -2.0, fmin, df, nf)
+    ref = cport.gls_exact(t, y, err, fmin, df, nf, True)
+    assert_power_close(p, ref)
+    low = int(n_per_peak)                                     # the sub-cycle bins themselves, elementwise
+    assert np.max(np.abs(p[:low] - ref[:low]) / np.maximum(np.abs(ref[:low]), 1e-3 * np.max(ref))) <= 1e-5
+    assert am == np.nanargmax(ref)

@@ -243,4 +243,5 @@ def test_julian_date_stamps_use_the_shifted_fast_path(gpu_ctx, offset):
     tc = offset + 0.25 * np.arange(20_000.0)                            # regular cadence: t / P exactly on bin edges
     xc = np.sin(2 * np.pi * tc / 2.5) + 0.3 * np.random.default_rng(5).standard_normal(tc.size)
     thc, amc, _ = gpu_ctx.pdm(tc, xc, periods[-7:], 10, 2)
-    np.testing.assert_allclose(thc, cport.pdm(tc, xc, periods[-7:], 10, 2), rtol=2e-6)
+    # (a single mis-binned sample of 20,000 would move theta by ~1e-4; the packed path's own quantisation is ~5e-6 here)
+    np.testing.assert_allclose(thc, cport.pdm(tc, xc, periods[-7:], 10, 2), rtol=TOL)
