@@ -976,7 +976,13 @@ def main():
     steps = min(args.steps, 3) if big else args.steps
     rec, ok = run_workload(env, wl, per_gpu if not strong else -(-per_gpu // world), scaling, steps, args.warmup,
                            want_cpu=not args.no_cpu_baseline,
-                           check_ref_peak=args.workload not in ("gls_c5", "gls_c5_full"))
+                           # the reference algorithm's peak index is asserted on the NAMED configs only.  The weak-scaled
+                           # primary grid at N > 1 (N x 1e5 frequencies) is not one: it runs N x past the Kepler cadence's
+                           # pseudo-Nyquist, where alias peaks of nearly equal height exist and the reference's own
+                           # approximation error (up to 3 % of the peak there) decides which of them it reports --
+                           # measured at N = 4, 8 in round 2: exact oracle and GPU agree on bin 31370, the FFT
+                           # extirpolation picks an alias
+                           check_ref_peak=args.workload not in ("gls_c5", "gls_c5_full") and (world == 1 or strong))
     all_ok = ok
     if default_run:
         cfgs = {}

@@ -114,6 +114,9 @@ struct CeArgs {
   long long n, np;
   int nphi, nm, cells, nsplit;
   int counts_only;      // 1: phase bins only (nm == 1, x is not read): the Gregory-Loredo passes
+  unsigned one;         // == 1, as a kernel ARGUMENT: with a literal 1 ptxas turns the update into ATOMS.POPC.INC (a
+                        // warp-aggregated increment that matches addresses across lanes first); the columns are private,
+                        // every lane has its own address, and plain ATOMS.ADD is what pdm.cu measured at 13.7 updates/clk/SM
 };
 
 // numpy's magnitude bin: scaled = (x - lo) / (hi - lo); min(int(scaled * nm), nm - 1)  (oracle/ce_numpy.py)
@@ -231,6 +234,7 @@ ce_hist_kernel(const CeArgs a) {
   const unsigned nphiu = (unsigned)nphi;
   const double xlo = a.meta->xmin, xrange = a.meta->xmax - a.meta->xmin;
   const unsigned mstride = (unsigned)nm * VT;   // words between consecutive phase bins of one column
+  const unsigned one = a.one;
 
   for (int k = threadIdx.x; k <= nphi; k += THREADS) s_thr[k] = (double)k / nphid;  // phase.py:138-140
   for (int k = threadIdx.x; k < CE_TILE_PAD; k += THREADS) s_t[CE_TILE + k] = 0.0;
@@ -318,7 +322,7 @@ ce_hist_kernel(const CeArgs a) {
 #pragma unroll
         for (int u = 0; u < CE_U; ++u) {
 #pragma unroll
-          for (int s = 0; s < PPT; ++s) add(c0 + s * THREADS, k[s][u], mo[u], 1u);
+          for (int s = 0; s < PPT; ++s) add(c0 + s * THREADS, k[s][u], mo[u], one);
         }
         if (pmin < guard2) {
           for (int u = 0; u < CE_U; ++u) {
@@ -330,8 +334,8 @@ ce_hist_kernel(const CeArgs a) {
                 double ph;
                 const unsigned ke = exact_bin(Ps[s], rPs[s], a.t[tile0 + i + u], ph);   // the ORIGINAL stamp
                 if (ke != kf) {
-                  add(c0 + s * THREADS, kf, s_m[i + u], 0u - 1u);   // counts are sums modulo 2^32: -1 undoes the update
-                  add(c0 + s * THREADS, ke, s_m[i + u], 1u);
+                  add(c0 + s * THREADS, kf, s_m[i + u], 0u - one);   // counts are sums modulo 2^32: -1 undoes the update
+                  add(c0 + s * THREADS, ke, s_m[i + u], one);
                 }
               }
             }
@@ -347,7 +351,7 @@ ce_hist_kernel(const CeArgs a) {
             double ph;
             kf = exact_bin(Ps[s], rPs[s], a.t[tile0 + i], ph);
           }
-          add(c0 + s * THREADS, kf, s_m[i], 1u);
+          add(c0 + s * THREADS, kf, s_m[i], one);
         }
       }
     } else {
@@ -361,7 +365,7 @@ ce_hist_kernel(const CeArgs a) {
           unsigned k = exact_bin(Ps[s], rPs[s], tvu, ph);
           if (!(ph == ph) || mo == 0xffffffffu) continue;
           k = min(k, nphiu - 1u);
-          add(cnt + s * THREADS + threadIdx.x, k, mo, 1u);
+          add(cnt + s * THREADS + threadIdx.x, k, mo, one);
         }
       }
     }
@@ -482,6 +486,7 @@ static int ce_hist_pass(pdc_ctx* ctx, const double* t, const double* x, int64_t 
   a.cells = cells;
   a.nsplit = nsplit;
   a.counts_only = x == nullptr;
+  a.one = 1u;
 
   ctx->hist_plane_dirty = true;
   PDC_TRY(ctx->main_begin(st));
