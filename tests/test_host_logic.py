@@ -53,6 +53,21 @@ class OracleContext:
         th = cport.pdm(t, x, periods, nb, nc)
         return th, int(np.nanargmin(th)), float(np.nanmin(th))
 
+    def gls_freqs(self, t, y, w, freqs, fit_mean=True, psd_scale=None):
+        err = None if w is None else np.asarray(w, dtype=np.float64) ** -0.5
+        p = cport.gls_exact_freqs(t, y, err, freqs, fit_mean, psd_scale is not None)
+        return p, int(np.nanargmax(p)), float(np.nanmax(p))
+
+    def ce(self, t, x, periods, nphi, nm):
+        from oracle import ce_numpy
+        h = ce_numpy.ce(np.asarray(t, dtype=np.float64), np.asarray(x, dtype=np.float64), periods, nphi, nm)
+        return h, int(np.nanargmin(h)), float(np.nanmin(h))
+
+    def gl(self, t, periods, m_max=12, nc=10):
+        from oracle import gl_numpy
+        lo = gl_numpy.gl(np.asarray(t, dtype=np.float64), periods, m_max, nc)
+        return lo, int(np.nanargmax(lo)), float(np.nanmax(lo))
+
     def stringlength(self, t, m, periods):
         ell = stringlength_numpy.string_lengths(np.asarray(t, dtype=np.float64), np.asarray(m), periods)
         return ell, int(np.nanargmin(ell)), float(np.nanmin(ell))
@@ -196,3 +211,38 @@ def test_stringlength_front_end_matches_reference(case):
     assert out is sl.periodogram and sl.signal.size == g["x"].size
     p = 1 / out.frequency[5]
     assert sl._stringlength(p) == pytest.approx(out.values[5], rel=1e-13)
+
+
+def test_new_method_classes_follow_pdm_grid_conventions():
+    """CE / GL (reference TODOs, phase.py:13-14) use PDM's period-grid options and FSeries wrap (phase.py:167-180,194);
+    GLS(frequency=...) evaluates on the user's grid, sorted ascending, with the same attribute side effects."""
+    from periodicity_b200 import CE, GL
+    from test_gl_oracle import events
+    rng = np.random.default_rng(0)
+    t = np.sort(rng.uniform(0, 60, 800))
+    x = np.sin(2 * np.pi * t / 3.3) + 0.2 * rng.standard_normal(t.size)
+    sig = TSeries(t, x)
+    pdm = PDM(n_periods=300)
+    pdm(sig)
+    ce = CE(n_periods=300)
+    pg = ce(sig)
+    np.testing.assert_array_equal(ce.periods, pdm.periods)                       # same defaults: 2*median_dt .. baseline
+    np.testing.assert_array_equal(pg.frequency, pdm.periodogram.frequency)      # FSeries over 1/P, ascending frequency
+    assert pg.values[::-1][ce.argmin_index] == ce.min_entropy
+    ce2 = CE(nb=8, nm=4, p_min=1.0, p_max=8.0, n_periods=None, oversample=2)
+    ce2(sig)
+    assert ce2.periods.size == int((1 / 1.0 - 1 / 8.0) * 2 * sig.baseline + 1)   # phase.py:176-179
+    assert abs(ce2.periods[ce2.argmin_index] - 3.3) < 0.1
+    ev = events(900, 4.1, 3, T=120.0)
+    gl = GL(m_max=5, nc=3, p_min=2.0, p_max=9.0, n_periods=200)
+    pg = gl(ev[::-1])                                                            # plain, unsorted array of event times
+    assert np.all(np.diff(gl.t) >= 0) and gl.periods[0] == 2.0 and gl.periods[-1] == 9.0
+    assert abs(gl.periods[gl.argmax_index] - 4.1) < 0.1 and pg.values[::-1][gl.argmax_index] == gl.max_lnodds
+    freqs = np.array([0.9, 0.1, 0.303, 0.5, 0.2])
+    gls = GLS(frequency=freqs, psd=True)
+    err = rng.uniform(0.1, 0.3, t.size)
+    out = gls(sig, err=err)
+    np.testing.assert_array_equal(out.frequency, np.sort(freqs))
+    np.testing.assert_array_equal(gls.frequency, np.sort(freqs))
+    assert gls.err is not None and out is gls.periodogram and out.frequency[out.argmax()] == 0.303
+    np.testing.assert_allclose(out.values, cport.gls_exact_freqs(t, x, err, np.sort(freqs), True, psd=True), rtol=1e-12)
