@@ -114,9 +114,6 @@ struct CeArgs {
   long long n, np;
   int nphi, nm, cells, nsplit;
   int counts_only;      // 1: phase bins only (nm == 1, x is not read): the Gregory-Loredo passes
-  unsigned one;         // == 1, as a kernel ARGUMENT: with a literal 1 ptxas turns the update into ATOMS.POPC.INC (a
-                        // warp-aggregated increment that matches addresses across lanes first); the columns are private,
-                        // every lane has its own address, and plain ATOMS.ADD is what pdm.cu measured at 13.7 updates/clk/SM
 };
 
 // numpy's magnitude bin: scaled = (x - lo) / (hi - lo); min(int(scaled * nm), nm - 1)  (oracle/ce_numpy.py)
@@ -233,8 +230,10 @@ ce_hist_kernel(const CeArgs a) {
   const double nphid = (double)nphi;
   const unsigned nphiu = (unsigned)nphi;
   const double xlo = a.meta->xmin, xrange = a.meta->xmax - a.meta->xmin;
-  const unsigned mstride = (unsigned)nm * VT;   // words between consecutive phase bins of one column
-  const unsigned one = a.one;
+  // Shared-memory addresses are formed in 32 bits, in BYTES: one IMAD per update (bin * stride + sample offset) and the
+  // column of the thread as an immediate -- the generic-pointer form cost 1.3 instructions more per update (ncu r02i).
+  const unsigned mstride = (unsigned)nm * VT * 4u;   // bytes between consecutive phase bins of one column
+  const unsigned col0 = (unsigned)__cvta_generic_to_shared(cnt + threadIdx.x);   // this thread's first column
 
   for (int k = threadIdx.x; k <= nphi; k += THREADS) s_thr[k] = (double)k / nphid;  // phase.py:138-140
   for (int k = threadIdx.x; k < CE_TILE_PAD; k += THREADS) s_t[CE_TILE + k] = 0.0;
@@ -269,9 +268,16 @@ ce_hist_kernel(const CeArgs a) {
     if (e < PDM_AMBIG) k = pdm_fix_bin(k, phi, s_thr, nphi);
     return (unsigned)k;
   };
-  auto add = [&](unsigned* col, unsigned k, unsigned moff, unsigned inc) {
-    asm volatile("" : "+r"(k));   // keep the bin index opaque: one IMAD on the high word of the 64-bit product (see pdm.cu)
-    atomicAdd(col + k * mstride + moff, inc);
+  // `base` = col0 + byte offset of the sample's magnitude bin (computed once per sample, shared by the thread's columns);
+  // S = which of the thread's columns.  The increment is a literal: ptxas emits ATOMS.POPC.INC for +1, measured faster
+  // here than ATOMS.ADD with a register operand (3.28 vs 3.39 ms on the C3 shape).
+  auto add1 = [&](auto sc, unsigned base, unsigned k) {
+    constexpr int S = decltype(sc)::value;
+    asm volatile("red.shared.add.u32 [%0+%1], 1;" :: "r"(base + k * mstride), "n"(S * THREADS * 4) : "memory");
+  };
+  auto sub1 = [&](auto sc, unsigned base, unsigned k) {
+    constexpr int S = decltype(sc)::value;
+    asm volatile("red.shared.add.u32 [%0+%1], 0xffffffff;" :: "r"(base + k * mstride), "n"(S * THREADS * 4) : "memory");
   };
 
   long long tile0 = sb;
@@ -282,14 +288,13 @@ ce_hist_kernel(const CeArgs a) {
     for (int i = threadIdx.x; i < cntv; i += THREADS) {
       s_t[i] = fast ? a.t[tile0 + i] - t0 : a.t[tile0 + i];
       const int mb = a.counts_only ? 0 : ce_mbin(a.x[tile0 + i], xlo, xrange, nm);
-      s_m[i] = mb < 0 ? 0xffffffffu : (unsigned)mb * VT;
+      s_m[i] = mb < 0 ? 0xffffffffu : (unsigned)mb * VT * 4u;   // byte offset of the magnitude bin inside a phase bin
     }
     __syncthreads();
 
     if (fast) {
       // every sample is finite and in range: CE_U samples x PPT periods per trip, atomics issued at once with the fast
       // bins, the rare trip with a sample on a bin edge re-bins those exactly afterwards and moves the increment
-      unsigned* c0 = cnt + threadIdx.x;
       int i = 0;
       double tv[CE_U];
 #pragma unroll
@@ -321,52 +326,50 @@ ce_hist_kernel(const CeArgs a) {
         }
 #pragma unroll
         for (int u = 0; u < CE_U; ++u) {
-#pragma unroll
-          for (int s = 0; s < PPT; ++s) add(c0 + s * THREADS, k[s][u], mo[u], one);
+          const unsigned base = col0 + mo[u];
+          static_for<PPT>([&](auto sc) { add1(sc, base, k[decltype(sc)::value][u]); });
         }
         if (pmin < guard2) {
           for (int u = 0; u < CE_U; ++u) {
-#pragma unroll
-            for (int s = 0; s < PPT; ++s) {
+            static_for<PPT>([&](auto sc) {
+              constexpr int s = decltype(sc)::value;
               unsigned p0;
               const unsigned kf = pdm_bin_fast_m(s_t[i + u], rPs[s], magic[s], nphiu, p0);
               if (p0 < guard2) {
                 double ph;
                 const unsigned ke = exact_bin(Ps[s], rPs[s], a.t[tile0 + i + u], ph);   // the ORIGINAL stamp
                 if (ke != kf) {
-                  add(c0 + s * THREADS, kf, s_m[i + u], 0u - one);   // counts are sums modulo 2^32: -1 undoes the update
-                  add(c0 + s * THREADS, ke, s_m[i + u], one);
+                  sub1(sc, col0 + s_m[i + u], kf);   // counts are sums modulo 2^32: -1 undoes the update
+                  add1(sc, col0 + s_m[i + u], ke);
                 }
               }
-            }
+            });
           }
         }
       }
       for (; i < cntv; ++i) {
-#pragma unroll
-        for (int s = 0; s < PPT; ++s) {
+        static_for<PPT>([&](auto sc) {
+          constexpr int s = decltype(sc)::value;
           unsigned p0;
           unsigned kf = pdm_bin_fast_m(s_t[i], rPs[s], magic[s], nphiu, p0);
           if (p0 < guard2) {
             double ph;
             kf = exact_bin(Ps[s], rPs[s], a.t[tile0 + i], ph);
           }
-          add(c0 + s * THREADS, kf, s_m[i], one);
-        }
+          add1(sc, col0 + s_m[i], kf);
+        });
       }
     } else {
       // exact FP64 phase for every sample; samples whose phase is NaN (non-finite stamp) or whose value is NaN are in no cell
       for (int i = 0; i < cntv; ++i) {
         const double tvu = s_t[i];
         const unsigned mo = s_m[i];
-#pragma unroll
-        for (int s = 0; s < PPT; ++s) {
+        static_for<PPT>([&](auto sc) {
+          constexpr int s = decltype(sc)::value;
           double ph;
           unsigned k = exact_bin(Ps[s], rPs[s], tvu, ph);
-          if (!(ph == ph) || mo == 0xffffffffu) continue;
-          k = min(k, nphiu - 1u);
-          add(cnt + s * THREADS + threadIdx.x, k, mo, one);
-        }
+          if (ph == ph && mo != 0xffffffffu) add1(sc, col0 + mo, min(k, nphiu - 1u));
+        });
       }
     }
     tile0 += CE_TILE;
@@ -486,7 +489,6 @@ static int ce_hist_pass(pdc_ctx* ctx, const double* t, const double* x, int64_t 
   a.cells = cells;
   a.nsplit = nsplit;
   a.counts_only = x == nullptr;
-  a.one = 1u;
 
   ctx->hist_plane_dirty = true;
   PDC_TRY(ctx->main_begin(st));
