@@ -233,8 +233,11 @@ struct PdmArgs {
 // PPT = trial periods per thread.  With PPT = 2 a thread owns columns tid and tid + THREADS: every sample read
 // from the tile (warp-uniform LDS.128) feeds two independent phase -> bin -> ATOMS chains, which halves the
 // shared-memory load traffic and the loop overhead per histogram update (the update itself stays one ATOMS.ADD).
+#ifndef PDM_MINB
+#define PDM_MINB 1   // tuning aid: minimum resident blocks per SM promised to ptxas for the two-periods-per-thread variants
+#endif
 template <int THREADS, int PPT>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, PPT == 2 ? PDM_MINB : 1)
 pdm_hist_kernel(const PdmArgs a) {
   constexpr int VT = THREADS * PPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
