@@ -351,32 +351,6 @@ argext_final_kernel(const double* __restrict__ red_val, const long long* __restr
   }
 }
 
-// Final arg-extremum of a shard, published to every rank (fused all-gather, see pdc_fanout): slot
-// `rank` of each rank's candidate table receives (value, global index as double).
-template <int SIGN>
-__global__ void __launch_bounds__(256)
-best_fanout_kernel(const double* __restrict__ red_val, const long long* __restrict__ red_idx, int nblk,
-                   const pdc_fanout fan, long long offset) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  double bv = 0.0;
-  long long bi = -1;
-  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
-    const double v = red_val[k];
-    const long long i = red_idx[k];
-    if (better<SIGN>(v, i, bv, bi)) { bv = v; bi = i; }
-  }
-  block_argext<SIGN>(bv, bi, sv, si);
-  if (threadIdx.x == 0) {
-    const double val = bi >= 0 ? bv : nan("");
-    const double arg = bi >= 0 ? (double)(bi + offset) : -1.0;
-    for (int r = 0; r < fan.world; ++r) {
-      fan.best[r][2 * fan.rank] = val;
-      fan.best[r][2 * fan.rank + 1] = arg;
-    }
-  }
-}
-
 #endif  // __CUDACC__
 
 }  // namespace pdc

@@ -44,14 +44,7 @@ constexpr double PDM_FAST_MAGIC = 1572864.0;   // 1.5 * 2^20
 constexpr double PDM_FAST_LIMIT = 262144.0;    // |t / P| < 2^18 keeps the sum inside [2^20, 2^21)
 constexpr unsigned PDM_FAST_GUARD = 4u;
 
-__device__ __forceinline__ unsigned pdm_bin_fast(double tv, double rP, unsigned m0u, unsigned guard, unsigned& edge) {
-  const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, PDM_FAST_MAGIC));
-  const unsigned long long w = (unsigned long long)u * m0u;
-  edge = ((unsigned)w + guard) < 2u * guard ? 1u : 0u;   // within guard of either edge of the bin
-  return (unsigned)(w >> 32);
-}
-
-// Same with the guard folded into the magic constant: the phase is shifted up by PDM_FAST_GUARD units of
+// The guard is folded into the magic constant: the phase is shifted up by PDM_FAST_GUARD units of
 // 2^-32 turn (exact: ulp of the sum is 2^-32), so `pos` = position inside the bin + guard, and
 // pos < 2 guard  <=>  the unshifted phase is within guard of a bin edge (then the bin index may be off by
 // one and the caller re-bins exactly); otherwise the shift cannot have carried into the bin index.
@@ -78,12 +71,6 @@ __device__ __forceinline__ double pdm_fast_magic(double t0, double rP, unsigned 
 }
 __device__ __forceinline__ unsigned pdm_bin_fast_m(double tv, double rP, double magic, unsigned m0u, unsigned& pos) {
   const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, magic));
-  const unsigned long long w = (unsigned long long)u * m0u;
-  pos = (unsigned)w;
-  return (unsigned)(w >> 32);
-}
-__device__ __forceinline__ unsigned pdm_bin_fast_g(double tv, double rP, unsigned m0u, unsigned& pos) {
-  const unsigned u = (unsigned)__double2loint(__fma_rn(tv, rP, PDM_FAST_MAGIC_G));
   const unsigned long long w = (unsigned long long)u * m0u;
   pos = (unsigned)w;
   return (unsigned)(w >> 32);
