@@ -160,16 +160,16 @@ def make_ce_c3(np_total):
     return wl
 
 
-def make_sl(np_total):
-    """String Length on a sparse light curve (the method's use case; SURVEY 8f row 2 has no BASELINE config)."""
+def make_sl(np_total, n=2000):
+    """String Length on a sparse light curve (the method's use case; SURVEY 8f row 2 has no BASELINE config).
+    n > 16,384 sorts in global scratch instead of shared memory (sl_kernel's fallback)."""
     from oracle import stringlength_numpy
     rng = np.random.default_rng(7)
-    n = 2000
     t = np.sort(rng.uniform(0, 1000.0, n))
     x = 12.0 + 0.4 * np.sin(2 * np.pi * t / 4.3) + 0.05 * rng.standard_normal(n)
     periods = stringlength_numpy.period_grid(t, dphi=0.1, n_periods=np_total)
     return dict(kind="sl", t=t, y=stringlength_numpy.scale(x), periods=periods, nf=np_total,
-                name=f"String Length 2,000 points x {np_total} trial periods (phase.py:18-72)")
+                name=f"String Length {n:,} points x {np_total} trial periods (phase.py:18-72)")
 
 
 def make_gls_c4(curves, first=0, total=None):
@@ -910,7 +910,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gls_c2",
                     choices=["gls_c2", "pdm_c3", "gls_c5", "gls_c5_full", "gls_c4", "gls_c4_full", "gls_c1", "gls_multi",
-                             "sl", "ce_c3", "pdm_c3_jd"])
+                             "sl", "sl_long", "ce_c3", "pdm_c3_jd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true",
                     help="default workload only: skip the `configs` block (C3 / C5 / C4 / C1 at their BASELINE sizes)")
@@ -927,7 +927,7 @@ def main():
 
     per_gpu = {"gls_c2": 100_000, "pdm_c3": 100_000, "gls_c5": 1_250_000, "gls_c5_full": 10_000_000,
                "gls_c4": 256, "gls_c4_full": 10_000, "gls_c1": 10_000, "gls_multi": 256, "sl": 100_000,
-               "ce_c3": 100_000, "pdm_c3_jd": 100_000}[args.workload]
+               "ce_c3": 100_000, "pdm_c3_jd": 100_000, "sl_long": 4_000}[args.workload]
     strong = args.strong or args.workload in ("gls_c5_full",)
     total_units = per_gpu if strong else per_gpu * max(world, 1)
     scaling = "strong" if (strong and world > 1) else "weak"
@@ -949,6 +949,8 @@ def main():
             return make_ce_c3(units)
         if workload == "sl":
             return make_sl(units)
+        if workload == "sl_long":
+            return make_sl(units, n=20_000)
         # survey batch: this rank's curves only
         from periodicity_b200 import dist as pdist
         b0, b1 = pdist.batch_shard_bounds(units, rank, world)

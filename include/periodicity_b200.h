@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define PDC_VERSION 100 /* 0.1.0 */
+#define PDC_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define PDC_API __attribute__((visibility("default")))

@@ -9,5 +9,5 @@ from .core import FSeries, TSeries  # noqa: F401
 from .phase import AOV, CE, GL, PDM, ConditionalEntropy, GregoryLoredo, StringLength  # noqa: F401
 from .spectral import GLS  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 __all__ = ["GLS", "PDM", "StringLength", "AOV", "CE", "ConditionalEntropy", "GL", "GregoryLoredo", "TSeries", "FSeries"]

@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_version_and_error_string():
     lib = _ffi.load_library()
-    assert lib.pdc_version() == 100
+    assert lib.pdc_version() == 200
     assert isinstance(lib.pdc_last_error(), bytes)
 
 
