@@ -418,7 +418,7 @@ def workload_config(wl, per_gpu, world, scaling):
             "l2": "flushed between timed steps (256 MiB memset, not timed); per-step CUDA events summed",
             "collective": "none (1 GPU)" if world == 1 else
                           ("all-gather fused into the epilogue kernel: stores to every rank's symmetric buffer over "
-                           "NVLink peer memory + 2 device barriers (no NCCL call); NCCL all-gather of "
+                           "NVLink peer memory + 1 device barrier (no NCCL call); NCCL all-gather of "
                            "[values, best, index] for the batch / String Length workloads or with --gather nccl")}
 
 

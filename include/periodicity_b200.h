@@ -163,8 +163,9 @@ PDC_API int pdc_gls_freqs_dev(pdc_ctx* ctx, const double* t, const double* y, co
  * store per destination), and its arg-max kernel stores (max, global argmax) into slot `rank` of
  * every rank's candidate table.  No NCCL call, no staging buffer: the "collective" is part of
  * the kernel that produces the data.  The caller provides buffers mapped into this process for
- * every rank (e.g. torch.distributed._symmetric_memory: `handle.buffer_ptrs`) and must separate
- * successive calls with a cross-rank barrier (`handle.barrier()`), see periodicity_b200/dist.py.
+ * every rank (e.g. torch.distributed._symmetric_memory: `handle.buffer_ptrs`) and must end every call
+ * with a cross-rank barrier (`handle.barrier()`) before reading the result; with two alternating sets of
+ * buffers no barrier is needed before the call (periodicity_b200/dist.py::_symm_buffer explains why).
  *
  *   power[r]  base of rank r's full-grid power array (float64[nf_total]); element j0 + j is written
  *   best[r]   rank r's candidate table (float64[2*world]); elements 2*rank, 2*rank+1 are written

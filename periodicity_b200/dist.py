@@ -322,18 +322,29 @@ _symm_cache = {}
 
 def _symm_buffer(n_doubles, device, group):
     """Symmetric float64 buffer of ``n_doubles`` on every rank, mapped into every process
-    (torch.distributed._symmetric_memory); cached per (size, device)."""
+    (torch.distributed._symmetric_memory); cached per (size, device).
+
+    TWO buffers per key, used alternately (every rank makes the same sequence of calls, so all ranks pick the same one).
+    That removes the barrier a single buffer needs BEFORE the kernel ("every rank has finished reading the previous
+    result"): call k+2 is the first to overwrite the buffer of call k, a peer's kernel of call k+2 starts only after it
+    has passed the barrier that ends call k+1, and that barrier completes only when this rank's stream has reached it --
+    i.e. after everything this rank enqueued between call k and call k+1, which includes its reads of result k (result
+    views are valid until the next call on the same stream)."""
     torch = _torch()
     import torch.distributed as dist
     import torch.distributed._symmetric_memory as symm_mem
     key = (int(n_doubles), str(device))
     ent = _symm_cache.get(key)
     if ent is None:
-        buf = symm_mem.empty(int(n_doubles), dtype=torch.float64, device=device)
-        hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
-        ent = (buf, hdl)
+        pair = []
+        for _ in range(2):
+            buf = symm_mem.empty(int(n_doubles), dtype=torch.float64, device=device)
+            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            pair.append((buf, hdl))
+        ent = [pair, 0]
         _symm_cache[key] = ent
-    return ent
+    ent[1] ^= 1
+    return ent[0][ent[1]]
 
 
 def gls_sharded_p2p_torch(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, ctx=None, group=None):
@@ -341,9 +352,10 @@ def gls_sharded_p2p_torch(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, 
 
     Every rank evaluates its slice; the epilogue stores each power value directly into the symmetric
     result buffer of ALL ranks through NVLink peer mappings (``pdc_gls_dev_fanout``), so when the
-    kernel ends the "all-gather" has already happened.  Two device-side barriers on the current
-    stream (``handle.barrier``) order successive calls.  Returns views ``(power[nf], best[W, 2])``
-    of this rank's symmetric buffer (valid until the next call) -- ``best[r] = (max, global argmax)``
+    kernel ends the "all-gather" has already happened.  ONE device-side barrier on the current
+    stream (``handle.barrier``) ends the call; two alternating result buffers make a barrier before the
+    kernel unnecessary (``_symm_buffer``).  Returns views ``(power[nf], best[W, 2])``
+    of this rank's symmetric buffer (valid until the next call on this stream) -- ``best[r] = (max, global argmax)``
     of rank r's slice."""
     torch = _torch()
     dist, rank, world = _dist_info(group)
@@ -357,14 +369,13 @@ def gls_sharded_p2p_torch(t, y, w, fmin, df, nf, fit_mean=True, psd_scale=None, 
     fan = _fanout_struct(hdl, nf, world, rank)
     flags = (_ffi.GLS_FIT_MEAN if fit_mean else 0) | (_ffi.GLS_PSD if psd_scale is not None else 0)
     stream = torch.cuda.current_stream(t.device).cuda_stream
-    hdl.barrier(channel=0)        # every rank has finished READING the previous result
     if stop > start:
         ctx.gls_dev_fanout(t.data_ptr(), y.data_ptr(), 0 if w is None else w.data_ptr(), t.numel(), fmin, df,
                            start, stop - start, flags, 1.0 if psd_scale is None else psd_scale, fan, stream)
     else:
         buf[int(nf) + 2 * rank: int(nf) + 2 * rank + 2] = torch.tensor([float("nan"), -1.0], dtype=torch.float64,
                                                                         device=t.device)
-    hdl.barrier(channel=1)        # every rank's stores have landed everywhere
+    hdl.barrier(channel=0)        # every rank's stores have landed everywhere (the only barrier: see _symm_buffer)
     return buf[: int(nf)], buf[int(nf):].view(world, 2)
 
 
@@ -391,14 +402,13 @@ def pdm_sharded_p2p_torch(t, x, periods, nb, nc, ctx=None, group=None):
     start, stop, _ = shard_bounds(npd, rank, world)
     fan = _fanout_struct(hdl, npd, world, rank)
     stream = torch.cuda.current_stream(t.device).cuda_stream
-    hdl.barrier(channel=0)
     if stop > start:
         ctx.pdm_dev_fanout(t.data_ptr(), x.data_ptr(), t.numel(), periods.data_ptr() + 8 * start, stop - start,
                            nb, nc, start, fan, stream)
     else:
         buf[npd + 2 * rank: npd + 2 * rank + 2] = torch.tensor([float("nan"), -1.0], dtype=torch.float64,
                                                               device=t.device)
-    hdl.barrier(channel=1)
+    hdl.barrier(channel=0)
     return buf[:npd], buf[npd:].view(world, 2)
 
 
