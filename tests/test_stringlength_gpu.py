@@ -61,11 +61,13 @@ def test_finds_the_period_of_a_sparse_light_curve(gpu_ctx):
     assert abs(best - 6.3) < 0.05 or abs(best - 12.6) < 0.1 or abs(best - 18.9) < 0.15
 
 
-def test_large_curve_uses_global_scratch(gpu_ctx):
-    """N > 16384 does not fit the shared-memory sort: same results from the global-memory path."""
+@pytest.mark.parametrize("n,ties", [(40_000, False), (17_000, False), (16_385, True), (70_000, True)])
+def test_large_curve_uses_global_scratch(gpu_ctx, n, ties):
+    """N > 16384 does not fit the shared-memory sort: same results from the hybrid path (chunks of 8192 records sorted /
+    merged in shared memory, only the chunk-spanning stages in global scratch), incl. tied phases (integer times), whose
+    order must be that of the stable sort."""
     rng = np.random.default_rng(12)
-    n = 40_000
-    t = np.sort(rng.uniform(0, 1000, n))
+    t = np.sort(rng.integers(0, 4000, n).astype(np.float64)) if ties else np.sort(rng.uniform(0, 1000, n))
     m = slo.scale(np.sin(2 * np.pi * t / 9.1) + 0.3 * rng.standard_normal(n))
     periods = np.linspace(2.0, 30.0, 24)
     ell, am, _ = gpu_ctx.stringlength(t, m, periods)
