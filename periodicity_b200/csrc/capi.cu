@@ -187,6 +187,8 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
   if (const char* g = getenv("PDC_GLS_GEOM")) { ctx->gls_geom = atoi(g); ctx->gls_geom_forced = true; }
   if (const char* g = getenv("PDC_GLS_THREE_TERM")) ctx->gls_three_term = atoi(g) != 0;
   if (const char* g = getenv("PDC_GLS_NSPLIT")) ctx->gls_nsplit_override = atoi(g);
+  if (const char* g = getenv("PDC_GLS_UMMA")) ctx->gls_umma = atoi(g);
+  if (const char* g = getenv("PDC_GLS_UMMA_NSPLIT")) ctx->gls_umma_nsplit = atoi(g);
   if (const char* g = getenv("PDC_PDM_PPT")) ctx->pdm_ppt_override = atoi(g);
   if (const char* g = getenv("PDC_BATCH_PIPE_BYTES")) ctx->pipe_min_bytes = (size_t)atoll(g);
   cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -212,7 +214,7 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   ctx->gls_curves.release(); ctx->gls_part.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->gls_cnt.release(); ctx->glsm_y.release();
   ctx->partial.release(); ctx->gls_plane.release(); ctx->hist_plane.release(); ctx->blockred.release(); ctx->pin_meta.release();
-  ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->gl_acc.release(); ctx->peak_cand.release();
+  ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->gl_acc.release(); ctx->peak_cand.release(); ctx->umma_status.release();
   ctx->main_resolve();
   for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);

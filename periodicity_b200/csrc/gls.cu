@@ -603,6 +603,8 @@ struct GlsEpiArgs {
   long long* arg_out;           // [B] or NULL
   double* max_out;              // [B] or NULL
   pdc_fanout fan;               // fan.world == 0: no fan-out
+  int double_angle;             // planes 4, 5 hold sum w cos 2x, sum w sin 2x (gls_umma_kernel) instead of sum w cos^2 x, sum w cos x sin x
+  const int* umma_status;       // non-NULL: gls_umma_kernel's protocol status; non-zero poisons the result with NaN
 };
 
 __global__ void __launch_bounds__(256)
@@ -624,8 +626,10 @@ gls_epilogue_kernel(const GlsEpiArgs a) {
     for (int q = 0; q < 6; ++q) raw[q] = __ldcg(p + (long long)q * a.nf_tot);   // written with RED at L2
 #pragma unroll
     for (int q = 0; q < 6; ++q) p[(long long)q * a.nf_tot] = 0ull;              // the plane is clean for the next call
+    bool c2_direct = a.double_angle != 0;
     if (j >= cv.low_begin && j < cv.low_begin + cv.low_count) {
       // sub-cycle frequency: the FP64 sums of gls_prep_kernel replace the strip kernel's FP32 ones
+      c2_direct = false;
       unsigned long long* lp = a.lowplane + (long long)curve * a.low_cap + (j - cv.low_begin);
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
@@ -636,8 +640,8 @@ gls_epilogue_kernel(const GlsEpiArgs a) {
 #pragma unroll
     for (int q = 0; q < 6; ++q) sums[q] = (double)(long long)raw[q] * a.inv_fix;
     inv_n = 1.0 / (double)cv.n;
-    power = gls_power_from_sums(sums, inv_n, a.flags, cv.yy, cv.psd_scale);
-    if (cv.bad) power = nan("");
+    power = gls_power_from_sums(sums, inv_n, a.flags, cv.yy, cv.psd_scale, c2_direct);
+    if (cv.bad || (a.umma_status && *a.umma_status)) power = nan("");
     if (a.power_out) a.power_out[(long long)curve * a.nf + j] = power;
     // fused all-gather: the value goes to every rank's buffer over NVLink peer mappings
     for (int r = 0; r < a.fan.world; ++r) a.fan.power[r][a.j0 + j] = power;
@@ -678,6 +682,13 @@ gls_epilogue_kernel(const GlsEpiArgs a) {
 // ---------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------
+// tensor-core formulation of the same sums (gls_umma.cu)
+bool gls_umma_eligible(const pdc_ctx* ctx, int64_t B, int64_t nf, long long ntot, long long nmax, bool weighted,
+                       const double* df_host);
+int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, const float4* rec2,
+                    unsigned long long* plane, int64_t B, int64_t nf, int64_t j0, long long nmax, bool weighted,
+                    float fix_scale, cudaStream_t st);
+
 // Strip-kernel geometries: K frequencies per thread, THREADS per block, MINB blocks per SM.
 struct GlsGeom {
   int K, threads, minb;
@@ -948,6 +959,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
 
   ctx->gls_plane_dirty = ctx->gls_low_dirty = true;   // until the epilogue that clears the planes has been enqueued
   PDC_TRY(ctx->main_begin(st));
+  const bool use_umma = !freqs_dev && gls_umma_eligible(ctx, B, nf, ntot, nmax, w != nullptr, df_host);
   if (freqs_dev) {
     GlsFreeArgs fa;
     fa.curves = dc;
@@ -962,6 +974,8 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     else gls_free_kernel<false><<<(unsigned)items, GLS_FREE_THREADS, 0, st>>>(fa);
     PDC_CUDA(cudaGetLastError());
     ctx->launches++;
+  } else if (use_umma) {
+    PDC_TRY(gls_umma_launch(ctx, dc, a.rec1, a.rec2, a.partial, B, nf, j0, nmax, w != nullptr, (float)fix_scale, st));
   } else {
     PDC_TRY(launch_strip(geom, ctx, a, w != nullptr, items, st));
   }
@@ -987,6 +1001,8 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     e.max_out = max_out;
     if (fanout) e.fan = *fanout;
     else memset(&e.fan, 0, sizeof(e.fan));
+    e.double_angle = use_umma ? 1 : 0;
+    e.umma_status = use_umma ? ctx->umma_status.as<int>() : nullptr;
     dim3 grid((unsigned)eblk, (unsigned)B);
     gls_epilogue_kernel<<<grid, 256, 0, st>>>(e);
     PDC_CUDA(cudaGetLastError());

@@ -105,12 +105,14 @@ __device__ __forceinline__ void gls_low_range(double fmin, double df, long long 
 // FP64 epilogue for one frequency: spectral.py:113-132 literally.
 //   sums = {sum w c, sum w s, sum w y c, sum w y s, sum w c^2, sum w c s} * (1 / inv_n)
 // y was pre-scaled to unit weighted RMS, so YY == 1 (spectral.py:120,132).
+// c2_direct: sums[4], sums[5] are sum w cos 2x, sum w sin 2x themselves (gls_umma.cu) instead of sum w cos^2 x, sum w cos x sin x.
 __device__ __forceinline__ double gls_power_from_sums(const double* sums, double inv_n, unsigned flags,
-                                                      double yy, double psd_scale) {
+                                                      double yy, double psd_scale, bool c2_direct = false) {
   const double C = sums[0] * inv_n, S = sums[1] * inv_n;
   const double Ch = sums[2] * inv_n, Sh = sums[3] * inv_n;
   // sum w cos(2x) = 2 sum w cos^2 x - 1,  sum w sin(2x) = 2 sum w sin x cos x   (sum w = 1)
-  const double C2 = 2.0 * sums[4] * inv_n - 1.0, S2 = 2.0 * sums[5] * inv_n;
+  const double C2 = c2_direct ? sums[4] * inv_n : 2.0 * sums[4] * inv_n - 1.0;
+  const double S2 = c2_direct ? sums[5] * inv_n : 2.0 * sums[5] * inv_n;
   const bool fit_mean = flags & PDC_GLS_FIT_MEAN;
   double tan2;
   if (fit_mean) tan2 = (S2 - 2.0 * S * C) / (C2 - (C * C - S * S));  // spectral.py:113

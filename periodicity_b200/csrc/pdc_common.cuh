@@ -67,6 +67,11 @@ struct pdc_ctx {
   bool gls_geom_forced = false;  // PDC_GLS_GEOM given: no automatic small-problem geometry
   bool gls_three_term = true;  // env PDC_GLS_THREE_TERM=0 forces the rotation form of the strip step (tuning aid)
   int pdm_ppt_override = 0;  // env PDC_PDM_PPT=1|2 forces the trial periods per thread of pdm_hist_kernel (tuning aid)
+  int gls_umma = -1;           // tensor-core formulation of the GLS sums (gls_umma.cu): -1 automatic, 0 off, 1 whenever eligible
+                               // (env PDC_GLS_UMMA)
+  int gls_umma_nsplit = 0;     // env PDC_GLS_UMMA_NSPLIT: sample splits of the tensor-core kernel (tuning aid)
+  pdc::DevBuf umma_status;     // int: set by gls_umma_kernel on a protocol time-out; the epilogue then writes NaN
+  bool umma_status_clean = false;
   int gls_geom = 0;  // index into kGlsGeoms (gls.cu); env PDC_GLS_GEOM overrides at ctx creation (tuning aid)
 
   // CUDA-event timing of the dominant kernel (GLS strip / PDM histogram), recorded on the
