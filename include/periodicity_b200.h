@@ -378,6 +378,13 @@ PDC_API double pdc_ctx_last_main_kernel_ms(pdc_ctx* ctx);
  * difference across its timed region: average launch duration = d(ms) / d(count). */
 PDC_API double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out);
 
+/* Diagnostics of the tensor-core GLS kernel (gls_umma.cu), filled only when the ctx was created with the environment
+ * variable PDC_GLS_UMMA_PROF=1: per work item (thread block) of the most recent launch four SM clock stamps
+ * {start, main loop begin, main loop end, end of flush} are copied to `out` (up to `cap` items x 4 values).
+ * Returns the number of work items of that launch (0 if profiling is off or the kernel has not run), < 0 on error.
+ * Synchronises the ctx. */
+PDC_API int64_t pdc_debug_umma_prof(pdc_ctx* ctx, int64_t* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

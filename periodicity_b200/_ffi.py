@@ -44,6 +44,7 @@ SIGNATURES = {
     "pdc_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "pdc_ctx_last_main_kernel_ms": (ctypes.c_double, [ctypes.c_void_p]),
     "pdc_ctx_main_kernel_ms_total": (ctypes.c_double, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    "pdc_debug_umma_prof": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "pdc_gls": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
@@ -216,6 +217,23 @@ class Context:
         cnt = ctypes.c_int64(0)
         ms = self._lib.pdc_ctx_main_kernel_ms_total(self._h, ctypes.byref(cnt))
         return ms, cnt.value
+
+    def umma_prof(self, cap=1 << 16):
+        """Clock stamps [jobs, 4] of the last tensor-core GLS launch (needs PDC_GLS_UMMA_PROF=1 at ctx creation)."""
+        out = np.zeros((cap, 4), dtype=np.int64)
+        n = self._lib.pdc_debug_umma_prof(self._h, _ptr(out), cap)
+        if n < 0:
+            raise RuntimeError("pdc_debug_umma_prof failed")
+        return out[:min(n, cap)]
+
+    def umma_trace(self):
+        """Per-pair clock stamps [1024, 8] of block 0 (PDC_GLS_UMMA_PROF=1 and PDC_GLS_UMMA_DBG & 16)."""
+        cap = 1 << 16
+        out = np.zeros((cap, 4), dtype=np.int64)
+        n = self._lib.pdc_debug_umma_prof(self._h, _ptr(out), cap)
+        if n <= 2048:
+            return np.zeros((0, 8), dtype=np.int64)
+        return out[n - 2048:n].reshape(1024, 8)
 
     def synchronize(self):
         _check(self._lib.pdc_ctx_synchronize(self._h))

@@ -189,6 +189,9 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
   if (const char* g = getenv("PDC_GLS_NSPLIT")) ctx->gls_nsplit_override = atoi(g);
   if (const char* g = getenv("PDC_GLS_UMMA")) ctx->gls_umma = atoi(g);
   if (const char* g = getenv("PDC_GLS_UMMA_NSPLIT")) ctx->gls_umma_nsplit = atoi(g);
+  if (const char* g = getenv("PDC_GLS_UMMA_CHUNK")) ctx->gls_umma_chunk = atoi(g);
+  if (const char* g = getenv("PDC_GLS_UMMA_DBG")) ctx->gls_umma_dbg = atoi(g);
+  if (const char* g = getenv("PDC_GLS_UMMA_PROF")) ctx->umma_prof_on = atoi(g) != 0;
   if (const char* g = getenv("PDC_PDM_PPT")) ctx->pdm_ppt_override = atoi(g);
   if (const char* g = getenv("PDC_BATCH_PIPE_BYTES")) ctx->pipe_min_bytes = (size_t)atoll(g);
   cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -214,7 +217,7 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   ctx->gls_curves.release(); ctx->gls_part.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->gls_cnt.release(); ctx->glsm_y.release();
   ctx->partial.release(); ctx->gls_plane.release(); ctx->hist_plane.release(); ctx->blockred.release(); ctx->pin_meta.release();
-  ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->gl_acc.release(); ctx->peak_cand.release(); ctx->umma_status.release();
+  ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->gl_acc.release(); ctx->peak_cand.release(); ctx->umma_status.release(); ctx->umma_prof.release();
   ctx->main_resolve();
   for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);
@@ -248,6 +251,19 @@ double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out) {
   if (ctx->main_resolve() != PDC_OK) return -1.0;
   if (count_out) *count_out = ctx->main_count;
   return ctx->main_ms_total;
+}
+
+int64_t pdc_debug_umma_prof(pdc_ctx* ctx, int64_t* out, int64_t cap) {
+  if (!ctx) return -1;
+  DeviceGuard guard(ctx->device);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -1;
+  /* the per-job records are followed by the 1024 x 8 trace stamps of block 0 (PDC_GLS_UMMA_DBG & 16) */
+  const int64_t have = ctx->umma_prof_jobs > 0 ? ctx->umma_prof_jobs + 2 * 1024 : 0;
+  const int64_t n = have < cap ? have : cap;
+  if (n > 0 && out &&
+      cudaMemcpy(out, ctx->umma_prof.p, sizeof(long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  return have;
 }
 
 struct SmallRec {

@@ -17,15 +17,19 @@
 // Precision.  fp16 inputs with FP32 accumulation, every operand split x = hi + lo (two fp16 numbers, 22 significant bits)
 // and the product taken as hi hi + hi lo + lo hi: three tcgen05.mma per K-step.  The TMEM accumulator TRUNCATES toward
 // zero (measured: tools/microbench/umma_probe.cu, profiles/r02/umma_probe.txt), a bias of up to one ulp per instruction,
-// so an accumulation run in TMEM is only UM_CHUNK_STAGES * 16 = 64 samples long (24 instructions): epilogue warps drain
+// so an accumulation run in TMEM is only chunk_stages * 16 = 64 samples long (24 instructions): epilogue warps drain
 // the tile (double-buffered in TMEM) and add it to FP32 master accumulators in registers with round-to-nearest.  The
 // masters leave the kernel once per job as 64-bit fixed point through RED.ADD.64 into the same plane gls_strip_kernel
 // uses, so everything downstream (FP64 sub-cycle bins, FP64 epilogue, arg-max, fan-out) is shared.
 //
-// Roles in a CTA of 640 threads, one CTA per SM:
-//   warps 0-7    epilogue: TMEM -> registers (+=), final flush
-//   warps 8-15   producers: records -> fp16 hi/lo operand tiles, 16 samples per stage, 4 stages
-//   warp 16      one elected lane issues tcgen05.mma / tcgen05.commit; the warp owns the TMEM allocation
+// One CTA of 640 threads per SM: 16 identical worker warps (records -> fp16 hi/lo operand tiles, 16 samples per stage, 4
+// stages; one accumulation run behind, TMEM -> FP32 masters in registers; final flush) and one warp group whose first
+// warp issues the tcgen05.mma + tcgen05.commit of every stage.  Issuing blocks while the tensor core is busy, so the
+// issuer cannot be a worker (tried: fixed worker warp 0.78 ms on C2, rotating duty 0.74 ms -- each issuer became the next
+// pair's straggler); a 17th warp caps the launch at 96 registers per thread, so the group gives its registers to the
+// workers (setmaxnreg 24 / 112).
+// (A first version had 8 dedicated epilogue warps with 128 masters each and 8 producer warps squeezed into 56
+// registers: 0.73 ms on C2, the producers latency-bound at a quarter of the issue rate.)
 // All waits are bounded (clock-based): a protocol error ends the kernel with a status word, it cannot hang the GPU.
 #include "gls_common.cuh"
 #include "umma.cuh"
@@ -37,15 +41,16 @@ using namespace umma;
 constexpr int UM_FINE = 128;           // fine indices per tile = MMA M = TMEM lanes
 constexpr int UM_STAGE_SAMPLES = 16;   // 32 K-slots = two K = 16 steps
 constexpr int UM_NSTAGES = 4;
-constexpr int UM_CHUNK_STAGES = 4;     // one TMEM accumulation run
-constexpr int UM_BLOCK = 256;          // samples per block of staged records
-constexpr int UM_THREADS = 640;
+constexpr int UM_BLOCK = 512;          // samples per block of staged records (one per worker thread)
+constexpr int UM_WORKERS = 512;        // 16 worker warps
+constexpr int UM_THREADS = UM_WORKERS + 128;   // + one warp group: warp 16 issues the tcgen05.mma, warps 17-19 only donate registers
+constexpr int UM_WORKER_REGS = 112, UM_MMA_REGS = 24;   // setmaxnreg: 640 x 96 at launch -> 512 x 112 + 128 x 24
 constexpr int UM_MAX_T1 = 64, UM_MAX_T2 = 128;   // coarse blocks per tile (N = 4 * 64 = 2 * 128 = 256 columns)
 // one stage in shared memory: [K-chunk of 8 slots][row][8 halves]; 16-byte rows, 8-row groups contiguous (SBO = 128 B)
 constexpr uint32_t UM_FINE_HI = 0, UM_FINE_LO = 8192, UM_COARSE_HI = 16384, UM_COARSE_LO = 32768;
 constexpr uint32_t UM_STAGE_BYTES = 49152;
 constexpr uint32_t UM_LBO_FINE = 128 * 16, UM_LBO_COARSE = 256 * 16, UM_SBO = 128;
-constexpr uint32_t UM_REC_BYTES = 2 * UM_BLOCK * (8 + 8 + 4 + 4);
+constexpr uint32_t UM_REC_BYTES = 2 * UM_BLOCK * (8 + 4 + 4 + 4);
 constexpr uint32_t UM_SMEM_BYTES = UM_NSTAGES * UM_STAGE_BYTES + UM_REC_BYTES + 256;
 constexpr long long UM_WAIT_CLOCKS = 4000000000LL;   // ~2 s: far beyond any legitimate wait
 
@@ -59,8 +64,11 @@ struct GlsUmmaArgs {
   int nt1, nt2, cpt1, cpt2;      // tiles per curve and coarse blocks per tile of each type
   int nsplit;
   int weighted;
+  int chunk_stages;              // stages (of 16 samples) per accumulation run in TMEM
   float fix_scale;
   int* status;                   // set non-zero on a protocol time-out
+  int dbg;                       // timing experiments (env PDC_GLS_UMMA_DBG): 1 no MMA, 2 no operand production, 4 no drain, 8 no proxy fence, 16 trace
+  long long* prof;               // optional [jobs][4] clock64 stamps (start, main loop begin, main loop end, flush end)
 };
 
 __device__ __forceinline__ bool um_wait(uint32_t bar, uint32_t parity, volatile int* s_abort, long long t_start) {
@@ -83,11 +91,6 @@ __device__ __forceinline__ void um_split2(float c, float s, uint32_t& hi, uint32
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void um_sincos_turns(double v, float& c, float& s) {
-  // v = phase + 1.5 * 2^20: the low mantissa word is the fraction in units of 2^-32 turn (two's complement)
-  const float x = (float)__double2loint(v) * 1.4629180792671596e-9f;   // 2 pi / 2^32
-  __sincosf(x, &s, &c);
-}
 __device__ __forceinline__ void um_sts128(uint32_t addr, const uint32_t (&v)[4]) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
@@ -101,6 +104,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
+// A worker warp
+//   * PRODUCES: per stage of 16 samples one fine task (row = 32 (warp & 3) + lane, sample quad = warp >> 2: four phases)
+//     and one coarse task of the same quad;
+//   * DRAINS: one accumulation run behind the producers it adds its 32 lanes x 64 columns of the finished TMEM
+//     accumulator to 64 FP32 masters in registers (TMEM lanes 32 (warp & 3).., columns 64 (warp >> 2)..);
+//   * FLUSHES the masters at the end of the job.
 __global__ void __launch_bounds__(UM_THREADS, 1)
 gls_umma_kernel(const GlsUmmaArgs a) {
   extern __shared__ __align__(1024) unsigned char um_smem[];
@@ -118,8 +127,8 @@ gls_umma_kernel(const GlsUmmaArgs a) {
   const int cpt = type2 ? a.cpt2 : a.cpt1;                       // coarse blocks per tile (padded to 4 / 8)
   const int cb0 = (type2 ? tile - a.nt1 : tile) * cpt;           // first coarse block of this tile
   const int ncb = min(cpt, a.nC - cb0);                          // real coarse blocks (> 0 by construction)
-  const int rows_per_cb = type2 ? 2 : 4;
-  const int N = cpt * rows_per_cb;                               // MMA N: multiple of 16, <= 256
+  const int N = cpt * (type2 ? 2 : 4);                           // MMA N: multiple of 16, <= 256
+  const int CS = a.chunk_stages;
 
   const GlsCurve* cvp = a.curves + curve;
   const long long cbegin = cvp->begin, cn = cvp->n;
@@ -127,36 +136,41 @@ gls_umma_kernel(const GlsUmmaArgs a) {
   const long long sb = (long long)split * per;
   const long long se = sb + per < cn ? sb + per : cn;
   const long long ns = se > sb ? se - sb : 0;
-  const int nchunks = (int)((ns + UM_CHUNK_STAGES * UM_STAGE_SAMPLES - 1) / (UM_CHUNK_STAGES * UM_STAGE_SAMPLES));
-  const int nstages = nchunks * UM_CHUNK_STAGES;                 // padded with zero-weight samples
+  const int nchunks = (int)((ns + CS * UM_STAGE_SAMPLES - 1) / (CS * UM_STAGE_SAMPLES));
+  const int nstages = nchunks * CS;                              // padded with zero-weight samples
   if (nchunks == 0) return;                                      // block-uniform: nothing to add
 
   // ---- shared memory ----
   const uint32_t smem0 = smem_u32(um_smem);
   unsigned char* recs = um_smem + UM_NSTAGES * UM_STAGE_BYTES;
-  double* s_b = reinterpret_cast<double*>(recs);                               // [2][UM_BLOCK] phase step per index (turns)
-  double* s_A = s_b + 2 * UM_BLOCK;                                            // [2][UM_BLOCK] phase at the tile's base frequency
-  float* s_wy = reinterpret_cast<float*>(s_A + 2 * UM_BLOCK);                  // [2][UM_BLOCK] w' y'
+  // per-sample records, two buffers of UM_BLOCK samples.  Phases are 2^-32-turn fixed point inside the loop: the per-index
+  // step b_i as a 64-bit fraction (so that (integer index) * b_i keeps 2^-32 turn after 15 bits of index), the phase at
+  // the tile's base frequency as a 32-bit fraction -- no FP64 arithmetic per stage.
+  unsigned long long* s_b64 = reinterpret_cast<unsigned long long*>(recs);     // [2][UM_BLOCK] frac(b_i) * 2^64
+  unsigned* s_A32 = reinterpret_cast<unsigned*>(s_b64 + 2 * UM_BLOCK);         // [2][UM_BLOCK] frac(kmul A_i) * 2^32
+  float* s_wy = reinterpret_cast<float*>(s_A32 + 2 * UM_BLOCK);                // [2][UM_BLOCK] w' y'
   float* s_w = s_wy + 2 * UM_BLOCK;                                            // [2][UM_BLOCK] w' (0 for padding samples)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + 2 * UM_BLOCK);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * UM_NSTAGES;
   const uint32_t bar_tfull = bar_empty + 8 * UM_NSTAGES, bar_tempty = bar_tfull + 16;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * UM_NSTAGES + 4);
+  const uint32_t bar_rec = bar_tempty + 16;   // [2] record buffer `b` staged by all 16 warps
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * UM_NSTAGES + 6);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
 
   if (tid == 0) {
     for (int s = 0; s < UM_NSTAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 8);     // one arrival per producer warp
-      mbar_init(bar_empty + 8 * s, 1);    // tcgen05.commit
+      mbar_init(bar_full + 8 * s, UM_WORKERS / 32);   // one arrival per worker warp
+      mbar_init(bar_empty + 8 * s, 1);                // tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_tfull + 8 * s, 1);    // tcgen05.commit
-      mbar_init(bar_tempty + 8 * s, 8);   // one arrival per epilogue warp
+      mbar_init(bar_tfull + 8 * s, 1);                // tcgen05.commit
+      mbar_init(bar_tempty + 8 * s, UM_WORKERS / 32); // one arrival per worker warp
+      mbar_init(bar_rec + 8 * s, UM_WORKERS / 32);
     }
     mbar_init_fence();
     *s_abort = 0;
   }
-  if (warp == 16) {
+  if (warp == 0) {
     tmem_alloc(smem_u32(s_tmem), 512);
     tmem_relinquish();
   }
@@ -164,76 +178,110 @@ gls_umma_kernel(const GlsUmmaArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
+  long long t_loop0 = 0, t_loop1 = 0;
 
-  if (warp < 8) {
+  const uint32_t idesc = idesc_f16_f32(UM_FINE, N);
+  if (warp >= 16) {
     // =====================================================================================================
-    // epilogue warps: lane quarter q = warp & 3 (TMEM lanes 32 q ..), column half h = warp >> 2
+    // MMA warp.  Issuing a tcgen05.mma blocks the issuing thread while the tensor core is busy (measured: the 12
+    // instructions of a pair of stages take ~1470 clocks to issue), so the issuer must have nothing else to do.
     // =====================================================================================================
-    setmaxnreg_inc<168>();
-    const int q = warp & 3, h = warp >> 2;
-    float m[128];
+    setmaxnreg_dec<UM_MMA_REGS>();
+    if (warp == 16) {
+      bool ok = true;
+      int cpos = 0, ch = 0;
+      long long* trace = (a.prof && (a.dbg & 16) && blockIdx.x == 0) ? a.prof + 4LL * gridDim.x : nullptr;
+      for (int g = 0; g < nstages && ok; g += 2) {
+        const int pslot = (g >> 1) & 1, acc = ch & 1;     // pair slot = stages (2 pslot, 2 pslot + 1) of the ring
+        if (trace && lane == 0 && g < 2 * 1024) trace[(g >> 1) * 8 + 2] = clock64();
+        if (cpos == 0) ok = um_wait(bar_tempty + 8 * acc, ((ch >> 1) & 1) ^ 1, s_abort, t_start);
+        if (ok) ok = um_wait(bar_full + 8 * pslot, (g >> 2) & 1, s_abort, t_start);
+        if (!ok) break;
+        if (trace && lane == 0 && g < 2 * 1024) trace[(g >> 1) * 8 + 3] = clock64();
+        tc_fence_after();
+        const uint32_t sbase = smem0 + pslot * 2 * UM_STAGE_BYTES;
+        const uint32_t d = tmem + acc * 256;
+        const uint64_t ah = smem_desc(sbase + UM_FINE_HI, UM_LBO_FINE, UM_SBO);
+        const uint64_t al = smem_desc(sbase + UM_FINE_LO, UM_LBO_FINE, UM_SBO);
+        const uint64_t bh = smem_desc(sbase + UM_COARSE_HI, UM_LBO_COARSE, UM_SBO);
+        const uint64_t bl = smem_desc(sbase + UM_COARSE_LO, UM_LBO_COARSE, UM_SBO);
+        // start-address field steps: second K-step of a stage, second stage of the pair
+        constexpr uint64_t KA = (2 * UM_LBO_FINE) >> 4, KB = (2 * UM_LBO_COARSE) >> 4, ST = UM_STAGE_BYTES >> 4;
+        const bool last = cpos + 2 == CS;
+        if (a.dbg & 1) {
+          if (elect_one()) {
+            mbar_arrive(bar_empty + 8 * pslot);
+            if (last) mbar_arrive(bar_tfull + 8 * acc);
+          }
+        } else if (elect_one()) {
+          // per K-step of eight samples: hi lo + lo hi + hi hi
 #pragma unroll
-    for (int c = 0; c < 128; ++c) m[c] = 0.f;
-    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + h * 128;
+          for (int q = 0; q < 4; ++q) {
+            const uint64_t oa = (q >> 1) * ST + (q & 1) * KA, ob = (q >> 1) * ST + (q & 1) * KB;
+            mma_f16_ss(d, al + oa, bh + ob, idesc, (cpos != 0 || q != 0) ? 1u : 0u);
+            mma_f16_ss(d, ah + oa, bl + ob, idesc, 1);
+            mma_f16_ss(d, ah + oa, bh + ob, idesc, 1);
+          }
+          mma_commit(bar_empty + 8 * pslot);
+          if (last) mma_commit(bar_tfull + 8 * acc);
+        }
+        __syncwarp();
+        if (trace && lane == 0 && g < 2 * 1024) trace[(g >> 1) * 8 + 4] = clock64();
+        cpos += 2;
+        if (cpos == CS) { cpos = 0; ++ch; }
+      }
+    }
+  } else {
+    setmaxnreg_inc<UM_WORKER_REGS>();
+    const int p = tid;
+    const int wq = warp & 3, quad = warp >> 2;
+    const int row = wq * 32 + lane;
+    const bool weighted_tt = a.weighted && cvp->three_term;
+    const int yslot = rec_slot(REC_Y), wslot = rec_slot(REC_W);
+    const unsigned kmul = type2 ? 2u : 1u;
+    // tile base frequency and its gauge (the per-index phase origin gamma of the records, see gls.cu)
+    const long long jT = a.j0 + (long long)cb0 * UM_FINE;
+    const double fT = cvp->fmin + (double)jT * cvp->df;
+    double gT = (double)jT * cvp->gamma;
+    gT -= floor(gT);
+    const unsigned kfine = kmul * (unsigned)row;                  // phase of the fine operand = kfine * b_i
+    // coarse task: type 1 (coarse block, plain | y-weighted pair of rows), type 2 (coarse block)
+    const int ccb = type2 ? row : wq * 16 + (lane & 15);
+    const int yy = type2 ? 0 : lane >> 4;
+    const unsigned kcoarse = kmul * (unsigned)(ccb * UM_FINE);    // phase of the coarse operand = A_i + kcoarse * b_i
+    const bool cactive = ccb < cpt;
+    const float* s_wsel = yy ? s_wy : s_w;
+    // byte offsets of this thread's operand rows inside a stage
+    const uint32_t fine_off = quad * UM_LBO_FINE + row * 16;
+    const uint32_t rowc_off = quad * UM_LBO_COARSE + (uint32_t)((type2 ? 0 : 2 * yy) * cpt + ccb) * 16;
+    const uint32_t rows_off = rowc_off + (uint32_t)cpt * 16;
+
+    float m[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) m[c] = 0.f;
+    const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16) + quad * 64;
     bool ok = true;
-    for (int ch = 0; ch < nchunks && ok; ++ch) {
+
+    auto drain = [&](int ch) {
       const int acc = ch & 1;
       ok = um_wait(bar_tfull + 8 * acc, (ch >> 1) & 1, s_abort, t_start);
       tc_fence_after();
-      if (ok) {
+      if (ok && !(a.dbg & 4)) {
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 16) {
-          if (h * 128 + c0 < N) {   // warp-uniform
-            uint32_t r[16];
-            tmem_ld16(tlane + acc * 256 + c0, r);
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          if (quad * 64 + c0 < N) {   // warp-uniform (N is a multiple of 16: a partial group reads columns nobody flushes)
+            uint32_t r[32];
+            tmem_ld32(tlane + acc * 256 + c0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 16; ++u) m[c0 + u] += __uint_as_float(r[u]);
+            for (int u = 0; u < 32; ++u) m[c0 + u] += __uint_as_float(r[u]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-    }
-    if (ok) {
-      // flush: column n = 128 h + c  ->  (sum s, coarse block cb) = (n / cpt, n % cpt); row = fine index k
-      const int k = q * 32 + lane;
-      int s = (h * 128) / cpt, cb = (h * 128) % cpt;
-      const int plane0 = type2 ? 4 : 0;
-#pragma unroll
-      for (int c = 0; c < 128; ++c) {
-        const long long j = (long long)(cb0 + cb) * UM_FINE + k;
-        if (h * 128 + c < N && cb < ncb && j < a.nf) {
-          unsigned long long* p = a.partial + (long long)(plane0 + s) * a.nf_tot + (long long)curve * a.nf + j;
-          atomicAdd(p, (unsigned long long)__float2ll_rn(m[c] * a.fix_scale));
-        }
-        if (++cb == cpt) { cb = 0; ++s; }
-      }
-    }
-  } else if (warp < 16) {
-    // =====================================================================================================
-    // producers
-    // =====================================================================================================
-    setmaxnreg_dec<56>();
-    const int p = tid - 256;
-    const bool weighted_tt = a.weighted && cvp->three_term;
-    const int yslot = rec_slot(REC_Y), wslot = rec_slot(REC_W);
-    const double kmul = type2 ? 2.0 : 1.0;
-    // tile base frequency and its gauge (the per-index phase origin gamma of the records, see gls.cu)
-    const long long jT = a.j0 + (long long)cb0 * UM_FINE;
-    const double fT = cvp->fmin + (double)jT * cvp->df;
-    double gT = (double)jT * cvp->gamma;
-    gT -= floor(gT);
-    const double MAGIC = 1572864.0;   // 1.5 * 2^20
-    // fine task: row prow, samples 8 phalf .. 8 phalf + 7 of every stage
-    const int prow = p & 127, phalf = p >> 7;
-    const double kd = kmul * (double)prow;
-    // coarse task(s)
-    const int ccb = type2 ? (p & 127) : (p & 63);
-    const double cd = kmul * (double)(ccb * UM_FINE);
-    const bool cactive = ccb < cpt;
-
+    };
     auto load_block = [&](int blk, double2& r1, float4& r2, bool& in) {
       const long long i = sb + (long long)blk * UM_BLOCK + p;
       in = i < se;
@@ -246,15 +294,67 @@ gls_umma_kernel(const GlsUmmaArgs a) {
       const int o = (blk & 1) * UM_BLOCK + p;
       if (in) {
         const float yv = rec_get(r2, yslot), wv = rec_get(r2, wslot);
-        s_b[o] = r1.y;
-        s_A[o] = kmul * (frac_of_product(fT, r1.x) + gT) + MAGIC;
+        const double bf = r1.y - floor(r1.y);                                        // [0, 1)
+        const double A = (double)kmul * (frac_of_product(fT, r1.x) + gT);            // |A| < 4 turns
+        s_b64[o] = __double2ull_rn(bf * 18446744073709551616.0);                     // 2^64: exact scaling, < 2^64
+        s_A32[o] = (unsigned)__double2ll_rn(A * 4294967296.0);                       // wraps mod 1 turn
         s_wy[o] = weighted_tt ? wv * yv : yv;      // three-term records carry sqrt(w'), sqrt(w') y'
         s_w[o] = weighted_tt ? wv * wv : wv;
       } else {
-        s_b[o] = 0.0;
-        s_A[o] = MAGIC;
+        s_b64[o] = 0ull;
+        s_A32[o] = 0u;
         s_wy[o] = 0.f;
         s_w[o] = 0.f;
+      }
+    };
+    // phase (2^-32 turn, two's complement) -> (cos, sin)
+    auto sincos_fx = [](unsigned fx, float& c, float& s) {
+      const float x = (float)(int)fx * 1.4629180792671596e-9f;   // 2 pi / 2^32
+      __sincosf(x, &s, &c);
+    };
+    // one stage (16 samples) of this thread's tasks: fine row `row` and coarse block `ccb`, sample quad `quad`.
+    // v[0..3] fine hi, v[4..7] fine lo, v[8..11] coarse hi, v[12..15] coarse lo: packed (c, s) pairs of four samples
+    auto compute = [&](int ro, uint32_t (&v)[16]) {
+      const uint4 b01 = *reinterpret_cast<const uint4*>(s_b64 + ro), b23 = *reinterpret_cast<const uint4*>(s_b64 + ro + 2);
+      const unsigned blo[4] = {b01.x, b01.z, b23.x, b23.z}, bhi[4] = {b01.y, b01.w, b23.y, b23.w};
+      const uint4 a4 = *reinterpret_cast<const uint4*>(s_A32 + ro);
+      const unsigned aq[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float4 wq4 = *reinterpret_cast<const float4*>(s_wsel + ro);
+      const float wv[4] = {wq4.x, wq4.y, wq4.z, wq4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float c, s;
+        sincos_fx(kfine * bhi[u] + __umulhi(kfine, blo[u]), c, s);
+        um_split2(c, s, v[u], v[4 + u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float c, s;
+        sincos_fx(aq[u] + kcoarse * bhi[u] + __umulhi(kcoarse, blo[u]), c, s);
+        um_split2(wv[u] * c, wv[u] * s, v[8 + u], v[12 + u]);
+      }
+    };
+    auto store = [&](uint32_t sbase, const uint32_t (&v)[16]) {
+      uint32_t rw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rw[u] = v[u];
+      um_sts128(sbase + UM_FINE_HI + fine_off, rw);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rw[u] = v[4 + u];
+      um_sts128(sbase + UM_FINE_LO + fine_off, rw);
+      if (cactive) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rw[u] = v[8 + u] ^ 0x80000000u;             // (w c, -w s)
+        um_sts128(sbase + UM_COARSE_HI + rowc_off, rw);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rw[u] = v[12 + u] ^ 0x80000000u;
+        um_sts128(sbase + UM_COARSE_LO + rowc_off, rw);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(v[8 + u], 0, 0x1032);   // (w s, w c)
+        um_sts128(sbase + UM_COARSE_HI + rows_off, rw);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(v[12 + u], 0, 0x1032);
+        um_sts128(sbase + UM_COARSE_LO + rows_off, rw);
       }
     };
     const int nblk = (nstages * UM_STAGE_SAMPLES + UM_BLOCK - 1) / UM_BLOCK;
@@ -265,145 +365,96 @@ gls_umma_kernel(const GlsUmmaArgs a) {
       load_block(0, r1, r2, in);
       store_block(0, r1, r2, in);
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    bool ok = true;
-    int g = 0;   // global stage counter
+    // (mbarriers instead of bar.sync: every wait in this kernel must be able to time out)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_rec);
+    ok = um_wait(bar_rec, 0, s_abort, t_start);
+    t_loop0 = clock64();
+    // optional trace of block 0 (dbg & 16): per pair 8 clock stamps behind the per-job records
+    long long* trace = (a.prof && (a.dbg & 16) && blockIdx.x == 0) ? a.prof + 4LL * gridDim.x : nullptr;
+    int g = 0;        // global stage counter; stages are processed in pairs (nstages is even: CS is)
+    int cpos = 0;     // position of stage g inside its accumulation run
+    int ch = 0;       // accumulation run of stage g
     for (int blk = 0; blk < nblk && ok; ++blk) {
       double2 n1 = make_double2(0.0, 0.0);
       float4 n2 = make_float4(0.f, 0.f, 0.f, 0.f);
       bool nin = false;
-      if (blk + 1 < nblk) load_block(blk + 1, n1, n2, nin);
-      const int rbase = (blk & 1) * UM_BLOCK;
-      for (int st = 0; st < UM_BLOCK / UM_STAGE_SAMPLES && g < nstages; ++st, ++g) {
-        const int slot = g % UM_NSTAGES;
-        ok = um_wait(bar_empty + 8 * slot, ((g / UM_NSTAGES) & 1) ^ 1, s_abort, t_start);
+      const bool more = blk + 1 < nblk;
+      if (more) load_block(blk + 1, n1, n2, nin);
+      const int rbase = (blk & 1) * UM_BLOCK + quad * 4;
+      for (int st = 0; st < UM_BLOCK / UM_STAGE_SAMPLES && g < nstages; st += 2, g += 2) {
+        if (st == 8 && more) {
+          // stage the next block of records early: buffer (blk + 1) & 1 was last read in block blk - 1, which every warp
+          // had finished when it arrived on this block's barrier; the wait for THIS arrival is at the end of the block
+          store_block(blk + 1, n1, n2, nin);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_rec + 8 * ((blk + 1) & 1));
+        }
+        // the first stage's operands go to registers before the wait for the pair slot (the wait overlaps the arithmetic;
+        // both stages would not fit beside the 64 masters)
+        const int pslot = (g >> 1) & 1;
+        uint32_t v[16];
+        if (!(a.dbg & 2)) compute(rbase + st * UM_STAGE_SAMPLES, v);
+        ok = um_wait(bar_empty + 8 * pslot, ((g >> 2) & 1) ^ 1, s_abort, t_start);
         if (!ok) break;
-        const uint32_t sbase = smem0 + slot * UM_STAGE_BYTES;
-        const int ro = rbase + st * UM_STAGE_SAMPLES;
-        // ---- fine operand: (cos, sin)(kmul k b_i) ----
-#pragma unroll
-        for (int hq = 0; hq < 2; ++hq) {
-          const int quad = 2 * phalf + hq;
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const double v = __fma_rn(kd, s_b[ro + quad * 4 + u], MAGIC);
-            float c, s;
-            um_sincos_turns(v, c, s);
-            um_split2(c, s, hi[u], lo[u]);
-          }
-          const uint32_t off = quad * UM_LBO_FINE + prow * 16;
-          um_sts128(sbase + UM_FINE_HI + off, hi);
-          um_sts128(sbase + UM_FINE_LO + off, lo);
+        if (trace && warp == 3 && lane == 0 && g < 2 * 1024) trace[(g >> 1) * 8 + 0] = clock64();
+        const uint32_t sbase = smem0 + pslot * 2 * UM_STAGE_BYTES;
+        if (!(a.dbg & 2)) {
+          store(sbase, v);
+          compute(rbase + (st + 1) * UM_STAGE_SAMPLES, v);
+          store(sbase + UM_STAGE_BYTES, v);
         }
-        // ---- coarse operand ----
-        if (cactive) {
-          if (!type2) {
-            const int quad = p >> 6;
-            float c[4], s[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const double v = __fma_rn(cd, s_b[ro + quad * 4 + u], s_A[ro + quad * 4 + u]);
-              um_sincos_turns(v, c[u], s[u]);
-            }
-            const uint32_t off = quad * UM_LBO_COARSE + ccb * 16;
-#pragma unroll
-            for (int yy = 0; yy < 2; ++yy) {
-              uint32_t ph[4], pl[4], rw[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float wv = yy ? s_wy[ro + quad * 4 + u] : s_w[ro + quad * 4 + u];
-                um_split2(wv * c[u], wv * s[u], ph[u], pl[u]);
-              }
-              const uint32_t rowc = off + (uint32_t)((2 * yy) * cpt) * 16, rows = off + (uint32_t)((2 * yy + 1) * cpt) * 16;
-#pragma unroll
-              for (int u = 0; u < 4; ++u) rw[u] = ph[u] ^ 0x80000000u;          // (w c, -w s)
-              um_sts128(sbase + UM_COARSE_HI + rowc, rw);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) rw[u] = pl[u] ^ 0x80000000u;
-              um_sts128(sbase + UM_COARSE_LO + rowc, rw);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(ph[u], 0, 0x1032);  // (w s, w c)
-              um_sts128(sbase + UM_COARSE_HI + rows, rw);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(pl[u], 0, 0x1032);
-              um_sts128(sbase + UM_COARSE_LO + rows, rw);
-            }
-          } else {
-#pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              const int quad = 2 * (p >> 7) + hq;
-              uint32_t ph[4], pl[4], rw[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const double v = __fma_rn(cd, s_b[ro + quad * 4 + u], s_A[ro + quad * 4 + u]);
-                float c, s;
-                um_sincos_turns(v, c, s);
-                const float wv = s_w[ro + quad * 4 + u];
-                um_split2(wv * c, wv * s, ph[u], pl[u]);
-              }
-              const uint32_t rowc = quad * UM_LBO_COARSE + ccb * 16, rows = rowc + (uint32_t)cpt * 16;
-#pragma unroll
-              for (int u = 0; u < 4; ++u) rw[u] = ph[u] ^ 0x80000000u;
-              um_sts128(sbase + UM_COARSE_HI + rowc, rw);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) rw[u] = pl[u] ^ 0x80000000u;
-              um_sts128(sbase + UM_COARSE_LO + rowc, rw);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(ph[u], 0, 0x1032);
-              um_sts128(sbase + UM_COARSE_HI + rows, rw);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(pl[u], 0, 0x1032);
-              um_sts128(sbase + UM_COARSE_LO + rows, rw);
-            }
-          }
-        }
-        fence_proxy_async_smem();
+        if (!(a.dbg & 8)) fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * slot);
+        if (lane == 0) mbar_arrive(bar_full + 8 * pslot);
+        if (trace && warp == 3 && lane == 0 && g < 2 * 1024) trace[(g >> 1) * 8 + 1] = clock64();
+        cpos += 2;
+        if (cpos == CS) {
+          // the run `ch` has all its stages; one run behind, add the finished accumulator of run ch - 1 to the masters
+          // (its last instruction was issued CS stages ago)
+          if (ch >= 1) {
+            if (trace && warp == 3 && lane == 0 && g < 2 * 1024) trace[(g >> 1) * 8 + 6] = clock64();
+            drain(ch - 1);
+            if (!ok) break;
+            if (trace && warp == 3 && lane == 0 && g < 2 * 1024) trace[(g >> 1) * 8 + 7] = clock64();
+          }
+          cpos = 0;
+          ++ch;
+        }
       }
-      if (blk + 1 < nblk) store_block(blk + 1, n1, n2, nin);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (more && ok) ok = um_wait(bar_rec + 8 * ((blk + 1) & 1), ((blk + 1) >> 1) & 1, s_abort, t_start);
     }
-  } else {
-    // =====================================================================================================
-    // MMA issuer (warp 16); warps 17-19 only give their registers away
-    // =====================================================================================================
-    setmaxnreg_dec<24>();
-    if (warp == 16 && lane == 0) {
-      const uint32_t idesc = idesc_f16_f32(UM_FINE, N);
-      bool ok = true;
-      for (int g = 0; g < nstages && ok; ++g) {
-        const int slot = g % UM_NSTAGES, ch = g / UM_CHUNK_STAGES, acc = ch & 1, first = (g % UM_CHUNK_STAGES) == 0;
-        if (first) {
-          ok = um_wait(bar_tempty + 8 * acc, ((ch >> 1) & 1) ^ 1, s_abort, t_start);
-          if (!ok) break;
-        }
-        ok = um_wait(bar_full + 8 * slot, (g / UM_NSTAGES) & 1, s_abort, t_start);
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t sbase = smem0 + slot * UM_STAGE_BYTES;
-        const uint32_t d = tmem + acc * 256;
+    if (ok) drain(nchunks - 1);
+    t_loop1 = clock64();
+    if (ok) {
+      // flush: column n = 64 quad + c  ->  (sum s, coarse block cb) = (n / cpt, n % cpt); row = fine index
+      int s = (quad * 64) / cpt, cb = (quad * 64) % cpt;
+      const int plane0 = type2 ? 4 : 0;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t ah = smem_desc(sbase + UM_FINE_HI + ks * 2 * UM_LBO_FINE, UM_LBO_FINE, UM_SBO);
-          const uint64_t al = smem_desc(sbase + UM_FINE_LO + ks * 2 * UM_LBO_FINE, UM_LBO_FINE, UM_SBO);
-          const uint64_t bh = smem_desc(sbase + UM_COARSE_HI + ks * 2 * UM_LBO_COARSE, UM_LBO_COARSE, UM_SBO);
-          const uint64_t bl = smem_desc(sbase + UM_COARSE_LO + ks * 2 * UM_LBO_COARSE, UM_LBO_COARSE, UM_SBO);
-          mma_f16_ss(d, al, bh, idesc, !(first && ks == 0));
-          mma_f16_ss(d, ah, bl, idesc, 1);
-          mma_f16_ss(d, ah, bh, idesc, 1);
+      for (int c = 0; c < 64; ++c) {
+        const long long j = (long long)(cb0 + cb) * UM_FINE + row;
+        if (quad * 64 + c < N && cb < ncb && j < a.nf) {
+          unsigned long long* pp = a.partial + (long long)(plane0 + s) * a.nf_tot + (long long)curve * a.nf + j;
+          atomicAdd(pp, (unsigned long long)__float2ll_rn(m[c] * a.fix_scale));
         }
-        mma_commit(bar_empty + 8 * slot);
-        if ((g % UM_CHUNK_STAGES) == UM_CHUNK_STAGES - 1) mma_commit(bar_tfull + 8 * acc);
+        if (++cb == cpt) { cb = 0; ++s; }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem, 512);
-  if (tid == 0 && *s_abort) *a.status = 1;
+  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (tid == 0) {
+    if (*s_abort) *a.status = 1;
+    if (a.prof) {
+      long long* pr = a.prof + 4LL * blockIdx.x;
+      pr[0] = t_start;
+      pr[1] = t_loop0;
+      pr[2] = t_loop1;
+      pr[3] = clock64();
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -440,7 +491,10 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
   while (a.nt1 > 1 && (long long)(a.nt1 - 1) * a.cpt1 >= a.nC) --a.nt1;
   while (a.nt2 > 1 && (long long)(a.nt2 - 1) * a.cpt2 >= a.nC) --a.nt2;
   a.weighted = weighted ? 1 : 0;
+  a.chunk_stages = ctx->gls_umma_chunk > 0 ? ((ctx->gls_umma_chunk + 1) & ~1) : 4;   // even: stages go in pairs
   a.fix_scale = fix_scale;
+  a.prof = nullptr;
+  a.dbg = ctx->gls_umma_dbg;
   PDC_TRY(ctx->umma_status.reserve(sizeof(int)));
   a.status = ctx->umma_status.as<int>();
 
@@ -473,6 +527,12 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
   if (!ctx->umma_status_clean) {
     PDC_CUDA(cudaMemsetAsync(a.status, 0, sizeof(int), st));
     ctx->umma_status_clean = true;
+  }
+  if (ctx->umma_prof_on) {
+    PDC_TRY(ctx->umma_prof.reserve(sizeof(long long) * (4 * (size_t)jobs + 8 * 1024)));
+    PDC_CUDA(cudaMemsetAsync(ctx->umma_prof.p, 0, sizeof(long long) * (4 * (size_t)jobs + 8 * 1024), st));
+    a.prof = ctx->umma_prof.as<long long>();
+    ctx->umma_prof_jobs = jobs;
   }
   gls_umma_kernel<<<(unsigned)jobs, UM_THREADS, UM_SMEM_BYTES, st>>>(a);
   PDC_CUDA(cudaGetLastError());

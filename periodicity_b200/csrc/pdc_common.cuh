@@ -69,9 +69,14 @@ struct pdc_ctx {
   int pdm_ppt_override = 0;  // env PDC_PDM_PPT=1|2 forces the trial periods per thread of pdm_hist_kernel (tuning aid)
   int gls_umma = -1;           // tensor-core formulation of the GLS sums (gls_umma.cu): -1 automatic, 0 off, 1 whenever eligible
                                // (env PDC_GLS_UMMA)
+  int gls_umma_chunk = 0;      // env PDC_GLS_UMMA_CHUNK: stages of 16 samples per TMEM accumulation run (default 4)
+  int gls_umma_dbg = 0;        // env PDC_GLS_UMMA_DBG: timing experiments (results are wrong when non-zero)
   int gls_umma_nsplit = 0;     // env PDC_GLS_UMMA_NSPLIT: sample splits of the tensor-core kernel (tuning aid)
   pdc::DevBuf umma_status;     // int: set by gls_umma_kernel on a protocol time-out; the epilogue then writes NaN
   bool umma_status_clean = false;
+  bool umma_prof_on = false;   // env PDC_GLS_UMMA_PROF=1
+  pdc::DevBuf umma_prof;       // long long [jobs][4] clock stamps of the last gls_umma_kernel launch
+  int64_t umma_prof_jobs = 0;
   int gls_geom = 0;  // index into kGlsGeoms (gls.cu); env PDC_GLS_GEOM overrides at ctx creation (tuning aid)
 
   // CUDA-event timing of the dominant kernel (GLS strip / PDM histogram), recorded on the
