@@ -191,6 +191,8 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
   if (const char* g = getenv("PDC_GLS_UMMA_NSPLIT")) ctx->gls_umma_nsplit = atoi(g);
   if (const char* g = getenv("PDC_GLS_UMMA_CHUNK")) ctx->gls_umma_chunk = atoi(g);
   if (const char* g = getenv("PDC_GLS_UMMA_DBG")) ctx->gls_umma_dbg = atoi(g);
+  if (const char* g = getenv("PDC_GLS_UMMA_FINE")) ctx->gls_umma_fine = atoi(g);
+  if (const char* g = getenv("PDC_GLS_UMMA_RZCOMP")) ctx->gls_umma_rzcomp = atoi(g);
   if (const char* g = getenv("PDC_GLS_UMMA_PROF")) ctx->umma_prof_on = atoi(g) != 0;
   if (const char* g = getenv("PDC_PDM_PPT")) ctx->pdm_ppt_override = atoi(g);
   if (const char* g = getenv("PDC_BATCH_PIPE_BYTES")) ctx->pipe_min_bytes = (size_t)atoll(g);
@@ -217,7 +219,7 @@ int pdc_ctx_destroy(pdc_ctx* ctx) {
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   ctx->gls_curves.release(); ctx->gls_part.release(); ctx->gls_rec1.release(); ctx->gls_rec2.release(); ctx->gls_low.release(); ctx->gls_cnt.release(); ctx->glsm_y.release();
   ctx->partial.release(); ctx->gls_plane.release(); ctx->hist_plane.release(); ctx->blockred.release(); ctx->pin_meta.release();
-  ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->gl_acc.release(); ctx->peak_cand.release(); ctx->umma_status.release(); ctx->umma_prof.release();
+  ctx->pdm_meta.release(); ctx->pdm_cnt.release(); ctx->gl_acc.release(); ctx->peak_cand.release(); ctx->umma_status.release(); ctx->umma_prof.release(); ctx->umma_fine.release();
   ctx->main_resolve();
   for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);

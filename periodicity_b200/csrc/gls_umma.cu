@@ -65,7 +65,10 @@ struct GlsUmmaArgs {
   int nsplit;
   int weighted;
   int chunk_stages;              // stages (of 16 samples) per accumulation run in TMEM
+  float rz_comp;                 // 1 + expected relative truncation loss of one accumulation run (see the drain)
   float fix_scale;
+  const unsigned char* fine_img; // FINE_PRE: fine operand of the whole curve as shared-memory images, [2 types][stage][16 KB] (gls_umma_fine_kernel)
+  long long fine_stages;         // stages per type in fine_img
   int* status;                   // set non-zero on a protocol time-out
   int dbg;                       // timing experiments (env PDC_GLS_UMMA_DBG): 1 no MMA, 2 no operand production, 4 no drain, 8 no proxy fence, 16 trace
   long long* prof;               // optional [jobs][4] clock64 stamps (start, main loop begin, main loop end, flush end)
@@ -94,6 +97,50 @@ __device__ __forceinline__ void um_split2(float c, float s, uint32_t& hi, uint32
 __device__ __forceinline__ void um_sts128(uint32_t addr, const uint32_t (&v)[4]) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
+// global -> shared bulk copy (TMA without a tensor map): completion is counted in bytes on `bar`
+__device__ __forceinline__ void um_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void um_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// phase (2^-32 turn, two's complement) -> (cos, sin)
+__device__ __forceinline__ void um_sincos_fx(unsigned fx, float& c, float& s) {
+  const float x = (float)(int)fx * 1.4629180792671596e-9f;   // 2 pi / 2^32
+  __sincosf(x, &s, &c);
+}
+
+// Fine operand of a whole curve, once per call, when many coarse tiles share it (one long curve: C2 has 13 + 7 tiles per
+// sample split, C5 1221 + 611): (cos, sin)(kmul k b_i) for k < 128 as fp16 hi / lo, written as the 16 KB shared-memory
+// image of every 16-sample stage ([hi | lo][K-chunk of 4 samples][row][8 halves]) so that a CTA fetches a stage with one
+// bulk copy.  Same integer phase arithmetic as the in-kernel path: both give bit-identical operands.
+// grid = (stages, 2 types), block = 128 (row).
+__global__ void __launch_bounds__(128)
+gls_umma_fine_kernel(const double2* __restrict__ rec1, long long n, unsigned char* __restrict__ img, long long stages) {
+  const long long stg = blockIdx.x;
+  const unsigned kfine = (blockIdx.y + 1u) * threadIdx.x;
+  unsigned char* out = img + ((long long)blockIdx.y * stages + stg) * 16384 + threadIdx.x * 16;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = stg * UM_STAGE_SAMPLES + q * 4 + u;
+      unsigned long long b64 = 0ull;
+      if (i < n) {
+        const double b = rec1[i].y;
+        b64 = __double2ull_rn((b - floor(b)) * 18446744073709551616.0);
+      }
+      float c, s;
+      um_sincos_fx(kfine * (unsigned)(b64 >> 32) + __umulhi(kfine, (unsigned)b64), c, s);
+      um_split2(c, s, hi[u], lo[u]);
+    }
+    *reinterpret_cast<uint4*>(out + q * UM_LBO_FINE) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out + 8192 + q * UM_LBO_FINE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -110,6 +157,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 //   * DRAINS: one accumulation run behind the producers it adds its 32 lanes x 64 columns of the finished TMEM
 //     accumulator to 64 FP32 masters in registers (TMEM lanes 32 (warp & 3).., columns 64 (warp >> 2)..);
 //   * FLUSHES the masters at the end of the job.
+template <bool FINE_PRE>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 gls_umma_kernel(const GlsUmmaArgs a) {
   extern __shared__ __align__(1024) unsigned char um_smem[];
@@ -132,7 +180,7 @@ gls_umma_kernel(const GlsUmmaArgs a) {
 
   const GlsCurve* cvp = a.curves + curve;
   const long long cbegin = cvp->begin, cn = cvp->n;
-  const long long per = (cn + a.nsplit - 1) / a.nsplit;
+  const long long per = (((cn + a.nsplit - 1) / a.nsplit) + 63) & ~63LL;   // whole stages (the fine images are per stage)
   const long long sb = (long long)split * per;
   const long long se = sb + per < cn ? sb + per : cn;
   const long long ns = se > sb ? se - sb : 0;
@@ -159,7 +207,7 @@ gls_umma_kernel(const GlsUmmaArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < UM_NSTAGES; ++s) {
-      mbar_init(bar_full + 8 * s, UM_WORKERS / 32);   // one arrival per worker warp
+      mbar_init(bar_full + 8 * s, UM_WORKERS / 32 + (FINE_PRE ? 1 : 0));   // one arrival per worker warp (+ the bulk copy's expect_tx)
       mbar_init(bar_empty + 8 * s, 1);                // tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
@@ -187,6 +235,23 @@ gls_umma_kernel(const GlsUmmaArgs a) {
     // instructions of a pair of stages take ~1470 clocks to issue), so the issuer must have nothing else to do.
     // =====================================================================================================
     setmaxnreg_dec<UM_MMA_REGS>();
+    if (FINE_PRE && warp == 17) {
+      // copy warp: the fine operand of both stages of a pair comes as two 16 KB bulk copies from the per-curve images
+      bool ok = true;
+      const unsigned char* src = a.fine_img + ((type2 ? a.fine_stages : 0) + (cbegin + sb) / UM_STAGE_SAMPLES) * 16384;
+      for (int g = 0; g < nstages && ok; g += 2) {
+        const int pslot = (g >> 1) & 1;
+        ok = um_wait(bar_empty + 8 * pslot, ((g >> 2) & 1) ^ 1, s_abort, t_start);
+        if (!ok) break;
+        if (elect_one()) {
+          const uint32_t dst = smem0 + pslot * 2 * UM_STAGE_BYTES + UM_FINE_HI;
+          um_arrive_expect_tx(bar_full + 8 * pslot, 32768);
+          um_bulk_g2s(dst, src + (long long)g * 16384, 16384, bar_full + 8 * pslot);
+          um_bulk_g2s(dst + UM_STAGE_BYTES, src + (long long)(g + 1) * 16384, 16384, bar_full + 8 * pslot);
+        }
+        __syncwarp();
+      }
+    }
     if (warp == 16) {
       bool ok = true;
       int cpos = 0, ch = 0;
@@ -274,7 +339,7 @@ gls_umma_kernel(const GlsUmmaArgs a) {
             tmem_ld32(tlane + acc * 256 + c0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 32; ++u) m[c0 + u] += __uint_as_float(r[u]);
+            for (int u = 0; u < 32; ++u) m[c0 + u] = fmaf(__uint_as_float(r[u]), a.rz_comp, m[c0 + u]);
           }
         }
       }
@@ -307,14 +372,19 @@ gls_umma_kernel(const GlsUmmaArgs a) {
         s_w[o] = 0.f;
       }
     };
-    // phase (2^-32 turn, two's complement) -> (cos, sin)
-    auto sincos_fx = [](unsigned fx, float& c, float& s) {
-      const float x = (float)(int)fx * 1.4629180792671596e-9f;   // 2 pi / 2^32
-      __sincosf(x, &s, &c);
+    // one stage (16 samples) of this thread's tasks: fine row `row` and coarse block `ccb`, sample quad `quad`;
+    // packed (c, s) pairs of four samples, fp16 hi and lo
+    auto compute_fine = [&](int ro, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+      const uint4 b01 = *reinterpret_cast<const uint4*>(s_b64 + ro), b23 = *reinterpret_cast<const uint4*>(s_b64 + ro + 2);
+      const unsigned blo[4] = {b01.x, b01.z, b23.x, b23.z}, bhi[4] = {b01.y, b01.w, b23.y, b23.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float c, s;
+        um_sincos_fx(kfine * bhi[u] + __umulhi(kfine, blo[u]), c, s);
+        um_split2(c, s, hi[u], lo[u]);
+      }
     };
-    // one stage (16 samples) of this thread's tasks: fine row `row` and coarse block `ccb`, sample quad `quad`.
-    // v[0..3] fine hi, v[4..7] fine lo, v[8..11] coarse hi, v[12..15] coarse lo: packed (c, s) pairs of four samples
-    auto compute = [&](int ro, uint32_t (&v)[16]) {
+    auto compute_coarse = [&](int ro, uint32_t (&ph)[4], uint32_t (&pl)[4]) {
       const uint4 b01 = *reinterpret_cast<const uint4*>(s_b64 + ro), b23 = *reinterpret_cast<const uint4*>(s_b64 + ro + 2);
       const unsigned blo[4] = {b01.x, b01.z, b23.x, b23.z}, bhi[4] = {b01.y, b01.w, b23.y, b23.w};
       const uint4 a4 = *reinterpret_cast<const uint4*>(s_A32 + ro);
@@ -324,36 +394,28 @@ gls_umma_kernel(const GlsUmmaArgs a) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float c, s;
-        sincos_fx(kfine * bhi[u] + __umulhi(kfine, blo[u]), c, s);
-        um_split2(c, s, v[u], v[4 + u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float c, s;
-        sincos_fx(aq[u] + kcoarse * bhi[u] + __umulhi(kcoarse, blo[u]), c, s);
-        um_split2(wv[u] * c, wv[u] * s, v[8 + u], v[12 + u]);
+        um_sincos_fx(aq[u] + kcoarse * bhi[u] + __umulhi(kcoarse, blo[u]), c, s);
+        um_split2(wv[u] * c, wv[u] * s, ph[u], pl[u]);
       }
     };
-    auto store = [&](uint32_t sbase, const uint32_t (&v)[16]) {
-      uint32_t rw[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rw[u] = v[u];
-      um_sts128(sbase + UM_FINE_HI + fine_off, rw);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rw[u] = v[4 + u];
-      um_sts128(sbase + UM_FINE_LO + fine_off, rw);
+    auto store_fine = [&](uint32_t sbase, const uint32_t (&hi)[4], const uint32_t (&lo)[4]) {
+      um_sts128(sbase + UM_FINE_HI + fine_off, hi);
+      um_sts128(sbase + UM_FINE_LO + fine_off, lo);
+    };
+    auto store_coarse = [&](uint32_t sbase, const uint32_t (&ph)[4], const uint32_t (&pl)[4]) {
       if (cactive) {
+        uint32_t rw[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) rw[u] = v[8 + u] ^ 0x80000000u;             // (w c, -w s)
+        for (int u = 0; u < 4; ++u) rw[u] = ph[u] ^ 0x80000000u;             // (w c, -w s)
         um_sts128(sbase + UM_COARSE_HI + rowc_off, rw);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) rw[u] = v[12 + u] ^ 0x80000000u;
+        for (int u = 0; u < 4; ++u) rw[u] = pl[u] ^ 0x80000000u;
         um_sts128(sbase + UM_COARSE_LO + rowc_off, rw);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(v[8 + u], 0, 0x1032);   // (w s, w c)
+        for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(ph[u], 0, 0x1032);   // (w s, w c)
         um_sts128(sbase + UM_COARSE_HI + rows_off, rw);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(v[12 + u], 0, 0x1032);
+        for (int u = 0; u < 4; ++u) rw[u] = __byte_perm(pl[u], 0, 0x1032);
         um_sts128(sbase + UM_COARSE_LO + rows_off, rw);
       }
     };
@@ -390,19 +452,37 @@ gls_umma_kernel(const GlsUmmaArgs a) {
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_rec + 8 * ((blk + 1) & 1));
         }
-        // the first stage's operands go to registers before the wait for the pair slot (the wait overlaps the arithmetic;
-        // both stages would not fit beside the 64 masters)
+        // operands go to registers before the wait for the pair slot (the wait overlaps the arithmetic): both stages'
+        // coarse rows when the fine operand comes by bulk copy, else the first stage (more would not fit beside the 64
+        // masters)
         const int pslot = (g >> 1) & 1;
-        uint32_t v[16];
-        if (!(a.dbg & 2)) compute(rbase + st * UM_STAGE_SAMPLES, v);
+        const int ro0 = rbase + st * UM_STAGE_SAMPLES, ro1 = ro0 + UM_STAGE_SAMPLES;
+        const uint32_t sbase = smem0 + pslot * 2 * UM_STAGE_BYTES;
+        uint32_t h0[4], l0[4], p0[4], q0[4];
+        if (!(a.dbg & 2)) {
+          if (FINE_PRE) {
+            compute_coarse(ro0, h0, l0);
+            compute_coarse(ro1, p0, q0);
+          } else {
+            compute_fine(ro0, h0, l0);
+            compute_coarse(ro0, p0, q0);
+          }
+        }
         ok = um_wait(bar_empty + 8 * pslot, ((g >> 2) & 1) ^ 1, s_abort, t_start);
         if (!ok) break;
         if (trace && warp == 3 && lane == 0 && g < 2 * 1024) trace[(g >> 1) * 8 + 0] = clock64();
-        const uint32_t sbase = smem0 + pslot * 2 * UM_STAGE_BYTES;
         if (!(a.dbg & 2)) {
-          store(sbase, v);
-          compute(rbase + (st + 1) * UM_STAGE_SAMPLES, v);
-          store(sbase + UM_STAGE_BYTES, v);
+          if (FINE_PRE) {
+            store_coarse(sbase, h0, l0);
+            store_coarse(sbase + UM_STAGE_BYTES, p0, q0);
+          } else {
+            store_fine(sbase, h0, l0);
+            store_coarse(sbase, p0, q0);
+            compute_fine(ro1, h0, l0);
+            store_fine(sbase + UM_STAGE_BYTES, h0, l0);
+            compute_coarse(ro1, p0, q0);
+            store_coarse(sbase + UM_STAGE_BYTES, p0, q0);
+          }
         }
         if (!(a.dbg & 8)) fence_proxy_async_smem();
         __syncwarp();
@@ -491,7 +571,12 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
   while (a.nt1 > 1 && (long long)(a.nt1 - 1) * a.cpt1 >= a.nC) --a.nt1;
   while (a.nt2 > 1 && (long long)(a.nt2 - 1) * a.cpt2 >= a.nC) --a.nt2;
   a.weighted = weighted ? 1 : 0;
-  a.chunk_stages = ctx->gls_umma_chunk > 0 ? ((ctx->gls_umma_chunk + 1) & ~1) : 4;   // even: stages go in pairs
+  a.chunk_stages = ctx->gls_umma_chunk > 0 ? ((ctx->gls_umma_chunk + 1) & ~1) : 16;   // even: stages go in pairs
+  // The TMEM accumulator truncates toward zero after every instruction: an expected loss of 0.5 ulp(acc) = 0.5 * ln 2 *
+  // 2^-23 |acc| per instruction.  Over a run of n = 6 * chunk_stages instructions with |acc| growing about linearly that
+  // is a relative loss of 2.07e-8 * n of the run's sum (measured: the power error grows from 1.0e-6 at 24 instructions to
+  // 1.9e-6 at 48 and 4.0e-6 at 96 without the correction).  The drain multiplies the run's sum back by 1 + that.
+  a.rz_comp = ctx->gls_umma_rzcomp ? 1.0f + 2.07e-8f * 6.0f * (float)a.chunk_stages : 1.0f;
   a.fix_scale = fix_scale;
   a.prof = nullptr;
   a.dbg = ctx->gls_umma_dbg;
@@ -521,8 +606,26 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
 
   static bool attr_set[64] = {};
   if (ctx->device >= 0 && ctx->device < 64 && !attr_set[ctx->device]) {
-    PDC_CUDA(cudaFuncSetAttribute(gls_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_BYTES));
+    PDC_CUDA(cudaFuncSetAttribute(gls_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_BYTES));
+    PDC_CUDA(cudaFuncSetAttribute(gls_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_BYTES));
     attr_set[ctx->device] = true;
+  }
+  // One curve with several coarse tiles per sample split: the fine operand is the same for all of them, compute it once
+  // (16 KB per 16 samples and type: 133 MB for C2, 2 GB for C5) and let the CTAs fetch it by bulk copy.
+  bool fine_pre = B == 1 && a.nt1 >= 3 && ctx->gls_umma_fine != 0;
+  if (ctx->gls_umma_fine == 1) fine_pre = B == 1;
+  a.fine_img = nullptr;
+  a.fine_stages = 0;
+  if (fine_pre) {
+    const long long per = ((((long long)nmax + nsplit - 1) / nsplit) + 63) & ~63LL;
+    const long long stages = per * nsplit / UM_STAGE_SAMPLES + 16;   // the last accumulation run of a split may read past it
+    PDC_TRY(ctx->umma_fine.reserve((size_t)stages * 2 * 16384));
+    a.fine_img = ctx->umma_fine.as<unsigned char>();
+    a.fine_stages = stages;
+    dim3 grid((unsigned)stages, 2);
+    gls_umma_fine_kernel<<<grid, 128, 0, st>>>(rec1, (long long)nmax, ctx->umma_fine.as<unsigned char>(), stages);
+    PDC_CUDA(cudaGetLastError());
+    ctx->launches++;
   }
   if (!ctx->umma_status_clean) {
     PDC_CUDA(cudaMemsetAsync(a.status, 0, sizeof(int), st));
@@ -534,7 +637,8 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
     a.prof = ctx->umma_prof.as<long long>();
     ctx->umma_prof_jobs = jobs;
   }
-  gls_umma_kernel<<<(unsigned)jobs, UM_THREADS, UM_SMEM_BYTES, st>>>(a);
+  if (fine_pre) gls_umma_kernel<true><<<(unsigned)jobs, UM_THREADS, UM_SMEM_BYTES, st>>>(a);
+  else gls_umma_kernel<false><<<(unsigned)jobs, UM_THREADS, UM_SMEM_BYTES, st>>>(a);
   PDC_CUDA(cudaGetLastError());
   ctx->launches++;
   return PDC_OK;

@@ -70,6 +70,9 @@ struct pdc_ctx {
   int gls_umma = -1;           // tensor-core formulation of the GLS sums (gls_umma.cu): -1 automatic, 0 off, 1 whenever eligible
                                // (env PDC_GLS_UMMA)
   int gls_umma_chunk = 0;      // env PDC_GLS_UMMA_CHUNK: stages of 16 samples per TMEM accumulation run (default 4)
+  int gls_umma_fine = -1;      // env PDC_GLS_UMMA_FINE: fine operand precomputed per curve: -1 automatic, 0 never, 1 whenever B == 1
+  pdc::DevBuf umma_fine;       // its shared-memory images [2 types][stage][16 KB]
+  int gls_umma_rzcomp = 1;     // env PDC_GLS_UMMA_RZCOMP=0: no compensation of the TMEM truncation bias (diagnostic)
   int gls_umma_dbg = 0;        // env PDC_GLS_UMMA_DBG: timing experiments (results are wrong when non-zero)
   int gls_umma_nsplit = 0;     // env PDC_GLS_UMMA_NSPLIT: sample splits of the tensor-core kernel (tuning aid)
   pdc::DevBuf umma_status;     // int: set by gls_umma_kernel on a protocol time-out; the epilogue then writes NaN
