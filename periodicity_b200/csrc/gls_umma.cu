@@ -52,6 +52,7 @@ constexpr uint32_t UM_STAGE_BYTES = 49152;
 constexpr uint32_t UM_LBO_FINE = 128 * 16, UM_LBO_COARSE = 256 * 16, UM_SBO = 128;
 constexpr uint32_t UM_REC_BYTES = 2 * UM_BLOCK * (8 + 4 + 4 + 4);
 constexpr uint32_t UM_SMEM_BYTES = UM_NSTAGES * UM_STAGE_BYTES + UM_REC_BYTES + 256;
+constexpr long long UM_MAX_JOB_SAMPLES = 16384;   // FP32 masters are flushed to the fixed-point plane at least this often
 constexpr long long UM_WAIT_CLOCKS = 4000000000LL;   // ~2 s: far beyond any legitimate wait
 
 struct GlsUmmaArgs {
@@ -65,7 +66,7 @@ struct GlsUmmaArgs {
   int nsplit;
   int weighted;
   int chunk_stages;              // stages (of 16 samples) per accumulation run in TMEM
-  float rz_comp;                 // 1 + expected relative truncation loss of one accumulation run (see the drain)
+  float rz_comp;                 // expected relative truncation loss of the accumulator per tcgen05.mma of a run (see the drain)
   float fix_scale;
   const unsigned char* fine_img; // FINE_PRE: fine operand of the whole curve as shared-memory images, [2 types][stage][16 KB] (gls_umma_fine_kernel)
   long long fine_stages;         // stages per type in fine_img
@@ -165,12 +166,13 @@ gls_umma_kernel(const GlsUmmaArgs a) {
   const long long t_start = clock64();
 
   // ---- job ----
+  // tile fastest: the CTAs that run together then work on the same sample split and share its fine-operand images in L2
   int job = blockIdx.x;
-  const int split = job % a.nsplit;
-  job /= a.nsplit;
   const int ntile = a.nt1 + a.nt2;
   const int tile = job % ntile;
-  const int curve = job / ntile;
+  job /= ntile;
+  const int split = job % a.nsplit;
+  const int curve = job / a.nsplit;
   const bool type2 = tile >= a.nt1;
   const int cpt = type2 ? a.cpt2 : a.cpt1;                       // coarse blocks per tile (padded to 4 / 8)
   const int cb0 = (type2 ? tile - a.nt1 : tile) * cpt;           // first coarse block of this tile
@@ -327,8 +329,13 @@ gls_umma_kernel(const GlsUmmaArgs a) {
     const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16) + quad * 64;
     bool ok = true;
 
+    // compensation factors of a full run and of the job's last run: 1 + loss per instruction * (instructions of the run
+    // that added real samples; zero padding adds exact zeros, which lose nothing)
+    const float comp_full = 1.0f + a.rz_comp * (float)(6 * CS);
+    const float comp_last = 1.0f + a.rz_comp * (float)(3 * (int)((ns - (long long)(nchunks - 1) * CS * UM_STAGE_SAMPLES + 7) >> 3));
     auto drain = [&](int ch) {
       const int acc = ch & 1;
+      const float comp = ch == nchunks - 1 ? comp_last : comp_full;
       ok = um_wait(bar_tfull + 8 * acc, (ch >> 1) & 1, s_abort, t_start);
       tc_fence_after();
       if (ok && !(a.dbg & 4)) {
@@ -339,7 +346,7 @@ gls_umma_kernel(const GlsUmmaArgs a) {
             tmem_ld32(tlane + acc * 256 + c0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 32; ++u) m[c0 + u] = fmaf(__uint_as_float(r[u]), a.rz_comp, m[c0 + u]);
+            for (int u = 0; u < 32; ++u) m[c0 + u] = fmaf(__uint_as_float(r[u]), comp, m[c0 + u]);
           }
         }
       }
@@ -571,36 +578,50 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
   while (a.nt1 > 1 && (long long)(a.nt1 - 1) * a.cpt1 >= a.nC) --a.nt1;
   while (a.nt2 > 1 && (long long)(a.nt2 - 1) * a.cpt2 >= a.nC) --a.nt2;
   a.weighted = weighted ? 1 : 0;
-  a.chunk_stages = ctx->gls_umma_chunk > 0 ? ((ctx->gls_umma_chunk + 1) & ~1) : 16;   // even: stages go in pairs
   // The TMEM accumulator truncates toward zero after every instruction: an expected loss of 0.5 ulp(acc) = 0.5 * ln 2 *
-  // 2^-23 |acc| per instruction.  Over a run of n = 6 * chunk_stages instructions with |acc| growing about linearly that
-  // is a relative loss of 2.07e-8 * n of the run's sum (measured: the power error grows from 1.0e-6 at 24 instructions to
-  // 1.9e-6 at 48 and 4.0e-6 at 96 without the correction).  The drain multiplies the run's sum back by 1 + that.
-  a.rz_comp = ctx->gls_umma_rzcomp ? 1.0f + 2.07e-8f * 6.0f * (float)a.chunk_stages : 1.0f;
+  // 2^-23 |acc| per instruction.  Over a run of n instructions with |acc| growing about linearly that is a relative loss
+  // of 2.07e-8 * n of the run's sum (measured on C2: the power error grows from 1.0e-6 at 24 instructions to 1.9e-6 at 48
+  // and 4.0e-6 at 96 without the correction, and stays at 1-3e-7 with it).  The drain multiplies the run's sum back by
+  // 1 + 2.07e-8 * (instructions of the run that added real samples).  The correction is exact in expectation for a sum
+  // that grows steadily (the peaks); for a partial sum that oscillates inside a run it is not, which shows as a relative
+  // error of up to ~1e-8 * n on weak bins of SHORT curves -- hence the shorter runs chosen for them in gls_umma_launch.
+  a.rz_comp = ctx->gls_umma_rzcomp ? 2.07e-8f : 0.0f;
   a.fix_scale = fix_scale;
   a.prof = nullptr;
   a.dbg = ctx->gls_umma_dbg;
   PDC_TRY(ctx->umma_status.reserve(sizeof(int)));
   a.status = ctx->umma_status.as<int>();
 
-  // sample splits: fill whole waves of one CTA per SM; a job should keep >= 1024 samples (its flush is 32768 REDs)
+  // Sample splits.  (i) A job keeps its 32768 sums in FP32 registers until its end: at most UM_MAX_JOB_SAMPLES samples per
+  // job bound the rounding of those masters (64 additions of 256-sample runs: ~2e-7 of their magnitude; C5 with one job
+  // per tile showed 4.7e-6 on weak bins).  (ii) Few tiles: fill whole waves of one CTA per SM, with >= 1024 samples per job
+  // (its set-up and its flush of 32768 REDs cost about as much as 300 samples).
   const long long base_jobs = (long long)B * (a.nt1 + a.nt2);
-  int nsplit = 1;
+  const long long smin = (nmax + UM_MAX_JOB_SAMPLES - 1) / UM_MAX_JOB_SAMPLES;
+  int nsplit = (int)smin;
   if (ctx->gls_umma_nsplit > 0) nsplit = ctx->gls_umma_nsplit;
-  else if (base_jobs < 6LL * ctx->sm_count) {
+  else if (base_jobs * smin < 6LL * ctx->sm_count) {
     long long cap = nmax / 1024;
-    if (cap < 1) cap = 1;
+    if (cap < smin) cap = smin;
     double best = 1e300;
-    for (long long s = 1; s <= cap && s <= 1024; ++s) {
+    for (long long s = smin; s <= cap && s <= 4096; ++s) {
       const long long jobs = base_jobs * s;
       const long long waves = (jobs + ctx->sm_count - 1) / ctx->sm_count;
-      const double per = (double)((nmax + s - 1) / s) + 768.0;   // per-job fixed cost (set-up + flush) in samples
+      const double per = (double)((nmax + s - 1) / s) + 300.0;   // per-job fixed cost (set-up + flush) in samples
       const double cost = (double)waves * per;
       if (cost < best * 0.999) { best = cost; nsplit = (int)s; }
       if (jobs > 16LL * ctx->sm_count) break;
     }
   }
   a.nsplit = nsplit;
+  {
+    // stages (16 samples) per accumulation run in TMEM; even, because stages go in pairs.  Longer runs mean fewer drains
+    // (C2: 0.48 ms at 4, 0.43 ms at 16); short curves keep short runs (see rz_comp above).
+    const long long per_job = (nmax + nsplit - 1) / nsplit;
+    int cs = per_job >= 8192 ? 16 : (per_job >= 2048 ? 8 : 4);
+    if (ctx->gls_umma_chunk > 0) cs = (ctx->gls_umma_chunk + 1) & ~1;
+    a.chunk_stages = cs;
+  }
   const long long jobs = base_jobs * nsplit;
   if (jobs > 0x7fffffffLL) { set_error("pdc_gls: problem too large for one call (%lld jobs)", jobs); return PDC_EINVAL; }
 

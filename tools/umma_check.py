@@ -166,7 +166,7 @@ if __name__ == "__main__":
     if "c2sweep" in which:
         case_big(ctx_t, ctx_s, 65000, 100000, 1470.0, "c2", nsplits=(7, 14, 22, 29, 37))
     if "c2chunk" in which:
-        case_big(ctx_t, ctx_s, 65000, 100000, 1470.0, "c2", chunks=(2, 4, 8, 16, 32))
+        case_big(ctx_t, ctx_s, 65000, 100000, 1470.0, "c2", chunks=(None,))
     if "trace" in which:
         case_trace()
     if "dbg" in which:
