@@ -25,10 +25,12 @@ gathered array, and -- where the reference's own algorithm fits in a second or s
 same.  A failed check makes the run exit non-zero AFTER printing the line.
 
 Printed line (rank 0): metric/value/unit/... as the driver contract asks, plus
-  roofline      dominant kernel vs the FP32 issue roofline (the path is FP32-pipe bound, not HBM or tensor bound;
-                SURVEY.md 8d): achieved = evals x 20 FLOP / kernel time (CUDA events on the launching stream inside
-                the library), peak = measured FFMA rate (profiles/r01/pipes_r01.json; MEASURED_PEAKS.json has no FP32
-                entry).  PDM: updates/s vs the measured shared-memory ATOMS.ADD rate.
+  roofline      dominant kernel: achieved = evals x 20 FLOP (SURVEY.md 8d's accounting figure) / kernel time (CUDA events
+                on the launching stream inside the library).  GLS on the tensor-core kernel (gls_umma_kernel, the default for
+                large calls): bound "tensor", peak = MEASURED_PEAKS.json bf16_tflops, plus `executed` (72 tensor FLOP per
+                evaluation) and the same figure against the FP32 roofline.  GLS on gls_strip_kernel (small calls,
+                PDC_GLS_UMMA=0): bound "fp32", peak = measured FFMA rate (profiles/r01/pipes_r01.json).  PDM: updates/s vs
+                the measured shared-memory ATOMS.ADD rate.
   cpu_baseline  the reference's CPU path timed on this box's host cores: the UNMODIFIED reference files when
                 oracle/_ref holds them (kind "reference"; staged by oracle/make_ref.py), else the numpy port (kind "port").
   e2e           same metric through the public host API with HOST buffers: N = 1 the host-pointer C-ABI call
@@ -59,6 +61,9 @@ FP32_PEAK_GINSTR_MEASURED = 36172.0  # same measurement as thread-instructions/s
 # 2 samples x 16 frequencies; 6 FFMA + 2 FADD per evaluation): the 20 FLOP of the accounting figure are NOT all executed
 GLS_EXECUTED_INSTR_PER_EVAL = 282.0 / 32.0
 GLS_EXECUTED_FLOP_PER_EVAL = 14.0
+# gls_umma_kernel (tcgen05): per evaluation 6 sums x 2 multiply-adds (angle addition: cos and sin slot), each taken as
+# hi*hi + hi*lo + lo*hi in fp16 -> 36 tensor-core multiply-adds = 72 FLOP executed for the 20 FLOP of the accounting figure
+GLS_UMMA_EXECUTED_FLOP_PER_EVAL = 72.0
 PDM_PEAK_GEVALS_MEASURED = 3841.3  # profiles/r01/pipes_r01.json smem_private_u32_atoms: private-column ATOMS.ADD, updates/s
 
 METRICS = {"pdm": "PDM sample*period evaluations per second",
@@ -75,6 +80,18 @@ def measured_hbm_gbs():
             return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_tflops(sustained=False):
+    """Dense bf16/fp16 tensor peak measured by the driver on this pool's B200s (cuBLAS 8192^3): the burst figure for a
+    kernel timed alone, the sustained one for seconds-long steps; fallback per B200_PROFILING.md."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        key = "bf16_tflops_sustained" if sustained else "bf16_tflops"
+        return float(d[key]), f"MEASURED_PEAKS.json {key} (of measured)"
+    except Exception:
+        return (1400.0 if sustained else 1590.0), "B200_PROFILING.md fallback (of fallback)"
 
 
 def ncu_traffic(kernel):
@@ -760,6 +777,32 @@ def run_workload(env, wl, per_gpu, scaling, steps, warmup, cpu_budget_s=10.0, wa
                 "peak_source": "profiles/r01/pipes_r01.json smem_private_u32_atoms (one shared-memory ATOMS.ADD on a private "
                                "32-bit column word per sample update, 13.7 per clk per SM: the floor of the "
                                "kernel's histogram update); path is shared-memory/issue bound, not HBM or tensor bound"}
+    elif kind != "gls_multi" and ctx.last_gls_path() in (1, 2):
+        # tensor-core formulation (gls_umma_kernel): bound = tcgen05 fp16 rate
+        ach = units_local * FLOP_PER_EVAL_GLS / (main_kernel_ms * 1e-3) / 1e12
+        executed = units_local * GLS_UMMA_EXECUTED_FLOP_PER_EVAL / (main_kernel_ms * 1e-3) / 1e12
+        nsamp = n if n is not None else int(off[-1] - off[0])
+        peak, peak_src = measured_tensor_tflops(sustained=main_kernel_ms > 100.0)
+        traffic, tfile = ncu_traffic("gls_umma")
+        roof = {"bound": "tensor", "kernel": "gls_umma_kernel" + ("<fine operand precomputed>" if ctx.last_gls_path() == 2 else ""),
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic if (kind == "gls" and world == 1 and nsamp == 65_000 and wl["nf"] == 100_000) else None,
+                "traffic_source": f"profiles/{tfile}",
+                "kernel_ms": main_kernel_ms, "flop_per_eval": FLOP_PER_EVAL_GLS,
+                "evals_per_s_kernel": units_local / (main_kernel_ms * 1e-3),
+                "executed": {"flop_per_eval": GLS_UMMA_EXECUTED_FLOP_PER_EVAL, "tflops": executed, "frac_of_peak": executed / peak,
+                             "note": "angle addition across blocks of the grid turns the six sums into fp16 GEMMs over the "
+                                     "sample axis: 12 multiply-adds per evaluation, each as hi*hi + hi*lo + lo*hi (fp16 pairs "
+                                     "carry 22 bits) = 72 executed tensor FLOP for the 20 FLOP of SURVEY 8d's accounting "
+                                     "figure; `frac` stays on the 20-FLOP figure as the contract prescribes, "
+                                     "frac_of_peak = executed tensor FLOP / measured cuBLAS bf16 peak"},
+                "vs_fp32_roofline": {"frac": ach / FP32_PEAK_TFLOPS_MEASURED, "peak": FP32_PEAK_TFLOPS_MEASURED,
+                                     "note": "the same 20-FLOP figure against the FP32 issue peak that bounds gls_strip_kernel "
+                                             "(0.93 there): the tensor-core formulation is past the SIMT roofline"},
+                "peak_source": peak_src,
+                "hbm": {"achieved_gbs": (32.0 * nsamp + 6 * 8 * 2 * (units_local / max(1, nsamp))) / (main_kernel_ms * 1e-3) / 1e9,
+                        "peak_gbs": measured_hbm_gbs()[0], "peak_source": measured_hbm_gbs()[1],
+                        "note": "algorithmic bytes: 32 B/sample record + fixed-point flush; compute bound"}}
     else:
         ach = units_local * FLOP_PER_EVAL_GLS / (main_kernel_ms * 1e-3) / 1e12
         traffic, tfile = ncu_traffic("gls_strip")
@@ -801,7 +844,8 @@ def run_workload(env, wl, per_gpu, scaling, steps, warmup, cpu_budget_s=10.0, wa
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None,
             "dtype": {"pdm": "f64 phase, integer (fixed-point) histograms", "ce": "f64 phase, integer count histograms",
-                      "sl": "f64"}.get(kind, "f32 sums, f64 phase/epilogue"),
+                      "sl": "f64"}.get(kind, "fp16 hi/lo tensor-core products, f32 accumulation, f64 phase/epilogue"
+                                       if roof.get("bound") == "tensor" else "f32 sums, f64 phase/epilogue"),
             "data": "synthetic",
             "config": workload_config(wl, per_gpu, world, scaling),
             "gather_used": "none" if world == 1 else gather_mode[0],

@@ -378,6 +378,12 @@ PDC_API double pdc_ctx_last_main_kernel_ms(pdc_ctx* ctx);
  * difference across its timed region: average launch duration = d(ms) / d(count). */
 PDC_API double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out);
 
+/* Which hot kernel the most recent GLS call on this ctx (primary device) used: 0 = gls_strip_kernel (FP32 SIMT; also the
+ * free-frequency kernel), 1 = gls_umma_kernel (tcgen05 tensor cores), 2 = gls_umma_kernel with the fine operand of the
+ * curve precomputed once (one long curve).  The choice is automatic (problem size, weights, grid direction); the
+ * environment variable PDC_GLS_UMMA=0|1 read at ctx creation forces it off / on whenever eligible.  < 0 on error. */
+PDC_API int pdc_ctx_last_gls_path(pdc_ctx* ctx);
+
 /* Diagnostics of the tensor-core GLS kernel (gls_umma.cu), filled only when the ctx was created with the environment
  * variable PDC_GLS_UMMA_PROF=1: per work item (thread block) of the most recent launch four SM clock stamps
  * {start, main loop begin, main loop end, end of flush} are copied to `out` (up to `cap` items x 4 values).

@@ -45,6 +45,7 @@ SIGNATURES = {
     "pdc_ctx_last_main_kernel_ms": (ctypes.c_double, [ctypes.c_void_p]),
     "pdc_ctx_main_kernel_ms_total": (ctypes.c_double, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "pdc_debug_umma_prof": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "pdc_ctx_last_gls_path": (ctypes.c_int, [ctypes.c_void_p]),
     "pdc_gls": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
@@ -217,6 +218,10 @@ class Context:
         cnt = ctypes.c_int64(0)
         ms = self._lib.pdc_ctx_main_kernel_ms_total(self._h, ctypes.byref(cnt))
         return ms, cnt.value
+
+    def last_gls_path(self):
+        """0 FP32 strip kernel, 1 tensor-core kernel, 2 tensor-core kernel with the precomputed fine operand."""
+        return self._lib.pdc_ctx_last_gls_path(self._h)
 
     def umma_prof(self, cap=1 << 16):
         """Clock stamps [jobs, 4] of the last tensor-core GLS launch (needs PDC_GLS_UMMA_PROF=1 at ctx creation)."""

@@ -255,6 +255,8 @@ double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out) {
   return ctx->main_ms_total;
 }
 
+int pdc_ctx_last_gls_path(pdc_ctx* ctx) { return ctx ? ctx->last_gls_path : -1; }
+
 int64_t pdc_debug_umma_prof(pdc_ctx* ctx, int64_t* out, int64_t cap) {
   if (!ctx) return -1;
   DeviceGuard guard(ctx->device);

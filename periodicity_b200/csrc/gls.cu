@@ -958,8 +958,9 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   a.fix_scale = (float)fix_scale;
 
   ctx->gls_plane_dirty = ctx->gls_low_dirty = true;   // until the epilogue that clears the planes has been enqueued
-  PDC_TRY(ctx->main_begin(st));
   const bool use_umma = !freqs_dev && gls_umma_eligible(ctx, B, nf, ntot, nmax, w != nullptr, df_host);
+  if (!use_umma) PDC_TRY(ctx->main_begin(st));   // (the tensor-core path times its main kernel itself, after its operand pre-pass)
+  ctx->last_gls_path = 0;
   if (freqs_dev) {
     GlsFreeArgs fa;
     fa.curves = dc;
@@ -979,7 +980,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
   } else {
     PDC_TRY(launch_strip(geom, ctx, a, w != nullptr, items, st));
   }
-  PDC_TRY(ctx->main_end(st));
+  if (!use_umma) PDC_TRY(ctx->main_end(st));
 
   {
     GlsEpiArgs e;

@@ -658,10 +658,13 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
     a.prof = ctx->umma_prof.as<long long>();
     ctx->umma_prof_jobs = jobs;
   }
+  PDC_TRY(ctx->main_begin(st));
   if (fine_pre) gls_umma_kernel<true><<<(unsigned)jobs, UM_THREADS, UM_SMEM_BYTES, st>>>(a);
   else gls_umma_kernel<false><<<(unsigned)jobs, UM_THREADS, UM_SMEM_BYTES, st>>>(a);
   PDC_CUDA(cudaGetLastError());
+  PDC_TRY(ctx->main_end(st));
   ctx->launches++;
+  ctx->last_gls_path = fine_pre ? 2 : 1;
   return PDC_OK;
 }
 

@@ -67,6 +67,8 @@ struct pdc_ctx {
   bool gls_geom_forced = false;  // PDC_GLS_GEOM given: no automatic small-problem geometry
   bool gls_three_term = true;  // env PDC_GLS_THREE_TERM=0 forces the rotation form of the strip step (tuning aid)
   int pdm_ppt_override = 0;  // env PDC_PDM_PPT=1|2 forces the trial periods per thread of pdm_hist_kernel (tuning aid)
+  int last_gls_path = 0;       // hot kernel of the most recent GLS call: 0 gls_strip_kernel (or free-frequency), 1 gls_umma_kernel,
+                               // 2 gls_umma_kernel with the precomputed fine operand
   int gls_umma = -1;           // tensor-core formulation of the GLS sums (gls_umma.cu): -1 automatic, 0 off, 1 whenever eligible
                                // (env PDC_GLS_UMMA)
   int gls_umma_chunk = 0;      // env PDC_GLS_UMMA_CHUNK: stages of 16 samples per TMEM accumulation run (default 4)
