@@ -88,10 +88,12 @@ __device__ __forceinline__ void gls_low_range(double fmin, double df, long long 
                                               int& low_begin, int& low_count, int cap = GLS_NLOW_MAX) {
   low_begin = 0;
   low_count = 0;
-  if (T > 0.0 && df > 0.0) {
+  if (T > 0.0 && df != 0.0 && df == df) {
     const double flim = GLS_LOW_CYCLES / T;
-    double ja = ceil((-flim - fmin) / df - (double)j0);
-    double jb = floor((flim - fmin) / df - (double)j0);
+    double lo = (-flim - fmin) / df - (double)j0, hi = (flim - fmin) / df - (double)j0;
+    if (df < 0.0) { const double tmp = lo; lo = hi; hi = tmp; }   // a backward grid crosses the range the other way
+    double ja = ceil(lo);
+    double jb = floor(hi);
     if (ja < 0.0) ja = 0.0;
     if (jb > (double)(nf - 1)) jb = (double)(nf - 1);
     if (jb >= ja) {
