@@ -777,14 +777,15 @@ def run_workload(env, wl, per_gpu, scaling, steps, warmup, cpu_budget_s=10.0, wa
                 "peak_source": "profiles/r01/pipes_r01.json smem_private_u32_atoms (one shared-memory ATOMS.ADD on a private "
                                "32-bit column word per sample update, 13.7 per clk per SM: the floor of the "
                                "kernel's histogram update); path is shared-memory/issue bound, not HBM or tensor bound"}
-    elif kind != "gls_multi" and ctx.last_gls_path() in (1, 2):
+    elif kind != "gls_multi" and ctx.last_gls_path() in (1, 2, 3):
         # tensor-core formulation (gls_umma_kernel): bound = tcgen05 fp16 rate
         ach = units_local * FLOP_PER_EVAL_GLS / (main_kernel_ms * 1e-3) / 1e12
         executed = units_local * GLS_UMMA_EXECUTED_FLOP_PER_EVAL / (main_kernel_ms * 1e-3) / 1e12
         nsamp = n if n is not None else int(off[-1] - off[0])
         peak, peak_src = measured_tensor_tflops(sustained=main_kernel_ms > 100.0)
-        traffic, tfile = ncu_traffic("gls_umma")
-        roof = {"bound": "tensor", "kernel": "gls_umma_kernel" + ("<fine operand precomputed>" if ctx.last_gls_path() == 2 else ""),
+        traffic, tfile = ncu_traffic("gls_umma2" if ctx.last_gls_path() == 3 else "gls_umma")
+        roof = {"bound": "tensor", "kernel": {1: "gls_umma_kernel", 2: "gls_umma_kernel<fine operand precomputed>",
+                                              3: "gls_umma2_kernel (cta_group::2, fine operand precomputed)"}[ctx.last_gls_path()],
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": traffic if (kind == "gls" and world == 1 and nsamp == 65_000 and wl["nf"] == 100_000) else None,
                 "traffic_source": f"profiles/{tfile}",

@@ -380,7 +380,7 @@ PDC_API double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out);
 
 /* Which hot kernel the most recent GLS call on this ctx (primary device) used: 0 = gls_strip_kernel (FP32 SIMT; also the
  * free-frequency kernel), 1 = gls_umma_kernel (tcgen05 tensor cores), 2 = gls_umma_kernel with the fine operand of the
- * curve precomputed once (one long curve).  The choice is automatic (problem size, weights, grid direction); the
+ * curve precomputed once (one long curve), 3 = gls_umma2_kernel (one long curve, a pair of CTAs per tile, cta_group::2).  The choice is automatic (problem size, weights, grid direction); the
  * environment variable PDC_GLS_UMMA=0|1 read at ctx creation forces it off / on whenever eligible.  < 0 on error. */
 PDC_API int pdc_ctx_last_gls_path(pdc_ctx* ctx);
 

@@ -220,7 +220,7 @@ class Context:
         return ms, cnt.value
 
     def last_gls_path(self):
-        """0 FP32 strip kernel, 1 tensor-core kernel, 2 tensor-core kernel with the precomputed fine operand."""
+        """0 FP32 strip kernel, 1 tensor-core kernel, 2 the same with the precomputed fine operand, 3 the 2-CTA tensor-core kernel."""
         return self._lib.pdc_ctx_last_gls_path(self._h)
 
     def umma_prof(self, cap=1 << 16):

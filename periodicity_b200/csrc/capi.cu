@@ -192,6 +192,7 @@ int pdc_ctx_create(pdc_ctx** out, int device) {
   if (const char* g = getenv("PDC_GLS_UMMA_CHUNK")) ctx->gls_umma_chunk = atoi(g);
   if (const char* g = getenv("PDC_GLS_UMMA_DBG")) ctx->gls_umma_dbg = atoi(g);
   if (const char* g = getenv("PDC_GLS_UMMA_FINE")) ctx->gls_umma_fine = atoi(g);
+  if (const char* g = getenv("PDC_GLS_UMMA_CG2")) ctx->gls_umma_cg2 = atoi(g);
   if (const char* g = getenv("PDC_GLS_UMMA_RZCOMP")) ctx->gls_umma_rzcomp = atoi(g);
   if (const char* g = getenv("PDC_GLS_UMMA_PROF")) ctx->umma_prof_on = atoi(g) != 0;
   if (const char* g = getenv("PDC_PDM_PPT")) ctx->pdm_ppt_override = atoi(g);

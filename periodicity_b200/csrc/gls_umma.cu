@@ -31,86 +31,9 @@
 // (A first version had 8 dedicated epilogue warps with 128 masters each and 8 producer warps squeezed into 56
 // registers: 0.73 ms on C2, the producers latency-bound at a quarter of the issue rate.)
 // All waits are bounded (clock-based): a protocol error ends the kernel with a status word, it cannot hang the GPU.
-#include "gls_common.cuh"
-#include "umma.cuh"
+#include "gls_umma_common.cuh"
 
 namespace pdc {
-
-using namespace umma;
-
-constexpr int UM_FINE = 128;           // fine indices per tile = MMA M = TMEM lanes
-constexpr int UM_STAGE_SAMPLES = 16;   // 32 K-slots = two K = 16 steps
-constexpr int UM_NSTAGES = 4;
-constexpr int UM_BLOCK = 512;          // samples per block of staged records (one per worker thread)
-constexpr int UM_WORKERS = 512;        // 16 worker warps
-constexpr int UM_THREADS = UM_WORKERS + 128;   // + one warp group: warp 16 issues the tcgen05.mma, warps 17-19 only donate registers
-constexpr int UM_WORKER_REGS = 112, UM_MMA_REGS = 24;   // setmaxnreg: 640 x 96 at launch -> 512 x 112 + 128 x 24
-constexpr int UM_MAX_T1 = 64, UM_MAX_T2 = 128;   // coarse blocks per tile (N = 4 * 64 = 2 * 128 = 256 columns)
-// one stage in shared memory: [K-chunk of 8 slots][row][8 halves]; 16-byte rows, 8-row groups contiguous (SBO = 128 B)
-constexpr uint32_t UM_FINE_HI = 0, UM_FINE_LO = 8192, UM_COARSE_HI = 16384, UM_COARSE_LO = 32768;
-constexpr uint32_t UM_STAGE_BYTES = 49152;
-constexpr uint32_t UM_LBO_FINE = 128 * 16, UM_LBO_COARSE = 256 * 16, UM_SBO = 128;
-constexpr uint32_t UM_REC_BYTES = 2 * UM_BLOCK * (8 + 4 + 4 + 4);
-constexpr uint32_t UM_SMEM_BYTES = UM_NSTAGES * UM_STAGE_BYTES + UM_REC_BYTES + 256;
-constexpr long long UM_MAX_JOB_SAMPLES = 16384;   // FP32 masters are flushed to the fixed-point plane at least this often
-constexpr long long UM_WAIT_CLOCKS = 4000000000LL;   // ~2 s: far beyond any legitimate wait
-
-struct GlsUmmaArgs {
-  const GlsCurve* curves;
-  const double2* rec1;
-  const float4* rec2;
-  unsigned long long* partial;   // [6][nf_tot] fixed point; planes 4, 5 receive sum w cos 2x, sum w sin 2x
-  long long nf, nf_tot, j0;
-  int nC;                        // coarse blocks per curve
-  int nt1, nt2, cpt1, cpt2;      // tiles per curve and coarse blocks per tile of each type
-  int nsplit;
-  int weighted;
-  int chunk_stages;              // stages (of 16 samples) per accumulation run in TMEM
-  float rz_comp;                 // expected relative truncation loss of the accumulator per tcgen05.mma of a run (see the drain)
-  float fix_scale;
-  const unsigned char* fine_img; // FINE_PRE: fine operand of the whole curve as shared-memory images, [2 types][stage][16 KB] (gls_umma_fine_kernel)
-  long long fine_stages;         // stages per type in fine_img
-  int* status;                   // set non-zero on a protocol time-out
-  int dbg;                       // timing experiments (env PDC_GLS_UMMA_DBG): 1 no MMA, 2 no operand production, 4 no drain, 8 no proxy fence, 16 trace
-  long long* prof;               // optional [jobs][4] clock64 stamps (start, main loop begin, main loop end, flush end)
-};
-
-__device__ __forceinline__ bool um_wait(uint32_t bar, uint32_t parity, volatile int* s_abort, long long t_start) {
-  for (;;) {
-#pragma unroll 1
-    for (int i = 0; i < 256; ++i)
-      if (mbar_try_wait(bar, parity)) return true;
-    if (*s_abort || clock64() - t_start > UM_WAIT_CLOCKS) {
-      *s_abort = 1;
-      return false;
-    }
-  }
-}
-
-// x = hi + lo with hi, lo fp16 (hi rounded to nearest, lo the rounded remainder): packed (c, s) pair
-__device__ __forceinline__ void um_split2(float c, float s, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(c, s);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(c - hf.x, s - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-__device__ __forceinline__ void um_sts128(uint32_t addr, const uint32_t (&v)[4]) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
-}
-// global -> shared bulk copy (TMA without a tensor map): completion is counted in bytes on `bar`
-__device__ __forceinline__ void um_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void um_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// phase (2^-32 turn, two's complement) -> (cos, sin)
-__device__ __forceinline__ void um_sincos_fx(unsigned fx, float& c, float& s) {
-  const float x = (float)(int)fx * 1.4629180792671596e-9f;   // 2 pi / 2^32
-  __sincosf(x, &s, &c);
-}
 
 // Fine operand of a whole curve, once per call, when many coarse tiles share it (one long curve: C2 has 13 + 7 tiles per
 // sample split, C5 1221 + 611): (cos, sin)(kmul k b_i) for k < 128 as fp16 hi / lo, written as the 16 KB shared-memory
@@ -547,6 +470,8 @@ gls_umma_kernel(const GlsUmmaArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+int gls_umma2_launch(pdc_ctx* ctx, GlsUmmaArgs a, int64_t nf, long long nmax, cudaStream_t st);   // gls_umma2.cu
+
 bool gls_umma_eligible(const pdc_ctx* ctx, int64_t B, int64_t nf, long long ntot, long long nmax, bool weighted,
                        const double* df_host) {
   if (ctx->gls_umma == 0) return false;
@@ -591,6 +516,11 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
   a.dbg = ctx->gls_umma_dbg;
   PDC_TRY(ctx->umma_status.reserve(sizeof(int)));
   a.status = ctx->umma_status.as<int>();
+
+  // one long curve with many tiles: a pair of CTAs per tile (gls_umma2.cu)
+  // (automatic from 16384 frequencies on: at least one full tile of 64 coarse blocks; PDC_GLS_UMMA_CG2=1 from 4096, =0 never)
+  if (B == 1 && ctx->gls_umma_fine != 0 && ctx->gls_umma_cg2 != 0 && nf >= (ctx->gls_umma_cg2 > 0 ? 4096 : 16384))
+    return gls_umma2_launch(ctx, a, nf, nmax, st);
 
   // Sample splits.  (i) A job keeps its 32768 sums in FP32 registers until its end: at most UM_MAX_JOB_SAMPLES samples per
   // job bound the rounding of those masters (64 additions of 256-sample runs: ~2e-7 of their magnitude; C5 with one job

@@ -68,10 +68,12 @@ struct pdc_ctx {
   bool gls_three_term = true;  // env PDC_GLS_THREE_TERM=0 forces the rotation form of the strip step (tuning aid)
   int pdm_ppt_override = 0;  // env PDC_PDM_PPT=1|2 forces the trial periods per thread of pdm_hist_kernel (tuning aid)
   int last_gls_path = 0;       // hot kernel of the most recent GLS call: 0 gls_strip_kernel (or free-frequency), 1 gls_umma_kernel,
-                               // 2 gls_umma_kernel with the precomputed fine operand
+                               // 2 gls_umma_kernel with the precomputed fine operand, 3 gls_umma2_kernel (pairs of CTAs)
   int gls_umma = -1;           // tensor-core formulation of the GLS sums (gls_umma.cu): -1 automatic, 0 off, 1 whenever eligible
                                // (env PDC_GLS_UMMA)
   int gls_umma_chunk = 0;      // env PDC_GLS_UMMA_CHUNK: stages of 16 samples per TMEM accumulation run (default 4)
+  int gls_umma_cg2 = -1;       // env PDC_GLS_UMMA_CG2: one long curve on pairs of CTAs (tcgen05 cta_group::2, gls_umma2.cu): -1 automatic
+                               // (>= 16384 frequencies), 0 never, 1 from 4096 frequencies on
   int gls_umma_fine = -1;      // env PDC_GLS_UMMA_FINE: fine operand precomputed per curve: -1 automatic, 0 never, 1 whenever B == 1
   pdc::DevBuf umma_fine;       // its shared-memory images [2 types][stage][16 KB]
   int gls_umma_rzcomp = 1;     // env PDC_GLS_UMMA_RZCOMP=0: no compensation of the TMEM truncation bias (diagnostic)

@@ -24,7 +24,8 @@ TOL = 1e-5
 
 def make_ctx(**env):
     from periodicity_b200 import _ffi
-    keys = ["PDC_GLS_UMMA", "PDC_GLS_UMMA_FINE", "PDC_GLS_UMMA_CHUNK", "PDC_GLS_UMMA_NSPLIT", "PDC_GLS_UMMA_RZCOMP"]
+    keys = ["PDC_GLS_UMMA", "PDC_GLS_UMMA_FINE", "PDC_GLS_UMMA_CHUNK", "PDC_GLS_UMMA_NSPLIT", "PDC_GLS_UMMA_RZCOMP",
+            "PDC_GLS_UMMA_CG2"]
     saved = {k: os.environ.get(k) for k in keys}
     try:
         for k in keys:
@@ -92,7 +93,7 @@ def test_tensor_core_kernel_vs_oracle_and_strip_kernel(ctx_t, ctx_s, N, nf, weig
     w = None if err is None else err ** -2.0
     ref = cport.gls_exact(t, y, err, fmin, df, nf, fit_mean=fit_mean)
     p, am, mx = ctx_t.gls(t, y, w, fmin, df, nf, fit_mean=fit_mean)
-    assert ctx_t.last_gls_path() in (1, 2)              # the tensor-core kernel really ran
+    assert ctx_t.last_gls_path() in (1, 2, 3)              # the tensor-core kernel really ran
     assert not np.isnan(p).any()
     assert_power_close(p, ref)
     assert am == int(np.nanargmax(ref)) and mx == p[am]
@@ -119,12 +120,13 @@ def test_automatic_choice_by_problem_size(gpu_ctx):
     assert gpu_ctx.last_gls_path() == 0
     t, y, err, fmin, df = synth(8000, 50.0, 30000, 1.0, 6)          # 2.4e8 evaluations -> tensor cores
     p, am, _ = gpu_ctx.gls(t, y, None, fmin, df, 30000)
-    assert gpu_ctx.last_gls_path() in (1, 2)
+    assert gpu_ctx.last_gls_path() in (1, 2, 3)
     assert_power_close(p, cport.gls_exact(t, y, None, fmin, df, 30000))
 
 
 def test_precomputed_fine_operand_is_bit_identical_to_the_in_kernel_one():
-    a, b = make_ctx(PDC_GLS_UMMA=1, PDC_GLS_UMMA_FINE=1), make_ctx(PDC_GLS_UMMA=1, PDC_GLS_UMMA_FINE=0)
+    a = make_ctx(PDC_GLS_UMMA=1, PDC_GLS_UMMA_FINE=1, PDC_GLS_UMMA_CG2=0)
+    b = make_ctx(PDC_GLS_UMMA=1, PDC_GLS_UMMA_FINE=0, PDC_GLS_UMMA_CG2=0)
     for (N, nf, weighted) in [(5000, 20000, False), (3001, 1500, True), (70000, 3000, False)]:
         t, y, err, fmin, df = synth(N, 100.0, nf, 1.0, 7 + N, weighted)
         w = None if err is None else err ** -2.0
@@ -138,6 +140,40 @@ def test_precomputed_fine_operand_is_bit_identical_to_the_in_kernel_one():
         np.testing.assert_array_equal(pa, pa2)
 
 
+# (N, nf, weighted): one to several tiles of both types, partial tiles, tile halves of odd size, short and long jobs
+CG2_CASES = [(3000, 4096, False), (5000, 20000, True), (4097, 8321, False), (2000, 70001, False), (30000, 16384, True),
+             (70000, 33000, False), (130, 50000, False)]
+
+
+@pytest.mark.parametrize("N,nf,weighted", CG2_CASES)
+def test_pair_of_ctas_kernel_vs_oracle(N, nf, weighted):
+    """gls_umma2_kernel (tcgen05 cta_group::2: a pair of CTAs per tile of 256 fine indices) against the oracle and against
+    the one-CTA kernel; automatic for one curve from 16384 frequencies on, forced here from 4096."""
+    ctx2, ctx1 = make_ctx(PDC_GLS_UMMA=1, PDC_GLS_UMMA_CG2=1), make_ctx(PDC_GLS_UMMA=1, PDC_GLS_UMMA_CG2=0)
+    t, y, err, fmin, df = synth(N, 100.0, nf, 1.0, 3 * N + nf, weighted)
+    w = None if err is None else err ** -2.0
+    p2, am2, mx2 = ctx2.gls(t, y, w, fmin, df, nf)
+    assert ctx2.last_gls_path() == 3
+    assert not np.isnan(p2).any()
+    idx = np.unique(np.concatenate([np.arange(0, nf, max(1, nf // 3000)), np.arange(max(am2 - 64, 0), min(am2 + 64, nf)),
+                                    np.arange(nf - 300, nf)]))
+    ref = cport.gls_exact_at(t, y, err, fmin, df, idx)
+    assert_power_close(p2[idx], ref)
+    assert idx[int(np.nanargmax(ref))] == am2 and mx2 == p2[am2]
+    p1, am1, _ = ctx1.gls(t, y, w, fmin, df, nf)
+    assert ctx1.last_gls_path() in (1, 2)
+    assert am1 == am2
+    assert np.nanmax(np.abs(p1 - p2)) <= 2e-6 * np.nanmax(p1)
+    p2b, _, _ = ctx2.gls(t, y, w, fmin, df, nf)
+    np.testing.assert_array_equal(p2, p2b)                     # bit-reproducible
+    # a shard of the grid (as the multi-GPU paths cut it) through the same kernel
+    j0, cnt = nf // 3, nf - nf // 3
+    if cnt >= 4096:
+        ps, a_, _ = ctx2.gls(t, y, w, fmin, df, cnt, j0=j0)
+        assert ctx2.last_gls_path() == 3
+        assert np.nanmax(np.abs(ps - p2[j0:])) <= 2e-6 * np.nanmax(p2)
+
+
 def test_frequency_shards_and_psd(ctx_t):
     N, nf = 6000, 12000
     t, y, err, fmin, df = synth(N, 100.0, nf, 1.0, 11, True)
@@ -148,7 +184,7 @@ def test_frequency_shards_and_psd(ctx_t):
     peak = np.nanmax(ref)
     for j0, cnt in [(0, 5000), (5000, 4096), (9096, 2904)]:       # shards of the grid, as the multi-GPU paths cut it
         p, a_, _ = ctx_t.gls(t, y, w, fmin, df, cnt, j0=j0)
-        assert ctx_t.last_gls_path() in (1, 2)
+        assert ctx_t.last_gls_path() in (1, 2, 3)
         assert np.nanmax(np.abs(p - ref[j0:j0 + cnt])) <= TOL * peak
         assert np.nanmax(np.abs(p - full[j0:j0 + cnt])) <= 2e-6 * peak
         assert a_ == int(np.nanargmax(ref[j0:j0 + cnt]))
@@ -196,7 +232,7 @@ def test_dense_grid_with_many_sub_cycle_bins(ctx_t):
     # n = 60 samples per peak: ~60 bins with f T < 1 take their FP64 sums from the small plane, the rest from the tensor path
     t, y, err, fmin, df = synth(3000, 100.0, 9000, 1.0, 41, nper=60)
     p, am, _ = ctx_t.gls(t, y, None, fmin, df, 9000)
-    assert ctx_t.last_gls_path() in (1, 2)
+    assert ctx_t.last_gls_path() in (1, 2, 3)
     assert_power_close(p, cport.gls_exact(t, y, None, fmin, df, 9000))
 
 

@@ -13,10 +13,13 @@ from oracle import cport  # noqa: E402
 from periodicity_b200 import _ffi  # noqa: E402
 
 
+CG2 = [None]
+
+
 def make_ctx(umma, nsplit=None, chunk=None, prof=False, dbg=None):
     os.environ["PDC_GLS_UMMA"] = str(umma)
     for key, val in (("PDC_GLS_UMMA_NSPLIT", nsplit), ("PDC_GLS_UMMA_CHUNK", chunk), ("PDC_GLS_UMMA_PROF", 1 if prof else None),
-                     ("PDC_GLS_UMMA_DBG", dbg)):
+                     ("PDC_GLS_UMMA_DBG", dbg), ("PDC_GLS_UMMA_CG2", CG2[0])):
         if val:
             os.environ[key] = str(val)
         else:
@@ -158,6 +161,8 @@ def case_trace(N=65000, nf=100000, T=1470.0):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["small", "c2"]
+    if "cg2" in which:
+        CG2[0] = 1
     ctx_t, ctx_s = make_ctx(1), make_ctx(0)
     if "small" in which:
         case_small(ctx_t, ctx_s)

@@ -7,6 +7,6 @@ M="sm__inst_executed_pipe_fma.sum,sm__inst_executed_pipe_xu.sum,sm__inst_execute
 # 1. launch list (every launch with its device time; cold-cache, serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_gls_c2_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs > $OUT/up0.log 2>&1
 # 2. pipe counters and one full capture of the hot kernel
-ncu --metrics $M --clock-control none -k regex:gls_umma_kernel -s 3 -c 1 --csv --log-file $OUT/pipes_gls_umma_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs > $OUT/up1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gls_umma_kernel -s 3 -c 1 -f -o $OUT/prof_gls_umma_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs > $OUT/up2.log 2>&1
+ncu --metrics $M --clock-control none -k regex:gls_umma2?_kernel -s 3 -c 1 --csv --log-file $OUT/pipes_gls_umma_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs > $OUT/up1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gls_umma2?_kernel -s 3 -c 1 -f -o $OUT/prof_gls_umma_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs > $OUT/up2.log 2>&1
 ls -la $OUT | tail -6
