@@ -36,6 +36,17 @@ ctx.stringlength(tt, mm, P[:8])                                 # global-scratch
 pw, _, _ = ctx.gls(t, y, None, 0.5 * df, df, 5000)
 idx, val = ctx.peaks_topk(pw, 5)
 ctx.peaks_halfmax(pw, idx)
+# tensor-core formulations of the GLS sums (forced on: the problems here are below the automatic threshold)
+for env in ({"PDC_GLS_UMMA": "1", "PDC_GLS_UMMA_CG2": "0", "PDC_GLS_UMMA_FINE": "0"},      # one CTA per tile, fine operand in the kernel
+            {"PDC_GLS_UMMA": "1", "PDC_GLS_UMMA_CG2": "0", "PDC_GLS_UMMA_FINE": "1"},      # ... precomputed, bulk copies
+            {"PDC_GLS_UMMA": "1", "PDC_GLS_UMMA_CG2": "1"}):                               # pairs of CTAs (cta_group::2)
+    os.environ.update(env)
+    cu = _ffi.Context(0)
+    for ww in (None, w):
+        cu.gls(t, y, ww, 0.5 * df, df, 5000)
+    cu.gls_batch(t, y, None, off, np.full(3, 0.5 * df), np.full(3, df), 700)
+    for k in env:
+        os.environ.pop(k)
 os.environ["PDC_BATCH_PIPE_BYTES"] = "1"                         # read at ctx creation: upload batches in pipelined runs
 ctx2 = _ffi.Context(0)
 ctx2.gls_batch(t, y, w, np.arange(17) * 375, np.full(16, 0.5 * df), np.full(16, df), 700)
