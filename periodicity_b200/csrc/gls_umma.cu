@@ -519,7 +519,10 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
 
   // one long curve with many tiles: a pair of CTAs per tile (gls_umma2.cu)
   // (automatic from 16384 frequencies on: at least one full tile of 64 coarse blocks; PDC_GLS_UMMA_CG2=1 from 4096, =0 never)
-  if (B == 1 && ctx->gls_umma_fine != 0 && ctx->gls_umma_cg2 != 0 && nf >= (ctx->gls_umma_cg2 > 0 ? 4096 : 16384))
+  // (the fine images take 64 KB per 16 samples there, 32 KB on the one-CTA kernel: beyond UM_MAX_FINE_BYTES the fine operand
+  //  is computed in the kernel instead)
+  if (B == 1 && ctx->gls_umma_fine != 0 && ctx->gls_umma_cg2 != 0 && nf >= (ctx->gls_umma_cg2 > 0 ? 4096 : 16384) &&
+      (nmax / UM_STAGE_SAMPLES + 64) * 65536 <= UM_MAX_FINE_BYTES)
     return gls_umma2_launch(ctx, a, nf, nmax, st);
 
   // Sample splits.  (i) A job keeps its 32768 sums in FP32 registers until its end: at most UM_MAX_JOB_SAMPLES samples per
@@ -565,6 +568,7 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
   // (16 KB per 16 samples and type: 133 MB for C2, 2 GB for C5) and let the CTAs fetch it by bulk copy.
   bool fine_pre = B == 1 && a.nt1 >= 3 && ctx->gls_umma_fine != 0;
   if (ctx->gls_umma_fine == 1) fine_pre = B == 1;
+  if ((nmax / UM_STAGE_SAMPLES + 64) * 32768 > UM_MAX_FINE_BYTES) fine_pre = false;
   a.fine_img = nullptr;
   a.fine_stages = 0;
   if (fine_pre) {

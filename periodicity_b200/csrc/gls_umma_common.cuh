@@ -23,6 +23,7 @@ constexpr uint32_t UM_LBO_FINE = 128 * 16, UM_LBO_COARSE = 256 * 16, UM_SBO = 12
 constexpr uint32_t UM_REC_BYTES = 2 * UM_BLOCK * (8 + 4 + 4 + 4);
 constexpr uint32_t UM_SMEM_BYTES = UM_NSTAGES * UM_STAGE_BYTES + UM_REC_BYTES + 256;
 constexpr long long UM_MAX_JOB_SAMPLES = 16384;   // FP32 masters are flushed to the fixed-point plane at least this often
+constexpr long long UM_MAX_FINE_BYTES = 16LL << 30;   // scratch for the precomputed fine operand of one curve (C5: 4 GB)
 constexpr long long UM_WAIT_CLOCKS = 4000000000LL;   // ~2 s: far beyond any legitimate wait
 
 struct GlsUmmaArgs {
