@@ -380,6 +380,11 @@ gls_umma2_kernel(const GlsUmmaArgs a) {
       const int rbase = (blk & 1) * UM_BLOCK + quad * 4 + half * 2;
       for (int st = 0; st < UM_BLOCK / UM_STAGE_SAMPLES && g < nstages; st += 2, g += 2) {
         if (st == 8 && more) {
+          // stage the next block of records early.  Buffer (blk + 1) & 1 was last read for the last pair of block blk - 1; this
+          // warp is four pairs into block blk and could only store those pairs after the tensor core had consumed the pair
+          // two (three in the 2-CTA kernel) before each, i.e. after EVERY warp had written that one: nobody is still in block
+          // blk - 1.  (Ordering by mbarriers only: compute-sanitizer's racecheck, which models bar.sync, reports these buffers.)
+          // The wait for THIS arrival is at the end of the block.
           store_block(blk + 1, n1, n2, nin);
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_rec + 8 * ((blk + 1) & 1));
