@@ -11,15 +11,18 @@
 //   type-1 tiles: {C, S, YC, YS}[cb][k]            coarse rows (w c, -w s), (w s, w c), (w y c, -w y s), (w y s, w y c)
 //   type-2 tiles: {C2, S2}[cb][k] at the doubled angle (the reference's second `_trig_sum` at 2 f, spectral.py:110)
 // Operands cost O((128 + nf / 128) N) sincos instead of O(nf N) FP32 steps; they never exist in global memory: producer
-// warps compute them from the per-sample records (phase reduced mod 1 in FP64, MUFU sin/cos) straight into shared memory
-// in the tcgen05 no-swizzle K-major layout.
+// warps compute them from the per-sample records (phases in 2^-32-turn integer arithmetic, MUFU sin/cos) straight into
+// shared memory in the tcgen05 no-swizzle K-major layout.  (One long curve: the fine operand is the same for all its coarse
+// tiles and is computed once per call, gls_umma_fine_kernel; from 16384 frequencies on a PAIR of CTAs works a tile of 256
+// fine indices, gls_umma2.cu.  This file is the one-CTA kernel: batches, short grids.)
 //
 // Precision.  fp16 inputs with FP32 accumulation, every operand split x = hi + lo (two fp16 numbers, 22 significant bits)
 // and the product taken as hi hi + hi lo + lo hi: three tcgen05.mma per K-step.  The TMEM accumulator TRUNCATES toward
 // zero (measured: tools/microbench/umma_probe.cu, profiles/r02/umma_probe.txt), a bias of up to one ulp per instruction,
-// so an accumulation run in TMEM is only chunk_stages * 16 = 64 samples long (24 instructions): epilogue warps drain
-// the tile (double-buffered in TMEM) and add it to FP32 master accumulators in registers with round-to-nearest.  The
-// masters leave the kernel once per job as 64-bit fixed point through RED.ADD.64 into the same plane gls_strip_kernel
+// so an accumulation run in TMEM is only chunk_stages * 16 = 64 ... 256 samples long: worker warps drain the tile
+// (double-buffered in TMEM), multiply it by 1 + the expected truncation loss of the run (see rz_comp in gls_umma_launch) and
+// add it to FP32 master accumulators in registers with round-to-nearest.  The masters leave the kernel once per job (at
+// most 16384 samples) as 64-bit fixed point through RED.ADD.64 into the same plane gls_strip_kernel
 // uses, so everything downstream (FP64 sub-cycle bins, FP64 epilogue, arg-max, fan-out) is shared.
 //
 // One CTA of 640 threads per SM: 16 identical worker warps (records -> fp16 hi/lo operand tiles, 16 samples per stage, 4
