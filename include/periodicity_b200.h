@@ -384,6 +384,15 @@ PDC_API double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out);
  * environment variable PDC_GLS_UMMA=0|1 read at ctx creation forces it off / on whenever eligible.  < 0 on error. */
 PDC_API int pdc_ctx_last_gls_path(pdc_ctx* ctx);
 
+/* Work decomposition the tensor-core GLS kernels would use for a call of B curves of at most nmax samples on nf
+ * frequencies on a device with sm_count SMs (pure host arithmetic, needs no GPU; knobs fine / cg2 / nsplit / chunk as the
+ * environment variables PDC_GLS_UMMA_FINE / _CG2 / _NSPLIT / _CHUNK, -1 or 0 = automatic).  out[0..10] = {path (1 one CTA per
+ * tile, 2 the same with the fine operand precomputed, 3 a pair of CTAs per tile), fine indices per tile, coarse blocks per
+ * curve, type-1 tiles, coarse blocks per type-1 tile, type-2 tiles, coarse blocks per type-2 tile, sample splits, stages of
+ * 16 samples per accumulation run, jobs, bytes of fine-operand scratch}. */
+PDC_API int pdc_debug_umma_plan(int sm_count, int64_t B, int64_t nf, int64_t nmax, int fine, int cg2, int nsplit, int chunk,
+                                int64_t* out);
+
 /* Diagnostics of the tensor-core GLS kernel (gls_umma.cu), filled only when the ctx was created with the environment
  * variable PDC_GLS_UMMA_PROF=1: per work item (thread block) of the most recent launch four SM clock stamps
  * {start, main loop begin, main loop end, end of flush} are copied to `out` (up to `cap` items x 4 values).

@@ -46,6 +46,8 @@ SIGNATURES = {
     "pdc_ctx_main_kernel_ms_total": (ctypes.c_double, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "pdc_debug_umma_prof": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "pdc_ctx_last_gls_path": (ctypes.c_int, [ctypes.c_void_p]),
+    "pdc_debug_umma_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "pdc_gls": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                ctypes.c_int64, ctypes.c_uint, ctypes.c_double,
@@ -479,6 +481,15 @@ class Context:
 
 _default_ctx = {}
 _default_lock = threading.Lock()
+
+
+def umma_plan(B, nf, nmax, sm_count=148, fine=-1, cg2=-1, nsplit=0, chunk=0):
+    """Work decomposition of the tensor-core GLS kernels for a call (pure host arithmetic: works without a GPU)."""
+    out = np.zeros(11, dtype=np.int64)
+    _check(load_library().pdc_debug_umma_plan(int(sm_count), int(B), int(nf), int(nmax), int(fine), int(cg2), int(nsplit),
+                                              int(chunk), _ptr(out)))
+    keys = ["path", "fine", "nC", "nt1", "cpt1", "nt2", "cpt2", "nsplit", "chunk_stages", "jobs", "fine_bytes"]
+    return dict(zip(keys, (int(v) for v in out)))
 
 
 def default_context(device=None):

@@ -7,6 +7,7 @@
 #include <new>
 
 #include "pdc_common.cuh"
+#include "gls_umma_common.cuh"
 
 namespace pdc {
 
@@ -257,6 +258,15 @@ double pdc_ctx_main_kernel_ms_total(pdc_ctx* ctx, int64_t* count_out) {
 }
 
 int pdc_ctx_last_gls_path(pdc_ctx* ctx) { return ctx ? ctx->last_gls_path : -1; }
+
+int pdc_debug_umma_plan(int sm_count, int64_t B, int64_t nf, int64_t nmax, int fine, int cg2, int nsplit, int chunk, int64_t* out) {
+  if (!out || sm_count < 2 || B < 1 || nf < 1 || nmax < 1) return PDC_EINVAL;
+  pdc::GlsUmmaPlan p;
+  pdc::gls_umma_plan(sm_count, B, nf, nmax, pdc::GlsUmmaKnobs{fine, cg2, nsplit, chunk}, &p);
+  out[0] = p.path; out[1] = p.fine; out[2] = p.nC; out[3] = p.nt1; out[4] = p.cpt1; out[5] = p.nt2; out[6] = p.cpt2;
+  out[7] = p.nsplit; out[8] = p.chunk_stages; out[9] = p.jobs; out[10] = p.fine_bytes;
+  return PDC_OK;
+}
 
 int64_t pdc_debug_umma_prof(pdc_ctx* ctx, int64_t* out, int64_t cap) {
   if (!ctx) return -1;

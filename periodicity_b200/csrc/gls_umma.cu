@@ -474,9 +474,75 @@ gls_umma_kernel(const GlsUmmaArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// work decomposition (pure host arithmetic)
+// ---------------------------------------------------------------------------------------------------------------
+void gls_umma_plan(int sm_count, long long B, long long nf, long long nmax, const GlsUmmaKnobs& k, GlsUmmaPlan* out) {
+  GlsUmmaPlan p;
+  // One long curve from 16384 frequencies on (at least one full tile of 64 coarse blocks; knob cg2 = 1: from 4096, 0: never):
+  // a pair of CTAs per tile of 256 fine indices (gls_umma2.cu), fine operand precomputed at 64 KB per 16 samples.  Beyond
+  // UM_MAX_FINE_BYTES of scratch the fine operand is computed in the kernel instead (one-CTA kernel).
+  const bool pair = B == 1 && k.fine != 0 && k.cg2 != 0 && nf >= (k.cg2 > 0 ? 4096 : 16384) &&
+                    (nmax / UM_STAGE_SAMPLES + 64) * 65536 <= UM_MAX_FINE_BYTES;
+  p.fine = pair ? 256 : UM_FINE;
+  p.nC = (int)((nf + p.fine - 1) / p.fine);
+  // tiles of (nearly) equal size; the number of coarse blocks per tile is rounded so that the MMA's N (4 cpt1, 2 cpt2) is a
+  // multiple of 16 -- and, in the pair kernel, the type-2 half per CTA (cpt2 / 2) a multiple of 8
+  const int r2 = pair ? 16 : 8;
+  p.nt1 = (p.nC + UM_MAX_T1 - 1) / UM_MAX_T1;
+  p.cpt1 = (((p.nC + p.nt1 - 1) / p.nt1) + 3) & ~3;
+  p.nt2 = (p.nC + UM_MAX_T2 - 1) / UM_MAX_T2;
+  p.cpt2 = (((p.nC + p.nt2 - 1) / p.nt2) + r2 - 1) & ~(r2 - 1);
+  // rounding up the tile size can leave the last tile(s) of a type empty: drop them
+  while (p.nt1 > 1 && (long long)(p.nt1 - 1) * p.cpt1 >= p.nC) --p.nt1;
+  while (p.nt2 > 1 && (long long)(p.nt2 - 1) * p.cpt2 >= p.nC) --p.nt2;
+
+  // Sample splits.  (i) A job keeps its 32768 sums in FP32 registers until its end: at most UM_MAX_JOB_SAMPLES samples per
+  // job bound the rounding of those masters (64 additions of 256-sample runs: ~2e-7 of their magnitude; C5 with one job
+  // per tile showed 4.7e-6 on weak bins).  (ii) Few tiles: fill whole waves of one CTA (pair) per SM (pair), with >= 1024
+  // samples per job (its set-up and its flush of 32768 REDs cost about as much as 300 samples).
+  const long long base_jobs = B * (p.nt1 + p.nt2);
+  const long long slots = pair ? sm_count / 2 : sm_count;
+  const long long smin = (nmax + UM_MAX_JOB_SAMPLES - 1) / UM_MAX_JOB_SAMPLES;
+  int nsplit = (int)smin;
+  if (k.nsplit > 0) nsplit = k.nsplit;
+  else if (base_jobs * smin < 6LL * slots) {
+    long long cap = nmax / 1024;
+    if (cap < smin) cap = smin;
+    double best = 1e300;
+    for (long long s = smin; s <= cap && s <= 4096; ++s) {
+      const long long jobs = base_jobs * s;
+      const long long waves = (jobs + slots - 1) / slots;
+      const double per = (double)((nmax + s - 1) / s) + 300.0;   // per-job fixed cost (set-up + flush) in samples
+      const double cost = (double)waves * per;
+      if (cost < best * 0.999) { best = cost; nsplit = (int)s; }
+      if (jobs > 16LL * slots) break;
+    }
+  }
+  p.nsplit = nsplit;
+  // stages (16 samples) per accumulation run in TMEM; even, because stages go in pairs.  Longer runs mean fewer drains (C2,
+  // one-CTA kernel: 0.48 ms at 4, 0.43 ms at 16; pair kernel with 5,000-sample jobs: 0.389 ms at 8, 0.367 ms at 16); short
+  // jobs keep short runs (see rz_comp in gls_umma_launch).
+  const long long per_job = (nmax + nsplit - 1) / nsplit;
+  int cs = per_job >= (pair ? 4096 : 8192) ? 16 : (per_job >= 2048 ? 8 : 4);
+  if (k.chunk > 0) cs = (k.chunk + 1) & ~1;
+  p.chunk_stages = cs;
+  p.jobs = base_jobs * nsplit;
+  // One curve with several coarse tiles per sample split: the fine operand is the same for all of them, compute it once
+  // (32 KB per 16 samples on the one-CTA kernel: 133 MB for C2, 2 GB for C5; twice that on the pair kernel)
+  bool fine_pre = pair || (B == 1 && p.nt1 >= 3 && k.fine != 0);
+  if (k.fine == 1 && B == 1) fine_pre = true;
+  if (!pair && (nmax / UM_STAGE_SAMPLES + 64) * 32768 > UM_MAX_FINE_BYTES) fine_pre = false;
+  const long long per = ((((long long)nmax + nsplit - 1) / nsplit) + 63) & ~63LL;      // samples per split: whole stages
+  const long long stages = per * nsplit / UM_STAGE_SAMPLES + 16;                       // the last run of a split may read past it
+  p.fine_bytes = fine_pre ? stages * (pair ? 65536 : 32768) : 0;
+  p.path = pair ? 3 : (fine_pre ? 2 : 1);
+  *out = p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-int gls_umma2_launch(pdc_ctx* ctx, GlsUmmaArgs a, int64_t nf, long long nmax, cudaStream_t st);   // gls_umma2.cu
+int gls_umma2_launch(pdc_ctx* ctx, GlsUmmaArgs a, const GlsUmmaPlan& plan, long long nmax, cudaStream_t st);   // gls_umma2.cu
 
 bool gls_umma_eligible(const pdc_ctx* ctx, int64_t B, int64_t nf, long long ntot, long long nmax, bool weighted,
                        const double* df_host) {
@@ -500,14 +566,16 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
   a.nf = nf;
   a.nf_tot = (long long)B * nf;
   a.j0 = j0;
-  a.nC = (int)((nf + UM_FINE - 1) / UM_FINE);
-  a.nt1 = (a.nC + UM_MAX_T1 - 1) / UM_MAX_T1;
-  a.cpt1 = (((a.nC + a.nt1 - 1) / a.nt1) + 3) & ~3;
-  a.nt2 = (a.nC + UM_MAX_T2 - 1) / UM_MAX_T2;
-  a.cpt2 = (((a.nC + a.nt2 - 1) / a.nt2) + 7) & ~7;
-  // rounding up the tile size can leave the last tile(s) of a type empty: drop them
-  while (a.nt1 > 1 && (long long)(a.nt1 - 1) * a.cpt1 >= a.nC) --a.nt1;
-  while (a.nt2 > 1 && (long long)(a.nt2 - 1) * a.cpt2 >= a.nC) --a.nt2;
+  GlsUmmaPlan plan;
+  gls_umma_plan(ctx->sm_count, B, nf, nmax, GlsUmmaKnobs{ctx->gls_umma_fine, ctx->gls_umma_cg2, ctx->gls_umma_nsplit, ctx->gls_umma_chunk},
+                &plan);
+  a.nC = plan.nC;
+  a.nt1 = plan.nt1;
+  a.cpt1 = plan.cpt1;
+  a.nt2 = plan.nt2;
+  a.cpt2 = plan.cpt2;
+  a.nsplit = plan.nsplit;
+  a.chunk_stages = plan.chunk_stages;
   a.weighted = weighted ? 1 : 0;
   // The TMEM accumulator truncates toward zero after every instruction: an expected loss of 0.5 ulp(acc) = 0.5 * ln 2 *
   // 2^-23 |acc| per instruction.  Over a run of n instructions with |acc| growing about linearly that is a relative loss
@@ -523,45 +591,9 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
   PDC_TRY(ctx->umma_status.reserve(sizeof(int)));
   a.status = ctx->umma_status.as<int>();
 
-  // one long curve with many tiles: a pair of CTAs per tile (gls_umma2.cu)
-  // (automatic from 16384 frequencies on: at least one full tile of 64 coarse blocks; PDC_GLS_UMMA_CG2=1 from 4096, =0 never)
-  // (the fine images take 64 KB per 16 samples there, 32 KB on the one-CTA kernel: beyond UM_MAX_FINE_BYTES the fine operand
-  //  is computed in the kernel instead)
-  if (B == 1 && ctx->gls_umma_fine != 0 && ctx->gls_umma_cg2 != 0 && nf >= (ctx->gls_umma_cg2 > 0 ? 4096 : 16384) &&
-      (nmax / UM_STAGE_SAMPLES + 64) * 65536 <= UM_MAX_FINE_BYTES)
-    return gls_umma2_launch(ctx, a, nf, nmax, st);
-
-  // Sample splits.  (i) A job keeps its 32768 sums in FP32 registers until its end: at most UM_MAX_JOB_SAMPLES samples per
-  // job bound the rounding of those masters (64 additions of 256-sample runs: ~2e-7 of their magnitude; C5 with one job
-  // per tile showed 4.7e-6 on weak bins).  (ii) Few tiles: fill whole waves of one CTA per SM, with >= 1024 samples per job
-  // (its set-up and its flush of 32768 REDs cost about as much as 300 samples).
-  const long long base_jobs = (long long)B * (a.nt1 + a.nt2);
-  const long long smin = (nmax + UM_MAX_JOB_SAMPLES - 1) / UM_MAX_JOB_SAMPLES;
-  int nsplit = (int)smin;
-  if (ctx->gls_umma_nsplit > 0) nsplit = ctx->gls_umma_nsplit;
-  else if (base_jobs * smin < 6LL * ctx->sm_count) {
-    long long cap = nmax / 1024;
-    if (cap < smin) cap = smin;
-    double best = 1e300;
-    for (long long s = smin; s <= cap && s <= 4096; ++s) {
-      const long long jobs = base_jobs * s;
-      const long long waves = (jobs + ctx->sm_count - 1) / ctx->sm_count;
-      const double per = (double)((nmax + s - 1) / s) + 300.0;   // per-job fixed cost (set-up + flush) in samples
-      const double cost = (double)waves * per;
-      if (cost < best * 0.999) { best = cost; nsplit = (int)s; }
-      if (jobs > 16LL * ctx->sm_count) break;
-    }
-  }
-  a.nsplit = nsplit;
-  {
-    // stages (16 samples) per accumulation run in TMEM; even, because stages go in pairs.  Longer runs mean fewer drains
-    // (C2: 0.48 ms at 4, 0.43 ms at 16); short curves keep short runs (see rz_comp above).
-    const long long per_job = (nmax + nsplit - 1) / nsplit;
-    int cs = per_job >= 8192 ? 16 : (per_job >= 2048 ? 8 : 4);
-    if (ctx->gls_umma_chunk > 0) cs = (ctx->gls_umma_chunk + 1) & ~1;
-    a.chunk_stages = cs;
-  }
-  const long long jobs = base_jobs * nsplit;
+  if (plan.path == 3) return gls_umma2_launch(ctx, a, plan, nmax, st);   // a pair of CTAs per tile (gls_umma2.cu)
+  const long long jobs = plan.jobs;
+  const int nsplit = plan.nsplit;
   if (jobs > 0x7fffffffLL) { set_error("pdc_gls: problem too large for one call (%lld jobs)", jobs); return PDC_EINVAL; }
 
   static bool attr_set[64] = {};
@@ -570,11 +602,7 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
     PDC_CUDA(cudaFuncSetAttribute(gls_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM_BYTES));
     attr_set[ctx->device] = true;
   }
-  // One curve with several coarse tiles per sample split: the fine operand is the same for all of them, compute it once
-  // (16 KB per 16 samples and type: 133 MB for C2, 2 GB for C5) and let the CTAs fetch it by bulk copy.
-  bool fine_pre = B == 1 && a.nt1 >= 3 && ctx->gls_umma_fine != 0;
-  if (ctx->gls_umma_fine == 1) fine_pre = B == 1;
-  if ((nmax / UM_STAGE_SAMPLES + 64) * 32768 > UM_MAX_FINE_BYTES) fine_pre = false;
+  const bool fine_pre = plan.path == 2;
   a.fine_img = nullptr;
   a.fine_stages = 0;
   if (fine_pre) {

@@ -457,40 +457,10 @@ gls_umma2_kernel(const GlsUmmaArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // host side (one curve, forward grid; called from gls_umma_launch when the pair kernel is selected)
 // ---------------------------------------------------------------------------------------------------------------
-int gls_umma2_launch(pdc_ctx* ctx, GlsUmmaArgs a, int64_t nf, long long nmax, cudaStream_t st) {
-  a.nC = (int)((nf + U2_CL_FINE - 1) / U2_CL_FINE);
-  a.nt1 = (a.nC + 63) / 64;
-  a.cpt1 = (((a.nC + a.nt1 - 1) / a.nt1) + 3) & ~3;
-  a.nt2 = (a.nC + 127) / 128;
-  a.cpt2 = (((a.nC + a.nt2 - 1) / a.nt2) + 15) & ~15;
-  while (a.nt1 > 1 && (long long)(a.nt1 - 1) * a.cpt1 >= a.nC) --a.nt1;
-  while (a.nt2 > 1 && (long long)(a.nt2 - 1) * a.cpt2 >= a.nC) --a.nt2;
-  const long long base_jobs = a.nt1 + a.nt2;                  // clusters per sample split
-  const long long clusters = ctx->sm_count / 2;
-  const long long smin = (nmax + UM_MAX_JOB_SAMPLES - 1) / UM_MAX_JOB_SAMPLES;
-  int nsplit = (int)smin;
-  if (ctx->gls_umma_nsplit > 0) nsplit = ctx->gls_umma_nsplit;
-  else if (base_jobs * smin < 6LL * clusters) {
-    long long cap = nmax / 1024;
-    if (cap < smin) cap = smin;
-    double best = 1e300;
-    for (long long s = smin; s <= cap && s <= 4096; ++s) {
-      const long long jobs = base_jobs * s;
-      const long long waves = (jobs + clusters - 1) / clusters;
-      const double per = (double)((nmax + s - 1) / s) + 300.0;
-      const double cost = (double)waves * per;
-      if (cost < best * 0.999) { best = cost; nsplit = (int)s; }
-      if (jobs > 16LL * clusters) break;
-    }
-  }
-  a.nsplit = nsplit;
-  {
-    const long long per_job = (nmax + nsplit - 1) / nsplit;
-    int cs = per_job >= 4096 ? 16 : (per_job >= 2048 ? 8 : 4);   // C2 (5,000-sample jobs): 0.389 ms at 8, 0.367 ms at 16
-    if (ctx->gls_umma_chunk > 0) cs = (ctx->gls_umma_chunk + 1) & ~1;
-    a.chunk_stages = cs;
-  }
-  const long long jobs = base_jobs * nsplit;
+int gls_umma2_launch(pdc_ctx* ctx, GlsUmmaArgs a, const GlsUmmaPlan& plan, long long nmax, cudaStream_t st) {
+  // (a already carries the plan's tiles, splits and run length; gls_umma_plan in gls_umma.cu)
+  const int nsplit = plan.nsplit;
+  const long long jobs = plan.jobs;                              // clusters
   if (2 * jobs > 0x7fffffffLL) { set_error("pdc_gls: problem too large for one call (%lld jobs)", jobs); return PDC_EINVAL; }
   static bool attr_set[64] = {};
   if (ctx->device >= 0 && ctx->device < 64 && !attr_set[ctx->device]) {

@@ -26,6 +26,24 @@ constexpr long long UM_MAX_JOB_SAMPLES = 16384;   // FP32 masters are flushed to
 constexpr long long UM_MAX_FINE_BYTES = 16LL << 30;   // scratch for the precomputed fine operand of one curve (C5: 4 GB)
 constexpr long long UM_WAIT_CLOCKS = 4000000000LL;   // ~2 s: far beyond any legitimate wait
 
+// Work decomposition of one call (pure host arithmetic; gls_umma_plan in gls_umma.cu, also exported for the CPU tests as
+// pdc_debug_umma_plan).  path: 1 one CTA per tile, 2 the same with the fine operand precomputed, 3 a pair of CTAs per tile.
+struct GlsUmmaPlan {
+  int path;
+  int fine;            // fine indices per tile: 128 (paths 1, 2) or 256 (path 3)
+  int nC;              // coarse blocks of `fine` frequencies per curve
+  int nt1, cpt1;       // type-1 tiles {C, S, YC, YS}: count and coarse blocks per tile (4 cpt1 <= 256 columns)
+  int nt2, cpt2;       // type-2 tiles {C2, S2}: count and coarse blocks per tile (2 cpt2 <= 256 columns)
+  int nsplit;          // sample splits per curve
+  int chunk_stages;    // stages of 16 samples per accumulation run in TMEM (even)
+  long long jobs;      // tiles x splits x curves (path 3: clusters)
+  long long fine_bytes;   // scratch for the precomputed fine operand (0 on path 1)
+};
+struct GlsUmmaKnobs {   // the ctx's tuning knobs (environment), -1 / 0 = automatic as documented in pdc_common.cuh
+  int fine, cg2, nsplit, chunk;
+};
+void gls_umma_plan(int sm_count, long long B, long long nf, long long nmax, const GlsUmmaKnobs& k, GlsUmmaPlan* out);
+
 struct GlsUmmaArgs {
   const GlsCurve* curves;
   const double2* rec1;
