@@ -1003,7 +1003,7 @@ int gls_run(pdc_ctx* ctx, const double* t, const double* y, const double* w,
     if (fanout) e.fan = *fanout;
     else memset(&e.fan, 0, sizeof(e.fan));
     e.double_angle = use_umma ? 1 : 0;
-    e.umma_status = use_umma ? ctx->umma_status.as<int>() : nullptr;
+    e.umma_status = use_umma ? ctx->umma_status_cur : nullptr;
     dim3 grid((unsigned)eblk, (unsigned)B);
     gls_epilogue_kernel<<<grid, 256, 0, st>>>(e);
     PDC_CUDA(cudaGetLastError());

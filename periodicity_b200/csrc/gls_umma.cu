@@ -453,6 +453,7 @@ gls_umma_kernel(const GlsUmmaArgs a) {
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
   if (tid == 0) {
+    if (blockIdx.x == 0) *a.status_next = 0;
     if (*s_abort) *a.status = 1;
     if (a.prof) {
       long long* pr = a.prof + 4LL * blockIdx.x;
@@ -579,8 +580,11 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
   a.fix_scale = fix_scale;
   a.prof = nullptr;
   a.dbg = ctx->gls_umma_dbg;
-  PDC_TRY(ctx->umma_status.reserve(sizeof(int)));
-  a.status = ctx->umma_status.as<int>();
+  PDC_TRY(ctx->umma_status.reserve(2 * sizeof(int)));
+  a.status = ctx->umma_status.as<int>() + (ctx->umma_calls & 1);
+  a.status_next = ctx->umma_status.as<int>() + ((ctx->umma_calls + 1) & 1);
+  ctx->umma_status_cur = a.status;
+  ctx->umma_calls++;
 
   if (plan.path == 3) return gls_umma2_launch(ctx, a, plan, nmax, st);   // a pair of CTAs per tile (gls_umma2.cu)
   const long long jobs = plan.jobs;
@@ -608,7 +612,7 @@ int gls_umma_launch(pdc_ctx* ctx, const GlsCurve* curves, const double2* rec1, c
     ctx->launches++;
   }
   if (!ctx->umma_status_clean) {
-    PDC_CUDA(cudaMemsetAsync(a.status, 0, sizeof(int), st));
+    PDC_CUDA(cudaMemsetAsync(ctx->umma_status.p, 0, 2 * sizeof(int), st));
     ctx->umma_status_clean = true;
   }
   if (ctx->umma_prof_on) {

@@ -443,6 +443,7 @@ gls_umma2_kernel(const GlsUmmaArgs a) {
   u2_cluster_sync();            // nobody leaves while the other CTA's instructions may still read this shared memory
   if (warp == 0) u2_tmem_dealloc(tmem, 512);
   if (tid == 0) {
+    if (blockIdx.x == 0) *a.status_next = 0;
     if (*s_abort) *a.status = 1;
     if (a.prof) {
       long long* pr = a.prof + 4LL * blockIdx.x;
@@ -479,7 +480,7 @@ int gls_umma2_launch(pdc_ctx* ctx, GlsUmmaArgs a, const GlsUmmaPlan& plan, long 
     ctx->launches++;
   }
   if (!ctx->umma_status_clean) {
-    PDC_CUDA(cudaMemsetAsync(a.status, 0, sizeof(int), st));
+    PDC_CUDA(cudaMemsetAsync(ctx->umma_status.p, 0, 2 * sizeof(int), st));
     ctx->umma_status_clean = true;
   }
   a.prof = nullptr;

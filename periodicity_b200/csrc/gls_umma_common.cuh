@@ -59,7 +59,8 @@ struct GlsUmmaArgs {
   float fix_scale;
   const unsigned char* fine_img; // FINE_PRE: fine operand of the whole curve as shared-memory images, [2 types][stage][16 KB] (gls_umma_fine_kernel)
   long long fine_stages;         // stages per type in fine_img
-  int* status;                   // set non-zero on a protocol time-out
+  int* status;                   // set non-zero on a protocol time-out (this call's word; the epilogue reads it)
+  int* status_next;              // the next call's word: cleared here, so that a time-out poisons one call, not the ctx
   int dbg;                       // timing experiments (env PDC_GLS_UMMA_DBG): 1 no MMA, 2 no operand production, 4 no drain, 8 no proxy fence, 16 trace
   long long* prof;               // optional [jobs][4] clock64 stamps (start, main loop begin, main loop end, flush end)
 };

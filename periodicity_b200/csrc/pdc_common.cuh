@@ -79,7 +79,10 @@ struct pdc_ctx {
   int gls_umma_rzcomp = 1;     // env PDC_GLS_UMMA_RZCOMP=0: no compensation of the TMEM truncation bias (diagnostic)
   int gls_umma_dbg = 0;        // env PDC_GLS_UMMA_DBG: timing experiments (results are wrong when non-zero)
   int gls_umma_nsplit = 0;     // env PDC_GLS_UMMA_NSPLIT: sample splits of the tensor-core kernel (tuning aid)
-  pdc::DevBuf umma_status;     // int: set by gls_umma_kernel on a protocol time-out; the epilogue then writes NaN
+  pdc::DevBuf umma_status;     // int[2]: word (call & 1) is set by the tensor-core kernel on a protocol time-out (the epilogue then
+                               // writes NaN); every call clears the other word for the next one
+  int64_t umma_calls = 0;
+  int* umma_status_cur = nullptr;   // this call's word (what the epilogue reads)
   bool umma_status_clean = false;
   bool umma_prof_on = false;   // env PDC_GLS_UMMA_PROF=1
   pdc::DevBuf umma_prof;       // long long [jobs][4] clock stamps of the last gls_umma_kernel launch
