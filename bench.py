@@ -789,6 +789,10 @@ def run_workload(env, wl, per_gpu, scaling, steps, warmup, cpu_budget_s=10.0, wa
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": traffic if (kind == "gls" and world == 1 and nsamp == 65_000 and wl["nf"] == 100_000) else None,
                 "traffic_source": f"profiles/{tfile}",
+                "traffic_note": "almost all of it is the precomputed fine operand (16 KB per 16 samples, type and 128 fine "
+                                "indices: 133 MB on C2 for the one-CTA kernel, 266 MB for the pair kernel), written once per "
+                                "call and read once per launch from HBM -- about 4 % of the HBM bandwidth, traded for half of "
+                                "the operand arithmetic; the algorithmic input is 1.9 MB",
                 "kernel_ms": main_kernel_ms, "flop_per_eval": FLOP_PER_EVAL_GLS,
                 "evals_per_s_kernel": units_local / (main_kernel_ms * 1e-3),
                 "executed": {"flop_per_eval": GLS_UMMA_EXECUTED_FLOP_PER_EVAL, "tflops": executed, "frac_of_peak": executed / peak,
